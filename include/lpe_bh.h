@@ -1,0 +1,157 @@
+/*
+ * lpe_bh.h — C ABI of the B200-native Barnes-Hut step (liblpe_bh.so).
+ *
+ * This is the drop-in boundary for ONE hot path of sean-peters-au/little-physics-engine:
+ *   Systems::BarnesHutSystem::update(entt::registry&)   reference src/systems/barnes_hut.cpp:50-99
+ *   Systems::MovementSystem::update(entt::registry&)    reference src/systems/movement.cpp:13-39
+ * The reference has no FFI layer of its own; the C++ class in
+ * little-physics-engine_b200/host/systems/barnes_hut.hpp keeps the reference's class/ISystem
+ * contract and calls these entry points. Plain pointers and sizes only; host buffers stay
+ * caller-owned. Every entry point returns 0 on success, non-zero on error with a message
+ * available from lpe_bh_last_error(). There is NO CPU fallback: without a CUDA device
+ * lpe_bh_create fails.
+ *
+ * Bodies are flat arrays in entity-creation order (index i = i-th entity), with a per-body
+ * component mask mirroring the registry (entity_components.hpp:21-29,111-116).
+ */
+#ifndef LPE_BH_H
+#define LPE_BH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LPE_BH_ABI_VERSION 1
+
+/* component mask bits (Position is implied) */
+#define LPE_HAS_MASS     1u /* Components::Mass      -> source if not Boundary (barnes_hut.cpp:117) */
+#define LPE_HAS_VELOCITY 2u /* Components::Velocity  -> target if it also has Mass (barnes_hut.cpp:89) */
+#define LPE_BOUNDARY     4u /* Components::Boundary  -> excluded from every view */
+#define LPE_LIQUID       8u /* ParticlePhase::Liquid -> not moved by MovementSystem (movement.cpp:25-29) */
+
+/* lpe_bh_params.precision */
+#define LPE_PREC_FAST   0 /* fp64 state + fp64 differences, fp32 interaction math, exact fp64 re-test of borderline theta decisions */
+#define LPE_PREC_STRICT 1 /* every interaction in fp64, in the reference's expression order */
+
+typedef struct lpe_bh_ctx lpe_bh_ctx;
+
+typedef struct {
+    double universe_size;        /* SharedSystemConfig::UniverseSizeMeters: root square is [0,U)^2 (barnes_hut.cpp:110-112) */
+    double softening;            /* SharedSystemConfig::GravitationalSoftener (barnes_hut.cpp:261) */
+    double theta;                /* BarnesHutConfig::theta (barnes_hut.hpp:36) */
+    double small_mass_threshold; /* BarnesHutConfig::smallMassThreshold, 0 disables (barnes_hut.hpp:45) */
+    double G;                    /* SimulatorConstants::RealG = 6.674e-11 (constants.cpp:8) */
+    double dt_kick;              /* SecondsPerTick*baseTimeAcceleration*timeScale (barnes_hut.cpp:284) */
+    double dt_drift;             /* SecondsPerTick*TimeAcceleration (movement.cpp:17); used when do_drift != 0 */
+    int32_t quirk_mode;          /* 1 (reference): every internal node counts its first occupant twice (barnes_hut.cpp:157-177); 0: textbook tree */
+    int32_t precision;           /* LPE_PREC_* */
+    int32_t do_drift;            /* 0: BarnesHutSystem only (velocity kick); 1: MovementSystem fused into the same step */
+    int32_t max_depth;           /* 0: automatic (softening bound, SURVEY.md Q4, capped at 30); else forced key depth 1..30 */
+} lpe_bh_params;
+
+typedef struct {
+    uint64_t n_bodies;       /* bodies uploaded */
+    uint64_t n_in_tree;      /* sources inside [0,U)^2 */
+    uint64_t n_terminals;    /* distinct depth-D cells (leaves + aggregated cells at the depth bound) */
+    uint64_t n_nodes;        /* nodes of the path-compressed tree in pre-order (terminals + branching cells) */
+    uint64_t interactions;   /* accepted node interactions of the last step (only counted when stats are enabled) */
+    uint64_t visits;         /* node visits (per lane) of the last step (only when stats are enabled) */
+    int32_t  depth;          /* key depth D used by the last step */
+    int32_t  sort_passes;
+    float ms_keygen, ms_sort, ms_build, ms_traverse, ms_total; /* last step, CUDA events; only when timing is enabled */
+} lpe_bh_stats;
+
+/* tree dump for parity tests; every pointer may be NULL. Arrays are sized by the caller from lpe_bh_get_stats. */
+typedef struct {
+    uint64_t* sorted_keys;   /* [n_bodies] Morton keys in sorted order (bit 2D set = not in tree) */
+    uint32_t* sorted_index;  /* [n_bodies] creation index of the body at each sorted position */
+    int32_t*  node_level;    /* [n_nodes] level of a branching cell; -1 single-body leaf; -2 aggregated cell at the depth bound */
+    uint64_t* node_key;      /* [n_nodes] Morton key (depth D) of the first body of the node */
+    uint32_t* node_skip;     /* [n_nodes] pre-order index of the first node after this node's subtree */
+    uint32_t* node_first;    /* [n_nodes] creation index of the node's first occupant (minimum insertion rank) */
+    uint32_t* node_count;    /* [n_nodes] bodies under the node */
+    double*   node_mass;     /* [n_nodes] node mass as the traversal sees it (includes the quirk when enabled) */
+    double*   node_comx;     /* [n_nodes] */
+    double*   node_comy;     /* [n_nodes] */
+} lpe_bh_tree_dump;
+
+/* device-resident views for zero-copy interop (torch / NCCL plumbing); valid until the next upload or destroy */
+typedef struct {
+    void* pos;        /* double2[n]  (x,y) per body, creation order */
+    void* vel;        /* double2[n] */
+    void* mass;       /* double[n] */
+    void* xchg_send;  /* double4[xchg_chunk]  this rank's packed slice (x,y,vx,vy), see lpe_bh_set_shard */
+    void* xchg_recv;  /* double4[xchg_chunk * nranks] */
+    uint64_t n;
+    uint64_t xchg_chunk; /* elements per rank in the exchange buffers */
+} lpe_bh_device_view;
+
+const char* lpe_bh_version(void);
+int  lpe_bh_device_count(void);
+
+int  lpe_bh_create(int device, lpe_bh_ctx** out);
+void lpe_bh_destroy(lpe_bh_ctx* ctx);
+const char* lpe_bh_last_error(const lpe_bh_ctx* ctx); /* ctx may be NULL: last creation error */
+
+/* Run all work of this context on an existing CUDA stream (cudaStream_t as void*); NULL restores the context's own stream. */
+int  lpe_bh_set_stream(lpe_bh_ctx* ctx, void* cuda_stream);
+/* flags: bit0 = per-phase CUDA-event timing, bit1 = count interactions/visits (slower; parity tests only) */
+int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
+
+/* Stage bodies into device SoA buffers. rank[i] = position of body i in the iteration of
+ * view<Position,Mass>(exclude<Boundary>) (the reference's insertion order); NULL = EnTT's default, newest
+ * entity first. comp NULL = every body has Mass and Velocity. vx/vy NULL = zero. Asynchronous on the context's
+ * stream when the host arrays are pinned. */
+int  lpe_bh_upload(lpe_bh_ctx* ctx, uint64_t n, const double* x, const double* y, const double* vx,
+                   const double* vy, const double* m, const uint32_t* rank, const uint8_t* comp);
+/* Positions only (e.g. after other ECS systems moved bodies); n must match the last upload. */
+int  lpe_bh_upload_positions(lpe_bh_ctx* ctx, const double* x, const double* y);
+int  lpe_bh_upload_velocities(lpe_bh_ctx* ctx, const double* vx, const double* vy);
+
+/* nsteps x { keygen, sort, tree build + aggregation, traversal, kick [, drift] } on device-resident state. Asynchronous. */
+int  lpe_bh_step(lpe_bh_ctx* ctx, const lpe_bh_params* p, int nsteps);
+
+/* Copy state back (synchronises). Any pointer may be NULL. */
+int  lpe_bh_download(lpe_bh_ctx* ctx, double* x, double* y, double* vx, double* vy);
+int  lpe_bh_synchronize(lpe_bh_ctx* ctx);
+
+/* One-call host round trip used by the ECS drop-in: upload, one step, download. x,y,vx,vy are updated in place. */
+int  lpe_bh_update_host(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n, double* x, double* y, double* vx,
+                        double* vy, const double* m, const uint32_t* rank, const uint8_t* comp);
+
+int  lpe_bh_get_stats(lpe_bh_ctx* ctx, lpe_bh_stats* out);          /* synchronises */
+int  lpe_bh_dump_tree(lpe_bh_ctx* ctx, lpe_bh_tree_dump* out);      /* tree of the last step; synchronises */
+/* per-body accepted / visited counts of the last step in creation order (instrumentation bit1 must be on) */
+int  lpe_bh_get_counts(lpe_bh_ctx* ctx, uint32_t* accepted, uint32_t* visited);
+
+/* Direct O(N^2) sum with the same force law, for the accuracy cross-check: accelerations of bodies
+ * [first, first+count) in creation order, fp64, from device-resident state. Synchronises. */
+int  lpe_bh_direct_accel(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t first, uint64_t count, double* ax,
+                         double* ay);
+
+/* ---- multi-GPU (one context per process/GPU; the collective itself is the caller's, e.g. NCCL allgather) ----
+ * Every rank holds all bodies and builds the same tree; rank r traverses and integrates the sorted-order blocks
+ * b with b % nranks == r (blocks of LPE_SHARD_BLOCK Morton-consecutive bodies), packs their new (x,y,vx,vy) into
+ * xchg_send, and after the caller's allgather into xchg_recv, lpe_bh_step_finish scatters every rank's slice
+ * back into the state arrays. nranks == 1 restores the single-GPU path. */
+#define LPE_SHARD_BLOCK 2048u
+int  lpe_bh_set_shard(lpe_bh_ctx* ctx, int rank, int nranks);
+int  lpe_bh_step_begin(lpe_bh_ctx* ctx, const lpe_bh_params* p);   /* build + own-slice traversal -> xchg_send */
+int  lpe_bh_step_finish(lpe_bh_ctx* ctx);                          /* xchg_recv -> state */
+int  lpe_bh_get_device_view(lpe_bh_ctx* ctx, lpe_bh_device_view* out);
+/* pure host helper (no GPU): which rank owns sorted position i, and where it sits in that rank's packed slice */
+int  lpe_bh_shard_owner(uint64_t sorted_pos, int nranks, int* rank_out, uint64_t* slot_out);
+uint64_t lpe_bh_shard_chunk(uint64_t n_bodies, int nranks);        /* elements per rank in the exchange buffers */
+
+/* ---- deterministic synthetic workloads (host, std::mt19937_64, u=(g()>>11)*2^-53) ----
+ * kind: 0 = uniform disk (C2), 1 = Plummer sphere projected (C3), 2 = two-galaxy collision (C4),
+ *       3 = Keplerian disk with the law of reference src/scenarios/keplerian_disk.cpp:78-147 (C1 stand-in) */
+int  lpe_bh_workload(int kind, uint64_t n, uint64_t seed, double universe_size, double* x, double* y,
+                     double* vx, double* vy, double* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,10 @@
+#!/usr/bin/env bash
+# Builds liblpe_bh.so (CUDA kernels + C ABI + host workloads) in-tree for sm_100a.
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+OUT="$HERE/liblpe_bh.so"
+"$NVCC" -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a \
+  -Xcompiler -fPIC,-O3,-Wall -Xptxas -v --shared \
+  -o "$OUT" "$HERE/csrc/lpe_bh.cu" "$HERE/csrc/workloads.cpp" -lcudart 2> "$HERE/build.log" || { cat "$HERE/build.log"; exit 1; }
+echo "built $OUT"

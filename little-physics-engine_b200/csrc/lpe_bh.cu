@@ -1,0 +1,691 @@
+// lpe_bh.cu — host side of the C ABI declared in include/lpe_bh.h: device buffers, staging, and the launch
+// sequence of one Barnes-Hut step. No CPU fallback: every entry point needs a CUDA device.
+//
+// One step, all on one stream, no host synchronisation (counts live in a device `Scal` block):
+//   keygen -> radix sort (u64 key, u32 index) -> gather -> head-flag scan -> terminals -> witnesses ->
+//   mask-popcount scan -> topology -> aggregate (walk-up) -> traverse + kick (+ drift)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lpe_bh.h"
+#include "bh_common.cuh"
+#include "bh_sort.cuh"
+#include "bh_build.cuh"
+#include "bh_traverse.cuh"
+
+using namespace lpe;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct lpe_bh_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int instr = 0;
+
+    uint64_t n = 0, cap = 0;
+    int shard_rank = 0, shard_n = 1;
+    uint64_t xchg_chunk = 0;
+
+    // state
+    double2 *pos = nullptr, *vel = nullptr;
+    double* mass = nullptr;
+    unsigned int* rank = nullptr;
+    unsigned char* comp = nullptr;
+    // staging
+    double* tmp = nullptr;  // 4*cap doubles
+    // sort
+    unsigned long long* keys[2] = {nullptr, nullptr};
+    unsigned int* vals[2] = {nullptr, nullptr};
+    unsigned int *table = nullptr, *totals = nullptr;
+    int sorted_sel = 0;
+    // sorted copies
+    double2* spos = nullptr;
+    double* smass = nullptr;
+    unsigned int *srank = nullptr, *selfnode = nullptr;
+    // scans
+    unsigned int *tileSums = nullptr, *headExcl = nullptr, *P = nullptr;
+    // terminals
+    unsigned long long* tkey = nullptr;
+    unsigned int *tfirst = nullptr, *mask = nullptr, *tnode = nullptr;
+    signed char* delta = nullptr;
+    // nodes
+    uint64_t node_cap = 0;
+    unsigned int *parent = nullptr, *child = nullptr, *arrived = nullptr, *nodeStart = nullptr;
+    Agg* agg = nullptr;
+    double2* nodeA = nullptr;
+    NodeB* nodeB = nullptr;
+    double* nodeM = nullptr;
+    signed char* nlevel = nullptr;
+    // stats
+    unsigned int *cntAcc = nullptr, *cntVis = nullptr;
+    Scal* scal = nullptr;
+    // exchange
+    double4 *xchg_send = nullptr, *xchg_recv = nullptr;
+    // timing
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    lpe_bh_stats last{};
+    StepConst last_c{};
+    bool have_step = false;
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+#define CU_TRY(ctx, expr)                                                                       \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                    \
+            return 1;                                                                           \
+        }                                                                                       \
+    } while (0)
+
+int fail(lpe_bh_ctx* c, const std::string& m) {
+    if (c) c->err = m; else g_create_error = m;
+    return 1;
+}
+
+template <class T>
+int dalloc(lpe_bh_ctx* c, T*& p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) {
+        c->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    c->allocs.push_back(q);
+    p = static_cast<T*>(q);
+    return 0;
+}
+
+void free_all(lpe_bh_ctx* c) {
+    for (void* p : c->allocs) cudaFree(p);
+    c->allocs.clear();
+    c->cap = 0;
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
+    if (n <= c->cap && c->cap != 0) return 0;
+    cudaStreamSynchronize(c->stream);
+    free_all(c);
+    const uint64_t cap = n < 1024 ? 1024 : n;
+    const uint64_t ncap = 2 * cap + 8;
+    const int sortTiles = cdiv((long long)cap, SORT_TILE);
+    const int scanTiles = cdiv((long long)cap + 1, SCAN_TILE);
+    int rc = 0;
+    rc |= dalloc(c, c->pos, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->mass, cap) | dalloc(c, c->rank, cap) |
+          dalloc(c, c->comp, cap) | dalloc(c, c->tmp, 4 * cap);
+    rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
+          dalloc(c, c->vals[1], cap) | dalloc(c, c->table, (size_t)256 * sortTiles) | dalloc(c, c->totals, 256 * 8);
+    rc |= dalloc(c, c->spos, cap) | dalloc(c, c->smass, cap) | dalloc(c, c->srank, cap) | dalloc(c, c->selfnode, cap);
+    rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
+    rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
+          dalloc(c, c->tnode, cap + 2) | dalloc(c, c->delta, cap + 2);
+    rc |= dalloc(c, c->parent, ncap) | dalloc(c, c->child, 4 * ncap) | dalloc(c, c->arrived, ncap) |
+          dalloc(c, c->nodeStart, ncap) | dalloc(c, c->agg, ncap) | dalloc(c, c->nodeA, ncap) |
+          dalloc(c, c->nodeB, ncap) | dalloc(c, c->nodeM, ncap) | dalloc(c, c->nlevel, ncap);
+    rc |= dalloc(c, c->cntAcc, cap) | dalloc(c, c->cntVis, cap) | dalloc(c, c->scal, 1);
+    if (rc) {
+        free_all(c);
+        return 1;
+    }
+    c->cap = cap;
+    c->node_cap = ncap;
+    c->xchg_send = c->xchg_recv = nullptr;
+    c->xchg_chunk = 0;
+    return 0;
+}
+
+int ensure_xchg(lpe_bh_ctx* c) {
+    const uint64_t chunk = lpe_bh_shard_chunk(c->n, c->shard_n);
+    if (c->xchg_send && c->xchg_chunk == chunk) return 0;
+    // (old exchange buffers, if any, stay in the allocation list and are released with the context)
+    if (dalloc(c, c->xchg_send, chunk) || dalloc(c, c->xchg_recv, chunk * (uint64_t)c->shard_n)) return 1;
+    c->xchg_chunk = chunk;
+    return 0;
+}
+
+__global__ void k_pack2(int n, const double* __restrict__ a, const double* __restrict__ b, double2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(a ? a[i] : 0.0, b ? b[i] : 0.0);
+}
+__global__ void k_unpack2(int n, const double2* __restrict__ in, double* __restrict__ a, double* __restrict__ b) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double2 v = in[i];
+        a[i] = v.x;
+        b[i] = v.y;
+    }
+}
+__global__ void k_default_meta(int n, unsigned int* __restrict__ rank, unsigned char* __restrict__ comp, int setRank,
+                               int setComp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        // EnTT iterates the leading pool back to front: newest entity is inserted first
+        if (setRank) rank[i] = (unsigned int)(n - 1 - i);
+        if (setComp) comp[i] = (unsigned char)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+    }
+}
+__global__ void k_init_self(int n, unsigned int* __restrict__ selfnode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) selfnode[i] = LPE_NONE;
+}
+
+// sharded mode: every rank's packed slice -> state arrays (creation order)
+__global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, const unsigned int* __restrict__ sidx,
+                               const double4* __restrict__ recv, double2* __restrict__ pos,
+                               double2* __restrict__ vel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int gblock = (unsigned int)i / LPE_SHARD_BLOCK;
+    const unsigned int r = gblock % (unsigned int)nranks, lblock = gblock / (unsigned int)nranks;
+    const unsigned long long slot = (unsigned long long)lblock * LPE_SHARD_BLOCK + ((unsigned int)i % LPE_SHARD_BLOCK);
+    const double4 v = recv[(unsigned long long)r * chunk + slot];
+    const unsigned int b = sidx[i];
+    pos[b] = make_double2(v.x, v.y);
+    vel[b] = make_double2(v.z, v.w);
+}
+
+// Direct O(N^2) sum in fp64 with the reference's force law (barnes_hut.cpp:257-282), tiled through shared memory.
+__global__ void __launch_bounds__(256)
+k_direct(int n, const double2* __restrict__ pos, const double* __restrict__ mass,
+         const unsigned char* __restrict__ comp, double U, double eps2, double G, int first, int count,
+         double* __restrict__ ax, double* __restrict__ ay) {
+    __shared__ double sx[256], sy[256], sm[256];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + k;
+    double2 p = make_double2(0.0, 0.0);
+    if (k < count) p = pos[i];
+    double accx = 0.0, accy = 0.0;
+    for (int base = 0; base < n; base += 256) {
+        const int j = base + threadIdx.x;
+        double2 q = make_double2(0.0, 0.0);
+        double m = 0.0;
+        if (j < n) {
+            const unsigned char cm = comp[j];
+            q = pos[j];
+            const bool src = (cm & 1u) && !(cm & 4u) && q.x >= 0.0 && q.x < U && q.y >= 0.0 && q.y < U;
+            m = src ? mass[j] : 0.0;
+        }
+        __syncthreads();
+        sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sm[threadIdx.x] = m;
+        __syncthreads();
+        const int lim = min(256, n - base);
+        for (int t = 0; t < lim; ++t) {
+            if (base + t == i) continue;
+            const double dx = sx[t] - p.x, dy = sy[t] - p.y;
+            const double d2 = dx * dx + dy * dy + eps2;
+            const double f = G * sm[t] / (d2 * sqrt(d2));
+            accx += dx * f;
+            accy += dy * f;
+        }
+    }
+    if (k < count) {
+        ax[k] = accx;
+        ay[k] = accy;
+    }
+}
+
+int choose_depth(const lpe_bh_params& p) {
+    if (p.max_depth > 0) return p.max_depth > LPE_MAX_DEPTH ? LPE_MAX_DEPTH : p.max_depth;
+    if (!(p.softening > 0.0) || !(p.theta > 0.0)) return LPE_MAX_DEPTH;
+    // a cell with s < theta*eps is accepted whatever the distance (s^2/(d^2+eps^2) < theta^2), so the
+    // reference never descends below the first level where that holds. A small safety margin keeps the fp64
+    // comparison in the reference (barnes_hut.cpp:269) strictly on the accepting side.
+    const double lim = p.theta * p.softening * (1.0 - 1e-9);
+    int D = 1;
+    while (D < LPE_MAX_DEPTH && std::ldexp(p.universe_size, -D) >= lim) ++D;
+    return D;
+}
+
+int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
+    if (!(p.universe_size > 0.0) || !std::isfinite(p.universe_size)) return fail(c, "universe_size must be positive and finite");
+    if (!(p.theta >= 0.0)) return fail(c, "theta must be >= 0");
+    if (p.precision != LPE_PREC_FAST && p.precision != LPE_PREC_STRICT) return fail(c, "unknown precision");
+    std::memset(&k, 0, sizeof(k));
+    k.U = p.universe_size;
+    int e = 0;
+    std::frexp(p.universe_size, &e);  // U = f * 2^e, f in [0.5,1)
+    k.S = std::ldexp(1.0, e);
+    k.invS = std::ldexp(1.0, -e);
+    k.eps = p.softening;
+    const double es = p.softening * k.invS;
+    k.eps2s = es * es;
+    k.theta = p.theta;
+    k.theta2 = p.theta * p.theta;
+    k.thr = p.small_mass_threshold;
+    k.G = p.G;
+    k.dtK = p.dt_kick;
+    k.dtD = p.dt_drift;
+    k.D = choose_depth(p);
+    k.h = std::ldexp(p.universe_size, -k.D);
+    k.invh = 1.0 / k.h;
+    k.quirk = p.quirk_mode ? 1 : 0;
+    k.do_drift = p.do_drift ? 1 : 0;
+    k.n = (int)c->n;
+    k.shard_rank = c->shard_rank;
+    k.shard_n = c->shard_n;
+    return 0;
+}
+
+template <class Load>
+void device_scan(lpe_bh_ctx* c, Load load, int n, unsigned int* out, unsigned int* total) {
+    // out[0..n] (n+1 entries): exclusive prefix, out[n] = total
+    const int tiles = cdiv((long long)n + 1, SCAN_TILE);
+    k_scan_reduce<<<tiles, SCAN_THREADS, 0, c->stream>>>(load, n, c->tileSums);
+    k_scan_spine<<<1, SCAN_THREADS, 0, c->stream>>>(c->tileSums, tiles, total);
+    k_scan_apply<<<tiles, SCAN_THREADS, 0, c->stream>>>(load, n, c->tileSums, out);
+}
+
+int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
+    StepConst k;
+    if (make_const(c, p, k)) return 1;
+    const int n = (int)c->n;
+    if (n == 0) return 0;
+    if (c->shard_n > 1 && ensure_xchg(c)) return 1;
+    cudaStream_t st = c->stream;
+    const bool timing = c->instr & 1;
+    const bool stats = c->instr & 2;
+    const int passes = (2 * k.D + 1 + 7) / 8;
+    const int sortTiles = cdiv(n, SORT_TILE);
+    const int g256 = cdiv(n, 256);
+
+    if (timing) cudaEventRecord(c->ev[0], st);
+    CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), st));
+    CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * 256 * passes, st));
+    CU_TRY(c, cudaMemsetAsync(c->mask, 0, sizeof(unsigned int) * ((size_t)n + 1), st));
+    CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * (2 * (size_t)n + 2), st));
+    CU_TRY(c, cudaMemsetAsync(c->arrived, 0, sizeof(unsigned int) * (2 * (size_t)n + 2), st));
+
+    k_keygen<<<g256, 256, 0, st>>>(k, c->pos, c->mass, c->comp, c->keys[0], c->vals[0], c->scal);
+    if (timing) cudaEventRecord(c->ev[1], st);
+
+    int sel = 0;
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = 8 * ps;
+        k_sort_count<<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], n, shift, sortTiles, c->table, c->totals + 256 * ps);
+        k_sort_scan<<<256, 256, 0, st>>>(c->table, c->totals + 256 * ps, sortTiles);
+        k_sort_scatter<<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
+                                                            n, shift, sortTiles, c->table);
+        sel ^= 1;
+    }
+    c->sorted_sel = sel;
+    const unsigned long long* skeys = c->keys[sel];
+    const unsigned int* sidx = c->vals[sel];
+    if (timing) cudaEventRecord(c->ev[2], st);
+
+    k_gather<<<g256, 256, 0, st>>>(n, sidx, c->pos, c->mass, c->rank, c->spos, c->smass, c->srank);
+    k_init_self<<<g256, 256, 0, st>>>(n, c->selfnode);
+    device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
+    k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
+    k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->scal);
+    device_scan(c, MaskPop{c->mask, c->scal}, n, c->P, nullptr);
+    k_topology<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->P, c->tnode, c->parent, c->child, c->nodeB,
+                                      c->nodeStart, c->scal);
+    NodeOut no{c->nodeA, c->nodeB, c->nodeM, c->nlevel};
+    k_aggregate<<<g256, 256, 0, st>>>(k, c->tfirst, c->tnode, c->spos, c->smass, c->srank, c->parent, c->child,
+                                       c->arrived, c->agg, no, c->selfnode, c->scal);
+    if (timing) cudaEventRecord(c->ev[3], st);
+
+    TravArgs ta{};
+    ta.nodeA = c->nodeA; ta.nodeB = c->nodeB; ta.nodeM = c->nodeM; ta.spos = c->spos; ta.smass = c->smass;
+    ta.sidx = sidx; ta.selfnode = c->selfnode; ta.comp = c->comp; ta.pos = c->pos; ta.vel = c->vel;
+    ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
+    const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
+    const unsigned int own = (nblocks + (unsigned int)c->shard_n - 1u - (unsigned int)c->shard_rank) / (unsigned int)c->shard_n;
+    ta.n_chunks_local = own * (LPE_SHARD_BLOCK / 32u);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int warpsPerBlock = TRAV_THREADS / 32;
+    int grid = cdiv(ta.n_chunks_local, warpsPerBlock);
+    const int maxGrid = sms * 8;
+    if (grid > maxGrid) grid = maxGrid;
+    if (grid < 1) grid = 1;
+    if (p.precision == LPE_PREC_FAST) {
+        if (stats) k_traverse<0, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+        else k_traverse<0, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+    } else {
+        if (stats) k_traverse<1, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+        else k_traverse<1, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+    }
+    if (timing) cudaEventRecord(c->ev[4], st);
+    CU_TRY(c, cudaGetLastError());
+    c->last_c = k;
+    c->have_step = true;
+    c->last.depth = k.D;
+    c->last.sort_passes = passes;
+    (void)sharded_begin;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* lpe_bh_version(void) { return "lpe_bh 0.1 (sm_100a, ABI 1)"; }
+
+int lpe_bh_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int lpe_bh_create(int device, lpe_bh_ctx** out) {
+    if (!out) return fail(nullptr, "out is NULL");
+    *out = nullptr;
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0)
+        return fail(nullptr, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= cnt) return fail(nullptr, "device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, cudaGetErrorString(e));
+    lpe_bh_ctx* c = new lpe_bh_ctx();
+    c->device = device;
+    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete c;
+        return fail(nullptr, cudaGetErrorString(e));
+    }
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    *out = c;
+    return 0;
+}
+
+void lpe_bh_destroy(lpe_bh_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_all(c);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* lpe_bh_last_error(const lpe_bh_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int lpe_bh_set_stream(lpe_bh_ctx* c, void* s) {
+    if (!c) return 1;
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return 0;
+}
+
+int lpe_bh_set_instrumentation(lpe_bh_ctx* c, int flags) {
+    if (!c) return 1;
+    c->instr = flags;
+    return 0;
+}
+
+int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, const double* vx, const double* vy,
+                  const double* m, const uint32_t* rank, const uint8_t* comp) {
+    if (!c) return 1;
+    if (n >= (1ull << 31) - 4096) return fail(c, "too many bodies (limit 2^31)");
+    if (n && (!x || !y || !m)) return fail(c, "x, y and m are required");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (ensure_capacity(c, n)) return 1;
+    c->n = n;
+    c->have_step = false;
+    if (n == 0) return 0;
+    cudaStream_t st = c->stream;
+    const size_t bytes = sizeof(double) * n;
+    const int g = cdiv((long long)n, 256);
+    double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
+    CU_TRY(c, cudaMemcpyAsync(t0, x, bytes, cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemcpyAsync(t1, y, bytes, cudaMemcpyHostToDevice, st));
+    k_pack2<<<g, 256, 0, st>>>((int)n, t0, t1, c->pos);
+    if (vx) CU_TRY(c, cudaMemcpyAsync(t2, vx, bytes, cudaMemcpyHostToDevice, st));
+    if (vy) CU_TRY(c, cudaMemcpyAsync(t3, vy, bytes, cudaMemcpyHostToDevice, st));
+    k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t2 : nullptr, vy ? t3 : nullptr, c->vel);
+    CU_TRY(c, cudaMemcpyAsync(c->mass, m, bytes, cudaMemcpyHostToDevice, st));
+    if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp, comp, n, cudaMemcpyHostToDevice, st));
+    if (!rank || !comp) k_default_meta<<<g, 256, 0, st>>>((int)n, c->rank, c->comp, rank ? 0 : 1, comp ? 0 : 1);
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_upload_positions(lpe_bh_ctx* c, const double* x, const double* y) {
+    if (!c || !x || !y) return 1;
+    if (c->n == 0) return 0;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * c->n;
+    double *t0 = c->tmp, *t1 = c->tmp + c->cap;
+    CU_TRY(c, cudaMemcpyAsync(t0, x, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(t1, y, bytes, cudaMemcpyHostToDevice, c->stream));
+    k_pack2<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t0, t1, c->pos);
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_upload_velocities(lpe_bh_ctx* c, const double* vx, const double* vy) {
+    if (!c || !vx || !vy) return 1;
+    if (c->n == 0) return 0;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const size_t bytes = sizeof(double) * c->n;
+    double *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
+    CU_TRY(c, cudaMemcpyAsync(t2, vx, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(t3, vy, bytes, cudaMemcpyHostToDevice, c->stream));
+    k_pack2<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t2, t3, c->vel);
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_step(lpe_bh_ctx* c, const lpe_bh_params* p, int nsteps) {
+    if (!c || !p) return 1;
+    if (c->shard_n > 1) return fail(c, "sharded context: use lpe_bh_step_begin / lpe_bh_step_finish");
+    CU_TRY(c, cudaSetDevice(c->device));
+    for (int s = 0; s < nsteps; ++s)
+        if (run_step(c, *p, false)) return 1;
+    return 0;
+}
+
+int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy) {
+    if (!c) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    const uint64_t n = c->n;
+    if (n) {
+        cudaStream_t st = c->stream;
+        const size_t bytes = sizeof(double) * n;
+        const int g = cdiv((long long)n, 256);
+        double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
+        if (x || y) {
+            k_unpack2<<<g, 256, 0, st>>>((int)n, c->pos, t0, t1);
+            if (x) CU_TRY(c, cudaMemcpyAsync(x, t0, bytes, cudaMemcpyDeviceToHost, st));
+            if (y) CU_TRY(c, cudaMemcpyAsync(y, t1, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        if (vx || vy) {
+            k_unpack2<<<g, 256, 0, st>>>((int)n, c->vel, t2, t3);
+            if (vx) CU_TRY(c, cudaMemcpyAsync(vx, t2, bytes, cudaMemcpyDeviceToHost, st));
+            if (vy) CU_TRY(c, cudaMemcpyAsync(vy, t3, bytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_synchronize(lpe_bh_ctx* c) {
+    if (!c) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
+                       const double* m, const uint32_t* rank, const uint8_t* comp) {
+    if (!c || !p) return 1;
+    if (lpe_bh_upload(c, n, x, y, vx, vy, m, rank, comp)) return 1;
+    if (lpe_bh_step(c, p, 1)) return 1;
+    // BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
+    return lpe_bh_download(c, p->do_drift ? x : nullptr, p->do_drift ? y : nullptr, vx, vy);
+}
+
+int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
+    if (!c || !out) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    lpe_bh_stats s = c->last;
+    s.n_bodies = c->n;
+    if (c->have_step && c->n) {
+        Scal h;
+        CU_TRY(c, cudaMemcpy(&h, c->scal, sizeof(h), cudaMemcpyDeviceToHost));
+        s.n_in_tree = h.n_in;
+        s.n_terminals = h.n_term;
+        s.n_nodes = (uint64_t)h.n_term + h.n_internal;
+        s.interactions = h.interactions;
+        s.visits = h.visits;
+        if (c->instr & 1) {
+            cudaEventElapsedTime(&s.ms_keygen, c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&s.ms_sort, c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&s.ms_build, c->ev[2], c->ev[3]);
+            cudaEventElapsedTime(&s.ms_traverse, c->ev[3], c->ev[4]);
+            cudaEventElapsedTime(&s.ms_total, c->ev[0], c->ev[4]);
+        }
+    }
+    *out = s;
+    return 0;
+}
+
+int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
+    if (!c || !o) return 1;
+    if (!c->have_step) return fail(c, "no step has been run since the last upload");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    const size_t n = c->n;
+    Scal h;
+    CU_TRY(c, cudaMemcpy(&h, c->scal, sizeof(h), cudaMemcpyDeviceToHost));
+    const size_t nn = (size_t)h.n_term + h.n_internal;
+    if (o->sorted_keys) CU_TRY(c, cudaMemcpy(o->sorted_keys, c->keys[c->sorted_sel], 8 * n, cudaMemcpyDeviceToHost));
+    std::vector<unsigned int> sidx(n);
+    CU_TRY(c, cudaMemcpy(sidx.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
+    if (o->sorted_index) std::memcpy(o->sorted_index, sidx.data(), 4 * n);
+    if (nn == 0) return 0;
+    std::vector<NodeB> nb(nn);
+    std::vector<double2> na(nn);
+    std::vector<double> nm(nn);
+    std::vector<signed char> nl(nn);
+    std::vector<unsigned int> ns(nn);
+    std::vector<Agg> ag(nn);
+    std::vector<unsigned long long> tk(h.n_term);
+    CU_TRY(c, cudaMemcpy(nb.data(), c->nodeB, sizeof(NodeB) * nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(na.data(), c->nodeA, sizeof(double2) * nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(nm.data(), c->nodeM, sizeof(double) * nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(nl.data(), c->nlevel, nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(ns.data(), c->nodeStart, 4 * nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(ag.data(), c->agg, sizeof(Agg) * nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(tk.data(), c->tkey, 8 * (size_t)h.n_term, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < nn; ++i) {
+        if (o->node_level) o->node_level[i] = nl[i];
+        if (o->node_key) o->node_key[i] = tk[ns[i]];
+        if (o->node_skip) o->node_skip[i] = nb[i].skip;
+        if (o->node_first) o->node_first[i] = sidx[ag[i].fidx];
+        if (o->node_count) o->node_count[i] = ag[i].count;
+        if (o->node_mass) o->node_mass[i] = nm[i];
+        if (o->node_comx) o->node_comx[i] = na[i].x * c->last_c.S;
+        if (o->node_comy) o->node_comy[i] = na[i].y * c->last_c.S;
+    }
+    return 0;
+}
+
+int lpe_bh_get_counts(lpe_bh_ctx* c, uint32_t* accepted, uint32_t* visited) {
+    if (!c) return 1;
+    if (!(c->instr & 2)) return fail(c, "enable instrumentation bit1 before the step");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (accepted) CU_TRY(c, cudaMemcpy(accepted, c->cntAcc, 4 * c->n, cudaMemcpyDeviceToHost));
+    if (visited) CU_TRY(c, cudaMemcpy(visited, c->cntVis, 4 * c->n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int lpe_bh_direct_accel(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t first, uint64_t count, double* ax, double* ay) {
+    if (!c || !p || !ax || !ay) return 1;
+    if (first + count > c->n) return fail(c, "target range out of bounds");
+    if (count == 0) return 0;
+    CU_TRY(c, cudaSetDevice(c->device));
+    double *dax = c->tmp, *day = c->tmp + c->cap;
+    k_direct<<<cdiv((long long)count, 256), 256, 0, c->stream>>>((int)c->n, c->pos, c->mass, c->comp, p->universe_size,
+                                                                  p->softening * p->softening, p->G, (int)first,
+                                                                  (int)count, dax, day);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(ax, dax, 8 * count, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(ay, day, 8 * count, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- multi-GPU
+uint64_t lpe_bh_shard_chunk(uint64_t n, int nranks) {
+    if (nranks < 1) nranks = 1;
+    const uint64_t nblocks = (n + LPE_SHARD_BLOCK - 1) / LPE_SHARD_BLOCK;
+    const uint64_t per = (nblocks + (uint64_t)nranks - 1) / (uint64_t)nranks;
+    return per * LPE_SHARD_BLOCK;
+}
+
+int lpe_bh_shard_owner(uint64_t pos, int nranks, int* rank_out, uint64_t* slot_out) {
+    if (nranks < 1) return 1;
+    const uint64_t gblock = pos / LPE_SHARD_BLOCK;
+    if (rank_out) *rank_out = (int)(gblock % (uint64_t)nranks);
+    if (slot_out) *slot_out = (gblock / (uint64_t)nranks) * LPE_SHARD_BLOCK + pos % LPE_SHARD_BLOCK;
+    return 0;
+}
+
+int lpe_bh_set_shard(lpe_bh_ctx* c, int rank, int nranks) {
+    if (!c) return 1;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(c, "bad shard rank / nranks");
+    c->shard_rank = rank;
+    c->shard_n = nranks;
+    return 0;
+}
+
+int lpe_bh_step_begin(lpe_bh_ctx* c, const lpe_bh_params* p) {
+    if (!c || !p) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_step(c, *p, true);
+}
+
+int lpe_bh_step_finish(lpe_bh_ctx* c) {
+    if (!c) return 1;
+    if (c->shard_n <= 1 || c->n == 0) return 0;
+    if (!c->have_step) return fail(c, "lpe_bh_step_begin has not run");
+    CU_TRY(c, cudaSetDevice(c->device));
+    k_xchg_scatter<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->shard_n, c->xchg_chunk,
+                                                                       c->vals[c->sorted_sel], c->xchg_recv, c->pos,
+                                                                       c->vel);
+    CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_get_device_view(lpe_bh_ctx* c, lpe_bh_device_view* o) {
+    if (!c || !o) return 1;
+    if (c->shard_n > 1 && c->n && ensure_xchg(c)) return 1;
+    o->pos = c->pos;
+    o->vel = c->vel;
+    o->mass = c->mass;
+    o->xchg_send = c->xchg_send;
+    o->xchg_recv = c->xchg_recv;
+    o->n = c->n;
+    o->xchg_chunk = c->xchg_chunk;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,258 @@
+"""ctypes binding of liblpe_bh.so (include/lpe_bh.h) — the reference-facing host API in Python form.
+
+Thin by design: every method is one C-ABI call. There is no CPU fallback; constructing a
+`BarnesHut` without a CUDA device raises. Used by tests/, bench.py and __graft_entry__.py.
+
+Reference interface mirrored (names and meaning of the knobs):
+  Systems::BarnesHutConfig{theta, smallMassThreshold}    include/systems/barnes_hut.hpp:31-46
+  SharedSystemConfig{UniverseSizeMeters, GravitationalSoftener, SecondsPerTick, TimeAcceleration}
+                                                         include/systems/shared_system_config.hpp:10-21
+  Components::SimulatorState{baseTimeAcceleration, timeScale}   include/entities/sim_components.hpp:4-11
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblpe_bh.so")
+
+HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID = 1, 2, 4, 8
+PREC_FAST, PREC_STRICT = 0, 1
+SHARD_BLOCK = 2048
+G_REAL = 6.674e-11  # SimulatorConstants::RealG, reference src/core/constants.cpp:8
+
+WORKLOADS = {"disk": 0, "plummer": 1, "two_galaxies": 2, "keplerian": 3}
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("universe_size", C.c_double), ("softening", C.c_double), ("theta", C.c_double),
+        ("small_mass_threshold", C.c_double), ("G", C.c_double), ("dt_kick", C.c_double),
+        ("dt_drift", C.c_double), ("quirk_mode", C.c_int32), ("precision", C.c_int32),
+        ("do_drift", C.c_int32), ("max_depth", C.c_int32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("n_bodies", C.c_uint64), ("n_in_tree", C.c_uint64), ("n_terminals", C.c_uint64),
+        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64),
+        ("depth", C.c_int32), ("sort_passes", C.c_int32), ("ms_keygen", C.c_float),
+        ("ms_sort", C.c_float), ("ms_build", C.c_float), ("ms_traverse", C.c_float), ("ms_total", C.c_float),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class TreeDump(C.Structure):
+    _fields_ = [
+        ("sorted_keys", C.c_void_p), ("sorted_index", C.c_void_p), ("node_level", C.c_void_p),
+        ("node_key", C.c_void_p), ("node_skip", C.c_void_p), ("node_first", C.c_void_p),
+        ("node_count", C.c_void_p), ("node_mass", C.c_void_p), ("node_comx", C.c_void_p),
+        ("node_comy", C.c_void_p),
+    ]
+
+
+class DeviceView(C.Structure):
+    _fields_ = [
+        ("pos", C.c_void_p), ("vel", C.c_void_p), ("mass", C.c_void_p), ("xchg_send", C.c_void_p),
+        ("xchg_recv", C.c_void_p), ("n", C.c_uint64), ("xchg_chunk", C.c_uint64),
+    ]
+
+
+def make_params(U, eps, theta=0.5, dt_kick=1.0 / 120, dt_drift=None, thr=0.0, quirk=True, precision=PREC_FAST,
+                do_drift=True, max_depth=0, G=G_REAL):
+    p = Params()
+    p.universe_size = U
+    p.softening = eps
+    p.theta = theta
+    p.small_mass_threshold = thr
+    p.G = G
+    p.dt_kick = dt_kick
+    p.dt_drift = dt_kick if dt_drift is None else dt_drift
+    p.quirk_mode = 1 if quirk else 0
+    p.precision = precision
+    p.do_drift = 1 if do_drift else 0
+    p.max_depth = max_depth
+    return p
+
+
+def build_library(force=False):
+    """Compile liblpe_bh.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    srcs.append(os.path.join(HERE, "..", "include", "lpe_bh.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    subprocess.check_call(["bash", os.path.join(HERE, "build.sh")])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """Load the CUDA library. Fails loudly when it has not been built: there is nothing to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run little-physics-engine_b200/build.sh (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    lib.lpe_bh_version.restype = C.c_char_p
+    lib.lpe_bh_last_error.restype = C.c_char_p
+    lib.lpe_bh_last_error.argtypes = [C.c_void_p]
+    lib.lpe_bh_shard_chunk.restype = C.c_uint64
+    lib.lpe_bh_shard_chunk.argtypes = [C.c_uint64, C.c_int]
+    _lib = lib
+    return lib
+
+
+def _dp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def workload(kind, n, seed, U):
+    """Deterministic synthetic bodies; returns x, y, vx, vy, m."""
+    lib = load_library()
+    arrs = [np.empty(n, np.float64) for _ in range(5)]
+    rc = lib.lpe_bh_workload(C.c_int(WORKLOADS[kind] if isinstance(kind, str) else kind), C.c_uint64(n),
+                             C.c_uint64(seed), C.c_double(U), *[_dp(a) for a in arrs])
+    if rc:
+        raise RuntimeError("lpe_bh_workload failed")
+    return tuple(arrs)
+
+
+def shard_chunk(n, nranks):
+    return int(load_library().lpe_bh_shard_chunk(C.c_uint64(n), C.c_int(nranks)))
+
+
+def shard_owner(pos, nranks):
+    r, s = C.c_int(0), C.c_uint64(0)
+    load_library().lpe_bh_shard_owner(C.c_uint64(pos), C.c_int(nranks), C.byref(r), C.byref(s))
+    return r.value, s.value
+
+
+class BarnesHut:
+    """One device context = one Systems::BarnesHutSystem instance with device-resident bodies."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.lpe_bh_create(C.c_int(device), C.byref(self.h))
+        if rc:
+            raise RuntimeError("lpe_bh_create: " + self.lib.lpe_bh_last_error(None).decode())
+        self.n = 0
+
+    def close(self):
+        if self.h:
+            self.lib.lpe_bh_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc, what):
+        if rc:
+            raise RuntimeError(f"{what}: {self.lib.lpe_bh_last_error(self.h).decode()}")
+
+    def set_stream(self, cuda_stream_ptr):
+        self._chk(self.lib.lpe_bh_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
+
+    def set_instrumentation(self, timing=False, counts=False):
+        self._chk(self.lib.lpe_bh_set_instrumentation(self.h, C.c_int((1 if timing else 0) | (2 if counts else 0))),
+                  "set_instrumentation")
+
+    def upload(self, x, y, vx, vy, m, rank=None, comp=None):
+        x, y, vx, vy, m = map(_f64, (x, y, vx, vy, m))
+        rank = None if rank is None else np.ascontiguousarray(rank, dtype=np.uint32)
+        comp = None if comp is None else np.ascontiguousarray(comp, dtype=np.uint8)
+        self.n = len(x)
+        self._keep = (x, y, vx, vy, m, rank, comp)
+        self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(self.n), _dp(x), _dp(y), _dp(vx), _dp(vy), _dp(m),
+                                         _dp(rank), _dp(comp)), "upload")
+
+    def upload_ptrs(self, n, x, y, vx, vy, m):
+        """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
+        self.n = n
+        self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(n), C.c_void_p(x), C.c_void_p(y), C.c_void_p(vx),
+                                         C.c_void_p(vy), C.c_void_p(m), None, None), "upload")
+
+    def step(self, params, nsteps=1):
+        self._chk(self.lib.lpe_bh_step(self.h, C.byref(params), C.c_int(nsteps)), "step")
+
+    def synchronize(self):
+        self._chk(self.lib.lpe_bh_synchronize(self.h), "synchronize")
+
+    def download(self):
+        out = [np.empty(self.n, np.float64) for _ in range(4)]
+        self._chk(self.lib.lpe_bh_download(self.h, *[_dp(a) for a in out]), "download")
+        return dict(x=out[0], y=out[1], vx=out[2], vy=out[3])
+
+    def download_ptrs(self, x, y, vx, vy):
+        self._chk(self.lib.lpe_bh_download(self.h, C.c_void_p(x), C.c_void_p(y), C.c_void_p(vx), C.c_void_p(vy)),
+                  "download")
+
+    def update_host(self, params, x, y, vx, vy, m, rank=None, comp=None):
+        """The drop-in call: upload, one step, download; arrays updated in place (must be float64 contiguous)."""
+        for a in (x, y, vx, vy, m):
+            assert a.dtype == np.float64 and a.flags.c_contiguous
+        rank = None if rank is None else np.ascontiguousarray(rank, dtype=np.uint32)
+        comp = None if comp is None else np.ascontiguousarray(comp, dtype=np.uint8)
+        self.n = len(x)
+        self._chk(self.lib.lpe_bh_update_host(self.h, C.byref(params), C.c_uint64(self.n), _dp(x), _dp(y), _dp(vx),
+                                              _dp(vy), _dp(m), _dp(rank), _dp(comp)), "update_host")
+
+    def stats(self):
+        s = Stats()
+        self._chk(self.lib.lpe_bh_get_stats(self.h, C.byref(s)), "get_stats")
+        return s.as_dict()
+
+    def dump_tree(self):
+        st = self.stats()
+        n, nn = st["n_bodies"], st["n_nodes"]
+        out = dict(
+            sorted_keys=np.zeros(n, np.uint64), sorted_index=np.zeros(n, np.uint32),
+            node_level=np.zeros(nn, np.int32), node_key=np.zeros(nn, np.uint64), node_skip=np.zeros(nn, np.uint32),
+            node_first=np.zeros(nn, np.uint32), node_count=np.zeros(nn, np.uint32), node_mass=np.zeros(nn),
+            node_comx=np.zeros(nn), node_comy=np.zeros(nn))
+        d = TreeDump(**{k: v.ctypes.data for k, v in out.items()})
+        self._chk(self.lib.lpe_bh_dump_tree(self.h, C.byref(d)), "dump_tree")
+        out["stats"] = st
+        return out
+
+    def counts(self):
+        acc, vis = np.zeros(self.n, np.uint32), np.zeros(self.n, np.uint32)
+        self._chk(self.lib.lpe_bh_get_counts(self.h, _dp(acc), _dp(vis)), "get_counts")
+        return acc, vis
+
+    def direct_accel(self, params, first=0, count=None):
+        count = self.n - first if count is None else count
+        ax, ay = np.empty(count), np.empty(count)
+        self._chk(self.lib.lpe_bh_direct_accel(self.h, C.byref(params), C.c_uint64(first), C.c_uint64(count), _dp(ax),
+                                               _dp(ay)), "direct_accel")
+        return ax, ay
+
+    # ---- multi-GPU ----
+    def set_shard(self, rank, nranks):
+        self._chk(self.lib.lpe_bh_set_shard(self.h, C.c_int(rank), C.c_int(nranks)), "set_shard")
+
+    def step_begin(self, params):
+        self._chk(self.lib.lpe_bh_step_begin(self.h, C.byref(params)), "step_begin")
+
+    def step_finish(self):
+        self._chk(self.lib.lpe_bh_step_finish(self.h), "step_finish")
+
+    def device_view(self):
+        v = DeviceView()
+        self._chk(self.lib.lpe_bh_get_device_view(self.h, C.byref(v)), "get_device_view")
+        return v
