@@ -141,9 +141,17 @@ int  lpe_bh_set_shard(lpe_bh_ctx* ctx, int rank, int nranks);
 int  lpe_bh_step_begin(lpe_bh_ctx* ctx, const lpe_bh_params* p);   /* build + own-slice traversal -> xchg_send */
 int  lpe_bh_step_finish(lpe_bh_ctx* ctx);                          /* xchg_recv -> state */
 int  lpe_bh_get_device_view(lpe_bh_ctx* ctx, lpe_bh_device_view* out);
+/* host-staged exchange (tests, or a transport without device pointers): copy this rank's packed slice out /
+ * another rank's slice in; each is 4*xchg_chunk doubles. Synchronises. */
+int  lpe_bh_xchg_read_send(lpe_bh_ctx* ctx, double* host);
+int  lpe_bh_xchg_write_recv(lpe_bh_ctx* ctx, int src_rank, const double* host);
 /* pure host helper (no GPU): which rank owns sorted position i, and where it sits in that rank's packed slice */
 int  lpe_bh_shard_owner(uint64_t sorted_pos, int nranks, int* rank_out, uint64_t* slot_out);
 uint64_t lpe_bh_shard_chunk(uint64_t n_bodies, int nranks);        /* elements per rank in the exchange buffers */
+
+/* page-locked host memory for staging buffers (full PCIe rate for upload/download) */
+void* lpe_bh_alloc_pinned(uint64_t bytes);
+void  lpe_bh_free_pinned(void* p);
 
 /* ---- deterministic synthetic workloads (host, std::mt19937_64, u=(g()>>11)*2^-53) ----
  * kind: 0 = uniform disk (C2), 1 = Plummer sphere projected (C3), 2 = two-galaxy collision (C4),

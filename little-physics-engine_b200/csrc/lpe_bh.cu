@@ -675,6 +675,36 @@ int lpe_bh_step_finish(lpe_bh_ctx* c) {
     return 0;
 }
 
+int lpe_bh_xchg_read_send(lpe_bh_ctx* c, double* host) {
+    if (!c || !host) return 1;
+    if (c->shard_n <= 1 || !c->xchg_send) return fail(c, "context is not sharded");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(host, c->xchg_send, sizeof(double4) * c->xchg_chunk, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lpe_bh_xchg_write_recv(lpe_bh_ctx* c, int src, const double* host) {
+    if (!c || !host) return 1;
+    if (c->shard_n <= 1 || !c->xchg_recv) return fail(c, "context is not sharded");
+    if (src < 0 || src >= c->shard_n) return fail(c, "source rank out of range");
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(c->xchg_recv + (size_t)src * c->xchg_chunk, host, sizeof(double4) * c->xchg_chunk,
+                              cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+void* lpe_bh_alloc_pinned(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void lpe_bh_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int lpe_bh_get_device_view(lpe_bh_ctx* c, lpe_bh_device_view* o) {
     if (!c || !o) return 1;
     if (c->shard_n > 1 && c->n && ensure_xchg(c)) return 1;

@@ -149,6 +149,7 @@ class BarnesHut:
         if rc:
             raise RuntimeError("lpe_bh_create: " + self.lib.lpe_bh_last_error(None).decode())
         self.n = 0
+        self._rank, self._nranks = 0, 1
 
     def close(self):
         if self.h:
@@ -245,12 +246,22 @@ class BarnesHut:
     # ---- multi-GPU ----
     def set_shard(self, rank, nranks):
         self._chk(self.lib.lpe_bh_set_shard(self.h, C.c_int(rank), C.c_int(nranks)), "set_shard")
+        self._rank, self._nranks = rank, nranks
 
     def step_begin(self, params):
         self._chk(self.lib.lpe_bh_step_begin(self.h, C.byref(params)), "step_begin")
 
     def step_finish(self):
         self._chk(self.lib.lpe_bh_step_finish(self.h), "step_finish")
+
+    def xchg_read_send(self):
+        buf = np.empty(4 * shard_chunk(self.n, self._nranks), np.float64)
+        self._chk(self.lib.lpe_bh_xchg_read_send(self.h, _dp(buf)), "xchg_read_send")
+        return buf
+
+    def xchg_write_recv(self, src_rank, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.float64)
+        self._chk(self.lib.lpe_bh_xchg_write_recv(self.h, C.c_int(src_rank), _dp(buf)), "xchg_write_recv")
 
     def device_view(self):
         v = DeviceView()

@@ -1,0 +1,109 @@
+"""GPU: BASELINE.json's full sizes. The oracle (8 host threads) still finishes the 1M disk in seconds per step, so
+config C2 gets a direct comparison; the 16M Plummer config is checked through size-independent properties."""
+import numpy as np
+import pytest
+
+import lpe_bh
+import oracle_py as O
+from parity import check_preorder, rel_err
+
+pytestmark = pytest.mark.gpu
+U = float(2 ** 20)
+EPS = 64.0
+
+
+def test_c2_one_million_disk_vs_oracle(bh, port):
+    x, y, vx, vy, m = lpe_bh.workload("disk", 1_000_000, 42, U)
+    ref = port.run(O.make_params(U, EPS), x, y, vx, vy, m, threads=0 or 8, per_body=True)
+    bh.set_instrumentation(counts=True)
+    bh.upload(x, y, vx, vy, m)
+    bh.step(lpe_bh.make_params(U, EPS), 1)
+    got = bh.download()
+    acc, _ = bh.counts()
+    assert np.array_equal(acc, ref["accepted"])               # one million bodies, every theta decision identical
+    dv = rel_err((got["vx"], got["vy"]), (ref["vx"], ref["vy"]))
+    assert dv["max"] <= 1e-4 and dv["norm"] <= 1e-5, dv
+    assert np.max(np.hypot(got["x"] - ref["x"], got["y"] - ref["y"])) / U <= 1e-9
+    st = bh.stats()
+    assert st["interactions"] == ref["stats"]["accepted"]
+    bh.set_instrumentation()
+
+
+def test_c5_theta_sweep_interaction_counts(bh, port):
+    """Accepted interactions per body fall with theta exactly as the oracle's do (subsample of C2 for the CPU side)."""
+    x, y, vx, vy, m = lpe_bh.workload("disk", 1_000_000, 42, U)
+    n = 100_000
+    x, y, vx, vy, m = x[:n], y[:n], vx[:n], vy[:n], m[:n]
+    bh.set_instrumentation(counts=True)
+    prev = None
+    for theta in (0.3, 0.5, 0.7, 1.0):
+        ref = port.run(O.make_params(U, EPS, theta=theta), x, y, vx, vy, m, threads=8)
+        bh.upload(x, y, vx, vy, m)
+        bh.step(lpe_bh.make_params(U, EPS, theta=theta), 1)
+        st = bh.stats()
+        assert st["interactions"] == ref["stats"]["accepted"]
+        if prev is not None:
+            assert st["interactions"] < prev
+        prev = st["interactions"]
+    bh.set_instrumentation()
+
+
+def test_c5_direct_sum_cross_check(bh, port):
+    """256k bodies: GPU direct O(N^2) vs the textbook (quirk-free) tree, and vs the reference-quirk tree (K3)."""
+    x, y, vx, vy, m = lpe_bh.workload("disk", 1_000_000, 42, U)
+    n = 262_144
+    x, y, m = x[:n], y[:n], m[:n]
+    z = np.zeros(n)
+    pq = lpe_bh.make_params(U, EPS, dt_kick=1.0, do_drift=False, quirk=False)
+    bh.upload(x, y, z, z, m)
+    ax, ay = bh.direct_accel(pq)
+    # the GPU direct kernel itself is checked against the oracle's direct sum on a few hundred targets
+    oax, oay = port.direct(O.make_params(U, EPS), x, y, m, first=1000, count=256, threads=8)
+    assert rel_err((ax[1000:1256], ay[1000:1256]), (oax, oay))["max"] <= 1e-10
+    bh.step(pq, 1)
+    tb = bh.download()
+    e_text = rel_err((tb["vx"], tb["vy"]), (ax, ay), floor_frac=1.0)
+    pr = lpe_bh.make_params(U, EPS, dt_kick=1.0, do_drift=False, quirk=True)
+    bh.upload(x, y, z, z, m)
+    bh.step(pr, 1)
+    rb = bh.download()
+    e_ref = rel_err((rb["vx"], rb["vy"]), (ax, ay), floor_frac=1.0)
+    assert e_text["median"] < 2e-2, e_text          # a proper theta=0.5 monopole tree
+    assert e_ref["median"] > 2 * e_text["median"]   # the reference's double count costs accuracy, and we reproduce it
+
+
+def test_c3_sixteen_million_plummer_properties(bh):
+    """16M bodies: sortedness, pre-order invariants, mass checksum, FAST vs STRICT agreement on a target sample,
+    and interaction-count sanity — properties that do not need a 7-minute CPU step."""
+    n = 16_000_000
+    x, y, vx, vy, m = lpe_bh.workload("plummer", n, 43, U)
+    pg = lpe_bh.make_params(U, EPS, do_drift=False)
+    bh.set_instrumentation(counts=True)
+    bh.upload(x, y, vx, vy, m)
+    bh.step(pg, 1)
+    fast = bh.download()
+    st = bh.stats()
+    assert st["n_in_tree"] == n and st["depth"] == 16
+    per_body = st["interactions"] / n
+    assert 300 < per_body < 900, per_body            # ~520 expected at 16M
+    dump = bh.dump_tree()
+    keys = dump["sorted_keys"]
+    assert np.all(keys[:-1] <= keys[1:])
+    assert np.array_equal(np.bincount(dump["sorted_index"], minlength=n), np.ones(n, np.int64))
+    skip = dump["node_skip"].astype(np.int64)
+    assert skip[0] == len(skip) and np.all(skip > np.arange(len(skip)))
+    # checksum of checksums: root mass = sum m + mass of the first inserted body (quirk), root count = n
+    first = int(dump["node_first"][0])
+    assert dump["node_count"][0] == n
+    assert abs(dump["node_mass"][0] - (m.sum() + m[first])) <= 1e-9 * m.sum()
+    assert first == n - 1                              # newest entity is inserted first and lies in the root
+    # leaves + aggregated terminals cover every body once
+    lv = dump["node_level"]
+    assert dump["node_count"][lv < 0].sum() == n
+    # FAST vs STRICT on the same tree
+    bh.set_instrumentation()
+    bh.upload(x, y, vx, vy, m)
+    bh.step(lpe_bh.make_params(U, EPS, do_drift=False, precision=lpe_bh.PREC_STRICT), 1)
+    strict = bh.download()
+    e = rel_err((fast["vx"], fast["vy"]), (strict["vx"], strict["vy"]))
+    assert e["norm"] <= 1e-5 and e["p999"] <= 1e-4, e
