@@ -58,6 +58,7 @@ typedef struct {
     uint64_t n_nodes;        /* nodes of the path-compressed tree in pre-order (terminals + branching cells) */
     uint64_t interactions;   /* accepted node interactions of the last step (only counted when stats are enabled) */
     uint64_t visits;         /* node visits (per lane) of the last step (only when stats are enabled) */
+    uint64_t warp_visits;    /* node visits per warp (loop iterations), summed over warps (only when stats are enabled) */
     int32_t  depth;          /* key depth D used by the last step */
     int32_t  sort_passes;
     float ms_keygen, ms_sort, ms_build, ms_traverse, ms_total; /* last step, CUDA events; only when timing is enabled */
@@ -148,6 +149,12 @@ int  lpe_bh_xchg_write_recv(lpe_bh_ctx* ctx, int src_rank, const double* host);
 /* pure host helper (no GPU): which rank owns sorted position i, and where it sits in that rank's packed slice */
 int  lpe_bh_shard_owner(uint64_t sorted_pos, int nranks, int* rank_out, uint64_t* slot_out);
 uint64_t lpe_bh_shard_chunk(uint64_t n_bodies, int nranks);        /* elements per rank in the exchange buffers */
+
+/* cumulative number of this library's kernels launched by the context (bench.py's gpu_launches) */
+uint64_t lpe_bh_launch_count(const lpe_bh_ctx* ctx);
+/* FP32 FMA peak of the device by a register-resident FMA loop, TFLOP/s (2 flops per FMA): the roofline denominator
+ * of the traversal, which is FP32-pipe bound, not HBM or tensor bound. Synchronises. */
+int  lpe_bh_fma_peak(lpe_bh_ctx* ctx, double* tflops);
 
 /* page-locked host memory for staging buffers (full PCIe rate for upload/download) */
 void* lpe_bh_alloc_pinned(uint64_t bytes);

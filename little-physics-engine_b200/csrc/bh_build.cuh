@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(256)
 k_topology(int D, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
            const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P,
            unsigned int* __restrict__ tnode, unsigned int* __restrict__ parent, unsigned int* __restrict__ child,
-           NodeB* __restrict__ nodeB, unsigned int* __restrict__ nodeStart, Scal* __restrict__ s) {
+           NodeB* __restrict__ nodeB, signed char* __restrict__ nlevel, unsigned int* __restrict__ nodeStart,
+           Scal* __restrict__ s) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_term = (int)s->n_term;
     if (t == 0) s->n_internal = P[n_term];
@@ -197,7 +198,7 @@ k_topology(int D, const unsigned long long* __restrict__ tkey, const signed char
         }
         parent[idx] = par;
         nodeB[idx].skip = (unsigned int)(b + 1) + P[b + 1];
-        nodeB[idx].level = L;
+        nlevel[idx] = (signed char)L;
         nodeStart[idx] = (unsigned int)t;
     }
 }
@@ -212,11 +213,14 @@ __device__ __forceinline__ double mass_scale_inv(unsigned long long max_mass_bit
 
 // ---- 6. aggregation: leaves write their record, the last child to arrive sums its siblings ------------------
 struct NodeOut {
-    double2* nodeA;
+    double2* nodeA;       // fp64 centre (scaled): exact re-test of borderline theta decisions, STRICT mode, dumps
+    float4* nodeC;        // two-float centre (scaled): the traversal's inner loop
     NodeB* nodeB;
     double* nodeM;
-    signed char* nlevel;  // true level (-1 leaf, -2 aggregated terminal), for parity dumps
+    signed char* nlevel;  // level of a branching cell, -1 leaf, -2 aggregated terminal
 };
+
+constexpr float OPEN_BAND = 4e-6f;  // relative half-width of the fp32 guard band around s^2/theta^2
 
 __device__ __forceinline__ void finalize_node(const StepConst& c, const NodeOut& o, unsigned int idx, const Agg& a,
                                               int level, double massScaleInv, const double2* __restrict__ spos,
@@ -240,22 +244,24 @@ __device__ __forceinline__ void finalize_node(const StepConst& c, const NodeOut&
         cx = sx / M;
         cy = sy / M;
     }
-    o.nodeA[idx] = make_double2(cx * c.invS, cy * c.invS);
+    const double cxs = cx * c.invS, cys = cy * c.invS;
+    o.nodeA[idx] = make_double2(cxs, cys);
+    const float hx = (float)cxs, hy = (float)cys;
+    o.nodeC[idx] = make_float4(hx, hy, (float)(cxs - (double)hx), (float)(cys - (double)hy));
     o.nodeM[idx] = M;
     // allSmall cells are skipped by the traversal but still feed their ancestors (barnes_hut.cpp:253, Q7):
     // a zero mass with "never open" is exactly that.
     const bool skipSmall = (c.thr > 0.0) && a.small;
-    float gm = skipSmall ? 0.0f : (float)(M * massScaleInv);
-    float od2 = -1.0f;
+    NodeB nb;
+    nb.skip = o.nodeB[idx].skip;  // written by k_topology
+    nb.gm = skipSmall ? 0.0f : (float)(M * massScaleInv);
+    nb.open_lo = nb.open_hi = skipSmall ? -2.0f : -1.0f;
     if (level >= 0 && !skipSmall) {
         const double s = ldexp(c.U, -level) * c.invS;
-        od2 = (float)((s * s) / c.theta2);
+        const float t = (float)((s * s) / c.theta2);
+        nb.open_lo = t * (1.0f - OPEN_BAND);
+        nb.open_hi = t * (1.0f + OPEN_BAND);
     }
-    NodeB nb = o.nodeB[idx];  // skip / level were written by k_topology
-    nb.gm = gm;
-    nb.open_d2 = od2;
-    // -3 marks a cell the traversal must treat as "accepted, contributes nothing" (small-mass rule)
-    nb.level = skipSmall ? -3 : (level < 0 ? level : nb.level);
     o.nodeB[idx] = nb;
     o.nlevel[idx] = (signed char)level;
 }
@@ -318,7 +324,7 @@ k_aggregate(StepConst c, const unsigned int* __restrict__ tfirst, const unsigned
             b.count += w2.x;
             b.small &= w2.y;
         }
-        finalize_node(c, o, p, b, o.nodeB[p].level, massScaleInv, spos, smass);
+        finalize_node(c, o, p, b, (int)o.nlevel[p], massScaleInv, spos, smass);
         agg[p] = b;
         p = parent[p];
     }

@@ -23,15 +23,20 @@ struct Scal {
     unsigned long long max_mass_bits;  // max source mass as raw double bits (positive doubles order like integers)
     unsigned long long interactions;
     unsigned long long visits;
-    unsigned int pad[2];
+    unsigned long long warp_visits;    // node visits summed over warps (one per loop iteration)
 };
 
-// Second half of a traversal node record: one 16-byte load.
+// Traversal node record, 32 bytes = two broadcast 16-byte loads per visited node.
+//   NodeC: centre of mass in scaled units as a two-float (hi + lo) pair per axis. hi = fl32(c), lo = fl32(c - hi), so
+//          (c_hi - p_hi) + (c_lo - p_lo) gives the fp64 difference rounded once to fp32 (relative error 2^-24 of |d|,
+//          wherever in the universe the pair sits) with no FP64 instruction and no conversion in the inner loop.
+//   NodeB: mass, the theta test as two thresholds around s^2/theta^2 (below open_lo: open; at or above open_hi:
+//          accept; in between the reference's fp64 expression decides), and the skip pointer.
 struct __align__(16) NodeB {
     float gm;            // node mass / mass scale (0 when the node is skipped by the small-mass rule)
-    float open_d2;       // open the node iff d2 <= open_d2 (= s^2/theta^2 in scaled units); -1 for leaves / terminals
+    float open_lo;       // d2 <= open_lo  => every fp64 evaluation would open the node
+    float open_hi;       // d2 >= open_hi  => every fp64 evaluation would accept it; -1 leaf/terminal, -2 small-mass skip
     unsigned int skip;   // pre-order index of the first node after this subtree
-    int level;           // level of a branching cell; -1 leaf; -2 aggregated terminal
 };
 
 // Per-node aggregate carried up the tree (exact sums, quirk applied only when a record is finalised).

@@ -9,11 +9,12 @@
 // node's descendants by remembering skipUntil = skip[j]; the warp descends while any lane still opens.
 // All lanes read the same node -> one broadcast 2 x 16 B load per visited node, served from L1/L2.
 //
-// FAST precision: state and node centres stay fp64; the difference is formed in fp64 and rounded once to fp32
-// (relative error 6e-8 of |d|, independent of where in the universe the pair sits); d^2, rsqrt and the
-// accumulation are fp32 with periodic fp64 flushes. The theta test is done in fp32 with a guard band; inside
-// the band the reference's own fp64 expression (barnes_hut.cpp:261-269) decides, so accept/open decisions are
-// the reference's, not an approximation of them.
+// FAST precision: state stays fp64. Node centres and lane positions enter the inner loop as two-float (hi + lo)
+// pairs, so d = (c_hi - p_hi) + (c_lo - p_lo) is the fp64 difference rounded once to fp32 (relative error 2^-24
+// of |d|, independent of where in the universe the pair sits) without any FP64 or conversion instruction; d^2,
+// rsqrt and the accumulation are fp32 with fp64 flushes every 64 nodes. The theta test is done in fp32 against
+// two thresholds bracketing s^2/theta^2; between them the reference's own fp64 expression
+// (barnes_hut.cpp:261-269) decides, so accept/open decisions are the reference's, not an approximation of them.
 // STRICT precision: every interaction in fp64, in the reference's expression order.
 #pragma once
 #include "bh_common.cuh"
@@ -21,10 +22,17 @@
 namespace lpe {
 
 constexpr int TRAV_THREADS = 256;
-constexpr float TRAV_BAND = 4e-6f;  // relative half-width of the fp32 guard band around s^2/theta^2
+constexpr int TRAV_WINDOW = 32;   // pre-order records staged per warp (one per lane)
+
+struct __align__(16) TravRec {
+    float4 c;
+    NodeB b;
+};
 
 struct TravArgs {
     const double2* nodeA;
+    const float4* nodeC;
+    const signed char* nlevel;
     const NodeB* nodeB;
     const double* nodeM;
     const double2* spos;
@@ -43,7 +51,9 @@ struct TravArgs {
 
 // The reference's test, barnes_hut.cpp:261-269, on exactly scaled operands (power-of-two scaling commutes
 // with IEEE rounding): returns true when the node must be opened.
-__device__ __noinline__ bool exact_open(double dxs, double dys, double eps2s, int level, double Us, double theta2) {
+__device__ __noinline__ bool exact_open(double2 A, double pxs, double pys, double eps2s, int level, double Us,
+                                        double theta2) {
+    const double dxs = A.x - pxs, dys = A.y - pys;
     const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dxs, dxs), __dmul_rn(dys, dys)), eps2s);
     const double size = ldexp(Us, -level);
     const double sizeSq = __dmul_rn(size, size);
@@ -52,7 +62,9 @@ __device__ __noinline__ bool exact_open(double dxs, double dys, double eps2s, in
 
 template <int PREC, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs a) {
+    __shared__ TravRec sWin[TRAV_THREADS / 32][TRAV_WINDOW];
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = (float)c.eps2s;
@@ -83,43 +95,68 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
         const bool target = valid && (cm & 1u) && (cm & 2u) && !(cm & 4u);
         const double pxs = p.x * c.invS, pys = p.y * c.invS;
         unsigned int skipUntil = target ? 0u : 0xFFFFFFFFu;
-        unsigned int nacc = 0, nvis = 0;
+        unsigned int nacc = 0, nvis = 0, nwarp = 0;
         double2 v = make_double2(0.0, 0.0);
         if (valid) v = a.vel[b];
 
         if constexpr (PREC == 0) {
-            float ax = 0.f, ay = 0.f;
+            // two-float lane position, negated once: d = (c_hi - p_hi) + (c_lo - p_lo)
+            const float phx = (float)pxs, phy = (float)pys;
+            const float nphx = -phx, nphy = -phy;
+            const float nplx = -(float)(pxs - (double)phx), nply = -(float)(pys - (double)phy);
+            // With softening, a body's own leaf contributes exactly +0 (d = 0, finite f), so the reference's
+            // "skip the leaf that holds the target" (barnes_hut.cpp:272) needs no test; without it d2 = 0 -> inf*0.
+            const bool selfTest = STATS || !(eps2f > 0.f);
+            const float INF = __int_as_float(0x7f800000);
             double AX = 0.0, AY = 0.0;
-            unsigned int j = 0, it = 0;
+            float ax = 0.f, ay = 0.f;
+            unsigned int j = 0, wbase = 0x80000000u;
+            TravRec* const win = &sWin[warp][0];
             while (j < n_nodes) {
-                const double2 A = a.nodeA[j];
-                const NodeB B = a.nodeB[j];
-                const double dxd = A.x - pxs, dyd = A.y - pys;
-                const float dx = (float)dxd, dy = (float)dyd;
-                const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
-                const bool active = j >= skipUntil;
-                bool open = d2 <= B.open_d2;
-                if (active && fabsf(d2 - B.open_d2) <= B.open_d2 * TRAV_BAND)
-                    open = exact_open(dxd, dyd, c.eps2s, B.level, Us, c.theta2);
-                open = open && active;
+                unsigned int off = j - wbase;
+                if (off >= (unsigned int)TRAV_WINDOW) {
+                    // stage the next TRAV_WINDOW pre-order records (line aligned) into shared memory: one coalesced
+                    // load per lane instead of one dependent L2 round trip per visited node
+                    __syncwarp();
+                    wbase = j & ~7u;
+                    off = j - wbase;
+                    const unsigned int k = wbase + lane;
+                    if (k < n_nodes) {
+                        win[lane].c = a.nodeC[k];
+                        win[lane].b = a.nodeB[k];
+                    }
+                    AX += (double)ax; AY += (double)ay;   // fp32 partial sums are flushed to fp64 at every refill
+                    ax = 0.f; ay = 0.f;
+                    __syncwarp();
+                }
+                const float4 C = win[off].c;
+                const NodeB B = win[off].b;
+                const float dx = (C.x + nphx) + (C.z + nplx);
+                const float dy = (C.y + nphy) + (C.w + nply);
+                float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+                // a lane that accepted an ancestor sees the node infinitely far away: never opens, contributes 0
+                d2 = (j >= skipUntil) ? d2 : INF;
+                float lo = B.open_lo;
+                if (d2 > lo && d2 < B.open_hi)   // rare: inside the guard band -> the reference's fp64 test decides
+                    lo = exact_open(a.nodeA[j], pxs, pys, c.eps2s, (int)a.nlevel[j], Us, c.theta2) ? INF : -1.f;
+                const bool open = d2 <= lo;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
-                const bool acc = active && !open;
-                if (acc) skipUntil = B.skip;
-                const float rinv = rsqrtf(d2);
-                float f = B.gm * rinv * (rinv * rinv);
-                const bool contrib = acc && (j != self);
-                f = contrib ? f : 0.f;
+                // accepted (or already skipping): descendants are ignored up to skip[j]; max() keeps an earlier,
+                // larger skip of a lane that accepted an ancestor
+                if (!open) skipUntil = max(skipUntil, B.skip);
+                float rinv;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
+                float f = (B.gm * rinv) * (rinv * rinv);
+                if (selfTest && j == self) f = 0.f;
                 ax = fmaf(dx, f, ax);
                 ay = fmaf(dy, f, ay);
                 if (STATS) {
+                    nwarp++;
+                    const bool active = d2 != INF;
                     nvis += active ? 1u : 0u;
-                    nacc += (contrib && B.level != -3) ? 1u : 0u;
+                    nacc += (active && !open && j != self && B.open_hi != -2.0f) ? 1u : 0u;
                 }
-                j = anyopen ? j + 1u : max(B.skip, j + 1u);  // max(): a corrupt skip can never stall the walk
-                if ((++it & 31u) == 0u) {
-                    AX += (double)ax; AY += (double)ay;
-                    ax = 0.f; ay = 0.f;
-                }
+                j = anyopen ? j + 1u : B.skip;
             }
             AX += (double)ax; AY += (double)ay;
             // a = G * sum M d / r^3 ; scaled units: M/Ms, d/S  =>  factor G*Ms/S^2
@@ -138,19 +175,20 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
                 const double2 A = a.nodeA[j];
                 const NodeB B = a.nodeB[j];
                 const double M = a.nodeM[j];
+                const int level = (int)a.nlevel[j];
                 const double dx = (A.x - pxs) * c.S, dy = (A.y - pys) * c.S;   // exact: S is a power of two
                 const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), eps2);
                 const bool active = j >= skipUntil;
                 bool open = false;
-                if (B.level >= 0) {
-                    const double size = ldexp(c.U, -B.level);
+                if (level >= 0 && B.open_hi != -2.0f) {
+                    const double size = ldexp(c.U, -level);
                     open = !(__ddiv_rn(__dmul_rn(size, size), distSq) < c.theta2);
                 }
                 open = open && active;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
                 const bool acc = active && !open;
                 if (acc) skipUntil = B.skip;
-                if (acc && j != self && B.level != -3) {
+                if (acc && j != self && B.open_hi != -2.0f) {
                     const double dist = sqrt(distSq);
                     const double force = __ddiv_rn(__dmul_rn(__dmul_rn(c.G, M), m), distSq);
                     const double invDistMass = __ddiv_rn(force, __dmul_rn(m, dist));
@@ -159,7 +197,7 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
                     if (STATS) nacc++;
                 }
                 if (STATS) nvis += active ? 1u : 0u;
-                j = anyopen ? j + 1u : max(B.skip, j + 1u);
+                j = anyopen ? j + 1u : B.skip;
             }
         }
 
@@ -190,6 +228,7 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
             if (lane == 0) {
                 atomicAdd(&a.s->interactions, (unsigned long long)nacc);
                 atomicAdd(&a.s->visits, (unsigned long long)nvis);
+                atomicAdd(&a.s->warp_visits, (unsigned long long)nwarp);
             }
         }
     }

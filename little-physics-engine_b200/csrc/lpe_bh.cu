@@ -40,6 +40,7 @@ struct lpe_bh_ctx {
     int instr = 0;
 
     uint64_t n = 0, cap = 0;
+    uint64_t launches = 0;
     int shard_rank = 0, shard_n = 1;
     uint64_t xchg_chunk = 0;
 
@@ -70,6 +71,7 @@ struct lpe_bh_ctx {
     unsigned int *parent = nullptr, *child = nullptr, *arrived = nullptr, *nodeStart = nullptr;
     Agg* agg = nullptr;
     double2* nodeA = nullptr;
+    float4* nodeC = nullptr;
     NodeB* nodeB = nullptr;
     double* nodeM = nullptr;
     signed char* nlevel = nullptr;
@@ -141,7 +143,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
           dalloc(c, c->tnode, cap + 2) | dalloc(c, c->delta, cap + 2);
     rc |= dalloc(c, c->parent, ncap) | dalloc(c, c->child, 4 * ncap) | dalloc(c, c->arrived, ncap) |
-          dalloc(c, c->nodeStart, ncap) | dalloc(c, c->agg, ncap) | dalloc(c, c->nodeA, ncap) |
+          dalloc(c, c->nodeStart, ncap) | dalloc(c, c->agg, ncap) | dalloc(c, c->nodeA, ncap) | dalloc(c, c->nodeC, ncap) |
           dalloc(c, c->nodeB, ncap) | dalloc(c, c->nodeM, ncap) | dalloc(c, c->nlevel, ncap);
     rc |= dalloc(c, c->cntAcc, cap) | dalloc(c, c->cntVis, cap) | dalloc(c, c->scal, 1);
     if (rc) {
@@ -245,6 +247,21 @@ k_direct(int n, const double2* __restrict__ pos, const double* __restrict__ mass
     }
 }
 
+// 16 independent FMA chains per thread, register resident
+__global__ void __launch_bounds__(256) k_fma_peak(int iters, float a, float* __restrict__ sink) {
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (float)(threadIdx.x + k) * 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = fmaf(v[k], a, 0.5f);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += v[k];
+    if (s == 123.456f) sink[threadIdx.x] = s;
+}
+
 int choose_depth(const lpe_bh_params& p) {
     if (p.max_depth > 0) return p.max_depth > LPE_MAX_DEPTH ? LPE_MAX_DEPTH : p.max_depth;
     if (!(p.softening > 0.0) || !(p.theta > 0.0)) return LPE_MAX_DEPTH;
@@ -340,14 +357,14 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->scal);
     device_scan(c, MaskPop{c->mask, c->scal}, n, c->P, nullptr);
     k_topology<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->P, c->tnode, c->parent, c->child, c->nodeB,
-                                      c->nodeStart, c->scal);
-    NodeOut no{c->nodeA, c->nodeB, c->nodeM, c->nlevel};
+                                      c->nlevel, c->nodeStart, c->scal);
+    NodeOut no{c->nodeA, c->nodeC, c->nodeB, c->nodeM, c->nlevel};
     k_aggregate<<<g256, 256, 0, st>>>(k, c->tfirst, c->tnode, c->spos, c->smass, c->srank, c->parent, c->child,
                                        c->arrived, c->agg, no, c->selfnode, c->scal);
     if (timing) cudaEventRecord(c->ev[3], st);
 
     TravArgs ta{};
-    ta.nodeA = c->nodeA; ta.nodeB = c->nodeB; ta.nodeM = c->nodeM; ta.spos = c->spos; ta.smass = c->smass;
+    ta.nodeA = c->nodeA; ta.nodeC = c->nodeC; ta.nlevel = c->nlevel; ta.nodeB = c->nodeB; ta.nodeM = c->nodeM; ta.spos = c->spos; ta.smass = c->smass;
     ta.sidx = sidx; ta.selfnode = c->selfnode; ta.comp = c->comp; ta.pos = c->pos; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
@@ -369,6 +386,8 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     }
     if (timing) cudaEventRecord(c->ev[4], st);
     CU_TRY(c, cudaGetLastError());
+    // keygen, 3 per sort pass, gather, init_self, 2 scans of 3, terminals, witness, topology, aggregate, traverse
+    c->launches += 1 + 3 * (uint64_t)passes + 2 + 3 + 2 + 3 + 2 + 1;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
@@ -554,6 +573,7 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
         s.n_nodes = (uint64_t)h.n_term + h.n_internal;
         s.interactions = h.interactions;
         s.visits = h.visits;
+        s.warp_visits = h.warp_visits;
         if (c->instr & 1) {
             cudaEventElapsedTime(&s.ms_keygen, c->ev[0], c->ev[1]);
             cudaEventElapsedTime(&s.ms_sort, c->ev[1], c->ev[2]);
@@ -692,6 +712,39 @@ int lpe_bh_xchg_write_recv(lpe_bh_ctx* c, int src, const double* host) {
     CU_TRY(c, cudaMemcpyAsync(c->xchg_recv + (size_t)src * c->xchg_chunk, host, sizeof(double4) * c->xchg_chunk,
                               cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+uint64_t lpe_bh_launch_count(const lpe_bh_ctx* c) { return c ? c->launches : 0; }
+
+int lpe_bh_fma_peak(lpe_bh_ctx* c, double* tflops) {
+    if (!c || !tflops) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    float* sink = nullptr;
+    CU_TRY(c, cudaMalloc(&sink, sizeof(float) * 1024));
+    const int iters = 1 << 14, blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        k_fma_peak<<<blocks, threads, 0, c->stream>>>(iters, 1.0001f, sink);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    CU_TRY(c, cudaGetLastError());
+    *tflops = best;
     return 0;
 }
 

@@ -38,7 +38,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("n_bodies", C.c_uint64), ("n_in_tree", C.c_uint64), ("n_terminals", C.c_uint64),
-        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64),
+        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64), ("warp_visits", C.c_uint64),
         ("depth", C.c_int32), ("sort_passes", C.c_int32), ("ms_keygen", C.c_float),
         ("ms_sort", C.c_float), ("ms_build", C.c_float), ("ms_traverse", C.c_float), ("ms_total", C.c_float),
     ]
@@ -104,6 +104,11 @@ def load_library():
     lib.lpe_bh_version.restype = C.c_char_p
     lib.lpe_bh_last_error.restype = C.c_char_p
     lib.lpe_bh_last_error.argtypes = [C.c_void_p]
+    lib.lpe_bh_launch_count.restype = C.c_uint64
+    lib.lpe_bh_launch_count.argtypes = [C.c_void_p]
+    lib.lpe_bh_alloc_pinned.restype = C.c_void_p
+    lib.lpe_bh_alloc_pinned.argtypes = [C.c_uint64]
+    lib.lpe_bh_free_pinned.argtypes = [C.c_void_p]
     lib.lpe_bh_shard_chunk.restype = C.c_uint64
     lib.lpe_bh_shard_chunk.argtypes = [C.c_uint64, C.c_int]
     _lib = lib
@@ -242,6 +247,14 @@ class BarnesHut:
         self._chk(self.lib.lpe_bh_direct_accel(self.h, C.byref(params), C.c_uint64(first), C.c_uint64(count), _dp(ax),
                                                _dp(ay)), "direct_accel")
         return ax, ay
+
+    def launch_count(self):
+        return int(self.lib.lpe_bh_launch_count(self.h))
+
+    def fma_peak_tflops(self):
+        t = C.c_double(0.0)
+        self._chk(self.lib.lpe_bh_fma_peak(self.h, C.byref(t)), "fma_peak")
+        return t.value
 
     # ---- multi-GPU ----
     def set_shard(self, rank, nranks):
