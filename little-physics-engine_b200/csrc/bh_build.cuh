@@ -13,10 +13,14 @@
 // t and t+1. Every t is a "witness" of the branching cell at level delta[t] that contains t and t+1; that
 // cell is identified by (a, L) with a = its first terminal. A 32-bit level mask per terminal collects the
 // levels of the cells that start there (atomicOr), and
-//     preorder(a, L) = a + P[a] + popc(mask[a] & ((1<<L)-1)),   P = exclusive scan of popc(mask)
-//     preorder(leaf t) = t + P[t] + popc(mask[t])
+//     ordinal(a, L)    = P[a] + popc(mask[a] & ((1<<L)-1))      P = exclusive scan of popc(mask)
+//     preorder(a, L)   = a + ordinal(a, L);   preorder(leaf t) = t + P[t] + popc(mask[t])
 //     skip(a..b)       = (b+1) + P[b+1]
 //     parent level     = max(delta[a-1], delta[b])
+// Aggregation is level-synchronous, deepest level first (one launch per level, nodes of a level listed by a
+// block-aggregated counting pass): a cell sums its <= 4 children in digit order (deterministic), and writes
+// their traversal records side by side into its CHILD BLOCK (one 128-byte line). The traversal always visits
+// all children of an opened cell, so every byte it fetches is used.
 #pragma once
 #include "bh_common.cuh"
 
@@ -122,21 +126,31 @@ k_terminals(int n, const unsigned long long* __restrict__ keys, const unsigned i
     if ((unsigned int)i == n_in - 1) tfirst[t + (head ? 1u : 0u)] = n_in;
 }
 
-// ---- 4. witnesses: delta[] and the per-terminal level masks -------------------------------------------------
+// ---- 4. witnesses: delta[], the per-terminal level masks, and the number of branching cells per level ------
 __global__ void __launch_bounds__(256)
 k_witness(int D, const unsigned long long* __restrict__ tkey, signed char* __restrict__ delta,
-          unsigned int* __restrict__ mask, const Scal* __restrict__ s) {
+          unsigned int* __restrict__ mask, unsigned int* __restrict__ levelCount, const Scal* __restrict__ s) {
+    __shared__ unsigned int cnt[32];
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_term = (int)s->n_term;
-    if (t >= n_term) return;
-    if (t == n_term - 1) {
-        delta[t] = -1;
-        return;
+    if (t < n_term) {
+        if (t == n_term - 1) {
+            delta[t] = -1;
+        } else {
+            const unsigned long long kt = tkey[t];
+            const int L = lca_level(kt, tkey[t + 1], D);
+            delta[t] = (signed char)L;
+            const int shift = 2 * (D - L);
+            const int a = cell_first(tkey, t, shift);
+            atomicOr(&mask[a], 1u << L);
+            // the witness that sits in the cell's first non-empty child counts the cell (once per cell)
+            if ((tkey[a] >> (shift - 2)) == (kt >> (shift - 2))) atomicAdd(&cnt[L], 1u);
+        }
     }
-    const int L = lca_level(tkey[t], tkey[t + 1], D);
-    delta[t] = (signed char)L;
-    const int a = cell_first(tkey, t, 2 * (D - L));
-    atomicOr(&mask[a], 1u << L);
+    __syncthreads();
+    if (threadIdx.x < 32 && cnt[threadIdx.x]) atomicAdd(&levelCount[threadIdx.x], cnt[threadIdx.x]);
 }
 
 struct MaskPop {
@@ -147,59 +161,93 @@ struct MaskPop {
     }
 };
 
-// ---- 5. topology: pre-order indices, skip pointers, parents, child slots ------------------------------------
+// levelBase = exclusive scan of levelCount (32 entries); levelCursor reset
+__global__ void k_level_scan(const unsigned int* __restrict__ levelCount, unsigned int* __restrict__ levelBase,
+                             unsigned int* __restrict__ levelCursor) {
+    if (threadIdx.x == 0) {
+        unsigned int run = 0;
+        for (int L = 0; L < 32; ++L) {
+            levelBase[L] = run;
+            run += levelCount[L];
+            levelCursor[L] = 0;
+        }
+    }
+}
+
+// ---- 5. topology: pre-order indices, skip pointers, child slots, per-level cell lists ------------------------
+struct Topo {
+    unsigned int* tnode;      // [terminal] pre-order index of the terminal's node
+    unsigned int* child;      // [4 * ordinal + digit] pre-order index of a branching cell's child, LPE_NONE if empty
+    NodeMeta* meta;           // [preorder] (terminal levels are refined to -1 / -2 by k_agg_terminals)
+    unsigned int* levelList;  // cells grouped by level: levelList[levelBase[L] + i]
+    const unsigned int* levelBase;
+    unsigned int* levelCursor;
+};
+
+__device__ __forceinline__ void register_child(int D, const unsigned long long* __restrict__ tkey,
+                                               const unsigned int* __restrict__ mask,
+                                               const unsigned int* __restrict__ P, int t, unsigned long long kt, int dl,
+                                               int dr, unsigned int idx, unsigned int* __restrict__ child) {
+    const int Lp = max(dl, dr);   // level of the nearest branching ancestor
+    if (Lp < 0) return;           // root
+    const int ap = (dl < Lp) ? t : cell_first(tkey, t, 2 * (D - Lp));
+    const unsigned int qpar = P[ap] + (unsigned int)__popc(mask[ap] & ((1u << Lp) - 1u));
+    const unsigned int digit = (unsigned int)(kt >> (2 * (D - Lp - 1))) & 3u;
+    child[(size_t)qpar * 4 + digit] = idx;
+}
+
 __global__ void __launch_bounds__(256)
 k_topology(int D, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
-           const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P,
-           unsigned int* __restrict__ tnode, unsigned int* __restrict__ parent, unsigned int* __restrict__ child,
-           NodeB* __restrict__ nodeB, signed char* __restrict__ nlevel, unsigned int* __restrict__ nodeStart,
-           Scal* __restrict__ s) {
+           const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P, Topo o, Scal* __restrict__ s) {
+    __shared__ unsigned int cnt[32], base[32];
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_term = (int)s->n_term;
     if (t == 0) s->n_internal = P[n_term];
-    if (t >= n_term) return;
-    const unsigned int mk = mask[t];
-    const unsigned int Pt = P[t];
-    const unsigned long long kt = tkey[t];
-    const int dl = (t > 0) ? (int)delta[t - 1] : -1;
-
-    // the terminal itself
-    {
-        const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk);
-        tnode[t] = idx;
-        const int dr = (int)delta[t];  // -1 for the last terminal
-        const int Lp = max(dl, dr);
-        unsigned int par = LPE_NONE;
-        if (Lp >= 0) {
-            const int ap = (dl < Lp) ? t : cell_first(tkey, t, 2 * (D - Lp));
-            par = (unsigned int)ap + P[ap] + (unsigned int)__popc(mask[ap] & ((1u << Lp) - 1u));
-            const unsigned int digit = (unsigned int)(kt >> (2 * (D - Lp - 1))) & 3u;
-            child[(size_t)par * 4 + digit] = idx;
+    const bool live = t < n_term;
+    unsigned int mk = 0, Pt = 0;
+    if (live) {
+        mk = mask[t];
+        Pt = P[t];
+        const unsigned long long kt = tkey[t];
+        const int dl = (t > 0) ? (int)delta[t - 1] : -1;
+        {   // the terminal itself
+            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk);
+            o.tnode[t] = idx;
+            NodeMeta mt;
+            mt.skip = idx + 1; mt.start = (unsigned int)t; mt.level = -1; mt.pad = 0;
+            o.meta[idx] = mt;
+            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[t], idx, o.child);
         }
-        parent[idx] = par;
-        nodeB[idx].skip = idx + 1;
-        nodeStart[idx] = (unsigned int)t;
+        unsigned int rest = mk;   // branching cells whose first terminal is t
+        while (rest) {
+            const int L = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
+            const int b = cell_last(tkey, t, 2 * (D - L), n_term);
+            NodeMeta mt;
+            mt.skip = (unsigned int)(b + 1) + P[b + 1]; mt.start = (unsigned int)t; mt.level = L; mt.pad = 0;
+            o.meta[idx] = mt;
+            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[b], idx, o.child);
+            atomicAdd(&cnt[L], 1u);
+        }
     }
-    // branching cells whose first terminal is t
+    // per-level lists: one global reservation per level per block, then block-local slots
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned int c = cnt[threadIdx.x];
+        base[threadIdx.x] = c ? atomicAdd(&o.levelCursor[threadIdx.x], c) : 0u;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
     unsigned int rest = mk;
     while (rest) {
         const int L = __ffs(rest) - 1;
         rest &= rest - 1;
         const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
-        const int b = cell_last(tkey, t, 2 * (D - L), n_term);
-        const int dr = (int)delta[b];
-        const int Lp = max(dl, dr);
-        unsigned int par = LPE_NONE;
-        if (Lp >= 0) {
-            const int ap = (dl < Lp) ? t : cell_first(tkey, t, 2 * (D - Lp));
-            par = (unsigned int)ap + P[ap] + (unsigned int)__popc(mask[ap] & ((1u << Lp) - 1u));
-            const unsigned int digit = (unsigned int)(kt >> (2 * (D - Lp - 1))) & 3u;
-            child[(size_t)par * 4 + digit] = idx;
-        }
-        parent[idx] = par;
-        nodeB[idx].skip = (unsigned int)(b + 1) + P[b + 1];
-        nlevel[idx] = (signed char)L;
-        nodeStart[idx] = (unsigned int)t;
+        const unsigned int local = atomicAdd(&cnt[L], 1u);
+        o.levelList[o.levelBase[L] + base[L] + local] = idx;
     }
 }
 
@@ -211,75 +259,59 @@ __device__ __forceinline__ double mass_scale_inv(unsigned long long max_mass_bit
     return ldexp(1.0, -(e + 1));
 }
 
-// ---- 6. aggregation: leaves write their record, the last child to arrive sums its siblings ------------------
+// ---- 6. aggregation and traversal records ---------------------------------------------------------------------
 struct NodeOut {
-    double2* nodeA;       // fp64 centre (scaled): exact re-test of borderline theta decisions, STRICT mode, dumps
-    float4* nodeC;        // two-float centre (scaled): the traversal's inner loop
-    NodeB* nodeB;
-    double* nodeM;
-    signed char* nlevel;  // level of a branching cell, -1 leaf, -2 aggregated terminal
+    NodeMeta* meta;       // [preorder]
+    Agg* agg;             // [preorder]
+    TravRec* rec;         // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
 };
 
-constexpr float OPEN_BAND = 4e-6f;  // relative half-width of the fp32 guard band around s^2/theta^2
-
-__device__ __forceinline__ void finalize_node(const StepConst& c, const NodeOut& o, unsigned int idx, const Agg& a,
-                                              int level, double massScaleInv, const double2* __restrict__ spos,
-                                              const double* __restrict__ smass) {
-    double M = a.m, sx = a.sx, sy = a.sy;
-    double cx, cy;
-    if (level == -1) {
-        // single-body leaf: exactly the body (barnes_hut.cpp:144-153)
-        const double2 p = spos[a.fidx];
-        cx = p.x;
-        cy = p.y;
-    } else {
-        if (c.quirk) {
-            // first occupant counted twice in every internal cell (barnes_hut.cpp:157-177)
-            const double mf = smass[a.fidx];
-            const double2 pf = spos[a.fidx];
-            M += mf;
-            sx += mf * pf.x;
-            sy += mf * pf.y;
-        }
-        cx = sx / M;
-        cy = sy / M;
-    }
+// Traversal record of a node from its aggregate.
+__device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a, int level, unsigned int skip,
+                                               unsigned int cblock, double massScaleInv) {
+    double M, cx, cy;
+    node_centre(a, level, c.quirk, M, cx, cy);
     const double cxs = cx * c.invS, cys = cy * c.invS;
-    o.nodeA[idx] = make_double2(cxs, cys);
+    TravRec r;
     const float hx = (float)cxs, hy = (float)cys;
-    o.nodeC[idx] = make_float4(hx, hy, (float)(cxs - (double)hx), (float)(cys - (double)hy));
-    o.nodeM[idx] = M;
+    r.c = make_float4(hx, hy, (float)(cxs - (double)hx), (float)(cys - (double)hy));
     // allSmall cells are skipped by the traversal but still feed their ancestors (barnes_hut.cpp:253, Q7):
     // a zero mass with "never open" is exactly that.
     const bool skipSmall = (c.thr > 0.0) && a.small;
-    NodeB nb;
-    nb.skip = o.nodeB[idx].skip;  // written by k_topology
-    nb.gm = skipSmall ? 0.0f : (float)(M * massScaleInv);
-    nb.open_lo = nb.open_hi = skipSmall ? -2.0f : -1.0f;
+    r.gm = skipSmall ? 0.0f : (float)(M * massScaleInv);
+    r.open_t = skipSmall ? -2.0f : -1.0f;
     if (level >= 0 && !skipSmall) {
         const double s = ldexp(c.U, -level) * c.invS;
-        const float t = (float)((s * s) / c.theta2);
-        nb.open_lo = t * (1.0f - OPEN_BAND);
-        nb.open_hi = t * (1.0f + OPEN_BAND);
+        r.open_t = (float)((s * s) / c.theta2);
     }
-    o.nodeB[idx] = nb;
-    o.nlevel[idx] = (signed char)level;
+    r.skip = skip;
+    r.cblock = (level >= 0) ? cblock : 0u;
+    return r;
 }
 
+__device__ __forceinline__ TravRec invalid_record() {
+    TravRec r;
+    r.c = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.gm = 0.f;
+    r.open_t = -1.f;
+    r.skip = 0u;   // skip == 0 marks an unused slot of a child block
+    r.cblock = 0u;
+    return r;
+}
+
+// terminals: per-cell sums over the bodies that share a depth-D cell (usually one)
 __global__ void __launch_bounds__(256)
-k_aggregate(StepConst c, const unsigned int* __restrict__ tfirst, const unsigned int* __restrict__ tnode,
-            const double2* __restrict__ spos, const double* __restrict__ smass,
-            const unsigned int* __restrict__ srank, const unsigned int* __restrict__ parent,
-            const unsigned int* __restrict__ child, unsigned int* __restrict__ arrived, Agg* __restrict__ agg,
-            NodeOut o, unsigned int* __restrict__ selfnode, const Scal* __restrict__ s) {
+k_agg_terminals(StepConst c, const unsigned int* __restrict__ tfirst, const unsigned int* __restrict__ tnode,
+                const double2* __restrict__ spos, const double* __restrict__ smass,
+                const unsigned int* __restrict__ srank, NodeOut o, unsigned int* __restrict__ selfnode,
+                const Scal* __restrict__ s) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_term = (int)s->n_term;
     if (t >= n_term) return;
-    const double massScaleInv = mass_scale_inv(s->max_mass_bits);
     const unsigned int first = tfirst[t], last = tfirst[t + 1];
     Agg a;
-    a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
-    a.pad[0] = a.pad[1] = 0u;
+    a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
+    a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
     for (unsigned int i = first; i < last; ++i) {
         const double m = smass[i];
         const double2 p = spos[i];
@@ -287,46 +319,75 @@ k_aggregate(StepConst c, const unsigned int* __restrict__ tfirst, const unsigned
         a.sx += m * p.x;
         a.sy += m * p.y;
         const unsigned int r = srank[i];
-        if (r < a.frank) { a.frank = r; a.fidx = i; }
+        if (r < a.frank) { a.frank = r; a.fidx = i; a.mf = m; a.xf = p.x; a.yf = p.y; }
         if (m >= c.thr) a.small = 0u;
     }
-    unsigned int idx = tnode[t];
+    const unsigned int idx = tnode[t];
     const bool single = (last - first) == 1;
-    finalize_node(c, o, idx, a, single ? -1 : -2, massScaleInv, spos, smass);
+    if (!single) o.meta[idx].level = -2;
+    o.agg[idx] = a;
     for (unsigned int i = first; i < last; ++i) selfnode[i] = single ? idx : LPE_NONE;
-    agg[idx] = a;
+    if (n_term == 1) {   // a tree of one terminal: it is the root
+        const double msi = mass_scale_inv(s->max_mass_bits);
+        o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
+        o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+    }
+}
 
-    // walk up: the last child to arrive at a cell owns it
-    unsigned int p = parent[idx];
-    for (int hop = 0; hop <= LPE_MAX_DEPTH + 1 && p != LPE_NONE; ++hop) {  // a branching chain is at most D cells long
-        const uint4 ch = reinterpret_cast<const uint4*>(child)[p];
-        const unsigned int need = (ch.x != LPE_NONE) + (ch.y != LPE_NONE) + (ch.z != LPE_NONE) + (ch.w != LPE_NONE);
-        __threadfence();
-        const unsigned int old = atomicAdd(&arrived[p], 1u);
-        if (old + 1u < need) return;
-        __threadfence();
-        Agg b;
-        b.m = 0.0; b.sx = 0.0; b.sy = 0.0; b.frank = 0xFFFFFFFFu; b.fidx = 0; b.count = 0; b.small = 1u;
-        b.pad[0] = b.pad[1] = 0u;
-        const unsigned int cs[4] = {ch.x, ch.y, ch.z, ch.w};
+// one branching cell: sum the children (digit order), write their records into this cell's child block
+__device__ __forceinline__ void aggregate_cell(const StepConst& c, const NodeOut& o, unsigned int p,
+                                               const unsigned int* __restrict__ child, double msi) {
+    const NodeMeta mp = o.meta[p];
+    const unsigned int q = p - mp.start;
+    const uint4 ch = reinterpret_cast<const uint4*>(child)[q];
+    const unsigned int cs[4] = {ch.x, ch.y, ch.z, ch.w};
+    Agg b;
+    b.m = 0.0; b.sx = 0.0; b.sy = 0.0; b.mf = 0.0; b.xf = 0.0; b.yf = 0.0;
+    b.frank = 0xFFFFFFFFu; b.fidx = 0; b.count = 0; b.small = 1u;
+    TravRec* blk = o.rec + 4 * (size_t)(q + 1);
+    int r = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (cs[q] == LPE_NONE) continue;
-            // written by another SM just before its atomicAdd: read through L2, not a stale L1 line
-            const double2* ad = reinterpret_cast<const double2*>(&agg[cs[q]]);
-            const double2 w0 = __ldcg(ad);
-            const double2 w1 = __ldcg(ad + 1);
-            const uint4 w2 = __ldcg(reinterpret_cast<const uint4*>(ad + 2));
-            const unsigned long long fr = (unsigned long long)__double_as_longlong(w1.y);
-            const unsigned int frank = (unsigned int)(fr & 0xFFFFFFFFull), fidx = (unsigned int)(fr >> 32);
-            b.m += w0.x; b.sx += w0.y; b.sy += w1.x;
-            if (frank < b.frank) { b.frank = frank; b.fidx = fidx; }
-            b.count += w2.x;
-            b.small &= w2.y;
-        }
-        finalize_node(c, o, p, b, (int)o.nlevel[p], massScaleInv, spos, smass);
-        agg[p] = b;
-        p = parent[p];
+    for (int g = 0; g < 4; ++g) {
+        const unsigned int ci = cs[g];
+        if (ci == LPE_NONE) continue;
+        const Agg a = o.agg[ci];
+        const NodeMeta mc = o.meta[ci];
+        b.m += a.m; b.sx += a.sx; b.sy += a.sy;
+        if (a.frank < b.frank) { b.frank = a.frank; b.fidx = a.fidx; b.mf = a.mf; b.xf = a.xf; b.yf = a.yf; }
+        b.count += a.count;
+        b.small &= a.small;
+        blk[r++] = make_record(c, a, mc.level, mc.skip, (ci - mc.start) + 1u, msi);
+    }
+    for (; r < 4; ++r) blk[r] = invalid_record();
+    o.agg[p] = b;
+    if (p == 0) {   // the root has no parent to write its record
+        o.rec[0] = make_record(c, b, mp.level, mp.skip, 1u, msi);
+        o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+    }
+}
+
+// all branching cells of one level (children are at deeper levels: finished by earlier launches)
+__global__ void __launch_bounds__(256)
+k_agg_level(StepConst c, int L, const unsigned int* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
+            const unsigned int* __restrict__ levelCount, const unsigned int* __restrict__ child, NodeOut o,
+            const Scal* __restrict__ s) {
+    const unsigned int count = levelCount[L], base = levelBase[L];
+    const double msi = mass_scale_inv(s->max_mass_bits);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        aggregate_cell(c, o, levelList[base + i], child, msi);
+}
+
+// the few cells of levels Ltop..0 in one block (a level has at most 4^L cells), one __syncthreads per level
+__global__ void __launch_bounds__(1024)
+k_agg_top(StepConst c, int Ltop, const unsigned int* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
+          const unsigned int* __restrict__ levelCount, const unsigned int* __restrict__ child, NodeOut o,
+          const Scal* __restrict__ s) {
+    const double msi = mass_scale_inv(s->max_mass_bits);
+    for (int L = Ltop; L >= 0; --L) {
+        const unsigned int count = levelCount[L], base = levelBase[L];
+        for (unsigned int i = threadIdx.x; i < count; i += blockDim.x)
+            aggregate_cell(c, o, levelList[base + i], child, msi);
+        __syncthreads();
     }
 }
 

@@ -4,7 +4,8 @@
 //   state (creation order):  pos double2[n], vel double2[n], mass f64[n], rank u32[n], comp u8[n]
 //   sorted (Morton order):   keys u64[n], sidx u32[n], spos double2[n], smass f64[n], srank u32[n]
 //   terminals (t < n_term):  tkey u64, tfirst u32, delta i8, mask u32, tnode u32
-//   nodes (pre-order index): nodeA double2 (scaled COM), nodeB NodeB (16 B), nodeM f64, parent u32, child uint4, agg Agg
+//   nodes (pre-order index): meta NodeMeta (16 B), agg Agg (64 B)
+//   cells (ordinal):         child uint4;  records: rec TravRec[4 * (cells + 1)] in child blocks of 128 B
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -26,30 +27,44 @@ struct Scal {
     unsigned long long warp_visits;    // node visits summed over warps (one per loop iteration)
 };
 
-// Traversal node record, 32 bytes = two broadcast 16-byte loads per visited node.
-//   NodeC: centre of mass in scaled units as a two-float (hi + lo) pair per axis. hi = fl32(c), lo = fl32(c - hi), so
-//          (c_hi - p_hi) + (c_lo - p_lo) gives the fp64 difference rounded once to fp32 (relative error 2^-24 of |d|,
-//          wherever in the universe the pair sits) with no FP64 instruction and no conversion in the inner loop.
-//   NodeB: mass, the theta test as two thresholds around s^2/theta^2 (below open_lo: open; at or above open_hi:
-//          accept; in between the reference's fp64 expression decides), and the skip pointer.
-struct __align__(16) NodeB {
+// Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.
+//   c:      centre of mass in scaled units as a two-float (hi + lo) pair per axis: hi = fl32(c), lo = fl32(c - hi), so
+//           (c_hi - p_hi) + (c_lo - p_lo) is the fp64 difference rounded once to fp32 (relative error 2^-24 of |d|,
+//           wherever in the universe the pair sits) with no FP64 instruction and no conversion in the inner loop.
+//   open_t: s^2/theta^2 in scaled units. d2 <= open_t*(1-band) opens, d2 >= open_t*(1+band) accepts, in between
+//           the reference's own fp64 expression decides. -1 for leaves / terminals, -2 for the small-mass skip.
+//   skip:   pre-order index of the first node after this subtree (0 marks an unused slot of a child block).
+//   cblock: index of the 128-byte block holding this cell's children (0 for leaves / terminals).
+struct __align__(16) TravRec {
+    float4 c;            // chx, chy, clx, cly
     float gm;            // node mass / mass scale (0 when the node is skipped by the small-mass rule)
-    float open_lo;       // d2 <= open_lo  => every fp64 evaluation would open the node
-    float open_hi;       // d2 >= open_hi  => every fp64 evaluation would accept it; -1 leaf/terminal, -2 small-mass skip
-    unsigned int skip;   // pre-order index of the first node after this subtree
+    float open_t;
+    unsigned int skip;
+    unsigned int cblock;
 };
+static_assert(sizeof(TravRec) == 32, "four records per 128-byte line");
+constexpr float OPEN_BAND = 4e-6f;  // relative half-width of the fp32 guard band around s^2/theta^2
 
-// Per-node aggregate carried up the tree (exact sums, quirk applied only when a record is finalised).
+// Per-node aggregate carried up the tree (exact sums; the quirk is applied only when a record is made). 64 bytes =
+// two sectors; it carries the first occupant's own mass and position so that no second lookup is needed.
 struct __align__(16) Agg {
     double m, sx;         // sum m, sum m*x over the bodies under the node
-    double sy;            // sum m*y
-    unsigned int frank;   // minimum insertion rank under the node
-    unsigned int fidx;    // sorted position of that first occupant
+    double sy, mf;        // sum m*y; mass of the first occupant (minimum insertion rank)
+    double xf, yf;        // position of the first occupant
+    unsigned int frank;   // its insertion rank
+    unsigned int fidx;    // its sorted position
     unsigned int count;   // bodies under the node
     unsigned int small;   // 1 if every mass under the node is < small_mass_threshold
-    unsigned int pad[2];
 };
-static_assert(sizeof(Agg) == 48, "Agg is read back as three 16-byte words");
+static_assert(sizeof(Agg) == 64, "Agg is two 32-byte sectors");
+
+// Per-node topology, one 16-byte word by pre-order index.
+struct __align__(16) NodeMeta {
+    unsigned int skip;    // pre-order index of the first node after this subtree
+    unsigned int start;   // first terminal under the node (ordinal of a branching cell = preorder - start)
+    int level;            // level of a branching cell; -1 single-body leaf; -2 aggregated terminal
+    unsigned int pad;
+};
 
 struct StepConst {
     double U, invS, S;        // universe size; power-of-two length scale and its inverse
@@ -65,6 +80,25 @@ struct StepConst {
     int n;                    // bodies
     int shard_rank, shard_n;  // multi-GPU block-cyclic ownership of sorted positions
 };
+
+// Mass and centre of mass of a node as the traversal sees it, in real units.
+//   leaf: exactly the body (barnes_hut.cpp:144-153); internal cell or aggregated terminal: with quirk, the first
+//   occupant counted twice (barnes_hut.cpp:157-177).
+__host__ __device__ __forceinline__ void node_centre(const Agg& a, int level, int quirk, double& M, double& cx, double& cy) {
+    if (level == -1) {
+        M = a.m; cx = a.xf; cy = a.yf;
+        return;
+    }
+    double sx = a.sx, sy = a.sy;
+    M = a.m;
+    if (quirk) {
+        M += a.mf;
+        sx += a.mf * a.xf;
+        sy += a.mf * a.yf;
+    }
+    cx = sx / M;
+    cy = sy / M;
+}
 
 __device__ __forceinline__ unsigned long long spread_bits32(unsigned int v) {
     unsigned long long x = v;

@@ -3,18 +3,22 @@
 // Replaces BarnesHutSystem::calculateForce (reference barnes_hut.cpp:240-294) and, when do_drift is set,
 // MovementSystem::update (movement.cpp:13-39).
 //
-// One warp walks the pre-order node array for 32 Morton-consecutive targets. The walk is stackless: the
-// node index only moves forward (j+1 = first child, skip[j] = next node outside the subtree). Each lane keeps
-// its OWN accept/open decision, as the reference does per body: a lane that accepted a node ignores that
-// node's descendants by remembering skipUntil = skip[j]; the warp descends while any lane still opens.
-// All lanes read the same node -> one broadcast 2 x 16 B load per visited node, served from L1/L2.
+// One warp walks the tree for 32 Morton-consecutive targets, depth first in the reference's child order
+// (nw, ne, sw, se = Morton digit order), so nodes are met in pre-order. Each lane keeps its OWN accept/open
+// decision, as the reference does per body: a lane that accepted a node ignores that node's descendants by
+// remembering skipUntil = skip[node] (a pre-order index); the warp descends while any lane still opens.
+//
+// Memory: the children of a cell sit side by side in one 128-byte CHILD BLOCK (4 x TravRec). Opening a cell is one
+// coalesced 128-byte load by 8 lanes into the warp's frame stack in shared memory; every visit then reads its
+// record with two broadcast LDS.128. All children of an opened cell are always visited, so nothing fetched is
+// wasted (the pre-order array this replaces needed a fresh L2 round trip for 39 % of its visits).
 //
 // FAST precision: state stays fp64. Node centres and lane positions enter the inner loop as two-float (hi + lo)
 // pairs, so d = (c_hi - p_hi) + (c_lo - p_lo) is the fp64 difference rounded once to fp32 (relative error 2^-24
 // of |d|, independent of where in the universe the pair sits) without any FP64 or conversion instruction; d^2,
-// rsqrt and the accumulation are fp32 with fp64 flushes every 64 nodes. The theta test is done in fp32 against
-// two thresholds bracketing s^2/theta^2; between them the reference's own fp64 expression
-// (barnes_hut.cpp:261-269) decides, so accept/open decisions are the reference's, not an approximation of them.
+// rsqrt and the accumulation are fp32, flushed to fp64 whenever a child block is finished. The theta test is
+// done in fp32 against two thresholds bracketing s^2/theta^2; between them the reference's own fp64 expression
+// (barnes_hut.cpp:261-269) decides, so accept/open decisions are the reference's, not an approximation.
 // STRICT precision: every interaction in fp64, in the reference's expression order.
 #pragma once
 #include "bh_common.cuh"
@@ -22,19 +26,13 @@
 namespace lpe {
 
 constexpr int TRAV_THREADS = 256;
-constexpr int TRAV_WINDOW = 32;   // pre-order records staged per warp (one per lane)
-
-struct __align__(16) TravRec {
-    float4 c;
-    NodeB b;
-};
+constexpr int TRAV_WARPS = TRAV_THREADS / 32;
+constexpr int TRAV_FRAMES = LPE_MAX_DEPTH + 2;   // a chain of branching cells is at most D+1 long
 
 struct TravArgs {
-    const double2* nodeA;
-    const float4* nodeC;
-    const signed char* nlevel;
-    const NodeB* nodeB;
-    const double* nodeM;
+    const TravRec* rec;        // child blocks
+    const Agg* agg;            // [preorder] exact sums: fp64 centre / mass for the rare exact test and STRICT mode
+    const NodeMeta* meta;      // [preorder]
     const double2* spos;
     const double* smass;
     const unsigned int* sidx;
@@ -51,24 +49,40 @@ struct TravArgs {
 
 // The reference's test, barnes_hut.cpp:261-269, on exactly scaled operands (power-of-two scaling commutes
 // with IEEE rounding): returns true when the node must be opened.
-__device__ __noinline__ bool exact_open(double2 A, double pxs, double pys, double eps2s, int level, double Us,
+__device__ __noinline__ bool exact_open(const Agg* __restrict__ agg, const NodeMeta* __restrict__ meta, unsigned int j,
+                                        int quirk, double invS, double pxs, double pys, double eps2s, double Us,
                                         double theta2) {
-    const double dxs = A.x - pxs, dys = A.y - pys;
+    const int level = meta[j].level;
+    double M, cx, cy;
+    node_centre(agg[j], level, quirk, M, cx, cy);
+    const double dxs = cx * invS - pxs, dys = cy * invS - pys;
     const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dxs, dxs), __dmul_rn(dys, dys)), eps2s);
     const double size = ldexp(Us, -level);
     const double sizeSq = __dmul_rn(size, size);
     return !(__ddiv_rn(sizeSq, distSq) < theta2);
 }
 
+// 8 lanes copy one 128-byte child block into a frame of the warp's stack
+__device__ __forceinline__ void load_block(const TravRec* __restrict__ rec, unsigned int block, TravRec* frame, int lane) {
+    __syncwarp();
+    if (lane < 8) {
+        const uint4 v = reinterpret_cast<const uint4*>(rec + 4 * (size_t)block)[lane];
+        reinterpret_cast<uint4*>(frame)[lane] = v;
+    }
+    __syncwarp();
+}
+
 template <int PREC, bool STATS>
-__global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs a) {
-    __shared__ TravRec sWin[TRAV_THREADS / 32][TRAV_WINDOW];
+__global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravArgs a) {
+    __shared__ TravRec sFrames[TRAV_WARPS][TRAV_FRAMES][4];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
+    TravRec* const frames = &sFrames[warp][0][0];
     const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = (float)c.eps2s;
     const double Us = c.U * c.invS;
+    const float INF = __int_as_float(0x7f800000);
     constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32
 
     while (true) {
@@ -99,6 +113,13 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
         double2 v = make_double2(0.0, 0.0);
         if (valid) v = a.vel[b];
 
+        // ---- depth-first walk over child blocks; d, k, j are warp-uniform ----
+        int d = 0, k = 0;
+        unsigned int j = 0;              // pre-order index of the node at frame d, slot k
+        unsigned long long kstack = 0;   // 2 bits per depth: slot being processed there
+        const bool alive = n_nodes != 0;
+        if (alive) load_block(a.rec, 0u, frames, lane);
+
         if constexpr (PREC == 0) {
             // two-float lane position, negated once: d = (c_hi - p_hi) + (c_lo - p_lo)
             const float phx = (float)pxs, phy = (float)pys;
@@ -107,46 +128,39 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
             // With softening, a body's own leaf contributes exactly +0 (d = 0, finite f), so the reference's
             // "skip the leaf that holds the target" (barnes_hut.cpp:272) needs no test; without it d2 = 0 -> inf*0.
             const bool selfTest = STATS || !(eps2f > 0.f);
-            const float INF = __int_as_float(0x7f800000);
+            const float bandLo = 1.0f - OPEN_BAND, bandHi = 1.0f + OPEN_BAND;
             double AX = 0.0, AY = 0.0;
             float ax = 0.f, ay = 0.f;
-            unsigned int j = 0, wbase = 0x80000000u;
-            TravRec* const win = &sWin[warp][0];
-            while (j < n_nodes) {
-                unsigned int off = j - wbase;
-                if (off >= (unsigned int)TRAV_WINDOW) {
-                    // stage the next TRAV_WINDOW pre-order records (line aligned) into shared memory: one coalesced
-                    // load per lane instead of one dependent L2 round trip per visited node
-                    __syncwarp();
-                    wbase = j & ~7u;
-                    off = j - wbase;
-                    const unsigned int k = wbase + lane;
-                    if (k < n_nodes) {
-                        win[lane].c = a.nodeC[k];
-                        win[lane].b = a.nodeB[k];
-                    }
-                    AX += (double)ax; AY += (double)ay;   // fp32 partial sums are flushed to fp64 at every refill
+            while (alive) {
+                const TravRec* R = frames + (d * 4 + k);
+                const float4 C = R->c;
+                const float4 Bq = *reinterpret_cast<const float4*>(&R->gm);   // gm, open_t, skip, cblock
+                const unsigned int skip = __float_as_uint(Bq.z);
+                if (k == 4 || skip == 0u) {
+                    // child block finished: flush the fp32 partial sums and return to the parent's next slot
+                    AX += (double)ax; AY += (double)ay;
                     ax = 0.f; ay = 0.f;
-                    __syncwarp();
+                    if (d == 0) break;
+                    --d;
+                    k = (int)((kstack >> (2 * d)) & 3ull) + 1;
+                    continue;
                 }
-                const float4 C = win[off].c;
-                const NodeB B = win[off].b;
                 const float dx = (C.x + nphx) + (C.z + nplx);
                 const float dy = (C.y + nphy) + (C.w + nply);
                 float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
                 // a lane that accepted an ancestor sees the node infinitely far away: never opens, contributes 0
                 d2 = (j >= skipUntil) ? d2 : INF;
-                float lo = B.open_lo;
-                if (d2 > lo && d2 < B.open_hi)   // rare: inside the guard band -> the reference's fp64 test decides
-                    lo = exact_open(a.nodeA[j], pxs, pys, c.eps2s, (int)a.nlevel[j], Us, c.theta2) ? INF : -1.f;
+                float lo = Bq.y * bandLo;
+                if (d2 > lo && d2 < Bq.y * bandHi)   // rare: inside the guard band -> the reference's fp64 test decides
+                    lo = exact_open(a.agg, a.meta, j, c.quirk, c.invS, pxs, pys, c.eps2s, Us, c.theta2) ? INF : -1.f;
                 const bool open = d2 <= lo;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
-                // accepted (or already skipping): descendants are ignored up to skip[j]; max() keeps an earlier,
+                // accepted (or already skipping): descendants are ignored up to skip; max() keeps an earlier,
                 // larger skip of a lane that accepted an ancestor
-                if (!open) skipUntil = max(skipUntil, B.skip);
+                if (!open) skipUntil = max(skipUntil, skip);
                 float rinv;
                 asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
-                float f = (B.gm * rinv) * (rinv * rinv);
+                float f = (Bq.x * rinv) * (rinv * rinv);
                 if (selfTest && j == self) f = 0.f;
                 ax = fmaf(dx, f, ax);
                 ay = fmaf(dy, f, ay);
@@ -154,11 +168,19 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
                     nwarp++;
                     const bool active = d2 != INF;
                     nvis += active ? 1u : 0u;
-                    nacc += (active && !open && j != self && B.open_hi != -2.0f) ? 1u : 0u;
+                    nacc += (active && !open && j != self && Bq.y != -2.0f) ? 1u : 0u;
                 }
-                j = anyopen ? j + 1u : B.skip;
+                if (anyopen) {
+                    kstack = (kstack & ~(3ull << (2 * d))) | ((unsigned long long)k << (2 * d));
+                    ++d;
+                    k = 0;
+                    ++j;   // first child follows its parent in pre-order
+                    load_block(a.rec, __float_as_uint(Bq.w), frames + d * 4, lane);
+                } else {
+                    j = skip;
+                    ++k;
+                }
             }
-            AX += (double)ax; AY += (double)ay;
             // a = G * sum M d / r^3 ; scaled units: M/Ms, d/S  =>  factor G*Ms/S^2
             const double accScale = c.G * massScale * c.invS * c.invS;
             if (target) {
@@ -170,25 +192,32 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
             // Pre-order == the reference's nw,ne,sw,se recursion order, so the velocity sum has the same order too.
             const double m = valid ? a.smass[i] : 1.0;
             const double eps2 = __dmul_rn(c.eps, c.eps);
-            unsigned int j = 0;
-            while (j < n_nodes) {
-                const double2 A = a.nodeA[j];
-                const NodeB B = a.nodeB[j];
-                const double M = a.nodeM[j];
-                const int level = (int)a.nlevel[j];
-                const double dx = (A.x - pxs) * c.S, dy = (A.y - pys) * c.S;   // exact: S is a power of two
+            while (alive) {
+                const TravRec* R = frames + (d * 4 + k);
+                const float open_t = R->open_t;
+                const unsigned int skip = R->skip, cblock = R->cblock;
+                if (k == 4 || skip == 0u) {
+                    if (d == 0) break;
+                    --d;
+                    k = (int)((kstack >> (2 * d)) & 3ull) + 1;
+                    continue;
+                }
+                const int level = a.meta[j].level;
+                double M, cx, cy;
+                node_centre(a.agg[j], level, c.quirk, M, cx, cy);
+                const double dx = (cx * c.invS - pxs) * c.S, dy = (cy * c.invS - pys) * c.S;   // exact: S is a power of two
                 const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), eps2);
                 const bool active = j >= skipUntil;
                 bool open = false;
-                if (level >= 0 && B.open_hi != -2.0f) {
+                if (level >= 0 && open_t != -2.0f) {
                     const double size = ldexp(c.U, -level);
                     open = !(__ddiv_rn(__dmul_rn(size, size), distSq) < c.theta2);
                 }
                 open = open && active;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
                 const bool acc = active && !open;
-                if (acc) skipUntil = B.skip;
-                if (acc && j != self && B.open_hi != -2.0f) {
+                if (acc) skipUntil = skip;
+                if (acc && j != self && open_t != -2.0f) {
                     const double dist = sqrt(distSq);
                     const double force = __ddiv_rn(__dmul_rn(__dmul_rn(c.G, M), m), distSq);
                     const double invDistMass = __ddiv_rn(force, __dmul_rn(m, dist));
@@ -196,8 +225,20 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
                     v.y = __dadd_rn(v.y, __dmul_rn(__dmul_rn(dy, invDistMass), c.dtK));
                     if (STATS) nacc++;
                 }
-                if (STATS) nvis += active ? 1u : 0u;
-                j = anyopen ? j + 1u : B.skip;
+                if (STATS) {
+                    nwarp++;
+                    nvis += active ? 1u : 0u;
+                }
+                if (anyopen) {
+                    kstack = (kstack & ~(3ull << (2 * d))) | ((unsigned long long)k << (2 * d));
+                    ++d;
+                    k = 0;
+                    ++j;
+                    load_block(a.rec, cblock, frames + d * 4, lane);
+                } else {
+                    j = skip;
+                    ++k;
+                }
             }
         }
 
@@ -231,6 +272,7 @@ __global__ void __launch_bounds__(TRAV_THREADS) k_traverse(StepConst c, TravArgs
                 atomicAdd(&a.s->warp_visits, (unsigned long long)nwarp);
             }
         }
+        __syncwarp();   // the frame stack is reused by the next chunk
     }
 }
 

@@ -66,15 +66,12 @@ struct lpe_bh_ctx {
     unsigned long long* tkey = nullptr;
     unsigned int *tfirst = nullptr, *mask = nullptr, *tnode = nullptr;
     signed char* delta = nullptr;
-    // nodes
+    // nodes (pre-order index), cells (ordinal), child blocks
     uint64_t node_cap = 0;
-    unsigned int *parent = nullptr, *child = nullptr, *arrived = nullptr, *nodeStart = nullptr;
+    unsigned int *child = nullptr, *levelList = nullptr, *levelMeta = nullptr;
+    NodeMeta* meta = nullptr;
     Agg* agg = nullptr;
-    double2* nodeA = nullptr;
-    float4* nodeC = nullptr;
-    NodeB* nodeB = nullptr;
-    double* nodeM = nullptr;
-    signed char* nlevel = nullptr;
+    TravRec* rec = nullptr;
     // stats
     unsigned int *cntAcc = nullptr, *cntVis = nullptr;
     Scal* scal = nullptr;
@@ -142,9 +139,8 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
           dalloc(c, c->tnode, cap + 2) | dalloc(c, c->delta, cap + 2);
-    rc |= dalloc(c, c->parent, ncap) | dalloc(c, c->child, 4 * ncap) | dalloc(c, c->arrived, ncap) |
-          dalloc(c, c->nodeStart, ncap) | dalloc(c, c->agg, ncap) | dalloc(c, c->nodeA, ncap) | dalloc(c, c->nodeC, ncap) |
-          dalloc(c, c->nodeB, ncap) | dalloc(c, c->nodeM, ncap) | dalloc(c, c->nlevel, ncap);
+    rc |= dalloc(c, c->child, 4 * (cap + 8)) | dalloc(c, c->meta, ncap) | dalloc(c, c->levelList, cap + 8) |
+          dalloc(c, c->levelMeta, 3 * 32) | dalloc(c, c->agg, ncap) | dalloc(c, c->rec, 4 * (cap + 8));
     rc |= dalloc(c, c->cntAcc, cap) | dalloc(c, c->cntVis, cap) | dalloc(c, c->scal, 1);
     if (rc) {
         free_all(c);
@@ -330,8 +326,8 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), st));
     CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * 256 * passes, st));
     CU_TRY(c, cudaMemsetAsync(c->mask, 0, sizeof(unsigned int) * ((size_t)n + 1), st));
-    CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * (2 * (size_t)n + 2), st));
-    CU_TRY(c, cudaMemsetAsync(c->arrived, 0, sizeof(unsigned int) * (2 * (size_t)n + 2), st));
+    CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * ((size_t)n + 1), st));
+    CU_TRY(c, cudaMemsetAsync(c->levelMeta, 0, sizeof(unsigned int) * 3 * 32, st));
 
     k_keygen<<<g256, 256, 0, st>>>(k, c->pos, c->mass, c->comp, c->keys[0], c->vals[0], c->scal);
     if (timing) cudaEventRecord(c->ev[1], st);
@@ -354,24 +350,38 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     k_init_self<<<g256, 256, 0, st>>>(n, c->selfnode);
     device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
     k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
-    k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->scal);
+    unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
+    k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, levelCount, c->scal);
     device_scan(c, MaskPop{c->mask, c->scal}, n, c->P, nullptr);
-    k_topology<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->P, c->tnode, c->parent, c->child, c->nodeB,
-                                      c->nlevel, c->nodeStart, c->scal);
-    NodeOut no{c->nodeA, c->nodeC, c->nodeB, c->nodeM, c->nlevel};
-    k_aggregate<<<g256, 256, 0, st>>>(k, c->tfirst, c->tnode, c->spos, c->smass, c->srank, c->parent, c->child,
-                                       c->arrived, c->agg, no, c->selfnode, c->scal);
+    k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
+    Topo topo{c->tnode, c->child, c->meta, c->levelList, levelBase, levelCursor};
+    k_topology<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
+    NodeOut no{c->meta, c->agg, c->rec};
+    k_agg_terminals<<<g256, 256, 0, st>>>(k, c->tfirst, c->tnode, c->spos, c->smass, c->srank, no, c->selfnode, c->scal);
+    // branching cells, deepest level first; the handful of cells of levels <= 5 share one single-block launch
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int Ltop = k.D - 1 < 5 ? k.D - 1 : 5;
+    int levelLaunches = 0;
+    for (int L = k.D - 1; L > Ltop; --L) {
+        // a level holds at most min(4^L, n/2) cells
+        long long maxCells = (L < 15) ? (1ll << (2 * L)) : (long long)n;
+        if (maxCells > n) maxCells = n;
+        int grid = cdiv(maxCells, 256);
+        if (grid > sms * 8) grid = sms * 8;
+        k_agg_level<<<grid, 256, 0, st>>>(k, L, c->levelList, levelBase, levelCount, c->child, no, c->scal);
+        ++levelLaunches;
+    }
+    k_agg_top<<<1, 1024, 0, st>>>(k, Ltop, c->levelList, levelBase, levelCount, c->child, no, c->scal);
     if (timing) cudaEventRecord(c->ev[3], st);
 
     TravArgs ta{};
-    ta.nodeA = c->nodeA; ta.nodeC = c->nodeC; ta.nlevel = c->nlevel; ta.nodeB = c->nodeB; ta.nodeM = c->nodeM; ta.spos = c->spos; ta.smass = c->smass;
+    ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta; ta.spos = c->spos; ta.smass = c->smass;
     ta.sidx = sidx; ta.selfnode = c->selfnode; ta.comp = c->comp; ta.pos = c->pos; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
     const unsigned int own = (nblocks + (unsigned int)c->shard_n - 1u - (unsigned int)c->shard_rank) / (unsigned int)c->shard_n;
     ta.n_chunks_local = own * (LPE_SHARD_BLOCK / 32u);
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     const int warpsPerBlock = TRAV_THREADS / 32;
     int grid = cdiv(ta.n_chunks_local, warpsPerBlock);
     const int maxGrid = sms * 8;
@@ -386,8 +396,9 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     }
     if (timing) cudaEventRecord(c->ev[4], st);
     CU_TRY(c, cudaGetLastError());
-    // keygen, 3 per sort pass, gather, init_self, 2 scans of 3, terminals, witness, topology, aggregate, traverse
-    c->launches += 1 + 3 * (uint64_t)passes + 2 + 3 + 2 + 3 + 2 + 1;
+    // keygen, 3 per sort pass, gather, init_self, 2 scans of 3, terminals, witness, level_scan, topology,
+    // agg_terminals, one per level above Ltop, agg_top, traverse
+    c->launches += 1 + 3 * (uint64_t)passes + 2 + 3 + 2 + 3 + 3 + (uint64_t)levelLaunches + 1 + 1;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
@@ -600,29 +611,23 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     CU_TRY(c, cudaMemcpy(sidx.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
     if (o->sorted_index) std::memcpy(o->sorted_index, sidx.data(), 4 * n);
     if (nn == 0) return 0;
-    std::vector<NodeB> nb(nn);
-    std::vector<double2> na(nn);
-    std::vector<double> nm(nn);
-    std::vector<signed char> nl(nn);
-    std::vector<unsigned int> ns(nn);
+    std::vector<NodeMeta> mt(nn);
     std::vector<Agg> ag(nn);
     std::vector<unsigned long long> tk(h.n_term);
-    CU_TRY(c, cudaMemcpy(nb.data(), c->nodeB, sizeof(NodeB) * nn, cudaMemcpyDeviceToHost));
-    CU_TRY(c, cudaMemcpy(na.data(), c->nodeA, sizeof(double2) * nn, cudaMemcpyDeviceToHost));
-    CU_TRY(c, cudaMemcpy(nm.data(), c->nodeM, sizeof(double) * nn, cudaMemcpyDeviceToHost));
-    CU_TRY(c, cudaMemcpy(nl.data(), c->nlevel, nn, cudaMemcpyDeviceToHost));
-    CU_TRY(c, cudaMemcpy(ns.data(), c->nodeStart, 4 * nn, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(mt.data(), c->meta, sizeof(NodeMeta) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(ag.data(), c->agg, sizeof(Agg) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(tk.data(), c->tkey, 8 * (size_t)h.n_term, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < nn; ++i) {
-        if (o->node_level) o->node_level[i] = nl[i];
-        if (o->node_key) o->node_key[i] = tk[ns[i]];
-        if (o->node_skip) o->node_skip[i] = nb[i].skip;
+        double M, cx, cy;
+        node_centre(ag[i], mt[i].level, c->last_c.quirk, M, cx, cy);
+        if (o->node_level) o->node_level[i] = mt[i].level;
+        if (o->node_key) o->node_key[i] = tk[mt[i].start];
+        if (o->node_skip) o->node_skip[i] = mt[i].skip;
         if (o->node_first) o->node_first[i] = sidx[ag[i].fidx];
         if (o->node_count) o->node_count[i] = ag[i].count;
-        if (o->node_mass) o->node_mass[i] = nm[i];
-        if (o->node_comx) o->node_comx[i] = na[i].x * c->last_c.S;
-        if (o->node_comy) o->node_comy[i] = na[i].y * c->last_c.S;
+        if (o->node_mass) o->node_mass[i] = M;
+        if (o->node_comx) o->node_comx[i] = cx;
+        if (o->node_comy) o->node_comy[i] = cy;
     }
     return 0;
 }
