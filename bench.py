@@ -175,9 +175,14 @@ class CudaArray:
         self.__cuda_array_interface__ = {"shape": (nelem,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
 
 
+def log(rank, msg):
+    print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+
 def our_arm(args, wl, rank, world, local_rank):
     import torch
     import lpe_bh
+    log(rank, f"start world={world} local_rank={local_rank} workload={wl['name']}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -187,6 +192,7 @@ def our_arm(args, wl, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = wl["n"]
     x, y, vx, vy, m = lpe_bh.workload(wl["kind"], n, wl["seed"], U)
+    log(rank, "workload generated")
     params = lpe_bh.make_params(U, EPS, theta=THETA, dt_kick=DT, dt_drift=DT)
     bh = lpe_bh.BarnesHut(local_rank)
     # a real (non-default) stream shared by torch and the library, so torch.cuda.Event brackets the library's kernels
@@ -226,6 +232,7 @@ def our_arm(args, wl, rank, world, local_rank):
     for _ in range(warmup):
         one_step()
     torch.cuda.synchronize()
+    log(rank, "warm-up done")
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = bh.launch_count()
