@@ -58,7 +58,8 @@ typedef struct {
     uint64_t n_nodes;        /* nodes of the path-compressed tree in pre-order (terminals + branching cells) */
     uint64_t interactions;   /* accepted node interactions of the last step (only counted when stats are enabled) */
     uint64_t visits;         /* node visits (per lane) of the last step (only when stats are enabled) */
-    uint64_t warp_visits;    /* node visits per warp (loop iterations), summed over warps (only when stats are enabled) */
+    uint64_t warp_visits;    /* list entries / node visits per warp, summed over warps (only when stats are enabled) */
+    uint64_t overflow_chunks;/* 32-body chunks the two-phase kernel handed to the depth-first kernel in the last step */
     int32_t  depth;          /* key depth D used by the last step */
     int32_t  sort_passes;
     float ms_keygen, ms_sort, ms_build, ms_traverse, ms_total; /* last step, CUDA events; only when timing is enabled */
@@ -98,7 +99,8 @@ const char* lpe_bh_last_error(const lpe_bh_ctx* ctx); /* ctx may be NULL: last c
 
 /* Run all work of this context on an existing CUDA stream (cudaStream_t as void*); NULL restores the context's own stream. */
 int  lpe_bh_set_stream(lpe_bh_ctx* ctx, void* cuda_stream);
-/* flags: bit0 = per-phase CUDA-event timing, bit1 = count interactions/visits (slower; parity tests only) */
+/* flags: bit0 = per-phase CUDA-event timing, bit1 = count interactions/visits (slower; parity tests only),
+ *        bit2 = FAST precision uses the depth-first kernel instead of the two-phase kernel (A/B testing) */
 int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
 
 /* Stage bodies into device SoA buffers. rank[i] = position of body i in the iteration of

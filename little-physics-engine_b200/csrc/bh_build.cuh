@@ -261,14 +261,16 @@ __device__ __forceinline__ double mass_scale_inv(unsigned long long max_mass_bit
 
 // ---- 6. aggregation and traversal records ---------------------------------------------------------------------
 struct NodeOut {
-    NodeMeta* meta;       // [preorder]
-    Agg* agg;             // [preorder]
-    TravRec* rec;         // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
+    NodeMeta* meta;         // [preorder]
+    Agg* agg;               // [preorder]
+    TravRec* rec;           // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
+    unsigned int* recnode;  // [4 * block + slot] pre-order index of the node stored in that slot
+    unsigned int* selfslot; // [sorted body] record slot of the body's own single-body leaf, LPE_NONE otherwise
 };
 
 // Traversal record of a node from its aggregate.
 __device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a, int level, unsigned int skip,
-                                               unsigned int cblock, double massScaleInv) {
+                                               unsigned int cblockIndex, double massScaleInv) {
     double M, cx, cy;
     node_centre(a, level, c.quirk, M, cx, cy);
     const double cxs = cx * c.invS, cys = cy * c.invS;
@@ -277,7 +279,7 @@ __device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a,
     r.c = make_float4(hx, hy, (float)(cxs - (double)hx), (float)(cys - (double)hy));
     // allSmall cells are skipped by the traversal but still feed their ancestors (barnes_hut.cpp:253, Q7):
     // a zero mass with "never open" is exactly that.
-    const bool skipSmall = (c.thr > 0.0) && a.small;
+    const bool skipSmall = (c.thr > 0.0) && (a.small & 1u);
     r.gm = skipSmall ? 0.0f : (float)(M * massScaleInv);
     r.open_t = skipSmall ? -2.0f : -1.0f;
     if (level >= 0 && !skipSmall) {
@@ -285,7 +287,7 @@ __device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a,
         r.open_t = (float)((s * s) / c.theta2);
     }
     r.skip = skip;
-    r.cblock = (level >= 0) ? cblock : 0u;
+    r.cblock = (level >= 0) ? ((cblockIndex << 2) | ((a.small >> 1) & 3u)) : 0u;
     return r;
 }
 
@@ -331,6 +333,8 @@ k_agg_terminals(StepConst c, const unsigned int* __restrict__ tfirst, const unsi
         const double msi = mass_scale_inv(s->max_mass_bits);
         o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
         o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+        o.recnode[0] = idx;
+        if (single) o.selfslot[first] = 0u;
     }
 }
 
@@ -355,14 +359,19 @@ __device__ __forceinline__ void aggregate_cell(const StepConst& c, const NodeOut
         b.m += a.m; b.sx += a.sx; b.sy += a.sy;
         if (a.frank < b.frank) { b.frank = a.frank; b.fidx = a.fidx; b.mf = a.mf; b.xf = a.xf; b.yf = a.yf; }
         b.count += a.count;
-        b.small &= a.small;
+        b.small &= (a.small & 1u);
+        const unsigned int slot = 4u * (q + 1u) + (unsigned int)r;
         blk[r++] = make_record(c, a, mc.level, mc.skip, (ci - mc.start) + 1u, msi);
+        o.recnode[slot] = ci;
+        if (mc.level == -1) o.selfslot[a.fidx] = slot;
     }
+    b.small |= (unsigned int)(r - 1) << 1;   // children - 1, read back when this cell's own record is made
     for (; r < 4; ++r) blk[r] = invalid_record();
     o.agg[p] = b;
     if (p == 0) {   // the root has no parent to write its record
         o.rec[0] = make_record(c, b, mp.level, mp.skip, 1u, msi);
         o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+        o.recnode[0] = 0u;
     }
 }
 

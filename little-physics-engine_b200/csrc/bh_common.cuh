@@ -25,6 +25,8 @@ struct Scal {
     unsigned long long interactions;
     unsigned long long visits;
     unsigned long long warp_visits;    // node visits summed over warps (one per loop iteration)
+    unsigned int ovf_count;     // chunks the two-phase traversal handed to the depth-first kernel (frontier overflow)
+    unsigned int work_counter2; // dispenser of that second launch
 };
 
 // Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.
@@ -34,7 +36,8 @@ struct Scal {
 //   open_t: s^2/theta^2 in scaled units. d2 <= open_t*(1-band) opens, d2 >= open_t*(1+band) accepts, in between
 //           the reference's own fp64 expression decides. -1 for leaves / terminals, -2 for the small-mass skip.
 //   skip:   pre-order index of the first node after this subtree (0 marks an unused slot of a child block).
-//   cblock: index of the 128-byte block holding this cell's children (0 for leaves / terminals).
+//   cblock: (index of the 128-byte block holding this cell's children) << 2 | (number of children - 1);
+//           0 for leaves / terminals.
 struct __align__(16) TravRec {
     float4 c;            // chx, chy, clx, cly
     float gm;            // node mass / mass scale (0 when the node is skipped by the small-mass rule)
@@ -54,7 +57,7 @@ struct __align__(16) Agg {
     unsigned int frank;   // its insertion rank
     unsigned int fidx;    // its sorted position
     unsigned int count;   // bodies under the node
-    unsigned int small;   // 1 if every mass under the node is < small_mass_threshold
+    unsigned int small;   // bit 0: every mass under the node is < small_mass_threshold; bits 1-2: children - 1 (cells)
 };
 static_assert(sizeof(Agg) == 64, "Agg is two 32-byte sectors");
 

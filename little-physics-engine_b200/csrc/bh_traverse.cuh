@@ -36,7 +36,10 @@ struct TravArgs {
     const double2* spos;
     const double* smass;
     const unsigned int* sidx;
-    const unsigned int* selfnode;
+    const unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf (depth-first kernel)
+    const unsigned int* selfslot;   // [sorted body] record slot of its own leaf (two-phase kernel)
+    const unsigned int* recnode;    // [record slot] pre-order index
+    const unsigned int* chunk_list; // depth-first kernel only: when set, process these chunks (two-phase overflow)
     const unsigned char* comp;
     double2* pos;
     double2* vel;
@@ -87,9 +90,16 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
 
     while (true) {
         unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(&a.s->work_counter, 1u);
-        q = __shfl_sync(0xFFFFFFFFu, q, 0);
-        if (q >= a.n_chunks_local) break;
+        if (a.chunk_list) {
+            if (lane == 0) q = atomicAdd(&a.s->work_counter2, 1u);
+            q = __shfl_sync(0xFFFFFFFFu, q, 0);
+            if (q >= a.s->ovf_count) break;
+            q = a.chunk_list[q];
+        } else {
+            if (lane == 0) q = atomicAdd(&a.s->work_counter, 1u);
+            q = __shfl_sync(0xFFFFFFFFu, q, 0);
+            if (q >= a.n_chunks_local) break;
+        }
         // block-cyclic ownership of sorted positions (identity when shard_n == 1)
         const unsigned int lblock = q / CHUNKS_PER_BLOCK, within = q % CHUNKS_PER_BLOCK;
         const unsigned int gblock = lblock * (unsigned int)c.shard_n + (unsigned int)c.shard_rank;
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     ++d;
                     k = 0;
                     ++j;   // first child follows its parent in pre-order
-                    load_block(a.rec, __float_as_uint(Bq.w), frames + d * 4, lane);
+                    load_block(a.rec, __float_as_uint(Bq.w) >> 2, frames + d * 4, lane);
                 } else {
                     j = skip;
                     ++k;
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     ++d;
                     k = 0;
                     ++j;
-                    load_block(a.rec, cblock, frames + d * 4, lane);
+                    load_block(a.rec, cblock >> 2, frames + d * 4, lane);
                 } else {
                     j = skip;
                     ++k;

@@ -1,0 +1,339 @@
+// bh_traverse2.cuh — two-phase traversal (FAST precision): the production force kernel.
+//
+// Same result as the depth-first walk in bh_traverse.cuh — every lane (body) takes the reference's own accept/open
+// decision for every node (barnes_hut.cpp:266-269) — but the work is organised so that the expensive part runs with
+// all 32 lanes busy and no per-node control flow:
+//
+//   phase 1 (cooperative, one NODE per lane): the warp expands the tree breadth first. A lane loads one record and
+//     classifies its node against the bounding box of the warp's 32 targets, conservatively:
+//       A  every target accepts it      (d2_min >= s^2/theta^2 + margin, or the node is a leaf / terminal)
+//       O  every target opens it        (d2_max <= s^2/theta^2 - margin)
+//       M  mixed / too close to call    -> each lane will decide for itself in phase 2
+//     O and M nodes push their children on the next level's frontier. A node is "dirty" if some ancestor was M:
+//     a lane that ACCEPTED that ancestor must not see the node. Clean A nodes go to the A list; M nodes and every
+//     dirty node go to the M list together with the list slot of their parent.
+//   phase 2 (dense, one BODY per lane): every lane runs over the lists.
+//       A list: no test at all — two-float difference, rsqrt, three multiplies, two FMAs per interaction.
+//       M list: each entry carries the mask of lanes that reach it (= the lanes that opened its mixed parent, one
+//               ballot per mixed node, kept for the previous level only). A lane in the mask applies the per-lane
+//               theta test exactly as the depth-first kernel does (fp32 against two thresholds, the reference's fp64
+//               expression inside the guard band) and accumulates if it accepted; the ballot of the lanes that
+//               opened becomes the mask of the node's children. Children reached by every target are clean again
+//               (classified afresh); children reached by nobody are dropped with their whole subtree.
+//
+// A warp whose frontier outgrows its shared-memory queue hands its chunk to the depth-first kernel (second launch).
+#pragma once
+#include "bh_common.cuh"
+#include "bh_traverse.cuh"
+
+namespace lpe {
+
+constexpr int T2_THREADS = 128;
+constexpr int T2_WARPS = T2_THREADS / 32;
+constexpr int T2_CAP = 512;                 // frontier entries per level and warp
+constexpr int T2_ROUNDS = T2_CAP / 32;      // classification rounds per level
+constexpr int T2_ABUF = 96;                 // A-list buffer (flushed at >= 64)
+constexpr unsigned int T2_CLEAN = 0xFFFFu;
+constexpr float T2_MARGIN = 2e-5f;          // relative safety margin of the group classification
+
+struct T2Warp {
+    unsigned int fslot[2][T2_CAP];          // frontier: record slot
+    unsigned short fpm[2][T2_CAP];          // frontier: M slot of the nearest dirty/mixed ancestor on the previous level
+    unsigned int reach[2][T2_CAP];          // [level parity][M slot]: lanes that reached AND opened that mixed node
+    float4 ac[T2_ABUF];                     // A list: centre (two-float)
+    float agm[T2_ABUF];                     //         mass
+    unsigned int aslot[T2_ABUF];            //         record slot (self test / stats only)
+    float4 mc[32];                          // M list of the current round: centre
+    float4 mg[32];                          //         gm, open_lo, open_hi, parent M slot (as uint bits)
+    unsigned int mslot[32];                 //         record slot
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
+    extern __shared__ __align__(16) unsigned char t2_smem[];
+    T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
+    const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
+    const float eps2f = (float)c.eps2s;
+    const double Us = c.U * c.invS;
+    const float INF = __int_as_float(0x7f800000);
+    const float FMAXV = 3.0e38f;
+    const bool selfTest = STATS || !(eps2f > 0.f);
+    constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32
+
+    while (true) {
+        unsigned int q = 0;
+        if (lane == 0) q = atomicAdd(&a.s->work_counter, 1u);
+        q = __shfl_sync(0xFFFFFFFFu, q, 0);
+        if (q >= a.n_chunks_local) break;
+        const unsigned int lblock = q / CHUNKS_PER_BLOCK, within = q % CHUNKS_PER_BLOCK;
+        const unsigned int gblock = lblock * (unsigned int)c.shard_n + (unsigned int)c.shard_rank;
+        const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
+        const bool valid = i < c.n;
+
+        unsigned int b = 0, self = LPE_NONE;
+        unsigned char cm = 0;
+        double2 p = make_double2(0.0, 0.0);
+        if (valid) {
+            b = a.sidx[i];
+            cm = a.comp[b];
+            p = a.spos[i];
+            self = a.selfslot[i];
+        }
+        const bool target = valid && (cm & 1u) && (cm & 2u) && !(cm & 4u);   // barnes_hut.cpp:89
+        const double pxs = p.x * c.invS, pys = p.y * c.invS;
+        const float phx = (float)pxs, phy = (float)pys;
+        const float nphx = -phx, nphy = -phy;
+        const float nplx = -(float)(pxs - (double)phx), nply = -(float)(pys - (double)phy);
+        unsigned int nacc = 0, nwarp = 0;
+        double AX = 0.0, AY = 0.0;
+        float ax = 0.f, ay = 0.f;
+        bool overflow = false;
+
+        const unsigned int tmask = __ballot_sync(0xFFFFFFFFu, target);
+        if (tmask != 0u && n_nodes != 0u) {
+            // ---- bounding box of the warp's targets (scaled units), as two-float edges ----
+            double bx0 = target ? pxs : 1e300, bx1 = target ? pxs : -1e300;
+            double by0 = target ? pys : 1e300, by1 = target ? pys : -1e300;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                bx0 = fmin(bx0, __shfl_xor_sync(0xFFFFFFFFu, bx0, o));
+                bx1 = fmax(bx1, __shfl_xor_sync(0xFFFFFFFFu, bx1, o));
+                by0 = fmin(by0, __shfl_xor_sync(0xFFFFFFFFu, by0, o));
+                by1 = fmax(by1, __shfl_xor_sync(0xFFFFFFFFu, by1, o));
+            }
+            const float x0h = (float)bx0, x1h = (float)bx1, y0h = (float)by0, y1h = (float)by1;
+            const float x0l = (float)(bx0 - (double)x0h), x1l = (float)(bx1 - (double)x1h);
+            const float y0l = (float)(by0 - (double)y0h), y1l = (float)(by1 - (double)y1h);
+
+            int cur = 0;
+            unsigned int ncur = 1, nA = 0;
+            if (lane == 0) {
+                W.fslot[0][0] = 0u;
+                W.fpm[0][0] = (unsigned short)T2_CLEAN;
+            }
+            __syncwarp();
+            int lvl = 0;
+            while (ncur > 0u) {
+                const int nxt = cur ^ 1;
+                unsigned int nnext = 0;
+                const unsigned int* prevreach = &W.reach[(lvl & 1) ^ 1][0];
+                unsigned int* curreach = &W.reach[lvl & 1][0];
+                int r = 0;
+                for (unsigned int base = 0; base < ncur; base += 32, ++r) {
+                    // ---------------- phase 1: one node per lane ----------------
+                    const unsigned int e = base + lane;
+                    bool has = e < ncur;
+                    unsigned int slot = 0, pm = T2_CLEAN, pmask = tmask;
+                    TravRec R;
+                    R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.skip = 0; R.cblock = 0;
+                    if (has) {
+                        slot = W.fslot[cur][e];
+                        pm = W.fpm[cur][e];
+                        if (pm != T2_CLEAN) {
+                            pmask = prevreach[pm];                    // lanes that opened the mixed parent
+                            if ((pmask & tmask) == tmask) pm = T2_CLEAN;   // everybody reaches it: clean again
+                            else if (pmask == 0u) has = false;        // nobody reaches it: drop the subtree
+                        }
+                    }
+                    if (has) {
+                        const uint4* src = reinterpret_cast<const uint4*>(a.rec + slot);
+                        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                        R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
+                        R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
+                    }
+                    // distance bounds from the node centre to the targets' box
+                    const float ax0 = (R.c.x - x0h) + (R.c.z - x0l), ax1 = (R.c.x - x1h) + (R.c.z - x1l);
+                    const float ay0 = (R.c.y - y0h) + (R.c.w - y0l), ay1 = (R.c.y - y1h) + (R.c.w - y1l);
+                    const float dxmin = fmaxf(fmaxf(-ax0, ax1), 0.f), dxmax = fmaxf(fabsf(ax0), fabsf(ax1));
+                    const float dymin = fmaxf(fmaxf(-ay0, ay1), 0.f), dymax = fmaxf(fabsf(ay0), fabsf(ay1));
+                    const float d2min = fmaf(dxmin, dxmin, fmaf(dymin, dymin, eps2f));
+                    const float d2max = fmaf(dxmax, dxmax, fmaf(dymax, dymax, eps2f));
+                    const float t = R.open_t;
+                    const float tlo = t * (1.0f - OPEN_BAND), thi = t * (1.0f + OPEN_BAND);
+                    const bool allAcc = (t < 0.f) || (d2min * (1.0f - T2_MARGIN) >= thi);
+                    const bool allOpen = (t >= 0.f) && (d2max * (1.0f + T2_MARGIN) <= tlo);
+                    const bool dirty = pm != T2_CLEAN;
+                    const bool toA = has && allAcc && !dirty;
+                    const bool toM = has && (dirty || (!allAcc && !allOpen));
+                    const bool expand = has && !allAcc;
+
+                    const unsigned int maskA = __ballot_sync(0xFFFFFFFFu, toA);
+                    const unsigned int maskM = __ballot_sync(0xFFFFFFFFu, toM);
+                    const unsigned int posM = __popc(maskM & lt);
+                    const unsigned int cntM = __popc(maskM);
+                    if (toA) {
+                        const unsigned int pos = nA + __popc(maskA & lt);
+                        W.ac[pos] = R.c;
+                        W.agm[pos] = R.gm;
+                        W.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
+                    }
+                    nA += __popc(maskA);
+                    if (toM) {
+                        W.mc[posM] = R.c;
+                        float lo, hi;
+                        if (allAcc) { lo = -1.f; hi = -1.f; }            // dirty, but nobody opens it
+                        else if (allOpen) { lo = FMAXV; hi = FMAXV; }    // dirty, everybody who reaches it opens it
+                        else { lo = tlo; hi = thi; }
+                        W.mg[posM] = make_float4(R.gm, lo, hi, __uint_as_float(dirty ? pmask : tmask));
+                        W.mslot[posM] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
+                    }
+                    // children of opened nodes -> next frontier (exclusive scan of child counts)
+                    const unsigned int nch = expand ? (R.cblock & 3u) + 1u : 0u;
+                    unsigned int inc = nch;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                        if (lane >= o) inc += v;
+                    }
+                    const unsigned int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                    if (nnext + total > (unsigned int)T2_CAP) { overflow = true; break; }
+                    if (nch) {
+                        const unsigned int at = nnext + inc - nch;
+                        const unsigned int cslot = (R.cblock >> 2) * 4u;
+                        const unsigned short cpm = (unsigned short)(toM ? (unsigned int)(r * 32) + posM : T2_CLEAN);
+                        for (unsigned int kk = 0; kk < nch; ++kk) {
+                            W.fslot[nxt][at + kk] = cslot + kk;
+                            W.fpm[nxt][at + kk] = cpm;
+                        }
+                    }
+                    nnext += total;
+                    __syncwarp();
+
+                    // ---------------- phase 2a: the mixed / dirty nodes of this round, one body per lane ----------------
+                    const unsigned int lanebit = 1u << lane;
+                    for (unsigned int m = 0; m < cntM; ++m) {
+                        const float4 C = W.mc[m];
+                        const float4 G = W.mg[m];
+                        const bool reached = (__float_as_uint(G.w) & lanebit) != 0u;
+                        const float dx = (C.x + nphx) + (C.z + nplx);
+                        const float dy = (C.y + nphy) + (C.w + nply);
+                        float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+                        d2 = reached ? d2 : INF;   // a lane that accepted an ancestor: never opens, contributes 0
+                        float lo = G.y;
+                        if (d2 > lo && d2 < G.z)   // rare: guard band -> the reference's fp64 test decides
+                            lo = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs, pys,
+                                            c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                        const bool open = d2 <= lo;
+                        const unsigned int omask = __ballot_sync(0xFFFFFFFFu, open);
+                        if (lane == 0) curreach[r * 32 + m] = omask;
+                        float rinv;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
+                        float f = (G.x * rinv) * (rinv * rinv);
+                        if (selfTest) {
+                            const unsigned int ms = W.mslot[m];
+                            if ((ms & 0x7FFFFFFFu) == self) f = 0.f;
+                            if (STATS) nacc += (reached && !open && (ms & 0x7FFFFFFFu) != self && !(ms >> 31)) ? 1u : 0u;
+                        }
+                        ax = fmaf(dx, f, ax);
+                        ay = fmaf(dy, f, ay);
+                    }
+                    if (cntM) {
+                        AX += (double)ax; AY += (double)ay;
+                        ax = 0.f; ay = 0.f;
+                    }
+                    if (STATS) nwarp += cntM;
+                    __syncwarp();
+
+                    // ---------------- phase 2b: the sure-accept list, flushed when it is long enough ----------------
+                    if (nA >= 64u) {
+#pragma unroll 4
+                        for (unsigned int m = 0; m < nA; ++m) {
+                            const float4 C = W.ac[m];
+                            const float g = W.agm[m];
+                            const float dx = (C.x + nphx) + (C.z + nplx);
+                            const float dy = (C.y + nphy) + (C.w + nply);
+                            const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+                            float rinv;
+                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
+                            float f = (g * rinv) * (rinv * rinv);
+                            if (selfTest) {
+                                const unsigned int as = W.aslot[m];
+                                if ((as & 0x7FFFFFFFu) == self) f = 0.f;
+                                if (STATS) nacc += ((as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+                            }
+                            ax = fmaf(dx, f, ax);
+                            ay = fmaf(dy, f, ay);
+                        }
+                        if (STATS) nwarp += nA;
+                        nA = 0;
+                        AX += (double)ax; AY += (double)ay;
+                        ax = 0.f; ay = 0.f;
+                        __syncwarp();
+                    }
+                }
+                if (overflow) break;
+                cur = nxt;
+                ncur = nnext;
+                ++lvl;
+            }
+            if (!overflow) {
+                for (unsigned int m = 0; m < nA; ++m) {
+                    const float4 C = W.ac[m];
+                    const float g = W.agm[m];
+                    const float dx = (C.x + nphx) + (C.z + nplx);
+                    const float dy = (C.y + nphy) + (C.w + nply);
+                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+                    float rinv;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
+                    float f = (g * rinv) * (rinv * rinv);
+                    if (selfTest) {
+                        const unsigned int as = W.aslot[m];
+                        if ((as & 0x7FFFFFFFu) == self) f = 0.f;
+                        if (STATS) nacc += ((as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+                    }
+                    ax = fmaf(dx, f, ax);
+                    ay = fmaf(dy, f, ay);
+                }
+                if (STATS) nwarp += nA;
+                AX += (double)ax; AY += (double)ay;
+            }
+            __syncwarp();
+        }
+
+        if (overflow) {
+            // frontier too wide for the shared-memory queue: the depth-first kernel redoes this chunk
+            if (lane == 0) ovf_list[atomicAdd(&a.s->ovf_count, 1u)] = q;
+            continue;
+        }
+
+        double2 v = make_double2(0.0, 0.0);
+        if (valid) v = a.vel[b];
+        const double accScale = c.G * massScale * c.invS * c.invS;   // a = G*sum M d/r^3; scaled units M/Ms, d/S
+        if (target) {
+            v.x += (AX * accScale) * c.dtK;   // barnes_hut.cpp:284-286
+            v.y += (AY * accScale) * c.dtK;
+        }
+        if (valid) {
+            const bool mover = (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
+            if (c.do_drift && mover) {
+                p.x += v.x * c.dtD;                                       // movement.cpp:32-33
+                p.y += v.y * c.dtD;
+            }
+            if (c.shard_n > 1) {
+                const unsigned long long slotx = (unsigned long long)lblock * 2048ull + within * 32ull + lane;
+                a.xchg_send[slotx] = make_double4(p.x, p.y, v.x, v.y);
+            } else {
+                if (target) a.vel[b] = v;
+                if (c.do_drift && mover) a.pos[b] = p;
+            }
+            if (STATS) {
+                a.cntAcc[b] = target ? nacc : 0u;
+                a.cntVis[b] = 0u;
+            }
+        }
+        if (STATS) {
+            unsigned int tot = target ? nacc : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+            if (lane == 0) {
+                atomicAdd(&a.s->interactions, (unsigned long long)tot);
+                atomicAdd(&a.s->warp_visits, (unsigned long long)nwarp);
+            }
+        }
+    }
+}
+
+}  // namespace lpe

@@ -18,6 +18,7 @@
 #include "bh_sort.cuh"
 #include "bh_build.cuh"
 #include "bh_traverse.cuh"
+#include "bh_traverse2.cuh"
 
 using namespace lpe;
 
@@ -38,6 +39,7 @@ struct lpe_bh_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int instr = 0;
+    bool force_dfs = false;  // instrumentation bit2: use the depth-first kernel in FAST mode too
 
     uint64_t n = 0, cap = 0;
     uint64_t launches = 0;
@@ -59,7 +61,7 @@ struct lpe_bh_ctx {
     // sorted copies
     double2* spos = nullptr;
     double* smass = nullptr;
-    unsigned int *srank = nullptr, *selfnode = nullptr;
+    unsigned int *srank = nullptr, *selfnode = nullptr, *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
     // scans
     unsigned int *tileSums = nullptr, *headExcl = nullptr, *P = nullptr;
     // terminals
@@ -135,7 +137,8 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
           dalloc(c, c->comp, cap) | dalloc(c, c->tmp, 4 * cap);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
           dalloc(c, c->vals[1], cap) | dalloc(c, c->table, (size_t)256 * sortTiles) | dalloc(c, c->totals, 256 * 8);
-    rc |= dalloc(c, c->spos, cap) | dalloc(c, c->smass, cap) | dalloc(c, c->srank, cap) | dalloc(c, c->selfnode, cap);
+    rc |= dalloc(c, c->spos, cap) | dalloc(c, c->smass, cap) | dalloc(c, c->srank, cap) | dalloc(c, c->selfnode, cap) |
+          dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
     rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
           dalloc(c, c->tnode, cap + 2) | dalloc(c, c->delta, cap + 2);
@@ -183,9 +186,12 @@ __global__ void k_default_meta(int n, unsigned int* __restrict__ rank, unsigned 
         if (setComp) comp[i] = (unsigned char)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
     }
 }
-__global__ void k_init_self(int n, unsigned int* __restrict__ selfnode) {
+__global__ void k_init_self(int n, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) selfnode[i] = LPE_NONE;
+    if (i < n) {
+        selfnode[i] = LPE_NONE;
+        selfslot[i] = LPE_NONE;
+    }
 }
 
 // sharded mode: every rank's packed slice -> state arrays (creation order)
@@ -347,7 +353,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (timing) cudaEventRecord(c->ev[2], st);
 
     k_gather<<<g256, 256, 0, st>>>(n, sidx, c->pos, c->mass, c->rank, c->spos, c->smass, c->srank);
-    k_init_self<<<g256, 256, 0, st>>>(n, c->selfnode);
+    k_init_self<<<g256, 256, 0, st>>>(n, c->selfnode, c->selfslot);
     device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
     k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
@@ -356,7 +362,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
     Topo topo{c->tnode, c->child, c->meta, c->levelList, levelBase, levelCursor};
     k_topology<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
-    NodeOut no{c->meta, c->agg, c->rec};
+    NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot};
     k_agg_terminals<<<g256, 256, 0, st>>>(k, c->tfirst, c->tnode, c->spos, c->smass, c->srank, no, c->selfnode, c->scal);
     // branching cells, deepest level first; the handful of cells of levels <= 5 share one single-block launch
     int sms = 148;
@@ -382,23 +388,44 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
     const unsigned int own = (nblocks + (unsigned int)c->shard_n - 1u - (unsigned int)c->shard_rank) / (unsigned int)c->shard_n;
     ta.n_chunks_local = own * (LPE_SHARD_BLOCK / 32u);
-    const int warpsPerBlock = TRAV_THREADS / 32;
-    int grid = cdiv(ta.n_chunks_local, warpsPerBlock);
-    const int maxGrid = sms * 8;
-    if (grid > maxGrid) grid = maxGrid;
-    if (grid < 1) grid = 1;
-    if (p.precision == LPE_PREC_FAST) {
-        if (stats) k_traverse<0, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
-        else k_traverse<0, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+    ta.selfslot = c->selfslot; ta.recnode = c->recnode; ta.chunk_list = nullptr;
+    const int maxGridCtas = sms * 8;
+    int travLaunches = 1;
+    if (p.precision == LPE_PREC_FAST && !c->force_dfs) {
+        // two-phase kernel, then the depth-first kernel for the (normally zero) chunks whose frontier overflowed
+        const size_t smem = sizeof(T2Warp) * T2_WARPS;
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        int grid = cdiv(ta.n_chunks_local, T2_WARPS);
+        if (grid > sms * 4) grid = sms * 4;
+        if (grid < 1) grid = 1;
+        if (stats) k_traverse2<true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        else k_traverse2<false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        ta.chunk_list = c->ovf_list;
+        if (stats) k_traverse<0, true><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
+        else k_traverse<0, false><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
+        travLaunches = 2;
     } else {
-        if (stats) k_traverse<1, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
-        else k_traverse<1, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+        int grid = cdiv(ta.n_chunks_local, TRAV_THREADS / 32);
+        if (grid > maxGridCtas) grid = maxGridCtas;
+        if (grid < 1) grid = 1;
+        if (p.precision == LPE_PREC_FAST) {
+            if (stats) k_traverse<0, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+            else k_traverse<0, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+        } else {
+            if (stats) k_traverse<1, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+            else k_traverse<1, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+        }
     }
     if (timing) cudaEventRecord(c->ev[4], st);
     CU_TRY(c, cudaGetLastError());
     // keygen, 3 per sort pass, gather, init_self, 2 scans of 3, terminals, witness, level_scan, topology,
     // agg_terminals, one per level above Ltop, agg_top, traverse
-    c->launches += 1 + 3 * (uint64_t)passes + 2 + 3 + 2 + 3 + 3 + (uint64_t)levelLaunches + 1 + 1;
+    c->launches += 1 + 3 * (uint64_t)passes + 2 + 3 + 2 + 3 + 3 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
@@ -462,6 +489,7 @@ int lpe_bh_set_stream(lpe_bh_ctx* c, void* s) {
 int lpe_bh_set_instrumentation(lpe_bh_ctx* c, int flags) {
     if (!c) return 1;
     c->instr = flags;
+    c->force_dfs = (flags & 4) != 0;
     return 0;
 }
 
@@ -585,6 +613,7 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
         s.interactions = h.interactions;
         s.visits = h.visits;
         s.warp_visits = h.warp_visits;
+        s.overflow_chunks = h.ovf_count;
         if (c->instr & 1) {
             cudaEventElapsedTime(&s.ms_keygen, c->ev[0], c->ev[1]);
             cudaEventElapsedTime(&s.ms_sort, c->ev[1], c->ev[2]);

@@ -38,7 +38,7 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("n_bodies", C.c_uint64), ("n_in_tree", C.c_uint64), ("n_terminals", C.c_uint64),
-        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64), ("warp_visits", C.c_uint64),
+        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64), ("warp_visits", C.c_uint64), ("overflow_chunks", C.c_uint64),
         ("depth", C.c_int32), ("sort_passes", C.c_int32), ("ms_keygen", C.c_float),
         ("ms_sort", C.c_float), ("ms_build", C.c_float), ("ms_traverse", C.c_float), ("ms_total", C.c_float),
     ]
@@ -174,8 +174,9 @@ class BarnesHut:
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.lpe_bh_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
 
-    def set_instrumentation(self, timing=False, counts=False):
-        self._chk(self.lib.lpe_bh_set_instrumentation(self.h, C.c_int((1 if timing else 0) | (2 if counts else 0))),
+    def set_instrumentation(self, timing=False, counts=False, force_dfs=False):
+        self._chk(self.lib.lpe_bh_set_instrumentation(
+            self.h, C.c_int((1 if timing else 0) | (2 if counts else 0) | (4 if force_dfs else 0))),
                   "set_instrumentation")
 
     def upload(self, x, y, vx, vy, m, rank=None, comp=None):
