@@ -60,6 +60,7 @@ typedef struct {
     uint64_t visits;         /* node visits (per lane) of the last step (only when stats are enabled) */
     uint64_t warp_visits;    /* list entries / node visits per warp, summed over warps (only when stats are enabled) */
     uint64_t overflow_chunks;/* 32-body chunks the two-phase kernel handed to the depth-first kernel in the last step */
+    uint64_t t2_kinds[8];    /* two-phase diagnostics (stats only): A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes */
     int32_t  depth;          /* key depth D used by the last step */
     int32_t  sort_passes;
     float ms_keygen, ms_sort, ms_build, ms_traverse, ms_total; /* last step, CUDA events; only when timing is enabled */

@@ -27,6 +27,7 @@ struct Scal {
     unsigned long long warp_visits;    // node visits summed over warps (one per loop iteration)
     unsigned int ovf_count;     // chunks the two-phase traversal handed to the depth-first kernel (frontier overflow)
     unsigned int work_counter2; // dispenser of that second launch
+    unsigned long long t2[8];   // two-phase diagnostics (STATS only): entries by kind
 };
 
 // Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.

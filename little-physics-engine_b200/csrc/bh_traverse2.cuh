@@ -41,26 +41,27 @@ struct T2Warp {
     unsigned short fpm[2][T2_CAP];          // frontier: M slot of the nearest dirty/mixed ancestor on the previous level
     unsigned int reach[2][T2_CAP];          // [level parity][M slot]: lanes that reached AND opened that mixed node
     float4 ac[T2_ABUF];                     // A list: centre (two-float)
-    float agm[T2_ABUF];                     //         mass
+    float2 ag[T2_ABUF];                     //         mass, mask of lanes that reach it (as uint bits)
     unsigned int aslot[T2_ABUF];            //         record slot (self test / stats only)
     float4 mc[32];                          // M list of the current round: centre
     float4 mg[32];                          //         gm, open_lo, open_hi, parent M slot (as uint bits)
     unsigned int mslot[32];                 //         record slot
 };
 
-template <bool STATS>
+template <bool STATS, bool SELF>
 __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const unsigned int lt = (1u << lane) - 1u;
+    const unsigned int lanebit = 1u << lane;
     const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = (float)c.eps2s;
     const double Us = c.U * c.invS;
     const float INF = __int_as_float(0x7f800000);
     const float FMAXV = 3.0e38f;
-    const bool selfTest = STATS || !(eps2f > 0.f);
+    constexpr bool selfTest = SELF;   // needed for stats, or when eps == 0 (d2 = 0 -> inf * 0)
     constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32
 
     while (true) {
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
         const float nphx = -phx, nphy = -phy;
         const float nplx = -(float)(pxs - (double)phx), nply = -(float)(pys - (double)phy);
         unsigned int nacc = 0, nwarp = 0;
+        unsigned int kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // STATS: A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes
         double AX = 0.0, AY = 0.0;
         float ax = 0.f, ay = 0.f;
         bool overflow = false;
@@ -156,8 +158,8 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
                     const bool allAcc = (t < 0.f) || (d2min * (1.0f - T2_MARGIN) >= thi);
                     const bool allOpen = (t >= 0.f) && (d2max * (1.0f + T2_MARGIN) <= tlo);
                     const bool dirty = pm != T2_CLEAN;
-                    const bool toA = has && allAcc && !dirty;
-                    const bool toM = has && (dirty || (!allAcc && !allOpen));
+                    const bool toA = has && allAcc;                      // clean or dirty: the entry carries the lane mask
+                    const bool toM = has && !allAcc && (dirty || !allOpen);
                     const bool expand = has && !allAcc;
 
                     const unsigned int maskA = __ballot_sync(0xFFFFFFFFu, toA);
@@ -167,15 +169,20 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
                     if (toA) {
                         const unsigned int pos = nA + __popc(maskA & lt);
                         W.ac[pos] = R.c;
-                        W.agm[pos] = R.gm;
+                        W.ag[pos] = make_float2(R.gm, __uint_as_float(dirty ? pmask : tmask));
                         W.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
                     }
                     nA += __popc(maskA);
+                    if (STATS) {
+                        kd[0] += __popc(__ballot_sync(0xFFFFFFFFu, toA && !dirty));
+                        kd[1] += __popc(__ballot_sync(0xFFFFFFFFu, toA && dirty));
+                        kd[2] += __popc(__ballot_sync(0xFFFFFFFFu, toM && allOpen));
+                        kd[6] += 1; kd[7] += __popc(__ballot_sync(0xFFFFFFFFu, has));
+                    }
                     if (toM) {
                         W.mc[posM] = R.c;
                         float lo, hi;
-                        if (allAcc) { lo = -1.f; hi = -1.f; }            // dirty, but nobody opens it
-                        else if (allOpen) { lo = FMAXV; hi = FMAXV; }    // dirty, everybody who reaches it opens it
+                        if (allOpen) { lo = FMAXV; hi = FMAXV; }         // dirty, everybody who reaches it opens it
                         else { lo = tlo; hi = thi; }
                         W.mg[posM] = make_float4(R.gm, lo, hi, __uint_as_float(dirty ? pmask : tmask));
                         W.mslot[posM] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
@@ -203,7 +210,6 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
                     __syncwarp();
 
                     // ---------------- phase 2a: the mixed / dirty nodes of this round, one body per lane ----------------
-                    const unsigned int lanebit = 1u << lane;
                     for (unsigned int m = 0; m < cntM; ++m) {
                         const float4 C = W.mc[m];
                         const float4 G = W.mg[m];
@@ -213,12 +219,19 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
                         float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
                         d2 = reached ? d2 : INF;   // a lane that accepted an ancestor: never opens, contributes 0
                         float lo = G.y;
-                        if (d2 > lo && d2 < G.z)   // rare: guard band -> the reference's fp64 test decides
-                            lo = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs, pys,
-                                            c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                        const bool band = d2 > lo && d2 < G.z;
+                        if (__any_sync(0xFFFFFFFFu, band)) {   // rare: guard band -> the reference's fp64 test decides
+                            if (band)
+                                lo = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs,
+                                                pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                        }
                         const bool open = d2 <= lo;
                         const unsigned int omask = __ballot_sync(0xFFFFFFFFu, open);
                         if (lane == 0) curreach[r * 32 + m] = omask;
+                        if (STATS && G.y >= 0.f && G.y < FMAXV) {
+                            const unsigned int pmk = __float_as_uint(G.w);
+                            if (omask == 0u) kd[3]++; else if (omask == pmk) kd[4]++; else kd[5]++;
+                        }
                         float rinv;
                         asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
                         float f = (G.x * rinv) * (rinv * rinv);
@@ -242,7 +255,9 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
 #pragma unroll 4
                         for (unsigned int m = 0; m < nA; ++m) {
                             const float4 C = W.ac[m];
-                            const float g = W.agm[m];
+                            const float2 Gm = W.ag[m];
+                            const bool reached = (__float_as_uint(Gm.y) & lanebit) != 0u;
+                            const float g = reached ? Gm.x : 0.f;   // lanes that accepted an ancestor contribute nothing
                             const float dx = (C.x + nphx) + (C.z + nplx);
                             const float dy = (C.y + nphy) + (C.w + nply);
                             const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
@@ -252,7 +267,7 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
                             if (selfTest) {
                                 const unsigned int as = W.aslot[m];
                                 if ((as & 0x7FFFFFFFu) == self) f = 0.f;
-                                if (STATS) nacc += ((as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+                                if (STATS) nacc += (reached && (as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
                             }
                             ax = fmaf(dx, f, ax);
                             ay = fmaf(dy, f, ay);
@@ -272,7 +287,9 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
             if (!overflow) {
                 for (unsigned int m = 0; m < nA; ++m) {
                     const float4 C = W.ac[m];
-                    const float g = W.agm[m];
+                    const float2 Gm = W.ag[m];
+                    const bool reached = (__float_as_uint(Gm.y) & lanebit) != 0u;
+                    const float g = reached ? Gm.x : 0.f;   // lanes that accepted an ancestor contribute nothing
                     const float dx = (C.x + nphx) + (C.z + nplx);
                     const float dy = (C.y + nphy) + (C.w + nply);
                     const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
@@ -282,7 +299,7 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
                     if (selfTest) {
                         const unsigned int as = W.aslot[m];
                         if ((as & 0x7FFFFFFFu) == self) f = 0.f;
-                        if (STATS) nacc += ((as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+                        if (STATS) nacc += (reached && (as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
                     }
                     ax = fmaf(dx, f, ax);
                     ay = fmaf(dy, f, ay);
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
             if (lane == 0) {
                 atomicAdd(&a.s->interactions, (unsigned long long)tot);
                 atomicAdd(&a.s->warp_visits, (unsigned long long)nwarp);
+                for (int z = 0; z < 8; ++z) atomicAdd(&a.s->t2[z], (unsigned long long)kd[z]);
             }
         }
     }

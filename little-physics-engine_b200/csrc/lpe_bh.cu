@@ -394,17 +394,20 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (p.precision == LPE_PREC_FAST && !c->force_dfs) {
         // two-phase kernel, then the depth-first kernel for the (normally zero) chunks whose frontier overflowed
         const size_t smem = sizeof(T2Warp) * T2_WARPS;
+        const bool selfT = stats || !(k.eps2s > 0.0) || (float)k.eps2s == 0.0f;
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_traverse2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(k_traverse2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
         if (grid > sms * 4) grid = sms * 4;
         if (grid < 1) grid = 1;
-        if (stats) k_traverse2<true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-        else k_traverse2<false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        if (stats) k_traverse2<true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        else if (selfT) k_traverse2<false, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        else k_traverse2<false, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
         ta.chunk_list = c->ovf_list;
         if (stats) k_traverse<0, true><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
         else k_traverse<0, false><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
@@ -614,6 +617,7 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
         s.visits = h.visits;
         s.warp_visits = h.warp_visits;
         s.overflow_chunks = h.ovf_count;
+        for (int z = 0; z < 8; ++z) s.t2_kinds[z] = h.t2[z];
         if (c->instr & 1) {
             cudaEventElapsedTime(&s.ms_keygen, c->ev[0], c->ev[1]);
             cudaEventElapsedTime(&s.ms_sort, c->ev[1], c->ev[2]);

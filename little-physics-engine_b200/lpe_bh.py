@@ -38,13 +38,15 @@ class Params(C.Structure):
 class Stats(C.Structure):
     _fields_ = [
         ("n_bodies", C.c_uint64), ("n_in_tree", C.c_uint64), ("n_terminals", C.c_uint64),
-        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64), ("warp_visits", C.c_uint64), ("overflow_chunks", C.c_uint64),
+        ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64), ("warp_visits", C.c_uint64), ("overflow_chunks", C.c_uint64), ("t2_kinds", C.c_uint64 * 8),
         ("depth", C.c_int32), ("sort_passes", C.c_int32), ("ms_keygen", C.c_float),
         ("ms_sort", C.c_float), ("ms_build", C.c_float), ("ms_traverse", C.c_float), ("ms_total", C.c_float),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["t2_kinds"] = list(d["t2_kinds"])
+        return d
 
 
 class TreeDump(C.Structure):

@@ -14,4 +14,5 @@ for wlname in sys.argv[1:] or ["c2"]:
     n = wl["n"]; nw = (n + 31) // 32
     print(wlname, "acc/body %.1f  lane-visits/body %.1f  warp-visits/warp %.1f  lane efficiency %.3f  nodes/body %.2f" % (
         st["interactions"] / n, st["visits"] / n, st["warp_visits"] / nw, st["visits"] / (32.0 * st["warp_visits"]), st["n_nodes"] / n))
+    nw_ = nw; print("   per warp:", dict(zip(["A-clean","A-dirty","O-dirty","M->accept","M->open","M->split","rounds","frontier"], [round(v/nw_,1) for v in st["t2_kinds"]])), "overflow", st["overflow_chunks"])
     bh.close()
