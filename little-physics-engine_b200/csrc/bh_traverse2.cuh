@@ -37,16 +37,40 @@ constexpr unsigned int T2_CLEAN = 0xFFFFu;
 constexpr float T2_MARGIN = 2e-5f;          // relative safety margin of the group classification
 
 struct T2Warp {
-    unsigned int fslot[2][T2_CAP];          // frontier: record slot
-    unsigned short fpm[2][T2_CAP];          // frontier: M slot of the nearest dirty/mixed ancestor on the previous level
-    unsigned int reach[2][T2_CAP];          // [level parity][M slot]: lanes that reached AND opened that mixed node
-    float4 ac[T2_ABUF];                     // A list: centre (two-float)
-    float2 ag[T2_ABUF];                     //         mass, mask of lanes that reach it (as uint bits)
-    unsigned int aslot[T2_ABUF];            //         record slot (self test / stats only)
-    float4 mc[32];                          // M list of the current round: centre
-    float4 mg[32];                          //         gm, open_lo, open_hi, parent M slot (as uint bits)
-    unsigned int mslot[32];                 //         record slot
+    unsigned int qslot[T2_CAP];             // FIFO ring of nodes to classify: record slot
+    unsigned int qmask[T2_CAP];             //   lanes (targets) that reach the node
+    float4 ac[T2_ABUF];                     // accept list: centre (two-float)
+    float2 ag[T2_ABUF];                     //   mass, lane mask (as uint bits)
+    unsigned int aslot[T2_ABUF];            //   record slot (self test / stats only)
+    float4 mc[32];                          // mixed nodes of the current round: centre
+    float4 mg[32];                          //   gm, open_lo, open_hi, lane mask (as uint bits)
+    unsigned int mslot[32];                 //   record slot
+    unsigned int momask[32];                //   result: lanes that reached AND opened it
 };
+
+// one accept-list entry for one lane
+template <bool STATS, bool SELF>
+__device__ __forceinline__ void t2_accept(const T2Warp& W, unsigned int m, unsigned int lanebit, unsigned int self,
+                                          float nphx, float nphy, float nplx, float nply, float eps2f, float& ax,
+                                          float& ay, unsigned int& nacc) {
+    const float4 C = W.ac[m];
+    const float2 Gm = W.ag[m];
+    const bool reached = (__float_as_uint(Gm.y) & lanebit) != 0u;
+    const float g = reached ? Gm.x : 0.f;   // a lane that accepted an ancestor of this node gets nothing from it
+    const float dx = (C.x + nphx) + (C.z + nplx);
+    const float dy = (C.y + nphy) + (C.w + nply);
+    const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+    float rinv;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
+    float f = (g * rinv) * (rinv * rinv);
+    if (SELF) {
+        const unsigned int as = W.aslot[m];
+        if ((as & 0x7FFFFFFFu) == self) f = 0.f;
+        if (STATS) nacc += (reached && (as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+    }
+    ax = fmaf(dx, f, ax);
+    ay = fmaf(dy, f, ay);
+}
 
 template <bool STATS, bool SELF>
 __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
@@ -61,8 +85,8 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
     const double Us = c.U * c.invS;
     const float INF = __int_as_float(0x7f800000);
     const float FMAXV = 3.0e38f;
-    constexpr bool selfTest = SELF;   // needed for stats, or when eps == 0 (d2 = 0 -> inf * 0)
     constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32
+    constexpr unsigned int QM = (unsigned int)T2_CAP - 1u;
 
     while (true) {
         unsigned int q = 0;
@@ -110,204 +134,141 @@ __global__ void __launch_bounds__(T2_THREADS) k_traverse2(StepConst c, TravArgs 
             const float x0l = (float)(bx0 - (double)x0h), x1l = (float)(bx1 - (double)x1h);
             const float y0l = (float)(by0 - (double)y0h), y1l = (float)(by1 - (double)y1h);
 
-            int cur = 0;
-            unsigned int ncur = 1, nA = 0;
+            unsigned int head = 0, tail = 1, nA = 0;
             if (lane == 0) {
-                W.fslot[0][0] = 0u;
-                W.fpm[0][0] = (unsigned short)T2_CLEAN;
+                W.qslot[0] = 0u;       // the root, reached by every target
+                W.qmask[0] = tmask;
             }
             __syncwarp();
-            int lvl = 0;
-            while (ncur > 0u) {
-                const int nxt = cur ^ 1;
-                unsigned int nnext = 0;
-                const unsigned int* prevreach = &W.reach[(lvl & 1) ^ 1][0];
-                unsigned int* curreach = &W.reach[lvl & 1][0];
-                int r = 0;
-                for (unsigned int base = 0; base < ncur; base += 32, ++r) {
-                    // ---------------- phase 1: one node per lane ----------------
-                    const unsigned int e = base + lane;
-                    bool has = e < ncur;
-                    unsigned int slot = 0, pm = T2_CLEAN, pmask = tmask;
-                    TravRec R;
-                    R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.skip = 0; R.cblock = 0;
-                    if (has) {
-                        slot = W.fslot[cur][e];
-                        pm = W.fpm[cur][e];
-                        if (pm != T2_CLEAN) {
-                            pmask = prevreach[pm];                    // lanes that opened the mixed parent
-                            if ((pmask & tmask) == tmask) pm = T2_CLEAN;   // everybody reaches it: clean again
-                            else if (pmask == 0u) has = false;        // nobody reaches it: drop the subtree
-                        }
-                    }
-                    if (has) {
-                        const uint4* src = reinterpret_cast<const uint4*>(a.rec + slot);
-                        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
-                        R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
-                        R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
-                    }
-                    // distance bounds from the node centre to the targets' box
-                    const float ax0 = (R.c.x - x0h) + (R.c.z - x0l), ax1 = (R.c.x - x1h) + (R.c.z - x1l);
-                    const float ay0 = (R.c.y - y0h) + (R.c.w - y0l), ay1 = (R.c.y - y1h) + (R.c.w - y1l);
-                    const float dxmin = fmaxf(fmaxf(-ax0, ax1), 0.f), dxmax = fmaxf(fabsf(ax0), fabsf(ax1));
-                    const float dymin = fmaxf(fmaxf(-ay0, ay1), 0.f), dymax = fmaxf(fabsf(ay0), fabsf(ay1));
-                    const float d2min = fmaf(dxmin, dxmin, fmaf(dymin, dymin, eps2f));
-                    const float d2max = fmaf(dxmax, dxmax, fmaf(dymax, dymax, eps2f));
-                    const float t = R.open_t;
-                    const float tlo = t * (1.0f - OPEN_BAND), thi = t * (1.0f + OPEN_BAND);
-                    const bool allAcc = (t < 0.f) || (d2min * (1.0f - T2_MARGIN) >= thi);
-                    const bool allOpen = (t >= 0.f) && (d2max * (1.0f + T2_MARGIN) <= tlo);
-                    const bool dirty = pm != T2_CLEAN;
-                    const bool toA = has && allAcc;                      // clean or dirty: the entry carries the lane mask
-                    const bool toM = has && !allAcc && (dirty || !allOpen);
-                    const bool expand = has && !allAcc;
-
-                    const unsigned int maskA = __ballot_sync(0xFFFFFFFFu, toA);
-                    const unsigned int maskM = __ballot_sync(0xFFFFFFFFu, toM);
-                    const unsigned int posM = __popc(maskM & lt);
-                    const unsigned int cntM = __popc(maskM);
-                    if (toA) {
-                        const unsigned int pos = nA + __popc(maskA & lt);
-                        W.ac[pos] = R.c;
-                        W.ag[pos] = make_float2(R.gm, __uint_as_float(dirty ? pmask : tmask));
-                        W.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
-                    }
-                    nA += __popc(maskA);
-                    if (STATS) {
-                        kd[0] += __popc(__ballot_sync(0xFFFFFFFFu, toA && !dirty));
-                        kd[1] += __popc(__ballot_sync(0xFFFFFFFFu, toA && dirty));
-                        kd[2] += __popc(__ballot_sync(0xFFFFFFFFu, toM && allOpen));
-                        kd[6] += 1; kd[7] += __popc(__ballot_sync(0xFFFFFFFFu, has));
-                    }
-                    if (toM) {
-                        W.mc[posM] = R.c;
-                        float lo, hi;
-                        if (allOpen) { lo = FMAXV; hi = FMAXV; }         // dirty, everybody who reaches it opens it
-                        else { lo = tlo; hi = thi; }
-                        W.mg[posM] = make_float4(R.gm, lo, hi, __uint_as_float(dirty ? pmask : tmask));
-                        W.mslot[posM] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
-                    }
-                    // children of opened nodes -> next frontier (exclusive scan of child counts)
-                    const unsigned int nch = expand ? (R.cblock & 3u) + 1u : 0u;
-                    unsigned int inc = nch;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                        if (lane >= o) inc += v;
-                    }
-                    const unsigned int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                    if (nnext + total > (unsigned int)T2_CAP) { overflow = true; break; }
-                    if (nch) {
-                        const unsigned int at = nnext + inc - nch;
-                        const unsigned int cslot = (R.cblock >> 2) * 4u;
-                        const unsigned short cpm = (unsigned short)(toM ? (unsigned int)(r * 32) + posM : T2_CLEAN);
-                        for (unsigned int kk = 0; kk < nch; ++kk) {
-                            W.fslot[nxt][at + kk] = cslot + kk;
-                            W.fpm[nxt][at + kk] = cpm;
-                        }
-                    }
-                    nnext += total;
-                    __syncwarp();
-
-                    // ---------------- phase 2a: the mixed / dirty nodes of this round, one body per lane ----------------
-                    for (unsigned int m = 0; m < cntM; ++m) {
-                        const float4 C = W.mc[m];
-                        const float4 G = W.mg[m];
-                        const bool reached = (__float_as_uint(G.w) & lanebit) != 0u;
-                        const float dx = (C.x + nphx) + (C.z + nplx);
-                        const float dy = (C.y + nphy) + (C.w + nply);
-                        float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
-                        d2 = reached ? d2 : INF;   // a lane that accepted an ancestor: never opens, contributes 0
-                        float lo = G.y;
-                        const bool band = d2 > lo && d2 < G.z;
-                        if (__any_sync(0xFFFFFFFFu, band)) {   // rare: guard band -> the reference's fp64 test decides
-                            if (band)
-                                lo = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs,
-                                                pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
-                        }
-                        const bool open = d2 <= lo;
-                        const unsigned int omask = __ballot_sync(0xFFFFFFFFu, open);
-                        if (lane == 0) curreach[r * 32 + m] = omask;
-                        if (STATS && G.y >= 0.f && G.y < FMAXV) {
-                            const unsigned int pmk = __float_as_uint(G.w);
-                            if (omask == 0u) kd[3]++; else if (omask == pmk) kd[4]++; else kd[5]++;
-                        }
-                        float rinv;
-                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
-                        float f = (G.x * rinv) * (rinv * rinv);
-                        if (selfTest) {
-                            const unsigned int ms = W.mslot[m];
-                            if ((ms & 0x7FFFFFFFu) == self) f = 0.f;
-                            if (STATS) nacc += (reached && !open && (ms & 0x7FFFFFFFu) != self && !(ms >> 31)) ? 1u : 0u;
-                        }
-                        ax = fmaf(dx, f, ax);
-                        ay = fmaf(dy, f, ay);
-                    }
-                    if (cntM) {
-                        AX += (double)ax; AY += (double)ay;
-                        ax = 0.f; ay = 0.f;
-                    }
-                    if (STATS) nwarp += cntM;
-                    __syncwarp();
-
-                    // ---------------- phase 2b: the sure-accept list, flushed when it is long enough ----------------
-                    if (nA >= 64u) {
-#pragma unroll 4
-                        for (unsigned int m = 0; m < nA; ++m) {
-                            const float4 C = W.ac[m];
-                            const float2 Gm = W.ag[m];
-                            const bool reached = (__float_as_uint(Gm.y) & lanebit) != 0u;
-                            const float g = reached ? Gm.x : 0.f;   // lanes that accepted an ancestor contribute nothing
-                            const float dx = (C.x + nphx) + (C.z + nplx);
-                            const float dy = (C.y + nphy) + (C.w + nply);
-                            const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
-                            float rinv;
-                            asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
-                            float f = (g * rinv) * (rinv * rinv);
-                            if (selfTest) {
-                                const unsigned int as = W.aslot[m];
-                                if ((as & 0x7FFFFFFFu) == self) f = 0.f;
-                                if (STATS) nacc += (reached && (as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
-                            }
-                            ax = fmaf(dx, f, ax);
-                            ay = fmaf(dy, f, ay);
-                        }
-                        if (STATS) nwarp += nA;
-                        nA = 0;
-                        AX += (double)ax; AY += (double)ay;
-                        ax = 0.f; ay = 0.f;
-                        __syncwarp();
-                    }
+            while (head != tail) {
+                // ---------------- phase 1: one node per lane ----------------
+                const unsigned int cnt = min(32u, tail - head);
+                const bool has = (unsigned int)lane < cnt;
+                unsigned int slot = 0, mask = tmask;
+                TravRec R;
+                R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.skip = 0; R.cblock = 0;
+                if (has) {
+                    slot = W.qslot[(head + lane) & QM];
+                    mask = W.qmask[(head + lane) & QM];
+                    const uint4* src = reinterpret_cast<const uint4*>(a.rec + slot);
+                    const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                    R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
+                    R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
                 }
-                if (overflow) break;
-                cur = nxt;
-                ncur = nnext;
-                ++lvl;
-            }
-            if (!overflow) {
-                for (unsigned int m = 0; m < nA; ++m) {
-                    const float4 C = W.ac[m];
-                    const float2 Gm = W.ag[m];
-                    const bool reached = (__float_as_uint(Gm.y) & lanebit) != 0u;
-                    const float g = reached ? Gm.x : 0.f;   // lanes that accepted an ancestor contribute nothing
+                head += cnt;
+                // distance bounds from the node centre to the targets' box
+                const float ax0 = (R.c.x - x0h) + (R.c.z - x0l), ax1 = (R.c.x - x1h) + (R.c.z - x1l);
+                const float ay0 = (R.c.y - y0h) + (R.c.w - y0l), ay1 = (R.c.y - y1h) + (R.c.w - y1l);
+                const float dxmin = fmaxf(fmaxf(-ax0, ax1), 0.f), dxmax = fmaxf(fabsf(ax0), fabsf(ax1));
+                const float dymin = fmaxf(fmaxf(-ay0, ay1), 0.f), dymax = fmaxf(fabsf(ay0), fabsf(ay1));
+                const float d2min = fmaf(dxmin, dxmin, fmaf(dymin, dymin, eps2f));
+                const float d2max = fmaf(dxmax, dxmax, fmaf(dymax, dymax, eps2f));
+                const float t = R.open_t;
+                const float tlo = t * (1.0f - OPEN_BAND), thi = t * (1.0f + OPEN_BAND);
+                const bool allAcc = (t < 0.f) || (d2min * (1.0f - T2_MARGIN) >= thi);
+                const bool allOpen = (t >= 0.f) && (d2max * (1.0f + T2_MARGIN) <= tlo);
+                const bool dirty = mask != tmask;                    // some target accepted an ancestor
+                const bool toA = has && allAcc;                      // clean or dirty: the entry carries the lane mask
+                const bool toM = has && !allAcc && (dirty || !allOpen);
+                const bool expand = has && !allAcc;
+
+                const unsigned int maskA = __ballot_sync(0xFFFFFFFFu, toA);
+                const unsigned int maskM = __ballot_sync(0xFFFFFFFFu, toM);
+                const unsigned int posM = __popc(maskM & lt);
+                const unsigned int cntM = __popc(maskM);
+                if (toA) {
+                    const unsigned int pos = nA + __popc(maskA & lt);
+                    W.ac[pos] = R.c;
+                    W.ag[pos] = make_float2(R.gm, __uint_as_float(mask));
+                    if (SELF) W.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
+                }
+                nA += __popc(maskA);
+                if (STATS) {
+                    kd[0] += __popc(__ballot_sync(0xFFFFFFFFu, toA && !dirty));
+                    kd[1] += __popc(__ballot_sync(0xFFFFFFFFu, toA && dirty));
+                    kd[2] += __popc(__ballot_sync(0xFFFFFFFFu, toM && allOpen));
+                    kd[6] += 1; kd[7] += cnt;
+                }
+                if (toM) {
+                    W.mc[posM] = R.c;
+                    // dirty and every lane that reaches it opens it: no test, the mask just passes through
+                    const float lo = allOpen ? FMAXV : tlo, hi = allOpen ? FMAXV : thi;
+                    W.mg[posM] = make_float4(R.gm, lo, hi, __uint_as_float(mask));
+                    W.mslot[posM] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
+                }
+                __syncwarp();
+
+                // ---------------- phase 2a: the mixed nodes of this round, one body per lane ----------------
+                for (unsigned int m = 0; m < cntM; ++m) {
+                    const float4 C = W.mc[m];
+                    const float4 G = W.mg[m];
+                    const bool reached = (__float_as_uint(G.w) & lanebit) != 0u;
                     const float dx = (C.x + nphx) + (C.z + nplx);
                     const float dy = (C.y + nphy) + (C.w + nply);
-                    const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+                    float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
+                    d2 = reached ? d2 : INF;   // a lane that accepted an ancestor: never opens, contributes 0
+                    float lo = G.y;
+                    const bool band = d2 > lo && d2 < G.z;
+                    if (__any_sync(0xFFFFFFFFu, band)) {   // rare: guard band -> the reference's fp64 test decides
+                        if (band)
+                            lo = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs,
+                                            pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                    }
+                    const bool open = d2 <= lo;
+                    const unsigned int omask = __ballot_sync(0xFFFFFFFFu, open);
+                    if (lane == 0) W.momask[m] = omask;
+                    if (STATS && G.y >= 0.f && G.y < FMAXV) {
+                        const unsigned int pmk = __float_as_uint(G.w);
+                        if (omask == 0u) kd[3]++; else if (omask == pmk) kd[4]++; else kd[5]++;
+                    }
                     float rinv;
-                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
-                    float f = (g * rinv) * (rinv * rinv);
-                    if (selfTest) {
-                        const unsigned int as = W.aslot[m];
-                        if ((as & 0x7FFFFFFFu) == self) f = 0.f;
-                        if (STATS) nacc += (reached && (as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
+                    float f = (G.x * rinv) * (rinv * rinv);
+                    if (SELF) {
+                        const unsigned int ms = W.mslot[m];
+                        if ((ms & 0x7FFFFFFFu) == self) f = 0.f;
+                        if (STATS) nacc += (reached && !open && (ms & 0x7FFFFFFFu) != self && !(ms >> 31)) ? 1u : 0u;
                     }
                     ax = fmaf(dx, f, ax);
                     ay = fmaf(dy, f, ay);
                 }
-                if (STATS) nwarp += nA;
-                AX += (double)ax; AY += (double)ay;
+                if (STATS) nwarp += cntM;
+                __syncwarp();
+
+                // ---------------- children of opened nodes join the queue with the mask of the lanes that opened ----------------
+                const unsigned int cmask = toM ? W.momask[posM] : mask;
+                const unsigned int nch = (expand && cmask != 0u) ? (R.cblock & 3u) + 1u : 0u;
+                unsigned int inc = nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int v = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                    if (lane >= o) inc += v;
+                }
+                const unsigned int total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if ((tail - head) + total > (unsigned int)T2_CAP) { overflow = true; break; }
+                if (nch) {
+                    const unsigned int at = tail + inc - nch;
+                    const unsigned int cslot = (R.cblock >> 2) * 4u;
+                    for (unsigned int kk = 0; kk < nch; ++kk) {
+                        W.qslot[(at + kk) & QM] = cslot + kk;
+                        W.qmask[(at + kk) & QM] = cmask;
+                    }
+                }
+                tail += total;
+
+                // ---------------- phase 2b: the accept list, flushed when it is long enough ----------------
+                if (nA >= 64u || head == tail) {
+                    __syncwarp();
+#pragma unroll 4
+                    for (unsigned int m = 0; m < nA; ++m)
+                        t2_accept<STATS, SELF>(W, m, lanebit, self, nphx, nphy, nplx, nply, eps2f, ax, ay, nacc);
+                    if (STATS) nwarp += nA;
+                    nA = 0;
+                }
+                AX += (double)ax; AY += (double)ay;   // fp32 partial sums go to fp64 every round
+                ax = 0.f; ay = 0.f;
+                __syncwarp();
             }
-            __syncwarp();
         }
 
         if (overflow) {
