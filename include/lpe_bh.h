@@ -82,9 +82,8 @@ typedef struct {
 
 /* device-resident views for zero-copy interop (torch / NCCL plumbing); valid until the next upload or destroy */
 typedef struct {
-    void* pos;        /* double2[n]  (x,y) per body, creation order */
+    void* body;       /* {double x, y, m; uint32 rank, comp}[n], 32 B per body, creation order */
     void* vel;        /* double2[n] */
-    void* mass;       /* double[n] */
     void* xchg_send;  /* double4[xchg_chunk]  this rank's packed slice (x,y,vx,vy), see lpe_bh_set_shard */
     void* xchg_recv;  /* double4[xchg_chunk * nranks] */
     uint64_t n;

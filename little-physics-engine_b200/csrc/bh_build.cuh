@@ -40,15 +40,15 @@ __device__ __forceinline__ unsigned int cell_index(double x, double h, double in
 }
 
 __global__ void __launch_bounds__(256)
-k_keygen(StepConst c, const double2* __restrict__ pos, const double* __restrict__ mass,
-         const unsigned char* __restrict__ comp, unsigned long long* __restrict__ keys,
+k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restrict__ keys,
          unsigned int* __restrict__ vals, Scal* __restrict__ s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int in = 0;
     unsigned long long mbits = 0;
     if (i < c.n) {
-        const unsigned char cm = comp[i];
-        const double2 p = pos[i];
+        const Body bd = body[i];
+        const unsigned int cm = bd.comp;
+        const double2 p = make_double2(bd.x, bd.y);
         // buildTree's view and bounds test, barnes_hut.cpp:117-124
         const bool src = (cm & 1u) && !(cm & 4u);
         const bool inside = src && p.x >= 0.0 && p.x < c.U && p.y >= 0.0 && p.y < c.U;
@@ -59,7 +59,7 @@ k_keygen(StepConst c, const double2* __restrict__ pos, const double* __restrict_
             const unsigned int iy = cell_index(p.y, c.h, c.invh, kmax);
             key = spread_bits32(ix) | (spread_bits32(iy) << 1);
             in = 1;
-            const double m = mass[i];
+            const double m = bd.m;
             if (m > 0.0) mbits = (unsigned long long)__double_as_longlong(m);
         }
         keys[i] = key;
@@ -83,17 +83,23 @@ k_keygen(StepConst c, const double2* __restrict__ pos, const double* __restrict_
     }
 }
 
-// ---- 2. gather into Morton order --------------------------------------------------------------------------
+// ---- 2. gather into Morton order: one 32-byte sector read and one written per body --------------------------
 __global__ void __launch_bounds__(256)
-k_gather(int n, const unsigned int* __restrict__ sidx, const double2* __restrict__ pos,
-         const double* __restrict__ mass, const unsigned int* __restrict__ rank, double2* __restrict__ spos,
-         double* __restrict__ smass, unsigned int* __restrict__ srank) {
+k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ body,
+         SBody* __restrict__ sbody, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned int b = sidx[i];
-    spos[i] = pos[b];
-    smass[i] = mass[b];
-    srank[i] = rank[b];
+    const Body bd = body[b];
+    SBody sb;
+    sb.x = bd.x; sb.y = bd.y; sb.m = bd.m;
+    sb.rankcomp = (bd.rank & 0x0FFFFFFFu) | (bd.comp << 28);
+    sb.idx = b;
+    sbody[i] = sb;
+    if (need_self) {
+        selfnode[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
+        selfslot[i] = LPE_NONE;
+    }
 }
 
 // scan loader: 1 where sorted position i starts a new depth-D cell
@@ -177,78 +183,31 @@ __global__ void k_level_scan(const unsigned int* __restrict__ levelCount, unsign
 // ---- 5. topology: pre-order indices, skip pointers, child slots, per-level cell lists ------------------------
 struct Topo {
     unsigned int* tnode;      // [terminal] pre-order index of the terminal's node
-    unsigned int* child;      // [4 * ordinal + digit] pre-order index of a branching cell's child, LPE_NONE if empty
-    NodeMeta* meta;           // [preorder] (terminal levels are refined to -1 / -2 by k_agg_terminals)
+    unsigned int* child;      // [4 * ordinal + digit] a cell's child: pre-order index, or LPE_LEAF_FLAG | sorted body
+                              // position for a single-body leaf, or LPE_NONE
+    NodeMeta* meta;           // [preorder]
+    Agg* agg;                 // [preorder] written here only for aggregated terminals (>= 2 bodies in a depth-D cell)
     unsigned int* levelList;  // cells grouped by level: levelList[levelBase[L] + i]
     const unsigned int* levelBase;
     unsigned int* levelCursor;
+    const unsigned int* tfirst;
+    const SBody* sbody;
+    unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf
+    unsigned int* selfslot;   // [sorted body] record slot of its own leaf (only written here for a one-terminal tree)
+    TravRec* rec;
+    unsigned int* recnode;
 };
 
 __device__ __forceinline__ void register_child(int D, const unsigned long long* __restrict__ tkey,
                                                const unsigned int* __restrict__ mask,
                                                const unsigned int* __restrict__ P, int t, unsigned long long kt, int dl,
-                                               int dr, unsigned int idx, unsigned int* __restrict__ child) {
+                                               int dr, unsigned int code, unsigned int* __restrict__ child) {
     const int Lp = max(dl, dr);   // level of the nearest branching ancestor
     if (Lp < 0) return;           // root
     const int ap = (dl < Lp) ? t : cell_first(tkey, t, 2 * (D - Lp));
     const unsigned int qpar = P[ap] + (unsigned int)__popc(mask[ap] & ((1u << Lp) - 1u));
     const unsigned int digit = (unsigned int)(kt >> (2 * (D - Lp - 1))) & 3u;
-    child[(size_t)qpar * 4 + digit] = idx;
-}
-
-__global__ void __launch_bounds__(256)
-k_topology(int D, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
-           const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P, Topo o, Scal* __restrict__ s) {
-    __shared__ unsigned int cnt[32], base[32];
-    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
-    __syncthreads();
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n_term = (int)s->n_term;
-    if (t == 0) s->n_internal = P[n_term];
-    const bool live = t < n_term;
-    unsigned int mk = 0, Pt = 0;
-    if (live) {
-        mk = mask[t];
-        Pt = P[t];
-        const unsigned long long kt = tkey[t];
-        const int dl = (t > 0) ? (int)delta[t - 1] : -1;
-        {   // the terminal itself
-            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk);
-            o.tnode[t] = idx;
-            NodeMeta mt;
-            mt.skip = idx + 1; mt.start = (unsigned int)t; mt.level = -1; mt.pad = 0;
-            o.meta[idx] = mt;
-            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[t], idx, o.child);
-        }
-        unsigned int rest = mk;   // branching cells whose first terminal is t
-        while (rest) {
-            const int L = __ffs(rest) - 1;
-            rest &= rest - 1;
-            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
-            const int b = cell_last(tkey, t, 2 * (D - L), n_term);
-            NodeMeta mt;
-            mt.skip = (unsigned int)(b + 1) + P[b + 1]; mt.start = (unsigned int)t; mt.level = L; mt.pad = 0;
-            o.meta[idx] = mt;
-            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[b], idx, o.child);
-            atomicAdd(&cnt[L], 1u);
-        }
-    }
-    // per-level lists: one global reservation per level per block, then block-local slots
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const unsigned int c = cnt[threadIdx.x];
-        base[threadIdx.x] = c ? atomicAdd(&o.levelCursor[threadIdx.x], c) : 0u;
-        cnt[threadIdx.x] = 0;
-    }
-    __syncthreads();
-    unsigned int rest = mk;
-    while (rest) {
-        const int L = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
-        const unsigned int local = atomicAdd(&cnt[L], 1u);
-        o.levelList[o.levelBase[L] + base[L] + local] = idx;
-    }
+    child[(size_t)qpar * 4 + digit] = code;
 }
 
 // Power-of-two mass unit just above the largest source mass: node masses then fit fp32 comfortably
@@ -259,14 +218,14 @@ __device__ __forceinline__ double mass_scale_inv(unsigned long long max_mass_bit
     return ldexp(1.0, -(e + 1));
 }
 
-// ---- 6. aggregation and traversal records ---------------------------------------------------------------------
-struct NodeOut {
-    NodeMeta* meta;         // [preorder]
-    Agg* agg;               // [preorder]
-    TravRec* rec;           // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
-    unsigned int* recnode;  // [4 * block + slot] pre-order index of the node stored in that slot
-    unsigned int* selfslot; // [sorted body] record slot of the body's own single-body leaf, LPE_NONE otherwise
-};
+// aggregate of one body
+__device__ __forceinline__ Agg body_agg(const SBody& sb, unsigned int pos, double thr) {
+    Agg a;
+    a.m = sb.m; a.sx = sb.m * sb.x; a.sy = sb.m * sb.y;
+    a.mf = sb.m; a.xf = sb.x; a.yf = sb.y;
+    a.frank = sb.rankcomp & 0x0FFFFFFFu; a.fidx = pos; a.count = 1u; a.small = (sb.m >= thr) ? 0u : 1u;
+    return a;
+}
 
 // Traversal record of a node from its aggregate.
 __device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a, int level, unsigned int skip,
@@ -296,47 +255,101 @@ __device__ __forceinline__ TravRec invalid_record() {
     r.c = make_float4(0.f, 0.f, 0.f, 0.f);
     r.gm = 0.f;
     r.open_t = -1.f;
-    r.skip = 0u;   // skip == 0 marks an unused slot of a child block
+    r.skip = 0u;
     r.cblock = 0u;
     return r;
 }
 
-// terminals: per-cell sums over the bodies that share a depth-D cell (usually one)
 __global__ void __launch_bounds__(256)
-k_agg_terminals(StepConst c, const unsigned int* __restrict__ tfirst, const unsigned int* __restrict__ tnode,
-                const double2* __restrict__ spos, const double* __restrict__ smass,
-                const unsigned int* __restrict__ srank, NodeOut o, unsigned int* __restrict__ selfnode,
-                const Scal* __restrict__ s) {
+k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
+           const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P, Topo o, Scal* __restrict__ s) {
+    __shared__ unsigned int cnt[32], base[32];
+    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int D = c.D;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int n_term = (int)s->n_term;
-    if (t >= n_term) return;
-    const unsigned int first = tfirst[t], last = tfirst[t + 1];
-    Agg a;
-    a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
-    a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
-    for (unsigned int i = first; i < last; ++i) {
-        const double m = smass[i];
-        const double2 p = spos[i];
-        a.m += m;
-        a.sx += m * p.x;
-        a.sy += m * p.y;
-        const unsigned int r = srank[i];
-        if (r < a.frank) { a.frank = r; a.fidx = i; a.mf = m; a.xf = p.x; a.yf = p.y; }
-        if (m >= c.thr) a.small = 0u;
+    if (t == 0) s->n_internal = P[n_term];
+    const bool live = t < n_term;
+    unsigned int mk = 0, Pt = 0;
+    if (live) {
+        mk = mask[t];
+        Pt = P[t];
+        const unsigned long long kt = tkey[t];
+        const int dl = (t > 0) ? (int)delta[t - 1] : -1;
+        {   // the terminal itself: a single-body leaf, or the sum of the bodies that share its depth-D cell
+            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk);
+            const unsigned int first = o.tfirst[t], last = o.tfirst[t + 1];
+            const bool single = (last - first) == 1u;
+            o.tnode[t] = idx;
+            NodeMeta mt;
+            mt.skip = idx + 1; mt.start = (unsigned int)t; mt.level = single ? -1 : -2; mt.pad = first;
+            o.meta[idx] = mt;
+            Agg a;
+            if (single) {
+                if (c.need_self) o.selfnode[first] = idx;
+                if (n_term == 1) a = body_agg(o.sbody[first], first, c.thr);
+            } else {
+                a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
+                a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
+                for (unsigned int i = first; i < last; ++i) {
+                    const SBody sb = o.sbody[i];
+                    a.m += sb.m; a.sx += sb.m * sb.x; a.sy += sb.m * sb.y;
+                    const unsigned int r = sb.rankcomp & 0x0FFFFFFFu;
+                    if (r < a.frank) { a.frank = r; a.fidx = i; a.mf = sb.m; a.xf = sb.x; a.yf = sb.y; }
+                    if (sb.m >= c.thr) a.small = 0u;
+                }
+                o.agg[idx] = a;
+            }
+            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[t], single ? (LPE_LEAF_FLAG | first) : idx, o.child);
+            if (n_term == 1) {   // a tree of one terminal: it is the root
+                const double msi = mass_scale_inv(s->max_mass_bits);
+                o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
+                o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+                o.recnode[0] = idx;
+                if (single && c.need_self) o.selfslot[first] = 0u;
+            }
+        }
+        unsigned int rest = mk;   // branching cells whose first terminal is t
+        while (rest) {
+            const int L = __ffs(rest) - 1;
+            rest &= rest - 1;
+            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
+            const int b = cell_last(tkey, t, 2 * (D - L), n_term);
+            NodeMeta mt;
+            mt.skip = (unsigned int)(b + 1) + P[b + 1]; mt.start = (unsigned int)t; mt.level = L; mt.pad = 0;
+            o.meta[idx] = mt;
+            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[b], idx, o.child);
+            atomicAdd(&cnt[L], 1u);
+        }
     }
-    const unsigned int idx = tnode[t];
-    const bool single = (last - first) == 1;
-    if (!single) o.meta[idx].level = -2;
-    o.agg[idx] = a;
-    for (unsigned int i = first; i < last; ++i) selfnode[i] = single ? idx : LPE_NONE;
-    if (n_term == 1) {   // a tree of one terminal: it is the root
-        const double msi = mass_scale_inv(s->max_mass_bits);
-        o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
-        o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
-        o.recnode[0] = idx;
-        if (single) o.selfslot[first] = 0u;
+    // per-level lists: one global reservation per level per block, then block-local slots
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const unsigned int cc = cnt[threadIdx.x];
+        base[threadIdx.x] = cc ? atomicAdd(&o.levelCursor[threadIdx.x], cc) : 0u;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    unsigned int rest = mk;
+    while (rest) {
+        const int L = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
+        const unsigned int local = atomicAdd(&cnt[L], 1u);
+        o.levelList[o.levelBase[L] + base[L] + local] = idx;
     }
 }
+
+// ---- 6. aggregation and traversal records ---------------------------------------------------------------------
+struct NodeOut {
+    NodeMeta* meta;         // [preorder]
+    Agg* agg;               // [preorder] (cells and aggregated terminals; single-body leaves have none)
+    TravRec* rec;           // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
+    unsigned int* recnode;  // [4 * block + slot] pre-order index of the cell stored in that slot (LPE_NONE for leaves)
+    unsigned int* selfslot; // [sorted body] record slot of the body's own single-body leaf, LPE_NONE otherwise
+    const SBody* sbody;
+};
 
 // one branching cell: sum the children (digit order), write their records into this cell's child block
 __device__ __forceinline__ void aggregate_cell(const StepConst& c, const NodeOut& o, unsigned int p,
@@ -354,16 +367,25 @@ __device__ __forceinline__ void aggregate_cell(const StepConst& c, const NodeOut
     for (int g = 0; g < 4; ++g) {
         const unsigned int ci = cs[g];
         if (ci == LPE_NONE) continue;
-        const Agg a = o.agg[ci];
-        const NodeMeta mc = o.meta[ci];
+        const unsigned int slot = 4u * (q + 1u) + (unsigned int)r;
+        Agg a;
+        if (ci & LPE_LEAF_FLAG) {
+            // a single-body leaf: read the body itself (one sector), no aggregate was ever stored for it
+            const unsigned int pos = ci & ~LPE_LEAF_FLAG;
+            a = body_agg(o.sbody[pos], pos, c.thr);
+            blk[r++] = make_record(c, a, -1, 0u, 0u, msi);
+            o.recnode[slot] = LPE_NONE;
+            if (c.need_self) o.selfslot[pos] = slot;
+        } else {
+            a = o.agg[ci];
+            const NodeMeta mc = o.meta[ci];
+            blk[r++] = make_record(c, a, mc.level, mc.skip, (ci - mc.start) + 1u, msi);
+            o.recnode[slot] = ci;
+        }
         b.m += a.m; b.sx += a.sx; b.sy += a.sy;
         if (a.frank < b.frank) { b.frank = a.frank; b.fidx = a.fidx; b.mf = a.mf; b.xf = a.xf; b.yf = a.yf; }
         b.count += a.count;
         b.small &= (a.small & 1u);
-        const unsigned int slot = 4u * (q + 1u) + (unsigned int)r;
-        blk[r++] = make_record(c, a, mc.level, mc.skip, (ci - mc.start) + 1u, msi);
-        o.recnode[slot] = ci;
-        if (mc.level == -1) o.selfslot[a.fidx] = slot;
     }
     b.small |= (unsigned int)(r - 1) << 1;   // children - 1, read back when this cell's own record is made
     for (; r < 4; ++r) blk[r] = invalid_record();

@@ -1,8 +1,8 @@
 // bh_common.cuh — shared device-side types for the B200 Barnes-Hut step.
 //
-// Data layout in HBM (all SoA):
-//   state (creation order):  pos double2[n], vel double2[n], mass f64[n], rank u32[n], comp u8[n]
-//   sorted (Morton order):   keys u64[n], sidx u32[n], spos double2[n], smass f64[n], srank u32[n]
+// Data layout in HBM:
+//   state (creation order):  body Body[n] (32 B: x, y, m, rank, comp), vel double2[n]
+//   sorted (Morton order):   keys u64[n], sidx u32[n], sbody SBody[n] (32 B: x, y, m, rank|comp, creation index)
 //   terminals (t < n_term):  tkey u64, tfirst u32, delta i8, mask u32, tnode u32
 //   nodes (pre-order index): meta NodeMeta (16 B), agg Agg (64 B)
 //   cells (ordinal):         child uint4;  records: rec TravRec[4 * (cells + 1)] in child blocks of 128 B
@@ -49,6 +49,20 @@ struct __align__(16) TravRec {
 static_assert(sizeof(TravRec) == 32, "four records per 128-byte line");
 constexpr float OPEN_BAND = 4e-6f;  // relative half-width of the fp32 guard band around s^2/theta^2
 
+// One body = one 32-byte sector, so a gather by index costs one sector instead of one per component.
+struct __align__(16) Body {
+    double x, y, m;
+    unsigned int rank;    // insertion rank (position in the reference's view iteration)
+    unsigned int comp;    // LPE_HAS_MASS | LPE_HAS_VELOCITY | LPE_BOUNDARY | LPE_LIQUID
+};
+struct __align__(16) SBody {   // the same body at its Morton-sorted position
+    double x, y, m;
+    unsigned int rankcomp;   // rank | comp << 28
+    unsigned int idx;        // creation index
+};
+static_assert(sizeof(Body) == 32 && sizeof(SBody) == 32, "one sector per body");
+#define LPE_LEAF_FLAG 0x80000000u   // child[] entry of a single-body leaf: LPE_LEAF_FLAG | sorted position of the body
+
 // Per-node aggregate carried up the tree (exact sums; the quirk is applied only when a record is made). 64 bytes =
 // two sectors; it carries the first occupant's own mass and position so that no second lookup is needed.
 struct __align__(16) Agg {
@@ -83,6 +97,7 @@ struct StepConst {
     int do_drift;
     int n;                    // bodies
     int shard_rank, shard_n;  // multi-GPU block-cyclic ownership of sorted positions
+    int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
 };
 
 // Mass and centre of mass of a node as the traversal sees it, in real units.

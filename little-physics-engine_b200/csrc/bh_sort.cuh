@@ -16,26 +16,28 @@ constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 
 // table[d * numTiles + tile] = number of elements of `tile` whose digit is d; totals[d] += the same.
+// `bins` is 256, or 512 for a 9-bit top digit (a 33-bit key then needs 4 passes instead of 5).
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_count(const unsigned long long* __restrict__ keys, int n, int shift, int numTiles,
+k_sort_count(const unsigned long long* __restrict__ keys, int n, int shift, int bins, int numTiles,
              unsigned int* __restrict__ table, unsigned int* __restrict__ totals) {
-    __shared__ unsigned int hist[256];
+    __shared__ unsigned int hist[512];
     const int tid = threadIdx.x;
     hist[tid] = 0;
+    hist[tid + 256] = 0;
     __syncthreads();
+    const unsigned int dmask = (unsigned int)bins - 1u;
     const long long base = (long long)blockIdx.x * SORT_TILE;
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const long long i = base + r * SORT_THREADS + tid;
-        if (i < n) {
-            const unsigned int d = (unsigned int)(keys[i] >> shift) & 255u;
-            atomicAdd(&hist[d], 1u);
-        }
+        if (i < n) atomicAdd(&hist[(unsigned int)(keys[i] >> shift) & dmask], 1u);
     }
     __syncthreads();
-    const unsigned int c = hist[tid];
-    table[(size_t)tid * numTiles + blockIdx.x] = c;
-    if (c) atomicAdd(&totals[tid], c);
+    for (int d = tid; d < bins; d += SORT_THREADS) {
+        const unsigned int c = hist[d];
+        table[(size_t)d * numTiles + blockIdx.x] = c;
+        if (c) atomicAdd(&totals[d], c);
+    }
 }
 
 // One block per digit: exclusive scan of that digit's row of the table, offset by the count of all smaller digits.
@@ -45,8 +47,8 @@ k_sort_scan(unsigned int* __restrict__ table, const unsigned int* __restrict__ t
     __shared__ unsigned int s_base;
     const int d = blockIdx.x;
     const int tid = threadIdx.x;
-    // base = sum of totals of smaller digits
-    sh[tid] = (tid < d) ? totals[tid] : 0u;
+    // base = sum of totals of smaller digits (up to 512 digits)
+    sh[tid] = ((tid < d) ? totals[tid] : 0u) + ((tid + 256 < d) ? totals[tid + 256] : 0u);
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
         if (tid < o) sh[tid] += sh[tid + o];
@@ -79,15 +81,18 @@ k_sort_scan(unsigned int* __restrict__ table, const unsigned int* __restrict__ t
     }
 }
 
+template <int BINS>
 __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
                unsigned long long* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
                int numTiles, const unsigned int* __restrict__ table) {
-    __shared__ unsigned int cnt[SORT_WARPS][256];
+    __shared__ unsigned int cnt[SORT_WARPS][BINS];
+    constexpr int bins = BINS;
     const int tid = threadIdx.x;
     const int w = tid >> 5;
     const int lane = tid & 31;
-    for (int k = tid; k < SORT_WARPS * 256; k += SORT_THREADS) (&cnt[0][0])[k] = 0;
+    const unsigned int dmask = (unsigned int)bins - 1u;
+    for (int k = tid; k < SORT_WARPS * BINS; k += SORT_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
 
     const long long wbase = (long long)blockIdx.x * SORT_TILE + (long long)w * (SORT_ITEMS * 32);
@@ -106,7 +111,7 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         const bool ok = i < n;
-        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & 255u) : 256u;
+        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & dmask) : 0xFFFFu;
         const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
         const unsigned int before = __popc(peers & lt);
         const int leader = __ffs(peers) - 1;
@@ -120,13 +125,13 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
         __syncwarp();
     }
     __syncthreads();
-    {
-        // thread tid owns digit tid: turn per-warp counts into global output offsets
-        unsigned int run = table[(size_t)tid * numTiles + blockIdx.x];
+    for (int d = tid; d < bins; d += SORT_THREADS) {
+        // thread owns digit d: turn per-warp counts into global output offsets
+        unsigned int run = table[(size_t)d * numTiles + blockIdx.x];
 #pragma unroll
         for (int ww = 0; ww < SORT_WARPS; ++ww) {
-            const unsigned int c = cnt[ww][tid];
-            cnt[ww][tid] = run;
+            const unsigned int c = cnt[ww][d];
+            cnt[ww][d] = run;
             run += c;
         }
     }
@@ -135,7 +140,7 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         if (i < n) {
-            const unsigned int d = (unsigned int)(key[r] >> shift) & 255u;
+            const unsigned int d = (unsigned int)(key[r] >> shift) & dmask;
             const unsigned int dst = cnt[w][d] + rk[r];
             keysOut[dst] = key[r];
             valsOut[dst] = val[r];

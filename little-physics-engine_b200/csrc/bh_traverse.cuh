@@ -33,15 +33,12 @@ struct TravArgs {
     const TravRec* rec;        // child blocks
     const Agg* agg;            // [preorder] exact sums: fp64 centre / mass for the rare exact test and STRICT mode
     const NodeMeta* meta;      // [preorder]
-    const double2* spos;
-    const double* smass;
-    const unsigned int* sidx;
+    const SBody* sbody;             // [sorted body] position, mass, rank|comp, creation index
     const unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf (depth-first kernel)
     const unsigned int* selfslot;   // [sorted body] record slot of its own leaf (two-phase kernel)
     const unsigned int* recnode;    // [record slot] pre-order index
     const unsigned int* chunk_list; // depth-first kernel only: when set, process these chunks (two-phase overflow)
-    const unsigned char* comp;
-    double2* pos;
+    Body* body;                     // state, creation order (positions are updated in place by the drift)
     double2* vel;
     double4* xchg_send;      // sharded mode: packed (x,y,vx,vy) of the own slice
     unsigned int* cntAcc;    // STATS only, creation order
@@ -106,14 +103,16 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
         const bool valid = i < c.n;
 
-        unsigned int b = 0, self = LPE_NONE;
-        unsigned char cm = 0;
+        unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
+        double bodyMass = 1.0;
         if (valid) {
-            b = a.sidx[i];
-            cm = a.comp[b];
-            p = a.spos[i];
-            self = a.selfnode[i];
+            const SBody sb = a.sbody[i];
+            b = sb.idx;
+            cm = sb.rankcomp >> 28;
+            p = make_double2(sb.x, sb.y);
+            bodyMass = sb.m;
+            if (c.need_self) self = a.selfnode[i];
         }
         // bodyView of update(): Position + Velocity + Mass, not Boundary (barnes_hut.cpp:89)
         const bool target = valid && (cm & 1u) && (cm & 2u) && !(cm & 4u);
@@ -127,6 +126,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         int d = 0, k = 0;
         unsigned int j = 0;              // pre-order index of the node at frame d, slot k
         unsigned long long kstack = 0;   // 2 bits per depth: slot being processed there
+        unsigned long long cstack = 0;   // 2 bits per depth: (number of children in that frame) - 1
         const bool alive = n_nodes != 0;
         if (alive) load_block(a.rec, 0u, frames, lane);
 
@@ -145,8 +145,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 const TravRec* R = frames + (d * 4 + k);
                 const float4 C = R->c;
                 const float4 Bq = *reinterpret_cast<const float4*>(&R->gm);   // gm, open_t, skip, cblock
-                const unsigned int skip = __float_as_uint(Bq.z);
-                if (k == 4 || skip == 0u) {
+                const unsigned int cb = __float_as_uint(Bq.w);
+                // a childless node (leaf / terminal) is followed in pre-order by the next index
+                const unsigned int skip = cb ? __float_as_uint(Bq.z) : j + 1u;
+                if (k > (int)((cstack >> (2 * d)) & 3ull)) {
                     // child block finished: flush the fp32 partial sums and return to the parent's next slot
                     AX += (double)ax; AY += (double)ay;
                     ax = 0.f; ay = 0.f;
@@ -183,9 +185,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 if (anyopen) {
                     kstack = (kstack & ~(3ull << (2 * d))) | ((unsigned long long)k << (2 * d));
                     ++d;
+                    cstack = (cstack & ~(3ull << (2 * d))) | ((unsigned long long)(cb & 3u) << (2 * d));
                     k = 0;
                     ++j;   // first child follows its parent in pre-order
-                    load_block(a.rec, __float_as_uint(Bq.w) >> 2, frames + d * 4, lane);
+                    load_block(a.rec, cb >> 2, frames + d * 4, lane);
                 } else {
                     j = skip;
                     ++k;
@@ -200,21 +203,28 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         } else {
             // STRICT: the reference's arithmetic, operation for operation (barnes_hut.cpp:257-286), in real units.
             // Pre-order == the reference's nw,ne,sw,se recursion order, so the velocity sum has the same order too.
-            const double m = valid ? a.smass[i] : 1.0;
+            const double m = bodyMass;
             const double eps2 = __dmul_rn(c.eps, c.eps);
             while (alive) {
                 const TravRec* R = frames + (d * 4 + k);
                 const float open_t = R->open_t;
-                const unsigned int skip = R->skip, cblock = R->cblock;
-                if (k == 4 || skip == 0u) {
+                const unsigned int cblock = R->cblock;
+                const unsigned int skip = cblock ? R->skip : j + 1u;
+                if (k > (int)((cstack >> (2 * d)) & 3ull)) {
                     if (d == 0) break;
                     --d;
                     k = (int)((kstack >> (2 * d)) & 3ull) + 1;
                     continue;
                 }
-                const int level = a.meta[j].level;
+                const NodeMeta mj = a.meta[j];
+                const int level = mj.level;
                 double M, cx, cy;
-                node_centre(a.agg[j], level, c.quirk, M, cx, cy);
+                if (level == -1) {   // single-body leaf: no aggregate is stored, the node is the body (meta.pad = its position)
+                    const SBody lb = a.sbody[mj.pad];
+                    M = lb.m; cx = lb.x; cy = lb.y;
+                } else {
+                    node_centre(a.agg[j], level, c.quirk, M, cx, cy);
+                }
                 const double dx = (cx * c.invS - pxs) * c.S, dy = (cy * c.invS - pys) * c.S;   // exact: S is a power of two
                 const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), eps2);
                 const bool active = j >= skipUntil;
@@ -242,6 +252,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 if (anyopen) {
                     kstack = (kstack & ~(3ull << (2 * d))) | ((unsigned long long)k << (2 * d));
                     ++d;
+                    cstack = (cstack & ~(3ull << (2 * d))) | ((unsigned long long)(cblock & 3u) << (2 * d));
                     k = 0;
                     ++j;
                     load_block(a.rec, cblock >> 2, frames + d * 4, lane);
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 a.xchg_send[slot] = make_double4(p.x, p.y, v.x, v.y);
             } else {
                 if (target) a.vel[b] = v;
-                if (c.do_drift && mover) a.pos[b] = p;
+                if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;
             }
             if (STATS) {
                 a.cntAcc[b] = nacc;

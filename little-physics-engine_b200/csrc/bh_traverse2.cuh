@@ -98,14 +98,14 @@ __global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravAr
         const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
         const bool valid = i < c.n;
 
-        unsigned int b = 0, self = LPE_NONE;
-        unsigned char cm = 0;
+        unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
         if (valid) {
-            b = a.sidx[i];
-            cm = a.comp[b];
-            p = a.spos[i];
-            self = a.selfslot[i];
+            const SBody sb = a.sbody[i];
+            b = sb.idx;
+            cm = sb.rankcomp >> 28;
+            p = make_double2(sb.x, sb.y);
+            if (SELF) self = a.selfslot[i];
         }
         const bool target = valid && (cm & 1u) && (cm & 2u) && !(cm & 4u);   // barnes_hut.cpp:89
         const double pxs = p.x * c.invS, pys = p.y * c.invS;
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravAr
                 a.xchg_send[slotx] = make_double4(p.x, p.y, v.x, v.y);
             } else {
                 if (target) a.vel[b] = v;
-                if (c.do_drift && mover) a.pos[b] = p;
+                if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;
             }
             if (STATS) {
                 a.cntAcc[b] = target ? nacc : 0u;

@@ -47,10 +47,10 @@ struct lpe_bh_ctx {
     uint64_t xchg_chunk = 0;
 
     // state
-    double2 *pos = nullptr, *vel = nullptr;
-    double* mass = nullptr;
-    unsigned int* rank = nullptr;
-    unsigned char* comp = nullptr;
+    Body* body = nullptr;
+    double2* vel = nullptr;
+    unsigned int* rank_in = nullptr;   // staging of the caller's rank / component arrays
+    unsigned char* comp_in = nullptr;
     // staging
     double* tmp = nullptr;  // 4*cap doubles
     // sort
@@ -59,9 +59,8 @@ struct lpe_bh_ctx {
     unsigned int *table = nullptr, *totals = nullptr;
     int sorted_sel = 0;
     // sorted copies
-    double2* spos = nullptr;
-    double* smass = nullptr;
-    unsigned int *srank = nullptr, *selfnode = nullptr, *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
+    SBody* sbody = nullptr;
+    unsigned int *selfnode = nullptr, *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
     // scans
     unsigned int *tileSums = nullptr, *headExcl = nullptr, *P = nullptr;
     // terminals
@@ -133,11 +132,11 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     const int sortTiles = cdiv((long long)cap, SORT_TILE);
     const int scanTiles = cdiv((long long)cap + 1, SCAN_TILE);
     int rc = 0;
-    rc |= dalloc(c, c->pos, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->mass, cap) | dalloc(c, c->rank, cap) |
-          dalloc(c, c->comp, cap) | dalloc(c, c->tmp, 4 * cap);
+    rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) |
+          dalloc(c, c->tmp, 4 * cap);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
-          dalloc(c, c->vals[1], cap) | dalloc(c, c->table, (size_t)256 * sortTiles) | dalloc(c, c->totals, 256 * 8);
-    rc |= dalloc(c, c->spos, cap) | dalloc(c, c->smass, cap) | dalloc(c, c->srank, cap) | dalloc(c, c->selfnode, cap) |
+          dalloc(c, c->vals[1], cap) | dalloc(c, c->table, (size_t)512 * sortTiles) | dalloc(c, c->totals, 512 * 8);
+    rc |= dalloc(c, c->sbody, cap) | dalloc(c, c->selfnode, cap) |
           dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
     rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
@@ -177,26 +176,35 @@ __global__ void k_unpack2(int n, const double2* __restrict__ in, double* __restr
         b[i] = v.y;
     }
 }
-__global__ void k_default_meta(int n, unsigned int* __restrict__ rank, unsigned char* __restrict__ comp, int setRank,
-                               int setComp) {
+// x, y, m (+ optional rank / component arrays) -> one 32-byte Body per entity
+__global__ void k_pack_body(int n, const double* __restrict__ x, const double* __restrict__ y,
+                            const double* __restrict__ m, const unsigned int* __restrict__ rank,
+                            const unsigned char* __restrict__ comp, Body* __restrict__ body) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        // EnTT iterates the leading pool back to front: newest entity is inserted first
-        if (setRank) rank[i] = (unsigned int)(n - 1 - i);
-        if (setComp) comp[i] = (unsigned char)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
-    }
+    if (i >= n) return;
+    Body b;
+    b.x = x[i]; b.y = y[i]; b.m = m[i];
+    // EnTT iterates the leading pool back to front: newest entity is inserted first
+    b.rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
+    b.comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+    body[i] = b;
 }
-__global__ void k_init_self(int n, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot) {
+__global__ void k_set_pos(int n, const double* __restrict__ x, const double* __restrict__ y, Body* __restrict__ body) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) *reinterpret_cast<double2*>(&body[i].x) = make_double2(x[i], y[i]);
+}
+__global__ void k_get_pos(int n, const Body* __restrict__ body, double* __restrict__ x, double* __restrict__ y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        selfnode[i] = LPE_NONE;
-        selfslot[i] = LPE_NONE;
+        const double2 v = *reinterpret_cast<const double2*>(&body[i].x);
+        x[i] = v.x;
+        y[i] = v.y;
     }
 }
 
 // sharded mode: every rank's packed slice -> state arrays (creation order)
 __global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, const unsigned int* __restrict__ sidx,
-                               const double4* __restrict__ recv, double2* __restrict__ pos,
+                               const double4* __restrict__ recv, Body* __restrict__ body,
                                double2* __restrict__ vel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -205,30 +213,30 @@ __global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, cons
     const unsigned long long slot = (unsigned long long)lblock * LPE_SHARD_BLOCK + ((unsigned int)i % LPE_SHARD_BLOCK);
     const double4 v = recv[(unsigned long long)r * chunk + slot];
     const unsigned int b = sidx[i];
-    pos[b] = make_double2(v.x, v.y);
+    *reinterpret_cast<double2*>(&body[b].x) = make_double2(v.x, v.y);
     vel[b] = make_double2(v.z, v.w);
 }
 
 // Direct O(N^2) sum in fp64 with the reference's force law (barnes_hut.cpp:257-282), tiled through shared memory.
 __global__ void __launch_bounds__(256)
-k_direct(int n, const double2* __restrict__ pos, const double* __restrict__ mass,
-         const unsigned char* __restrict__ comp, double U, double eps2, double G, int first, int count,
+k_direct(int n, const Body* __restrict__ body, double U, double eps2, double G, int first, int count,
          double* __restrict__ ax, double* __restrict__ ay) {
     __shared__ double sx[256], sy[256], sm[256];
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = first + k;
     double2 p = make_double2(0.0, 0.0);
-    if (k < count) p = pos[i];
+    if (k < count) p = make_double2(body[i].x, body[i].y);
     double accx = 0.0, accy = 0.0;
     for (int base = 0; base < n; base += 256) {
         const int j = base + threadIdx.x;
         double2 q = make_double2(0.0, 0.0);
         double m = 0.0;
         if (j < n) {
-            const unsigned char cm = comp[j];
-            q = pos[j];
+            const Body bj = body[j];
+            const unsigned int cm = bj.comp;
+            q = make_double2(bj.x, bj.y);
             const bool src = (cm & 1u) && !(cm & 4u) && q.x >= 0.0 && q.x < U && q.y >= 0.0 && q.y < U;
-            m = src ? mass[j] : 0.0;
+            m = src ? bj.m : 0.0;
         }
         __syncthreads();
         sx[threadIdx.x] = q.x; sy[threadIdx.x] = q.y; sm[threadIdx.x] = m;
@@ -303,6 +311,9 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     k.n = (int)c->n;
     k.shard_rank = c->shard_rank;
     k.shard_n = c->shard_n;
+    // the body's-own-leaf bookkeeping is only needed when a self interaction would not vanish by itself (eps == 0)
+    // or when interactions are counted
+    k.need_self = ((c->instr & 2) || !((float)k.eps2s > 0.0f)) ? 1 : 0;
     return 0;
 }
 
@@ -324,27 +335,38 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     cudaStream_t st = c->stream;
     const bool timing = c->instr & 1;
     const bool stats = c->instr & 2;
-    const int passes = (2 * k.D + 1 + 7) / 8;
+    // 8-bit digits; a key of 8p+1 bits (33 for D = 16) gets a 9-bit top digit instead of one more pass
+    const int keyBits = 2 * k.D + 1;
+    int passes = (keyBits + 7) / 8;
+    int topBits = keyBits - 8 * (passes - 1);
+    if (passes > 1 && topBits == 1) { --passes; topBits = 9; }
+    if (topBits < 8) topBits = 8;
     const int sortTiles = cdiv(n, SORT_TILE);
     const int g256 = cdiv(n, 256);
 
     if (timing) cudaEventRecord(c->ev[0], st);
     CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), st));
-    CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * 256 * passes, st));
+    CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * 512 * passes, st));
     CU_TRY(c, cudaMemsetAsync(c->mask, 0, sizeof(unsigned int) * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->levelMeta, 0, sizeof(unsigned int) * 3 * 32, st));
 
-    k_keygen<<<g256, 256, 0, st>>>(k, c->pos, c->mass, c->comp, c->keys[0], c->vals[0], c->scal);
+    k_keygen<<<g256, 256, 0, st>>>(k, c->body, c->keys[0], c->vals[0], c->scal);
     if (timing) cudaEventRecord(c->ev[1], st);
 
     int sel = 0;
     for (int ps = 0; ps < passes; ++ps) {
         const int shift = 8 * ps;
-        k_sort_count<<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], n, shift, sortTiles, c->table, c->totals + 256 * ps);
-        k_sort_scan<<<256, 256, 0, st>>>(c->table, c->totals + 256 * ps, sortTiles);
-        k_sort_scatter<<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                            n, shift, sortTiles, c->table);
+        const int bins = (ps == passes - 1) ? (1 << topBits) : 256;
+        unsigned int* totals = c->totals + 512 * ps;
+        k_sort_count<<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], n, shift, bins, sortTiles, c->table, totals);
+        k_sort_scan<<<bins, 256, 0, st>>>(c->table, totals, sortTiles);
+        if (bins == 512)
+            k_sort_scatter<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1],
+                                                                     c->vals[sel ^ 1], n, shift, sortTiles, c->table);
+        else
+            k_sort_scatter<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1],
+                                                                     c->vals[sel ^ 1], n, shift, sortTiles, c->table);
         sel ^= 1;
     }
     c->sorted_sel = sel;
@@ -352,18 +374,17 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     const unsigned int* sidx = c->vals[sel];
     if (timing) cudaEventRecord(c->ev[2], st);
 
-    k_gather<<<g256, 256, 0, st>>>(n, sidx, c->pos, c->mass, c->rank, c->spos, c->smass, c->srank);
-    k_init_self<<<g256, 256, 0, st>>>(n, c->selfnode, c->selfslot);
+    k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot);
     device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
     k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
     k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, levelCount, c->scal);
     device_scan(c, MaskPop{c->mask, c->scal}, n, c->P, nullptr);
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
-    Topo topo{c->tnode, c->child, c->meta, c->levelList, levelBase, levelCursor};
-    k_topology<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
-    NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot};
-    k_agg_terminals<<<g256, 256, 0, st>>>(k, c->tfirst, c->tnode, c->spos, c->smass, c->srank, no, c->selfnode, c->scal);
+    Topo topo{c->tnode, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
+              c->selfnode, c->selfslot, c->rec, c->recnode};
+    k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
+    NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->sbody};
     // branching cells, deepest level first; the handful of cells of levels <= 5 share one single-block launch
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -382,8 +403,8 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (timing) cudaEventRecord(c->ev[3], st);
 
     TravArgs ta{};
-    ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta; ta.spos = c->spos; ta.smass = c->smass;
-    ta.sidx = sidx; ta.selfnode = c->selfnode; ta.comp = c->comp; ta.pos = c->pos; ta.vel = c->vel;
+    ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta; ta.sbody = c->sbody;
+    ta.selfnode = c->selfnode; ta.body = c->body; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
     const unsigned int own = (nblocks + (unsigned int)c->shard_n - 1u - (unsigned int)c->shard_rank) / (unsigned int)c->shard_n;
@@ -394,7 +415,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (p.precision == LPE_PREC_FAST && !c->force_dfs) {
         // two-phase kernel, then the depth-first kernel for the (normally zero) chunks whose frontier overflowed
         const size_t smem = sizeof(T2Warp) * T2_WARPS;
-        const bool selfT = stats || !(k.eps2s > 0.0) || (float)k.eps2s == 0.0f;
+        const bool selfT = k.need_self != 0;
         static bool attr_set = false;
         if (!attr_set) {
             cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -426,9 +447,9 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     }
     if (timing) cudaEventRecord(c->ev[4], st);
     CU_TRY(c, cudaGetLastError());
-    // keygen, 3 per sort pass, gather, init_self, 2 scans of 3, terminals, witness, level_scan, topology,
-    // agg_terminals, one per level above Ltop, agg_top, traverse
-    c->launches += 1 + 3 * (uint64_t)passes + 2 + 3 + 2 + 3 + 3 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
+    // keygen, 3 per sort pass, gather, 2 scans of 3, terminals, witness, level_scan, topology,
+    // one per level above Ltop, agg_top, traverse (+ overflow pass)
+    c->launches += 1 + 3 * (uint64_t)passes + 1 + 3 + 2 + 3 + 2 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
@@ -509,17 +530,16 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
     cudaStream_t st = c->stream;
     const size_t bytes = sizeof(double) * n;
     const int g = cdiv((long long)n, 256);
-    double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
+    double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap;
     CU_TRY(c, cudaMemcpyAsync(t0, x, bytes, cudaMemcpyHostToDevice, st));
     CU_TRY(c, cudaMemcpyAsync(t1, y, bytes, cudaMemcpyHostToDevice, st));
-    k_pack2<<<g, 256, 0, st>>>((int)n, t0, t1, c->pos);
-    if (vx) CU_TRY(c, cudaMemcpyAsync(t2, vx, bytes, cudaMemcpyHostToDevice, st));
-    if (vy) CU_TRY(c, cudaMemcpyAsync(t3, vy, bytes, cudaMemcpyHostToDevice, st));
-    k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t2 : nullptr, vy ? t3 : nullptr, c->vel);
-    CU_TRY(c, cudaMemcpyAsync(c->mass, m, bytes, cudaMemcpyHostToDevice, st));
-    if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
-    if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp, comp, n, cudaMemcpyHostToDevice, st));
-    if (!rank || !comp) k_default_meta<<<g, 256, 0, st>>>((int)n, c->rank, c->comp, rank ? 0 : 1, comp ? 0 : 1);
+    CU_TRY(c, cudaMemcpyAsync(t2, m, bytes, cudaMemcpyHostToDevice, st));
+    if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank_in, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+    if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp_in, comp, n, cudaMemcpyHostToDevice, st));
+    k_pack_body<<<g, 256, 0, st>>>((int)n, t0, t1, t2, rank ? c->rank_in : nullptr, comp ? c->comp_in : nullptr, c->body);
+    if (vx) CU_TRY(c, cudaMemcpyAsync(t0, vx, bytes, cudaMemcpyHostToDevice, st));
+    if (vy) CU_TRY(c, cudaMemcpyAsync(t1, vy, bytes, cudaMemcpyHostToDevice, st));
+    k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t0 : nullptr, vy ? t1 : nullptr, c->vel);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -532,7 +552,7 @@ int lpe_bh_upload_positions(lpe_bh_ctx* c, const double* x, const double* y) {
     double *t0 = c->tmp, *t1 = c->tmp + c->cap;
     CU_TRY(c, cudaMemcpyAsync(t0, x, bytes, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(t1, y, bytes, cudaMemcpyHostToDevice, c->stream));
-    k_pack2<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t0, t1, c->pos);
+    k_set_pos<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t0, t1, c->body);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -569,7 +589,7 @@ int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy)
         const int g = cdiv((long long)n, 256);
         double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
         if (x || y) {
-            k_unpack2<<<g, 256, 0, st>>>((int)n, c->pos, t0, t1);
+            k_get_pos<<<g, 256, 0, st>>>((int)n, c->body, t0, t1);
             if (x) CU_TRY(c, cudaMemcpyAsync(x, t0, bytes, cudaMemcpyDeviceToHost, st));
             if (y) CU_TRY(c, cudaMemcpyAsync(y, t1, bytes, cudaMemcpyDeviceToHost, st));
         }
@@ -647,17 +667,26 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     std::vector<NodeMeta> mt(nn);
     std::vector<Agg> ag(nn);
     std::vector<unsigned long long> tk(h.n_term);
+    std::vector<SBody> sb(n);
     CU_TRY(c, cudaMemcpy(mt.data(), c->meta, sizeof(NodeMeta) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(ag.data(), c->agg, sizeof(Agg) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(tk.data(), c->tkey, 8 * (size_t)h.n_term, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(sb.data(), c->sbody, sizeof(SBody) * n, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < nn; ++i) {
+        Agg a = ag[i];
+        if (mt[i].level == -1) {   // single-body leaves keep no aggregate on the device: rebuild it from the body
+            const unsigned int pos = mt[i].pad;
+            const SBody& s0 = sb[pos];
+            a.m = s0.m; a.sx = s0.m * s0.x; a.sy = s0.m * s0.y; a.mf = s0.m; a.xf = s0.x; a.yf = s0.y;
+            a.frank = s0.rankcomp & 0x0FFFFFFFu; a.fidx = pos; a.count = 1; a.small = 0;
+        }
         double M, cx, cy;
-        node_centre(ag[i], mt[i].level, c->last_c.quirk, M, cx, cy);
+        node_centre(a, mt[i].level, c->last_c.quirk, M, cx, cy);
         if (o->node_level) o->node_level[i] = mt[i].level;
         if (o->node_key) o->node_key[i] = tk[mt[i].start];
         if (o->node_skip) o->node_skip[i] = mt[i].skip;
-        if (o->node_first) o->node_first[i] = sidx[ag[i].fidx];
-        if (o->node_count) o->node_count[i] = ag[i].count;
+        if (o->node_first) o->node_first[i] = sidx[a.fidx];
+        if (o->node_count) o->node_count[i] = a.count;
         if (o->node_mass) o->node_mass[i] = M;
         if (o->node_comx) o->node_comx[i] = cx;
         if (o->node_comy) o->node_comy[i] = cy;
@@ -681,7 +710,7 @@ int lpe_bh_direct_accel(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t first, u
     if (count == 0) return 0;
     CU_TRY(c, cudaSetDevice(c->device));
     double *dax = c->tmp, *day = c->tmp + c->cap;
-    k_direct<<<cdiv((long long)count, 256), 256, 0, c->stream>>>((int)c->n, c->pos, c->mass, c->comp, p->universe_size,
+    k_direct<<<cdiv((long long)count, 256), 256, 0, c->stream>>>((int)c->n, c->body, p->universe_size,
                                                                   p->softening * p->softening, p->G, (int)first,
                                                                   (int)count, dax, day);
     CU_TRY(c, cudaGetLastError());
@@ -727,7 +756,7 @@ int lpe_bh_step_finish(lpe_bh_ctx* c) {
     if (!c->have_step) return fail(c, "lpe_bh_step_begin has not run");
     CU_TRY(c, cudaSetDevice(c->device));
     k_xchg_scatter<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->shard_n, c->xchg_chunk,
-                                                                       c->vals[c->sorted_sel], c->xchg_recv, c->pos,
+                                                                       c->vals[c->sorted_sel], c->xchg_recv, c->body,
                                                                        c->vel);
     CU_TRY(c, cudaGetLastError());
     return 0;
@@ -799,9 +828,8 @@ void lpe_bh_free_pinned(void* p) {
 int lpe_bh_get_device_view(lpe_bh_ctx* c, lpe_bh_device_view* o) {
     if (!c || !o) return 1;
     if (c->shard_n > 1 && c->n && ensure_xchg(c)) return 1;
-    o->pos = c->pos;
+    o->body = c->body;
     o->vel = c->vel;
-    o->mass = c->mass;
     o->xchg_send = c->xchg_send;
     o->xchg_recv = c->xchg_recv;
     o->n = c->n;

@@ -60,7 +60,7 @@ class TreeDump(C.Structure):
 
 class DeviceView(C.Structure):
     _fields_ = [
-        ("pos", C.c_void_p), ("vel", C.c_void_p), ("mass", C.c_void_p), ("xchg_send", C.c_void_p),
+        ("body", C.c_void_p), ("vel", C.c_void_p), ("xchg_send", C.c_void_p),
         ("xchg_recv", C.c_void_p), ("n", C.c_uint64), ("xchg_chunk", C.c_uint64),
     ]
 

@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(lpe_bh.Params) == 7 * 8 + 4 * 4
     assert C.sizeof(lpe_bh.Stats) == 16 * 8 + 2 * 4 + 5 * 4 + 4  # padded to 8
     assert C.sizeof(lpe_bh.TreeDump) == 10 * 8
-    assert C.sizeof(lpe_bh.DeviceView) == 7 * 8
+    assert C.sizeof(lpe_bh.DeviceView) == 6 * 8
 
 
 def test_workloads_are_deterministic_and_in_bounds():
