@@ -42,6 +42,9 @@ WORKLOADS = {
     "c4": dict(kind="two_galaxies", n=4_000_000, seed=44, name="C4: 4M-body two-galaxy collision, theta=0.5, U=2^20, eps=U/2^14"),
 }
 FLOPS_PER_INTERACTION = 20.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_traverse2 launch, from the committed ncu --set full capture
+# (profiles/r01_ncu_traverse2_c2.txt); the kernel is not DRAM-bound, the figure only shows that nothing is re-read.
+NCU_TRAFFIC_BYTES = {"c2": 190.9e6}
 HBM_BYTES_PER_BODY = 340.0     # keygen + sort + gather + node arrays, 64-bit keys
 
 
@@ -65,7 +68,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -77,12 +80,17 @@ class ClockSampler:
             self.t.append(time.time())
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_first(self, timeout=5.0):
+        t0 = time.time()
+        while self.proc and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
-        sel = [r for r, t in zip(self.rows, self.t) if t0 - 0.05 <= t <= t1 + 0.05] or self.rows
+        sel = [r for r, t in zip(self.rows, self.t) if t0 - 0.03 <= t <= t1 + 0.03] or self.rows
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in sel:
@@ -229,12 +237,15 @@ def our_arm(args, wl, rank, world, local_rank):
             bh.step_finish()
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
+    t_busy0 = time.time()
     for _ in range(warmup):
         one_step()
     torch.cuda.synchronize()
     log(rank, "warm-up done")
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = bh.launch_count()
     if dist:
         dist.barrier()
@@ -261,7 +272,6 @@ def our_arm(args, wl, rank, world, local_rank):
         t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     ms_per_step = total_ms / args.steps
     value = n / (ms_per_step * 1e-3)
     ph = np.mean(np.array(phases), axis=0)
@@ -287,6 +297,11 @@ def our_arm(args, wl, rank, world, local_rank):
         e2e = {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "path": "multi-GPU runs keep bodies resident; host round trip measured at N=1 only"}
 
+    # clocks / throttle reasons sampled by nvidia-smi every 20 ms from the first warm-up step to the end of the
+    # end-to-end loop (the timed region alone is only tens of milliseconds long)
+    clocks = sampler.stop(t_busy0, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + e2e loop"
     if rank == 0:
         trav_ms = float(ph[3])
         flops = FLOPS_PER_INTERACTION * interactions / max(world, 1)    # this rank's share of the targets
@@ -304,8 +319,9 @@ def our_arm(args, wl, rank, world, local_rank):
                        f"{world} GPUs: replicated tree, block-cyclic Morton-slice traversal, NCCL allgather of (x,y,vx,vy)"},
             "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": trav_ms},
             "interactions_per_body": interactions / n,
-            "roofline": {"bound": "fp32_fma", "kernel": "k_traverse", "achieved": achieved, "peak": fma_peak,
-                         "unit": "TFLOP/s", "frac": achieved / fma_peak if fma_peak else None, "traffic": None,
+            "roofline": {"bound": "fp32_fma", "kernel": "k_traverse2 (two-phase traversal)", "achieved": achieved,
+                         "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak if fma_peak else None,
+                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload or ("c2" if world == 1 else "c3")),
                          "peak_source": "lpe_bh_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                          "algorithmic": f"{FLOPS_PER_INTERACTION:.0f} flop x {interactions} accepted interactions / launch"},
             "roofline_hbm": {"bound": "hbm", "kernels": "k_keygen + k_sort_* + build kernels", "achieved": hbm_ach,
