@@ -86,7 +86,14 @@ __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
                unsigned long long* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
                int numTiles, const unsigned int* __restrict__ table) {
-    __shared__ unsigned int cnt[SORT_WARPS][BINS];
+    // The tile is first sorted by digit INSIDE shared memory, then written out: consecutive threads then store
+    // consecutive addresses within each digit's run, so every 32-byte sector written is fully used (a direct
+    // scatter from registers wrote 8-byte keys and 4-byte payloads to 32 different sectors per instruction).
+    __shared__ unsigned int cnt[SORT_WARPS][BINS];     // per-warp digit counts -> tile-local offsets
+    __shared__ unsigned int dbase[BINS];               // tile-local start of each digit's run
+    __shared__ unsigned int gbase[BINS];               // global start of this tile's run of each digit
+    __shared__ unsigned long long skey[SORT_TILE];
+    __shared__ unsigned int sval[SORT_TILE];
     constexpr int bins = BINS;
     const int tid = threadIdx.x;
     const int w = tid >> 5;
@@ -95,7 +102,8 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
     for (int k = tid; k < SORT_WARPS * BINS; k += SORT_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
 
-    const long long wbase = (long long)blockIdx.x * SORT_TILE + (long long)w * (SORT_ITEMS * 32);
+    const long long tbase = (long long)blockIdx.x * SORT_TILE;
+    const long long wbase = tbase + (long long)w * (SORT_ITEMS * 32);
     unsigned long long key[SORT_ITEMS];
     unsigned int val[SORT_ITEMS];
     unsigned short rk[SORT_ITEMS];
@@ -125,15 +133,38 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
         __syncwarp();
     }
     __syncthreads();
+    // per digit: total in this tile, and the exclusive offsets of the warps inside the digit's run
     for (int d = tid; d < bins; d += SORT_THREADS) {
-        // thread owns digit d: turn per-warp counts into global output offsets
-        unsigned int run = table[(size_t)d * numTiles + blockIdx.x];
+        unsigned int run = 0;
 #pragma unroll
         for (int ww = 0; ww < SORT_WARPS; ++ww) {
             const unsigned int c = cnt[ww][d];
             cnt[ww][d] = run;
             run += c;
         }
+        dbase[d] = run;   // digit total for now
+        gbase[d] = table[(size_t)d * numTiles + blockIdx.x];
+    }
+    __syncthreads();
+    // exclusive scan of the digit totals (bins <= 512, 256 threads: two per thread, Hillis-Steele over pair sums)
+    {
+        __shared__ unsigned int pair[SORT_THREADS];
+        constexpr int PER = BINS / SORT_THREADS;   // 1 or 2
+        unsigned int v[PER];
+        unsigned int sum = 0;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { v[k] = dbase[tid * PER + k]; sum += v[k]; }
+        pair[tid] = sum;
+        __syncthreads();
+        for (int o = 1; o < SORT_THREADS; o <<= 1) {
+            const unsigned int t = (tid >= o) ? pair[tid - o] : 0u;
+            __syncthreads();
+            pair[tid] += t;
+            __syncthreads();
+        }
+        unsigned int run = pair[tid] - sum;
+#pragma unroll
+        for (int k = 0; k < PER; ++k) { dbase[tid * PER + k] = run; run += v[k]; }
     }
     __syncthreads();
 #pragma unroll
@@ -141,10 +172,19 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
         const long long i = wbase + r * 32 + lane;
         if (i < n) {
             const unsigned int d = (unsigned int)(key[r] >> shift) & dmask;
-            const unsigned int dst = cnt[w][d] + rk[r];
-            keysOut[dst] = key[r];
-            valsOut[dst] = val[r];
+            const unsigned int lp = dbase[d] + cnt[w][d] + rk[r];
+            skey[lp] = key[r];
+            sval[lp] = val[r];
         }
+    }
+    __syncthreads();
+    const int tileCount = (int)min((long long)SORT_TILE, (long long)n - tbase);
+    for (int j = tid; j < tileCount; j += SORT_THREADS) {
+        const unsigned long long kx = skey[j];
+        const unsigned int d = (unsigned int)(kx >> shift) & dmask;
+        const unsigned int dst = gbase[d] + ((unsigned int)j - dbase[d]);
+        keysOut[dst] = kx;
+        valsOut[dst] = sval[j];
     }
 }
 
