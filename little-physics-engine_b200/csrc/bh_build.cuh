@@ -260,7 +260,7 @@ __device__ __forceinline__ TravRec invalid_record() {
     return r;
 }
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
            const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P, Topo o, Scal* __restrict__ s) {
     __shared__ unsigned int cnt[32], base[32];

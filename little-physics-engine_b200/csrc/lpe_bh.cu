@@ -383,7 +383,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
     Topo topo{c->tnode, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
               c->selfnode, c->selfslot, c->rec, c->recnode};
-    k_topology<<<cdiv(n, 1024), 1024, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
+    k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
     NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->sbody};
     // branching cells, deepest level first; the handful of cells of levels <= 5 share one single-block launch
     int sms = 148;
