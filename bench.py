@@ -152,7 +152,7 @@ def reference_arm(args, wl, rank, world):
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def cpu_baseline_n1(wl):
@@ -195,6 +195,10 @@ def our_arm(args, wl, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dist = None
+    # NCCL prints its version banner on stdout; the contract is ONE JSON line there, so everything but the final
+    # print goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -299,6 +303,7 @@ def our_arm(args, wl, rank, world, local_rank):
 
     # clocks / throttle reasons sampled by nvidia-smi every 20 ms from the first warm-up step to the end of the
     # end-to-end loop (the timed region alone is only tens of milliseconds long)
+    log(rank, "timed region done")
     clocks = sampler.stop(t_busy0, time.time()) if sampler else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region + e2e loop"
@@ -332,7 +337,10 @@ def our_arm(args, wl, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_n1(wl)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        log(rank, "result printed")
     bh.close()
     if dist:
         dist.destroy_process_group()
