@@ -351,61 +351,94 @@ struct NodeOut {
     const SBody* sbody;
 };
 
-// one branching cell: sum the children (digit order), write their records into this cell's child block
-__device__ __forceinline__ void aggregate_cell(const StepConst& c, const NodeOut& o, unsigned int p,
-                                               const unsigned int* __restrict__ child, double msi) {
+// One branching cell, handled by a QUAD of lanes: lane q owns child slot q. The four child reads are independent
+// (4x the memory parallelism of one thread per cell), the four 32-byte records of the child block are written by four
+// neighbouring lanes (one 128-byte line), and the sums are combined with two shuffle steps: (c0 + c1) + (c2 + c3),
+// deterministic. `p` is uniform across the quad; lanes of a quad must call this together.
+__device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const NodeOut& o, unsigned int p,
+                                                    const unsigned int* __restrict__ child, double msi, int q,
+                                                    unsigned int quadShift, bool live) {
+    // every lane of the warp runs this (the ballot / shuffles use the full mask); quads past the end of the list
+    // carry live = false and neither read children nor store anything
     const NodeMeta mp = o.meta[p];
-    const unsigned int q = p - mp.start;
-    const uint4 ch = reinterpret_cast<const uint4*>(child)[q];
-    const unsigned int cs[4] = {ch.x, ch.y, ch.z, ch.w};
-    Agg b;
-    b.m = 0.0; b.sx = 0.0; b.sy = 0.0; b.mf = 0.0; b.xf = 0.0; b.yf = 0.0;
-    b.frank = 0xFFFFFFFFu; b.fidx = 0; b.count = 0; b.small = 1u;
-    TravRec* blk = o.rec + 4 * (size_t)(q + 1);
-    int r = 0;
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        const unsigned int ci = cs[g];
-        if (ci == LPE_NONE) continue;
-        const unsigned int slot = 4u * (q + 1u) + (unsigned int)r;
-        Agg a;
+    const unsigned int qd = p - mp.start;
+    const unsigned int ci = live ? child[(size_t)qd * 4 + q] : LPE_NONE;
+    const bool valid = ci != LPE_NONE;
+    Agg a;
+    a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
+    a.frank = 0xFFFFFFFFu; a.fidx = 0; a.count = 0; a.small = 1u;
+    int level = -1;
+    unsigned int skip = 0, cbi = 0, leafpos = LPE_NONE;
+    if (valid) {
         if (ci & LPE_LEAF_FLAG) {
             // a single-body leaf: read the body itself (one sector), no aggregate was ever stored for it
-            const unsigned int pos = ci & ~LPE_LEAF_FLAG;
-            a = body_agg(o.sbody[pos], pos, c.thr);
-            blk[r++] = make_record(c, a, -1, 0u, 0u, msi);
-            o.recnode[slot] = LPE_NONE;
-            if (c.need_self) o.selfslot[pos] = slot;
+            leafpos = ci & ~LPE_LEAF_FLAG;
+            a = body_agg(o.sbody[leafpos], leafpos, c.thr);
         } else {
             a = o.agg[ci];
             const NodeMeta mc = o.meta[ci];
-            blk[r++] = make_record(c, a, mc.level, mc.skip, (ci - mc.start) + 1u, msi);
-            o.recnode[slot] = ci;
+            level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + 1u;
         }
-        b.m += a.m; b.sx += a.sx; b.sy += a.sy;
-        if (a.frank < b.frank) { b.frank = a.frank; b.fidx = a.fidx; b.mf = a.mf; b.xf = a.xf; b.yf = a.yf; }
-        b.count += a.count;
-        b.small &= (a.small & 1u);
     }
-    b.small |= (unsigned int)(r - 1) << 1;   // children - 1, read back when this cell's own record is made
-    for (; r < 4; ++r) blk[r] = invalid_record();
-    o.agg[p] = b;
-    if (p == 0) {   // the root has no parent to write its record
-        o.rec[0] = make_record(c, b, mp.level, mp.skip, 1u, msi);
-        o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
-        o.recnode[0] = 0u;
+    const unsigned int vmask = (__ballot_sync(0xFFFFFFFFu, valid) >> quadShift) & 0xFu;
+    const unsigned int below = (1u << q) - 1u;
+    const unsigned int nvalid = __popc(vmask);
+    const unsigned int r = valid ? __popc(vmask & below) : nvalid + __popc(~vmask & below & 0xFu);
+    const unsigned int slot = 4u * (qd + 1u) + r;
+    if (valid) {
+        o.rec[slot] = make_record(c, a, level, skip, cbi, msi);
+        o.recnode[slot] = (leafpos != LPE_NONE) ? LPE_NONE : ci;
+        if (leafpos != LPE_NONE && c.need_self) o.selfslot[leafpos] = slot;
+    } else if (live) {
+        o.rec[slot] = invalid_record();
+    }
+    // quad reduction
+    a.small &= 1u;
+#pragma unroll
+    for (int sft = 1; sft <= 2; sft <<= 1) {
+        const double om = __shfl_xor_sync(0xFFFFFFFFu, a.m, sft), osx = __shfl_xor_sync(0xFFFFFFFFu, a.sx, sft);
+        const double osy = __shfl_xor_sync(0xFFFFFFFFu, a.sy, sft), omf = __shfl_xor_sync(0xFFFFFFFFu, a.mf, sft);
+        const double oxf = __shfl_xor_sync(0xFFFFFFFFu, a.xf, sft), oyf = __shfl_xor_sync(0xFFFFFFFFu, a.yf, sft);
+        const unsigned int ofr = __shfl_xor_sync(0xFFFFFFFFu, a.frank, sft), ofi = __shfl_xor_sync(0xFFFFFFFFu, a.fidx, sft);
+        const unsigned int ocn = __shfl_xor_sync(0xFFFFFFFFu, a.count, sft), osm = __shfl_xor_sync(0xFFFFFFFFu, a.small, sft);
+        // the lower lane of each pair adds (own + other) so that the order is the same on both sides
+        const bool lower = (q & sft) == 0;
+        a.m = lower ? a.m + om : om + a.m;
+        a.sx = lower ? a.sx + osx : osx + a.sx;
+        a.sy = lower ? a.sy + osy : osy + a.sy;
+        if (ofr < a.frank) { a.frank = ofr; a.fidx = ofi; a.mf = omf; a.xf = oxf; a.yf = oyf; }
+        a.count += ocn;
+        a.small &= osm;
+    }
+    if (q == 0 && live) {
+        a.small |= (nvalid - 1u) << 1;   // children - 1, read back when this cell's own record is made
+        o.agg[p] = a;
+        if (p == 0) {   // the root has no parent to write its record
+            o.rec[0] = make_record(c, a, mp.level, mp.skip, 1u, msi);
+            o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+            o.recnode[0] = 0u;
+        }
     }
 }
 
-// all branching cells of one level (children are at deeper levels: finished by earlier launches)
+// all branching cells of one level (children are at deeper levels: finished by earlier launches); 4 lanes per cell
 __global__ void __launch_bounds__(256)
 k_agg_level(StepConst c, int L, const unsigned int* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
             const unsigned int* __restrict__ levelCount, const unsigned int* __restrict__ child, NodeOut o,
             const Scal* __restrict__ s) {
     const unsigned int count = levelCount[L], base = levelBase[L];
     const double msi = mass_scale_inv(s->max_mass_bits);
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-        aggregate_cell(c, o, levelList[base + i], child, msi);
+    const int q = threadIdx.x & 3;
+    const unsigned int quadShift = (threadIdx.x & 31) & ~3u;
+    const unsigned int quads = (gridDim.x * blockDim.x) >> 2;
+    // whole warps stay in the loop together (the ballot inside needs all 32 lanes)
+    const unsigned int rounds = (count + quads - 1) / quads;
+    unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    for (unsigned int k = 0; k < rounds; ++k, i += quads) {
+        const bool live = i < count;
+        const unsigned int p = levelList[base + (live ? i : 0u)];
+        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, p, child, msi, q, quadShift, live);
+    }
 }
 
 // the few cells of levels Ltop..0 in one block (a level has at most 4^L cells), one __syncthreads per level
@@ -414,10 +447,18 @@ k_agg_top(StepConst c, int Ltop, const unsigned int* __restrict__ levelList, con
           const unsigned int* __restrict__ levelCount, const unsigned int* __restrict__ child, NodeOut o,
           const Scal* __restrict__ s) {
     const double msi = mass_scale_inv(s->max_mass_bits);
+    const int q = threadIdx.x & 3;
+    const unsigned int quadShift = (threadIdx.x & 31) & ~3u;
+    const unsigned int quads = blockDim.x >> 2;
     for (int L = Ltop; L >= 0; --L) {
         const unsigned int count = levelCount[L], base = levelBase[L];
-        for (unsigned int i = threadIdx.x; i < count; i += blockDim.x)
-            aggregate_cell(c, o, levelList[base + i], child, msi);
+        const unsigned int rounds = (count + quads - 1) / quads;
+        unsigned int i = threadIdx.x >> 2;
+        for (unsigned int k = 0; k < rounds; ++k, i += quads) {
+            const bool live = i < count;
+            const unsigned int p = levelList[base + (live ? i : 0u)];
+            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, p, child, msi, q, quadShift, live);
+        }
         __syncthreads();
     }
 }

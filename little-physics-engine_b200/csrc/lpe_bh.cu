@@ -394,7 +394,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         // a level holds at most min(4^L, n/2) cells
         long long maxCells = (L < 15) ? (1ll << (2 * L)) : (long long)n;
         if (maxCells > n) maxCells = n;
-        int grid = cdiv(maxCells, 256);
+        int grid = cdiv(maxCells * 4, 256);   // four lanes per cell
         if (grid > sms * 8) grid = sms * 8;
         k_agg_level<<<grid, 256, 0, st>>>(k, L, c->levelList, levelBase, levelCount, c->child, no, c->scal);
         ++levelLaunches;
