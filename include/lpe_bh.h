@@ -100,7 +100,8 @@ const char* lpe_bh_last_error(const lpe_bh_ctx* ctx); /* ctx may be NULL: last c
 /* Run all work of this context on an existing CUDA stream (cudaStream_t as void*); NULL restores the context's own stream. */
 int  lpe_bh_set_stream(lpe_bh_ctx* ctx, void* cuda_stream);
 /* flags: bit0 = per-phase CUDA-event timing, bit1 = count interactions/visits (slower; parity tests only),
- *        bit2 = FAST precision uses the depth-first kernel instead of the two-phase kernel (A/B testing) */
+ *        bit2 = FAST precision uses the depth-first kernel instead of the two-phase kernel (A/B testing),
+ *        bit3 = the two-phase kernel hands every chunk to its overflow path (tests of that path) */
 int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
 
 /* Stage bodies into device SoA buffers. rank[i] = position of body i in the iteration of

@@ -98,6 +98,7 @@ struct StepConst {
     int n;                    // bodies
     int shard_rank, shard_n;  // multi-GPU block-cyclic ownership of sorted positions
     int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
+    int test_overflow;        // tests only: pretend every two-phase frontier overflows
 };
 
 // Mass and centre of mass of a node as the traversal sees it, in real units.

@@ -116,10 +116,10 @@ __global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravAr
         unsigned int kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // STATS: A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes
         double AX = 0.0, AY = 0.0;
         float ax = 0.f, ay = 0.f;
-        bool overflow = false;
+        bool overflow = c.test_overflow != 0;
 
         const unsigned int tmask = __ballot_sync(0xFFFFFFFFu, target);
-        if (tmask != 0u && n_nodes != 0u) {
+        if (tmask != 0u && n_nodes != 0u && !overflow) {
             // ---- bounding box of the warp's targets (scaled units), as two-float edges ----
             double bx0 = target ? pxs : 1e300, bx1 = target ? pxs : -1e300;
             double by0 = target ? pys : 1e300, by1 = target ? pys : -1e300;

@@ -40,6 +40,7 @@ struct lpe_bh_ctx {
     std::string err;
     int instr = 0;
     bool force_dfs = false;  // instrumentation bit2: use the depth-first kernel in FAST mode too
+    bool force_overflow = false;  // instrumentation bit3: the two-phase kernel hands EVERY chunk to the overflow path
 
     uint64_t n = 0, cap = 0;
     uint64_t launches = 0;
@@ -314,6 +315,7 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     // the body's-own-leaf bookkeeping is only needed when a self interaction would not vanish by itself (eps == 0)
     // or when interactions are counted
     k.need_self = ((c->instr & 2) || !((float)k.eps2s > 0.0f)) ? 1 : 0;
+    k.test_overflow = c->force_overflow ? 1 : 0;
     return 0;
 }
 
@@ -514,6 +516,7 @@ int lpe_bh_set_instrumentation(lpe_bh_ctx* c, int flags) {
     if (!c) return 1;
     c->instr = flags;
     c->force_dfs = (flags & 4) != 0;
+    c->force_overflow = (flags & 8) != 0;
     return 0;
 }
 

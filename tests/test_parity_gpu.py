@@ -168,6 +168,34 @@ def test_multi_step_trajectory(bh, port):
     assert np.max(np.hypot(got["x"] - ref["x"], got["y"] - ref["y"])) / 6e9 <= 1e-9
 
 
+@pytest.mark.parametrize("n,eps", [(30000, 0.25), (30000, 0.0), (3000, 0.25)])
+def test_traversal_kernels_agree(bh, port, n, eps):
+    """FAST precision has two kernels: the two-phase production kernel and the depth-first kernel (also its overflow
+    path). All three routes must take identical per-body decisions (= the oracle's) and agree to fp32 rounding."""
+    x, y, vx, vy, m = gen_uniform(n, 1024.0, 41)
+    pg = lpe_bh.make_params(1024.0, eps, dt_drift=0.004)
+    ref = port.run(O.make_params(1024.0, eps, dt_drift=0.004), x, y, vx, vy, m, threads=8, per_body=True)
+    outs = {}
+    for name, kw in (("two_phase", {}), ("depth_first", dict(force_dfs=True)), ("overflow", dict(force_overflow=True))):
+        bh.set_instrumentation(counts=True, **kw)
+        bh.upload(x, y, vx, vy, m)
+        bh.step(pg, 1)
+        outs[name] = bh.download()
+        acc, _ = bh.counts()
+        st = bh.stats()
+        assert np.array_equal(acc, ref["accepted"]), name
+        if name == "overflow":
+            assert st["overflow_chunks"] == ((n + 2047) // 2048) * 64   # every 32-body chunk of every 2048-body block
+        if name == "two_phase":
+            assert st["overflow_chunks"] == 0
+        dv = rel_err((outs[name]["vx"] - vx, outs[name]["vy"] - vy), (ref["vx"] - vx, ref["vy"] - vy))
+        assert dv["max"] <= FAST_TOL, (name, dv)
+    bh.set_instrumentation()
+    # the overflow route IS the depth-first kernel: bit-identical
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(outs["depth_first"][k], outs["overflow"][k])
+
+
 def test_two_rank_sharded_step_on_one_gpu(port):
     """Two contexts on one device play ranks 0 and 1 (launched one after the other: no kernel waits on another);
     the allgather is done through the host. Result must equal the unsharded GPU step bit for bit."""
