@@ -32,15 +32,18 @@ constexpr int T2_THREADS = 128;
 constexpr int T2_WARPS = T2_THREADS / 32;
 constexpr int T2_CAP = 512;                 // frontier entries per level and warp
 constexpr int T2_ROUNDS = T2_CAP / 32;      // classification rounds per level
-constexpr int T2_ABUF = 96;                 // A-list buffer (flushed at >= 64)
+constexpr int T2_ABUF = 98;                 // A-list buffer (flushed at >= 64; + 1 pad entry, even size)
 constexpr unsigned int T2_CLEAN = 0xFFFFu;
 constexpr float T2_MARGIN = 2e-5f;          // relative safety margin of the group classification
 
 struct T2Warp {
     unsigned int qslot[T2_CAP];             // FIFO ring of nodes to classify: record slot
     unsigned int qmask[T2_CAP];             //   lanes (targets) that reach the node
-    float4 ac[T2_ABUF];                     // accept list: centre (two-float)
-    float2 ag[T2_ABUF];                     //   mass, lane mask (as uint bits)
+    // accept list, one array per component so that LDS.64 fetches the same component of two consecutive entries
+    float axh[T2_ABUF], ayh[T2_ABUF];       //   centre, high parts
+    float axl[T2_ABUF], ayl[T2_ABUF];       //   centre, low parts
+    float agm[T2_ABUF];                     //   mass
+    unsigned int amask[T2_ABUF];            //   lanes that reach the entry
     unsigned int aslot[T2_ABUF];            //   record slot (self test / stats only)
     float4 mc[32];                          // mixed nodes of the current round: centre
     float4 mg[32];                          //   gm, open_lo, open_hi, lane mask (as uint bits)
@@ -48,28 +51,72 @@ struct T2Warp {
     unsigned int momask[32];                //   result: lanes that reached AND opened it
 };
 
-// one accept-list entry for one lane
+// ---- packed FP32 (sm_100: FADD2 / FMUL2 / FFMA2 do two fp32 operations in ONE issue slot) ----------------------
+// The traversal is instruction-issue bound, not FMA-pipe bound (ncu: issue slots 75 % busy, FMA pipe 37 %), so the
+// list evaluation works on TWO entries at a time with every add / multiply / fma packed across the pair.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+    return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo2(f32x2_t v) { return __uint_as_float((unsigned int)v); }
+__device__ __forceinline__ float hi2(f32x2_t v) { return __uint_as_float((unsigned int)(v >> 32)); }
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct LanePos2 {   // the lane's negated two-float position, each component duplicated into a register pair
+    f32x2_t nphx, nphy, nplx, nply, eps2;
+};
+
+// two consecutive accept-list entries (m even) for one lane; the sums go to two partial accumulators per axis
 template <bool STATS, bool SELF>
-__device__ __forceinline__ void t2_accept(const T2Warp& W, unsigned int m, unsigned int lanebit, unsigned int self,
-                                          float nphx, float nphy, float nplx, float nply, float eps2f, float& ax,
-                                          float& ay, unsigned int& nacc) {
-    const float4 C = W.ac[m];
-    const float2 Gm = W.ag[m];
-    const bool reached = (__float_as_uint(Gm.y) & lanebit) != 0u;
-    const float g = reached ? Gm.x : 0.f;   // a lane that accepted an ancestor of this node gets nothing from it
-    const float dx = (C.x + nphx) + (C.z + nplx);
-    const float dy = (C.y + nphy) + (C.w + nply);
-    const float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
-    float rinv;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(d2));
-    float f = (g * rinv) * (rinv * rinv);
+__device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, unsigned int lanebit, unsigned int self,
+                                               const LanePos2& P, f32x2_t& AX2, f32x2_t& AY2, unsigned int& nacc) {
+    const f32x2_t xh = *reinterpret_cast<const f32x2_t*>(&W.axh[m]);
+    const f32x2_t yh = *reinterpret_cast<const f32x2_t*>(&W.ayh[m]);
+    const f32x2_t xl = *reinterpret_cast<const f32x2_t*>(&W.axl[m]);
+    const f32x2_t yl = *reinterpret_cast<const f32x2_t*>(&W.ayl[m]);
+    const float2 g = *reinterpret_cast<const float2*>(&W.agm[m]);
+    const uint2 mk = *reinterpret_cast<const uint2*>(&W.amask[m]);
+    const bool r0 = (mk.x & lanebit) != 0u, r1 = (mk.y & lanebit) != 0u;
+    // a lane that accepted an ancestor of an entry gets nothing from it
+    const float g0 = r0 ? g.x : 0.f, g1 = r1 ? g.y : 0.f;
+    bool self0 = false, self1 = false;
     if (SELF) {
-        const unsigned int as = W.aslot[m];
-        if ((as & 0x7FFFFFFFu) == self) f = 0.f;
-        if (STATS) nacc += (reached && (as & 0x7FFFFFFFu) != self && !(as >> 31)) ? 1u : 0u;
+        const uint2 as = *reinterpret_cast<const uint2*>(&W.aslot[m]);
+        self0 = (as.x & 0x7FFFFFFFu) == self;
+        self1 = (as.y & 0x7FFFFFFFu) == self;
+        if (STATS) {
+            nacc += (r0 && (as.x & 0x7FFFFFFFu) != self && !(as.x >> 31)) ? 1u : 0u;
+            nacc += (r1 && (as.y & 0x7FFFFFFFu) != self && !(as.y >> 31)) ? 1u : 0u;
+        }
     }
-    ax = fmaf(dx, f, ax);
-    ay = fmaf(dy, f, ay);
+    const f32x2_t dx = add2(add2(xh, P.nphx), add2(xl, P.nplx));
+    const f32x2_t dy = add2(add2(yh, P.nphy), add2(yl, P.nply));
+    const f32x2_t d2 = fma2(dx, dx, fma2(dy, dy, P.eps2));
+    const f32x2_t rinv = pack2(rsqrt_approx(lo2(d2)), rsqrt_approx(hi2(d2)));
+    f32x2_t f = mul2(mul2(pack2(g0, g1), rinv), mul2(rinv, rinv));
+    // without softening a body's own leaf has d2 = 0 (0 * inf): drop it explicitly (barnes_hut.cpp:272)
+    if (SELF) f = pack2(self0 ? 0.f : lo2(f), self1 ? 0.f : hi2(f));
+    AX2 = fma2(dx, f, AX2);
+    AY2 = fma2(dy, f, AY2);
 }
 
 template <bool STATS, bool SELF>
@@ -112,6 +159,10 @@ __global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravAr
         const float phx = (float)pxs, phy = (float)pys;
         const float nphx = -phx, nphy = -phy;
         const float nplx = -(float)(pxs - (double)phx), nply = -(float)(pys - (double)phy);
+        LanePos2 LP;
+        LP.nphx = pack2(nphx, nphx); LP.nphy = pack2(nphy, nphy);
+        LP.nplx = pack2(nplx, nplx); LP.nply = pack2(nply, nply);
+        LP.eps2 = pack2(eps2f, eps2f);
         unsigned int nacc = 0, nwarp = 0;
         unsigned int kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // STATS: A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes
         double AX = 0.0, AY = 0.0;
@@ -178,8 +229,9 @@ __global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravAr
                 const unsigned int cntM = __popc(maskM);
                 if (toA) {
                     const unsigned int pos = nA + __popc(maskA & lt);
-                    W.ac[pos] = R.c;
-                    W.ag[pos] = make_float2(R.gm, __uint_as_float(mask));
+                    W.axh[pos] = R.c.x; W.ayh[pos] = R.c.y; W.axl[pos] = R.c.z; W.ayl[pos] = R.c.w;
+                    W.agm[pos] = R.gm;
+                    W.amask[pos] = mask;
                     if (SELF) W.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
                 }
                 nA += __popc(maskA);
@@ -258,10 +310,17 @@ __global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravAr
 
                 // ---------------- phase 2b: the accept list, flushed when it is long enough ----------------
                 if (nA >= 64u || head == tail) {
+                    if ((nA & 1u) && lane == 0) {   // pad to an even count with an entry nobody reaches
+                        W.axh[nA] = 4.f; W.ayh[nA] = 4.f; W.axl[nA] = 0.f; W.ayl[nA] = 0.f;   // outside the universe
+                        W.agm[nA] = 0.f; W.amask[nA] = 0u; W.aslot[nA] = LPE_NONE;
+                    }
                     __syncwarp();
-#pragma unroll 4
-                    for (unsigned int m = 0; m < nA; ++m)
-                        t2_accept<STATS, SELF>(W, m, lanebit, self, nphx, nphy, nplx, nply, eps2f, ax, ay, nacc);
+                    f32x2_t AX2 = pack2(ax, 0.f), AY2 = pack2(ay, 0.f);
+#pragma unroll 2
+                    for (unsigned int m = 0; m < nA; m += 2)
+                        t2_accept_pair<STATS, SELF>(W, m, lanebit, self, LP, AX2, AY2, nacc);
+                    ax = lo2(AX2) + hi2(AX2);
+                    ay = lo2(AY2) + hi2(AY2);
                     if (STATS) nwarp += nA;
                     nA = 0;
                 }
