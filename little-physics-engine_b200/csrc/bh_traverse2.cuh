@@ -30,7 +30,7 @@ namespace lpe {
 
 constexpr int T2_THREADS = 128;
 constexpr int T2_WARPS = T2_THREADS / 32;
-constexpr int T2_CAP = 512;                 // frontier entries per level and warp
+constexpr int T2_CAP = 256;                 // frontier entries per level and warp
 constexpr int T2_ROUNDS = T2_CAP / 32;      // classification rounds per level
 constexpr int T2_ABUF = 98;                 // A-list buffer (flushed at >= 64; + 1 pad entry, even size)
 constexpr unsigned int T2_CLEAN = 0xFFFFu;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
 }
 
 template <bool STATS, bool SELF>
-__global__ void __launch_bounds__(T2_THREADS, 5) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
+__global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;

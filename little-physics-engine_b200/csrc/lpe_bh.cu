@@ -426,7 +426,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
             attr_set = true;
         }
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
-        if (grid > sms * 5) grid = sms * 5;
+        if (grid > sms * 6) grid = sms * 6;
         if (grid < 1) grid = 1;
         if (stats) k_traverse2<true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
         else if (selfT) k_traverse2<false, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
