@@ -35,6 +35,11 @@ extern "C" {
 #define LPE_PREC_FAST   0 /* fp64 state + fp64 differences, fp32 interaction math, exact fp64 re-test of borderline theta decisions */
 #define LPE_PREC_STRICT 1 /* every interaction in fp64, in the reference's expression order */
 
+/* lpe_bh_params.key_order */
+#define LPE_KEYS_AUTO    0 /* Hilbert for FAST precision (compact warps: measured 8-12 % faster traversal), Morton for STRICT */
+#define LPE_KEYS_MORTON  1 /* Z-order: child digit = (x >= mid) + 2*(y >= mid), the reference's nw,ne,sw,se recursion order */
+#define LPE_KEYS_HILBERT 2 /* Hilbert index of the same depth-D cell */
+
 typedef struct lpe_bh_ctx lpe_bh_ctx;
 
 typedef struct {
@@ -49,6 +54,8 @@ typedef struct {
     int32_t precision;           /* LPE_PREC_* */
     int32_t do_drift;            /* 0: BarnesHutSystem only (velocity kick); 1: MovementSystem fused into the same step */
     int32_t max_depth;           /* 0: automatic (softening bound, SURVEY.md Q4, capped at 30); else forced key depth 1..30 */
+    int32_t key_order;           /* LPE_KEYS_*: space-filling curve of the sort keys (same cells, same tree, same results) */
+    int32_t reserved;
 } lpe_bh_params;
 
 typedef struct {
@@ -63,6 +70,8 @@ typedef struct {
     uint64_t t2_kinds[8];    /* two-phase diagnostics (stats only): A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes */
     int32_t  depth;          /* key depth D used by the last step */
     int32_t  sort_passes;
+    int32_t  hilbert;        /* 1 if the last step sorted by Hilbert index, 0 for Morton code */
+    int32_t  pad_;
     float ms_keygen, ms_sort, ms_build, ms_traverse, ms_total; /* last step, CUDA events; only when timing is enabled */
 } lpe_bh_stats;
 

@@ -39,6 +39,26 @@ __device__ __forceinline__ unsigned int cell_index(double x, double h, double in
     return (unsigned int)k;
 }
 
+// Hilbert index of cell (x, y) at depth D: like the Morton code it is hierarchical (two bits per level, the bodies of
+// every cell stay contiguous, so the same tree falls out of the sorted keys), but consecutive indices are always
+// edge-adjacent cells: 32 consecutive bodies form a compact blob instead of straddling a Z-curve jump, which is what
+// the traversal's per-warp grouping wants.
+__device__ __forceinline__ unsigned long long hilbert_index(unsigned int x, unsigned int y, int D) {
+    unsigned long long d = 0;
+    const unsigned int n1 = (1u << D) - 1u;
+    for (int b = D - 1; b >= 0; --b) {
+        const unsigned int s = 1u << b;
+        const unsigned int rx = (x >> b) & 1u, ry = (y >> b) & 1u;
+        d |= (unsigned long long)((3u * rx) ^ ry) << (2 * b);
+        if (ry == 0u) {
+            if (rx == 1u) { x = n1 - x; y = n1 - y; }
+            const unsigned int t = x; x = y; y = t;
+        }
+        (void)s;
+    }
+    return d;
+}
+
 __global__ void __launch_bounds__(256)
 k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restrict__ keys,
          unsigned int* __restrict__ vals, Scal* __restrict__ s) {
@@ -57,7 +77,7 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
             const unsigned int kmax = (1u << c.D) - 1u;
             const unsigned int ix = cell_index(p.x, c.h, c.invh, kmax);
             const unsigned int iy = cell_index(p.y, c.h, c.invh, kmax);
-            key = spread_bits32(ix) | (spread_bits32(iy) << 1);
+            key = c.hilbert ? hilbert_index(ix, iy, c.D) : (spread_bits32(ix) | (spread_bits32(iy) << 1));
             in = 1;
             const double m = bd.m;
             if (m > 0.0) mbits = (unsigned long long)__double_as_longlong(m);

@@ -99,6 +99,7 @@ struct StepConst {
     int shard_rank, shard_n;  // multi-GPU block-cyclic ownership of sorted positions
     int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
     int test_overflow;        // tests only: pretend every two-phase frontier overflows
+    int hilbert;              // sort key: 0 = Morton code, 1 = Hilbert index of the same depth-D cell
 };
 
 // Mass and centre of mass of a node as the traversal sees it, in real units.

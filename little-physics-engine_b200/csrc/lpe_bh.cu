@@ -316,6 +316,8 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     // or when interactions are counted
     k.need_self = ((c->instr & 2) || !((float)k.eps2s > 0.0f)) ? 1 : 0;
     k.test_overflow = c->force_overflow ? 1 : 0;
+    if (p.key_order < 0 || p.key_order > 2) return fail(c, "unknown key_order");
+    k.hilbert = (p.key_order == LPE_KEYS_HILBERT || (p.key_order == LPE_KEYS_AUTO && p.precision == LPE_PREC_FAST)) ? 1 : 0;
     return 0;
 }
 
@@ -456,6 +458,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     c->have_step = true;
     c->last.depth = k.D;
     c->last.sort_passes = passes;
+    c->last.hilbert = k.hilbert;
     (void)sharded_begin;
     return 0;
 }

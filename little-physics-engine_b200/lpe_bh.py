@@ -20,6 +20,7 @@ LIB_PATH = os.path.join(HERE, "liblpe_bh.so")
 
 HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID = 1, 2, 4, 8
 PREC_FAST, PREC_STRICT = 0, 1
+KEYS_AUTO, KEYS_MORTON, KEYS_HILBERT = 0, 1, 2
 SHARD_BLOCK = 2048
 G_REAL = 6.674e-11  # SimulatorConstants::RealG, reference src/core/constants.cpp:8
 
@@ -31,7 +32,7 @@ class Params(C.Structure):
         ("universe_size", C.c_double), ("softening", C.c_double), ("theta", C.c_double),
         ("small_mass_threshold", C.c_double), ("G", C.c_double), ("dt_kick", C.c_double),
         ("dt_drift", C.c_double), ("quirk_mode", C.c_int32), ("precision", C.c_int32),
-        ("do_drift", C.c_int32), ("max_depth", C.c_int32),
+        ("do_drift", C.c_int32), ("max_depth", C.c_int32), ("key_order", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -39,7 +40,8 @@ class Stats(C.Structure):
     _fields_ = [
         ("n_bodies", C.c_uint64), ("n_in_tree", C.c_uint64), ("n_terminals", C.c_uint64),
         ("n_nodes", C.c_uint64), ("interactions", C.c_uint64), ("visits", C.c_uint64), ("warp_visits", C.c_uint64), ("overflow_chunks", C.c_uint64), ("t2_kinds", C.c_uint64 * 8),
-        ("depth", C.c_int32), ("sort_passes", C.c_int32), ("ms_keygen", C.c_float),
+        ("depth", C.c_int32), ("sort_passes", C.c_int32), ("hilbert", C.c_int32), ("pad_", C.c_int32),
+        ("ms_keygen", C.c_float),
         ("ms_sort", C.c_float), ("ms_build", C.c_float), ("ms_traverse", C.c_float), ("ms_total", C.c_float),
     ]
 
@@ -66,7 +68,7 @@ class DeviceView(C.Structure):
 
 
 def make_params(U, eps, theta=0.5, dt_kick=1.0 / 120, dt_drift=None, thr=0.0, quirk=True, precision=PREC_FAST,
-                do_drift=True, max_depth=0, G=G_REAL):
+                do_drift=True, max_depth=0, G=G_REAL, key_order=KEYS_AUTO):
     p = Params()
     p.universe_size = U
     p.softening = eps
@@ -79,6 +81,8 @@ def make_params(U, eps, theta=0.5, dt_kick=1.0 / 120, dt_drift=None, thr=0.0, qu
     p.precision = precision
     p.do_drift = 1 if do_drift else 0
     p.max_depth = max_depth
+    p.key_order = key_order
+    p.reserved = 0
     return p
 
 

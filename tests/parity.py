@@ -28,6 +28,31 @@ def deinterleave(key):
     return compact(key), compact(key >> np.uint64(1))
 
 
+def hilbert_to_xy(h, D):
+    """Hilbert index -> (ix, iy) at depth D (inverse of hilbert_index in csrc/bh_build.cuh), vectorised."""
+    t = np.asarray(h, dtype=np.uint64).copy()
+    x = np.zeros(len(t), np.int64)
+    y = np.zeros(len(t), np.int64)
+    for b in range(D):
+        s = 1 << b
+        rx = ((t >> np.uint64(1)) & np.uint64(1)).astype(np.int64)
+        ry = ((t ^ rx.astype(np.uint64)) & np.uint64(1)).astype(np.int64)
+        flip = (ry == 0) & (rx == 1)
+        x = np.where(flip, s - 1 - x, x)
+        y = np.where(flip, s - 1 - y, y)
+        swap = ry == 0
+        x, y = np.where(swap, y, x), np.where(swap, x, y)
+        x = x + s * rx
+        y = y + s * ry
+        t = t >> np.uint64(2)
+    return x.astype(np.uint64), y.astype(np.uint64)
+
+
+def keys_to_xy(keys, D, hilbert):
+    """Depth-D cell coordinates of sort keys, whichever curve they are on."""
+    return hilbert_to_xy(keys, D) if hilbert else deinterleave(keys)
+
+
 def oracle_cells(nodes, U):
     """Index the oracle's dumped nodes by (level, ix, iy)."""
     level = np.rint(np.log2(U / nodes["bsize"])).astype(np.int64)
@@ -54,7 +79,7 @@ def compare_tree(dump, nodes, U, rtol=1e-12):
     D = dump["stats"]["depth"]
     cells, nchild = oracle_cells(nodes, U)
     lv = dump["node_level"]
-    ix, iy = deinterleave(dump["node_key"])
+    ix, iy = keys_to_xy(dump["node_key"], D, dump["stats"]["hilbert"])
     worst = 0.0
     n_branch = n_leaf = n_aggr = 0
     for i in range(len(lv)):

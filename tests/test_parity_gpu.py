@@ -11,7 +11,7 @@ import pytest
 import lpe_bh
 import oracle_py as O
 from conftest import golden_names, load_golden
-from parity import check_preorder, compare_tree, deinterleave, gen_uniform, rel_err
+from parity import check_preorder, compare_tree, gen_uniform, keys_to_xy, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -19,9 +19,9 @@ FAST_TOL = 1e-4     # north_star: "within a stated relative tolerance (e.g. 1e-4
 STRICT_TOL = 1e-8
 
 
-def run_gpu(bh, d, c, precision, quirk=True, counts=True):
+def run_gpu(bh, d, c, precision, quirk=True, counts=True, key_order=lpe_bh.KEYS_AUTO):
     pg = lpe_bh.make_params(c["U"], c["eps"], theta=c["theta"], thr=c["thr"], dt_kick=c["dt_kick"],
-                            dt_drift=c["dt_drift"], quirk=quirk, precision=precision)
+                            dt_drift=c["dt_drift"], quirk=quirk, precision=precision, key_order=key_order)
     bh.set_instrumentation(timing=False, counts=counts)
     bh.upload(d["x"], d["y"], d["vx"], d["vy"], d["m"], rank=d.get("rank"), comp=d.get("comp"))
     bh.step(pg, c["steps"])
@@ -43,14 +43,16 @@ def test_golden_vectors(bh, name, precision):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_golden_tree_topology_and_aggregates(bh, name):
+@pytest.mark.parametrize("key_order", [lpe_bh.KEYS_MORTON, lpe_bh.KEYS_HILBERT], ids=["morton", "hilbert"])
+def test_golden_tree_topology_and_aggregates(bh, name, key_order):
     g, c = load_golden(name)
     if c["thr"] > 0 and name == "all_small":
         pass  # the tree is still built on the device; the reference returned before building it: nothing to compare
     d = {k: g[k] for k in ("x", "y", "vx", "vy", "m", "rank", "comp")}
     c1 = dict(c, steps=1)
-    run_gpu(bh, d, c1, lpe_bh.PREC_STRICT)
+    run_gpu(bh, d, c1, lpe_bh.PREC_STRICT, key_order=key_order)
     dump = bh.dump_tree()
+    assert dump["stats"]["hilbert"] == (1 if key_order == lpe_bh.KEYS_HILBERT else 0)
     check_preorder(dump)
     rep = compare_tree(dump, g["tree"], c["U"])
     assert rep["worst_rel"] <= 1e-12
@@ -100,10 +102,27 @@ def test_seeded_cases_vs_oracle(bh, port, name, n, seed, epsdiv, theta, thr):
             # keys are bit-exact: recompute from the fp64 positions with the reference's comparisons
             D = dump["stats"]["depth"]
             h = U / 2 ** D
-            ix, iy = deinterleave(keys[:nin])
+            ix, iy = keys_to_xy(keys[:nin], D, dump["stats"]["hilbert"])
             b = dump["sorted_index"][:nin]
             assert np.all(ix * h <= x[b]) and np.all(x[b] < (ix + 1) * h)
             assert np.all(iy * h <= y[b]) and np.all(y[b] < (iy + 1) * h)
+
+
+@pytest.mark.parametrize("key_order", [lpe_bh.KEYS_MORTON, lpe_bh.KEYS_HILBERT], ids=["morton", "hilbert"])
+def test_key_order_does_not_change_decisions(bh, port, key_order):
+    """Morton or Hilbert sort keys: same cells, same tree, so the same per-body accept/open decisions in both
+    precisions (only the summation order differs)."""
+    x, y, vx, vy, m = gen_uniform(20000, 1024.0, 51)
+    ref = port.run(O.make_params(1024.0, 0.25, dt_drift=0.004), x, y, vx, vy, m, threads=8, per_body=True)
+    for precision, tol in ((lpe_bh.PREC_STRICT, STRICT_TOL), (lpe_bh.PREC_FAST, FAST_TOL)):
+        bh.set_instrumentation(counts=True)
+        bh.upload(x, y, vx, vy, m)
+        bh.step(lpe_bh.make_params(1024.0, 0.25, dt_drift=0.004, precision=precision, key_order=key_order), 1)
+        got = bh.download()
+        acc, _ = bh.counts()
+        assert np.array_equal(acc, ref["accepted"])
+        assert rel_err((got["vx"] - vx, got["vy"] - vy), (ref["vx"] - vx, ref["vy"] - vy))["max"] <= tol
+    bh.set_instrumentation()
 
 
 def test_empty_and_no_source_inputs(bh):
