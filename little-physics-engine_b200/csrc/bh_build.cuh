@@ -153,9 +153,11 @@ k_terminals(int n, const unsigned long long* __restrict__ keys, const unsigned i
 }
 
 // ---- 4. witnesses: delta[], the per-terminal level masks, and the number of branching cells per level ------
+// wstart[t] = first terminal of the cell that t witnesses (the only galloping search of the whole build).
 __global__ void __launch_bounds__(256)
 k_witness(int D, const unsigned long long* __restrict__ tkey, signed char* __restrict__ delta,
-          unsigned int* __restrict__ mask, unsigned int* __restrict__ levelCount, const Scal* __restrict__ s) {
+          unsigned int* __restrict__ mask, unsigned int* __restrict__ wstart, unsigned int* __restrict__ levelCount,
+          const Scal* __restrict__ s) {
     __shared__ unsigned int cnt[32];
     if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -170,6 +172,7 @@ k_witness(int D, const unsigned long long* __restrict__ tkey, signed char* __res
             delta[t] = (signed char)L;
             const int shift = 2 * (D - L);
             const int a = cell_first(tkey, t, shift);
+            wstart[t] = (unsigned int)a;
             atomicOr(&mask[a], 1u << L);
             // the witness that sits in the cell's first non-empty child counts the cell (once per cell)
             if ((tkey[a] >> (shift - 2)) == (kt >> (shift - 2))) atomicAdd(&cnt[L], 1u);
@@ -203,6 +206,7 @@ __global__ void k_level_scan(const unsigned int* __restrict__ levelCount, unsign
 // ---- 5. topology: pre-order indices, skip pointers, child slots, per-level cell lists ------------------------
 struct Topo {
     unsigned int* tnode;      // [terminal] pre-order index of the terminal's node
+    const unsigned int* wstart; // [terminal] first terminal of the cell that t witnesses
     unsigned int* child;      // [4 * ordinal + digit] a cell's child: pre-order index, or LPE_LEAF_FLAG | sorted body
                               // position for a single-body leaf, or LPE_NONE
     NodeMeta* meta;           // [preorder]
@@ -217,18 +221,6 @@ struct Topo {
     TravRec* rec;
     unsigned int* recnode;
 };
-
-__device__ __forceinline__ void register_child(int D, const unsigned long long* __restrict__ tkey,
-                                               const unsigned int* __restrict__ mask,
-                                               const unsigned int* __restrict__ P, int t, unsigned long long kt, int dl,
-                                               int dr, unsigned int code, unsigned int* __restrict__ child) {
-    const int Lp = max(dl, dr);   // level of the nearest branching ancestor
-    if (Lp < 0) return;           // root
-    const int ap = (dl < Lp) ? t : cell_first(tkey, t, 2 * (D - Lp));
-    const unsigned int qpar = P[ap] + (unsigned int)__popc(mask[ap] & ((1u << Lp) - 1u));
-    const unsigned int digit = (unsigned int)(kt >> (2 * (D - Lp - 1))) & 3u;
-    child[(size_t)qpar * 4 + digit] = code;
-}
 
 // Power-of-two mass unit just above the largest source mass: node masses then fit fp32 comfortably
 // (<= 2N units) whatever the caller's units are (1e36 kg in the Keplerian scenario).
@@ -280,6 +272,10 @@ __device__ __forceinline__ TravRec invalid_record() {
     return r;
 }
 
+// No searches here: a cell's FIRST child is the next deeper cell that starts at the same terminal (pre-order index
+// + 1) or the terminal itself; every OTHER child starts right after a witness of the cell (terminal t + 1 where
+// delta[t] = level of the cell) and is the shallowest cell starting there, or that terminal. Skip pointers are filled
+// bottom-up by the aggregation (a cell ends where its last child ends).
 __global__ void __launch_bounds__(256)
 k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
            const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P, Topo o, Scal* __restrict__ s) {
@@ -296,51 +292,67 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         mk = mask[t];
         Pt = P[t];
         const unsigned long long kt = tkey[t];
-        const int dl = (t > 0) ? (int)delta[t - 1] : -1;
-        {   // the terminal itself: a single-body leaf, or the sum of the bodies that share its depth-D cell
-            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk);
-            const unsigned int first = o.tfirst[t], last = o.tfirst[t + 1];
-            const bool single = (last - first) == 1u;
-            o.tnode[t] = idx;
-            NodeMeta mt;
-            mt.skip = idx + 1; mt.start = (unsigned int)t; mt.level = single ? -1 : -2; mt.pad = first;
-            o.meta[idx] = mt;
-            Agg a;
-            if (single) {
-                if (c.need_self) o.selfnode[first] = idx;
-                if (n_term == 1) a = body_agg(o.sbody[first], first, c.thr);
-            } else {
-                a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
-                a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
-                for (unsigned int i = first; i < last; ++i) {
-                    const SBody sb = o.sbody[i];
-                    a.m += sb.m; a.sx += sb.m * sb.x; a.sy += sb.m * sb.y;
-                    const unsigned int r = sb.rankcomp & 0x0FFFFFFFu;
-                    if (r < a.frank) { a.frank = r; a.fidx = i; a.mf = sb.m; a.xf = sb.x; a.yf = sb.y; }
-                    if (sb.m >= c.thr) a.small = 0u;
-                }
-                o.agg[idx] = a;
+        const unsigned int ncell = (unsigned int)__popc(mk);
+        // the terminal itself: a single-body leaf, or the sum of the bodies that share its depth-D cell
+        const unsigned int idx = (unsigned int)t + Pt + ncell;
+        const unsigned int first = o.tfirst[t], last = o.tfirst[t + 1];
+        const bool single = (last - first) == 1u;
+        o.tnode[t] = idx;
+        NodeMeta mt;
+        mt.skip = idx + 1; mt.start = (unsigned int)t; mt.level = single ? -1 : -2; mt.pad = first;
+        o.meta[idx] = mt;
+        Agg a;
+        if (single) {
+            if (c.need_self) o.selfnode[first] = idx;
+            if (n_term == 1) a = body_agg(o.sbody[first], first, c.thr);
+        } else {
+            a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
+            a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
+            for (unsigned int i = first; i < last; ++i) {
+                const SBody sb = o.sbody[i];
+                a.m += sb.m; a.sx += sb.m * sb.x; a.sy += sb.m * sb.y;
+                const unsigned int r = sb.rankcomp & 0x0FFFFFFFu;
+                if (r < a.frank) { a.frank = r; a.fidx = i; a.mf = sb.m; a.xf = sb.x; a.yf = sb.y; }
+                if (sb.m >= c.thr) a.small = 0u;
             }
-            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[t], single ? (LPE_LEAF_FLAG | first) : idx, o.child);
-            if (n_term == 1) {   // a tree of one terminal: it is the root
-                const double msi = mass_scale_inv(s->max_mass_bits);
-                o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
-                o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
-                o.recnode[0] = idx;
-                if (single && c.need_self) o.selfslot[first] = 0u;
-            }
+            o.agg[idx] = a;
         }
-        unsigned int rest = mk;   // branching cells whose first terminal is t
+        const unsigned int tcode = single ? (LPE_LEAF_FLAG | first) : idx;
+        if (n_term == 1) {   // a tree of one terminal: it is the root
+            const double msi = mass_scale_inv(s->max_mass_bits);
+            o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
+            o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
+            o.recnode[0] = idx;
+            if (single && c.need_self) o.selfslot[first] = 0u;
+        }
+        // branching cells whose first terminal is t, shallow to deep: ordinal Pt + i, pre-order t + Pt + i
+        unsigned int rest = mk, i = 0;
         while (rest) {
             const int L = __ffs(rest) - 1;
             rest &= rest - 1;
-            const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
-            const int b = cell_last(tkey, t, 2 * (D - L), n_term);
-            NodeMeta mt;
-            mt.skip = (unsigned int)(b + 1) + P[b + 1]; mt.start = (unsigned int)t; mt.level = L; mt.pad = 0;
-            o.meta[idx] = mt;
-            register_child(D, tkey, mask, P, t, kt, dl, (int)delta[b], idx, o.child);
+            const unsigned int cidx = (unsigned int)t + Pt + i;
+            NodeMeta mc;
+            mc.skip = 0; mc.start = (unsigned int)t; mc.level = L; mc.pad = 0;
+            o.meta[cidx] = mc;
+            // first child: the next deeper cell starting here, else the terminal
+            const unsigned int digit = (unsigned int)(kt >> (2 * (D - L - 1))) & 3u;
+            o.child[(size_t)(Pt + i) * 4 + digit] = rest ? cidx + 1u : tcode;
             atomicAdd(&cnt[L], 1u);
+            ++i;
+        }
+        // as the witness of the cell at level delta[t]: the child that starts at terminal t + 1
+        if (t < n_term - 1) {
+            const int L = (int)delta[t];
+            const unsigned int a0 = o.wstart[t];
+            const unsigned int q = P[a0] + (unsigned int)__popc(mask[a0] & ((1u << L) - 1u));
+            const unsigned int mk1 = mask[t + 1];
+            unsigned int code = (unsigned int)(t + 1) + P[t + 1];   // shallowest cell starting at t+1, or that terminal's node
+            if (mk1 == 0u) {
+                const unsigned int f1 = o.tfirst[t + 1];
+                if (o.tfirst[t + 2] - f1 == 1u) code = LPE_LEAF_FLAG | f1;
+            }
+            const unsigned int digit = (unsigned int)(tkey[t + 1] >> (2 * (D - L - 1))) & 3u;
+            o.child[(size_t)q * 4 + digit] = code;
         }
     }
     // per-level lists: one global reservation per level per block, then block-local slots
@@ -351,13 +363,13 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         cnt[threadIdx.x] = 0;
     }
     __syncthreads();
-    unsigned int rest = mk;
+    unsigned int rest = mk, i = 0;
     while (rest) {
         const int L = __ffs(rest) - 1;
         rest &= rest - 1;
-        const unsigned int idx = (unsigned int)t + Pt + (unsigned int)__popc(mk & ((1u << L) - 1u));
         const unsigned int local = atomicAdd(&cnt[L], 1u);
-        o.levelList[o.levelBase[L] + base[L] + local] = idx;
+        o.levelList[o.levelBase[L] + base[L] + local] = (unsigned int)t + Pt + i;
+        ++i;
     }
 }
 
@@ -397,16 +409,35 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         } else {
             a = o.agg[ci];
             const NodeMeta mc = o.meta[ci];
-            level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + 1u;
+            level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + 1u;   // a deeper cell's skip is already final
         }
     }
     const unsigned int vmask = (__ballot_sync(0xFFFFFFFFu, valid) >> quadShift) & 0xFu;
     const unsigned int below = (1u << q) - 1u;
     const unsigned int nvalid = __popc(vmask);
     const unsigned int r = valid ? __popc(vmask & below) : nvalid + __popc(~vmask & below & 0xFu);
+    // Skip pointers, bottom up: children are consecutive in pre-order, so child k starts where child k-1's subtree
+    // ends, the first child starts at p + 1, and the cell ends where its last child ends. A childless node
+    // (leaf / aggregated terminal) ends at its own index + 1.
+    unsigned int myskip = 0;
+    {
+        const int lane = (int)(threadIdx.x & 31u);
+        const int qbase = lane & ~3;
+        unsigned int start = p + 1u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // lane k of the quad: subtree end of its child, given where it starts
+            const unsigned int endk = (cbi != 0u) ? skip : start + 1u;
+            const unsigned int e = __shfl_sync(0xFFFFFFFFu, endk, qbase + k);
+            const bool vk = (vmask >> k) & 1u;
+            if (k == q) myskip = endk;
+            if (vk) start = e;
+        }
+        skip = start;   // every lane of the quad now holds the end of the whole cell
+    }
     const unsigned int slot = 4u * (qd + 1u) + r;
     if (valid) {
-        o.rec[slot] = make_record(c, a, level, skip, cbi, msi);
+        o.rec[slot] = make_record(c, a, level, myskip, cbi, msi);
         o.recnode[slot] = (leafpos != LPE_NONE) ? LPE_NONE : ci;
         if (leafpos != LPE_NONE && c.need_self) o.selfslot[leafpos] = slot;
     } else if (live) {
@@ -433,8 +464,9 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
     if (q == 0 && live) {
         a.small |= (nvalid - 1u) << 1;   // children - 1, read back when this cell's own record is made
         o.agg[p] = a;
+        o.meta[p].skip = skip;
         if (p == 0) {   // the root has no parent to write its record
-            o.rec[0] = make_record(c, a, mp.level, mp.skip, 1u, msi);
+            o.rec[0] = make_record(c, a, mp.level, skip, 1u, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
             o.recnode[0] = 0u;
         }

@@ -66,7 +66,7 @@ struct lpe_bh_ctx {
     unsigned int *tileSums = nullptr, *headExcl = nullptr, *P = nullptr;
     // terminals
     unsigned long long* tkey = nullptr;
-    unsigned int *tfirst = nullptr, *mask = nullptr, *tnode = nullptr;
+    unsigned int *tfirst = nullptr, *mask = nullptr, *tnode = nullptr, *wstart = nullptr;
     signed char* delta = nullptr;
     // nodes (pre-order index), cells (ordinal), child blocks
     uint64_t node_cap = 0;
@@ -141,7 +141,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
           dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
     rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
-          dalloc(c, c->tnode, cap + 2) | dalloc(c, c->delta, cap + 2);
+          dalloc(c, c->tnode, cap + 2) | dalloc(c, c->wstart, cap + 2) | dalloc(c, c->delta, cap + 2);
     rc |= dalloc(c, c->child, 4 * (cap + 8)) | dalloc(c, c->meta, ncap) | dalloc(c, c->levelList, cap + 8) |
           dalloc(c, c->levelMeta, 3 * 32) | dalloc(c, c->agg, ncap) | dalloc(c, c->rec, 4 * (cap + 8));
     rc |= dalloc(c, c->cntAcc, cap) | dalloc(c, c->cntVis, cap) | dalloc(c, c->scal, 1);
@@ -382,10 +382,10 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
     k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
-    k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, levelCount, c->scal);
+    k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->wstart, levelCount, c->scal);
     device_scan(c, MaskPop{c->mask, c->scal}, n, c->P, nullptr);
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
-    Topo topo{c->tnode, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
+    Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
               c->selfnode, c->selfslot, c->rec, c->recnode};
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
     NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->sbody};
