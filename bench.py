@@ -290,13 +290,12 @@ def our_arm(args, wl, rank, world, local_rank):
             if it == 2:
                 torch.cuda.synchronize()
                 te0 = time.perf_counter()
-            bh.upload_ptrs(n, *ptrs)
-            bh.step(params, 1)
-            bh.download_ptrs(*ptrs[:4])      # synchronises; the result lands in the pinned host arrays
+            bh.update_host_ptrs(params, n, *ptrs)   # synchronises; the result lands in the pinned host arrays
         e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
         e2e = {"value": n / (e2e_ms * 1e-3), "unit": "body-steps/s", "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 32 * n,
-               "path": "pinned host SoA -> lpe_bh_upload -> lpe_bh_step -> lpe_bh_download (host wall clock incl. sync)"}
+               "path": "pinned host SoA -> lpe_bh_update_host (uploads on a copy stream behind the step, kick + drift, "
+                       "x/y/vx/vy downloaded; host wall clock incl. sync)"}
     else:
         e2e = {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "path": "multi-GPU runs keep bodies resident; host round trip measured at N=1 only"}

@@ -64,11 +64,10 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
          unsigned int* __restrict__ vals, Scal* __restrict__ s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int in = 0;
-    unsigned long long mbits = 0;
     if (i < c.n) {
-        const Body bd = body[i];
-        const unsigned int cm = bd.comp;
-        const double2 p = make_double2(bd.x, bd.y);
+        // positions and components only: masses and ranks may still be on their way over PCIe (lpe_bh_update_host)
+        const double2 p = *reinterpret_cast<const double2*>(&body[i].x);
+        const unsigned int cm = body[i].comp;
         // buildTree's view and bounds test, barnes_hut.cpp:117-124
         const bool src = (cm & 1u) && !(cm & 4u);
         const bool inside = src && p.x >= 0.0 && p.x < c.U && p.y >= 0.0 && p.y < c.U;
@@ -79,16 +78,37 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
             const unsigned int iy = cell_index(p.y, c.h, c.invh, kmax);
             key = c.hilbert ? hilbert_index(ix, iy, c.D) : (spread_bits32(ix) | (spread_bits32(iy) << 1));
             in = 1;
-            const double m = bd.m;
-            if (m > 0.0) mbits = (unsigned long long)__double_as_longlong(m);
         }
         keys[i] = key;
         vals[i] = (unsigned int)i;
     }
-    // block reduce: count and max
     const unsigned int cnt = __syncthreads_count(in);
+    if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_in, cnt);
+}
+
+// ---- 2. gather into Morton order: one 32-byte sector read and one written per body --------------------------
+__global__ void __launch_bounds__(256)
+k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ body,
+         SBody* __restrict__ sbody, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot,
+         Scal* __restrict__ s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long mx = 0;
+    if (i < n) {
+        const unsigned int b = sidx[i];
+        const Body bd = body[b];
+        SBody sb;
+        sb.x = bd.x; sb.y = bd.y; sb.m = bd.m;
+        sb.rankcomp = (bd.rank & 0x0FFFFFFFu) | (bd.comp << 28);
+        sb.idx = b;
+        sbody[i] = sb;
+        if (need_self) {
+            selfnode[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
+            selfslot[i] = LPE_NONE;
+        }
+        // largest source mass (bodies in the tree sort first): fixes the power-of-two mass unit of the records
+        if ((unsigned int)i < s->n_in && bd.m > 0.0) mx = (unsigned long long)__double_as_longlong(bd.m);
+    }
     __shared__ unsigned long long shm[8];
-    unsigned long long mx = mbits;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
@@ -98,27 +118,7 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < 8; ++w) mx = shm[w] > mx ? shm[w] : mx;
-        if (cnt) atomicAdd(&s->n_in, cnt);
         if (mx) atomicMax(&s->max_mass_bits, mx);
-    }
-}
-
-// ---- 2. gather into Morton order: one 32-byte sector read and one written per body --------------------------
-__global__ void __launch_bounds__(256)
-k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ body,
-         SBody* __restrict__ sbody, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const unsigned int b = sidx[i];
-    const Body bd = body[b];
-    SBody sb;
-    sb.x = bd.x; sb.y = bd.y; sb.m = bd.m;
-    sb.rankcomp = (bd.rank & 0x0FFFFFFFu) | (bd.comp << 28);
-    sb.idx = b;
-    sbody[i] = sb;
-    if (need_self) {
-        selfnode[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
-        selfslot[i] = LPE_NONE;
     }
 }
 

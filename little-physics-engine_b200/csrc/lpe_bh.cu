@@ -53,7 +53,11 @@ struct lpe_bh_ctx {
     unsigned int* rank_in = nullptr;   // staging of the caller's rank / component arrays
     unsigned char* comp_in = nullptr;
     // staging
-    double* tmp = nullptr;  // 4*cap doubles
+    double* tmp = nullptr;  // 5*cap doubles
+    // lpe_bh_update_host: uploads run on a second stream, the step waits for each array only where it first reads it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t evc[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool pend_mass = false, pend_vel = false, pend_rank = false;
     // sort
     unsigned long long* keys[2] = {nullptr, nullptr};
     unsigned int* vals[2] = {nullptr, nullptr};
@@ -134,7 +138,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     const int scanTiles = cdiv((long long)cap + 1, SCAN_TILE);
     int rc = 0;
     rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) |
-          dalloc(c, c->tmp, 4 * cap);
+          dalloc(c, c->tmp, 5 * cap);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
           dalloc(c, c->vals[1], cap) | dalloc(c, c->table, (size_t)512 * sortTiles) | dalloc(c, c->totals, 512 * 8);
     rc |= dalloc(c, c->sbody, cap) | dalloc(c, c->selfnode, cap) |
@@ -189,6 +193,21 @@ __global__ void k_pack_body(int n, const double* __restrict__ x, const double* _
     b.rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
     b.comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
     body[i] = b;
+}
+// the two halves of k_pack_body, for the pipelined host path: positions + components first, masses + ranks later
+__global__ void k_pack_pos(int n, const double* __restrict__ x, const double* __restrict__ y,
+                           const unsigned char* __restrict__ comp, Body* __restrict__ body) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<double2*>(&body[i].x) = make_double2(x[i], y[i]);
+    body[i].comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+}
+__global__ void k_pack_mass(int n, const double* __restrict__ m, const unsigned int* __restrict__ rank,
+                            Body* __restrict__ body) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    body[i].m = m[i];
+    body[i].rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
 }
 __global__ void k_set_pos(int n, const double* __restrict__ x, const double* __restrict__ y, Body* __restrict__ body) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,7 +397,12 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     const unsigned int* sidx = c->vals[sel];
     if (timing) cudaEventRecord(c->ev[2], st);
 
-    k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot);
+    if (c->pend_mass) {   // host path: masses and ranks were uploaded behind the key generation and the sort
+        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[2], 0));
+        k_pack_mass<<<g256, 256, 0, st>>>(n, c->tmp + 2 * c->cap, c->pend_rank ? c->rank_in : nullptr, c->body);
+        c->pend_mass = false;
+    }
+    k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal);
     device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
     k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
@@ -405,6 +429,11 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     }
     k_agg_top<<<1, 1024, 0, st>>>(k, Ltop, c->levelList, levelBase, levelCount, c->child, no, c->scal);
     if (timing) cudaEventRecord(c->ev[3], st);
+    if (c->pend_vel) {   // host path: velocities were uploaded behind the build; the kick is their first reader
+        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
+        k_pack2<<<g256, 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel);
+        c->pend_vel = false;
+    }
 
     TravArgs ta{};
     ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta; ta.sbody = c->sbody;
@@ -491,7 +520,9 @@ int lpe_bh_create(int device, lpe_bh_ctx** out) {
         return fail(nullptr, cudaGetErrorString(e));
     }
     c->stream = c->own_stream;
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev) cudaEventCreate(&ev);
+    for (auto& ev : c->evc) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = c;
     return 0;
 }
@@ -502,6 +533,8 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     cudaStreamSynchronize(c->stream);
     free_all(c);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->evc) if (ev) cudaEventDestroy(ev);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -621,8 +654,50 @@ int lpe_bh_synchronize(lpe_bh_ctx* c) {
 int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
                        const double* m, const uint32_t* rank, const uint8_t* comp) {
     if (!c || !p) return 1;
-    if (lpe_bh_upload(c, n, x, y, vx, vy, m, rank, comp)) return 1;
-    if (lpe_bh_step(c, p, 1)) return 1;
+    if (c->shard_n > 1) return fail(c, "sharded context: use lpe_bh_step_begin / lpe_bh_step_finish");
+    if (!vx || !vy || n == 0) {
+        if (lpe_bh_upload(c, n, x, y, vx, vy, m, rank, comp)) return 1;
+        if (lpe_bh_step(c, p, 1)) return 1;
+        return lpe_bh_download(c, p->do_drift ? x : nullptr, p->do_drift ? y : nullptr, vx, vy);
+    }
+    // Pipelined tick: the arrays go up on the copy stream in the order the step first reads them (positions and
+    // components -> keys; masses and ranks -> gather; velocities -> kick) and the step waits per array, so only the
+    // 17 B/body of the first group and the download sit on the critical path next to the kernels.
+    if (n >= (1ull << 31) - 4096) return fail(c, "too many bodies (limit 2^31)");
+    if (!x || !y || !m) return fail(c, "x, y and m are required");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (ensure_capacity(c, n)) return 1;
+    c->n = n;
+    c->have_step = false;
+    {
+        cudaStream_t st = c->stream, cs = c->copy_stream;
+        const size_t bytes = sizeof(double) * n;
+        double* t = c->tmp;
+        const size_t cap = c->cap;
+        CU_TRY(c, cudaEventRecord(c->evc[0], st));           // the staging buffers are free once earlier work is done
+        CU_TRY(c, cudaStreamWaitEvent(cs, c->evc[0], 0));
+        CU_TRY(c, cudaMemcpyAsync(t, x, bytes, cudaMemcpyHostToDevice, cs));
+        CU_TRY(c, cudaMemcpyAsync(t + cap, y, bytes, cudaMemcpyHostToDevice, cs));
+        if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp_in, comp, n, cudaMemcpyHostToDevice, cs));
+        CU_TRY(c, cudaEventRecord(c->evc[1], cs));
+        CU_TRY(c, cudaMemcpyAsync(t + 2 * cap, m, bytes, cudaMemcpyHostToDevice, cs));
+        if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank_in, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, cs));
+        CU_TRY(c, cudaEventRecord(c->evc[2], cs));
+        CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vx, bytes, cudaMemcpyHostToDevice, cs));
+        CU_TRY(c, cudaMemcpyAsync(t + 4 * cap, vy, bytes, cudaMemcpyHostToDevice, cs));
+        CU_TRY(c, cudaEventRecord(c->evc[3], cs));
+        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[1], 0));
+        k_pack_pos<<<cdiv((long long)n, 256), 256, 0, st>>>((int)n, t, t + cap, comp ? c->comp_in : nullptr, c->body);
+        c->pend_mass = true;
+        c->pend_rank = rank != nullptr;
+        c->pend_vel = true;
+        const int rc = run_step(c, *p, false);
+        if (rc || c->pend_mass || c->pend_vel) {   // a failed step must not leave waits dangling for the next one
+            c->pend_mass = c->pend_vel = false;
+            cudaStreamSynchronize(cs);
+            if (rc) return 1;
+        }
+    }
     // BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
     return lpe_bh_download(c, p->do_drift ? x : nullptr, p->do_drift ? y : nullptr, vx, vy);
 }

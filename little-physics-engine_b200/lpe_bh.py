@@ -201,6 +201,13 @@ class BarnesHut:
         self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(n), C.c_void_p(x), C.c_void_p(y), C.c_void_p(vx),
                                          C.c_void_p(vy), C.c_void_p(m), None, None), "upload")
 
+    def update_host_ptrs(self, params, n, x, y, vx, vy, m, rank=None, comp=None):
+        """lpe_bh_update_host on raw host pointers (pinned memory makes the uploads overlap the step)."""
+        self.n = n
+        vp = lambda a: None if a is None else C.c_void_p(a)
+        self._chk(self.lib.lpe_bh_update_host(self.h, C.byref(params), C.c_uint64(n), vp(x), vp(y), vp(vx), vp(vy),
+                                              vp(m), vp(rank), vp(comp)), "update_host")
+
     def step(self, params, nsteps=1):
         self._chk(self.lib.lpe_bh_step(self.h, C.byref(params), C.c_int(nsteps)), "step")
 
