@@ -37,16 +37,17 @@ constexpr unsigned int T2_CLEAN = 0xFFFFu;
 constexpr float T2_MARGIN = 2e-5f;          // relative safety margin of the group classification
 
 struct T2Warp {
-    unsigned int qslot[T2_CAP];             // FIFO ring of nodes to classify: record slot
-    unsigned int qmask[T2_CAP];             //   lanes (targets) that reach the node
+    uint2 q[T2_CAP];                        // FIFO ring of nodes to classify: {record slot, lanes (targets) that reach it}
     // accept list, one array per component so that LDS.64 fetches the same component of two consecutive entries
     float axh[T2_ABUF], ayh[T2_ABUF];       //   centre, high parts
     float axl[T2_ABUF], ayl[T2_ABUF];       //   centre, low parts
     float agm[T2_ABUF];                     //   mass
     unsigned int amask[T2_ABUF];            //   lanes that reach the entry
     unsigned int aslot[T2_ABUF];            //   record slot (self test / stats only)
-    float4 mc[32];                          // mixed nodes of the current round: centre
-    float4 mg[32];                          //   gm, open_lo, open_hi, lane mask (as uint bits)
+    // mixed nodes of the current round, same one-array-per-component layout (evaluated in pairs as well)
+    float mxh[32], myh[32], mxl[32], myl[32];
+    float mgm[32], mlo[32], mhi[32];        //   mass, guard band of the opening threshold
+    unsigned int mmask[32];                 //   lanes that reach the node
     unsigned int mslot[32];                 //   record slot
     unsigned int momask[32];                //   result: lanes that reached AND opened it
 };
@@ -166,7 +167,6 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
         unsigned int nacc = 0, nwarp = 0;
         unsigned int kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // STATS: A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes
         double AX = 0.0, AY = 0.0;
-        float ax = 0.f, ay = 0.f;
         bool overflow = c.test_overflow != 0;
 
         const unsigned int tmask = __ballot_sync(0xFFFFFFFFu, target);
@@ -186,10 +186,7 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
             const float y0l = (float)(by0 - (double)y0h), y1l = (float)(by1 - (double)y1h);
 
             unsigned int head = 0, tail = 1, nA = 0;
-            if (lane == 0) {
-                W.qslot[0] = 0u;       // the root, reached by every target
-                W.qmask[0] = tmask;
-            }
+            if (lane == 0) W.q[0] = make_uint2(0u, tmask);   // the root, reached by every target
             __syncwarp();
             while (head != tail) {
                 // ---------------- phase 1: one node per lane ----------------
@@ -199,8 +196,9 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 TravRec R;
                 R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.skip = 0; R.cblock = 0;
                 if (has) {
-                    slot = W.qslot[(head + lane) & QM];
-                    mask = W.qmask[(head + lane) & QM];
+                    const uint2 e = W.q[(head + lane) & QM];
+                    slot = e.x;
+                    mask = e.y;
                     const uint4* src = reinterpret_cast<const uint4*>(a.rec + slot);
                     const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
                     R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
@@ -220,7 +218,7 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 const bool allOpen = (t >= 0.f) && (d2max * (1.0f + T2_MARGIN) <= tlo);
                 const bool dirty = mask != tmask;                    // some target accepted an ancestor
                 const bool toA = has && allAcc;                      // clean or dirty: the entry carries the lane mask
-                const bool toM = has && !allAcc && (dirty || !allOpen);
+                const bool toM = has && !allAcc && !allOpen;         // all-open nodes just pass their mask on
                 const bool expand = has && !allAcc;
 
                 const unsigned int maskA = __ballot_sync(0xFFFFFFFFu, toA);
@@ -238,51 +236,70 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 if (STATS) {
                     kd[0] += __popc(__ballot_sync(0xFFFFFFFFu, toA && !dirty));
                     kd[1] += __popc(__ballot_sync(0xFFFFFFFFu, toA && dirty));
-                    kd[2] += __popc(__ballot_sync(0xFFFFFFFFu, toM && allOpen));
+                    kd[2] += __popc(__ballot_sync(0xFFFFFFFFu, expand && allOpen && dirty));
                     kd[6] += 1; kd[7] += cnt;
                 }
                 if (toM) {
-                    W.mc[posM] = R.c;
-                    // dirty and every lane that reaches it opens it: no test, the mask just passes through
-                    const float lo = allOpen ? FMAXV : tlo, hi = allOpen ? FMAXV : thi;
-                    W.mg[posM] = make_float4(R.gm, lo, hi, __uint_as_float(mask));
+                    W.mxh[posM] = R.c.x; W.myh[posM] = R.c.y; W.mxl[posM] = R.c.z; W.myl[posM] = R.c.w;
+                    W.mgm[posM] = R.gm; W.mlo[posM] = tlo; W.mhi[posM] = thi;
+                    W.mmask[posM] = mask;
                     W.mslot[posM] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
                 }
+                if ((cntM & 1u) && lane == 0) {   // pad to an even count with an entry nobody reaches
+                    W.mxh[cntM] = 4.f; W.myh[cntM] = 4.f; W.mxl[cntM] = 0.f; W.myl[cntM] = 0.f;
+                    W.mgm[cntM] = 0.f; W.mlo[cntM] = -1.f; W.mhi[cntM] = -1.f;
+                    W.mmask[cntM] = 0u; W.mslot[cntM] = LPE_NONE;
+                }
                 __syncwarp();
+                f32x2_t AX2 = pack2(0.f, 0.f), AY2 = AX2;   // this round's partial sums, two lanes of fp32 per axis
 
                 // ---------------- phase 2a: the mixed nodes of this round, one body per lane ----------------
-                for (unsigned int m = 0; m < cntM; ++m) {
-                    const float4 C = W.mc[m];
-                    const float4 G = W.mg[m];
-                    const bool reached = (__float_as_uint(G.w) & lanebit) != 0u;
-                    const float dx = (C.x + nphx) + (C.z + nplx);
-                    const float dy = (C.y + nphy) + (C.w + nply);
-                    float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
-                    d2 = reached ? d2 : INF;   // a lane that accepted an ancestor: never opens, contributes 0
-                    float lo = G.y;
-                    const bool band = d2 > lo && d2 < G.z;
-                    if (__any_sync(0xFFFFFFFFu, band)) {   // rare: guard band -> the reference's fp64 test decides
-                        if (band)
-                            lo = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs,
-                                            pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                for (unsigned int m = 0; m < cntM; m += 2) {
+                    const f32x2_t xh = *reinterpret_cast<const f32x2_t*>(&W.mxh[m]);
+                    const f32x2_t yh = *reinterpret_cast<const f32x2_t*>(&W.myh[m]);
+                    const f32x2_t xl = *reinterpret_cast<const f32x2_t*>(&W.mxl[m]);
+                    const f32x2_t yl = *reinterpret_cast<const f32x2_t*>(&W.myl[m]);
+                    const float2 g = *reinterpret_cast<const float2*>(&W.mgm[m]);
+                    const float2 tl = *reinterpret_cast<const float2*>(&W.mlo[m]);
+                    const float2 th = *reinterpret_cast<const float2*>(&W.mhi[m]);
+                    const uint2 mk = *reinterpret_cast<const uint2*>(&W.mmask[m]);
+                    const f32x2_t dx = add2(add2(xh, LP.nphx), add2(xl, LP.nplx));
+                    const f32x2_t dy = add2(add2(yh, LP.nphy), add2(yl, LP.nply));
+                    const f32x2_t d2p = fma2(dx, dx, fma2(dy, dy, LP.eps2));
+                    const bool reached0 = (mk.x & lanebit) != 0u, reached1 = (mk.y & lanebit) != 0u;
+                    // a lane that accepted an ancestor: never opens, contributes 0
+                    const float d20 = reached0 ? lo2(d2p) : INF, d21 = reached1 ? hi2(d2p) : INF;
+                    float lo0 = tl.x, lo1 = tl.y;
+                    const bool band0 = d20 > lo0 && d20 < th.x, band1 = d21 > lo1 && d21 < th.y;
+                    if (__any_sync(0xFFFFFFFFu, band0 || band1)) {   // rare: guard band -> the reference's fp64 test decides
+                        if (band0)
+                            lo0 = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs,
+                                             pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                        if (band1)
+                            lo1 = exact_open(a.agg, a.meta, a.recnode[W.mslot[m + 1] & 0x7FFFFFFFu], c.quirk, c.invS,
+                                             pxs, pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
                     }
-                    const bool open = d2 <= lo;
-                    const unsigned int omask = __ballot_sync(0xFFFFFFFFu, open);
-                    if (lane == 0) W.momask[m] = omask;
-                    if (STATS && G.y >= 0.f && G.y < FMAXV) {
-                        const unsigned int pmk = __float_as_uint(G.w);
-                        if (omask == 0u) kd[3]++; else if (omask == pmk) kd[4]++; else kd[5]++;
+                    const bool open0 = d20 <= lo0, open1 = d21 <= lo1;
+                    const unsigned int om0 = __ballot_sync(0xFFFFFFFFu, open0);
+                    const unsigned int om1 = __ballot_sync(0xFFFFFFFFu, open1);
+                    if (lane == 0) *reinterpret_cast<uint2*>(&W.momask[m]) = make_uint2(om0, om1);
+                    if (STATS) {
+                        if (m < cntM) { if (om0 == 0u) kd[3]++; else if (om0 == mk.x) kd[4]++; else kd[5]++; }
+                        if (m + 1 < cntM) { if (om1 == 0u) kd[3]++; else if (om1 == mk.y) kd[4]++; else kd[5]++; }
                     }
-                    float rinv;
-                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
-                    float f = (G.x * rinv) * (rinv * rinv);
+                    const f32x2_t rinv = pack2(rsqrt_approx(open0 ? INF : d20), rsqrt_approx(open1 ? INF : d21));
+                    f32x2_t f = mul2(mul2(pack2(g.x, g.y), rinv), mul2(rinv, rinv));
                     if (SELF) {
-                        const unsigned int ms = W.mslot[m];
-                        if ((ms & 0x7FFFFFFFu) == self) f = 0.f;
-                        if (STATS) nacc += (reached && !open && (ms & 0x7FFFFFFFu) != self && !(ms >> 31)) ? 1u : 0u;
+                        const uint2 ms = *reinterpret_cast<const uint2*>(&W.mslot[m]);
+                        const bool self0 = (ms.x & 0x7FFFFFFFu) == self, self1 = (ms.y & 0x7FFFFFFFu) == self;
+                        f = pack2(self0 ? 0.f : lo2(f), self1 ? 0.f : hi2(f));
+                        if (STATS) {
+                            nacc += (reached0 && !open0 && !self0 && !(ms.x >> 31)) ? 1u : 0u;
+                            nacc += (reached1 && !open1 && !self1 && !(ms.y >> 31)) ? 1u : 0u;
+                        }
                     }
-                    ax = fmaf(dx, f, ax);
-                    ay = fmaf(dy, f, ay);
+                    AX2 = fma2(dx, f, AX2);
+                    AY2 = fma2(dy, f, AY2);
                 }
                 if (STATS) nwarp += cntM;
                 __syncwarp();
@@ -301,10 +318,10 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 if (nch) {
                     const unsigned int at = tail + inc - nch;
                     const unsigned int cslot = (R.cblock >> 2) * 4u;
-                    for (unsigned int kk = 0; kk < nch; ++kk) {
-                        W.qslot[(at + kk) & QM] = cslot + kk;
-                        W.qmask[(at + kk) & QM] = cmask;
-                    }
+                    W.q[at & QM] = make_uint2(cslot, cmask);
+                    if (nch > 1u) W.q[(at + 1u) & QM] = make_uint2(cslot + 1u, cmask);
+                    if (nch > 2u) W.q[(at + 2u) & QM] = make_uint2(cslot + 2u, cmask);
+                    if (nch > 3u) W.q[(at + 3u) & QM] = make_uint2(cslot + 3u, cmask);
                 }
                 tail += total;
 
@@ -315,17 +332,15 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                         W.agm[nA] = 0.f; W.amask[nA] = 0u; W.aslot[nA] = LPE_NONE;
                     }
                     __syncwarp();
-                    f32x2_t AX2 = pack2(ax, 0.f), AY2 = pack2(ay, 0.f);
 #pragma unroll 2
                     for (unsigned int m = 0; m < nA; m += 2)
                         t2_accept_pair<STATS, SELF>(W, m, lanebit, self, LP, AX2, AY2, nacc);
-                    ax = lo2(AX2) + hi2(AX2);
-                    ay = lo2(AY2) + hi2(AY2);
                     if (STATS) nwarp += nA;
                     nA = 0;
                 }
-                AX += (double)ax; AY += (double)ay;   // fp32 partial sums go to fp64 every round
-                ax = 0.f; ay = 0.f;
+                // fp32 partial sums go to fp64 every round
+                AX += (double)(lo2(AX2) + hi2(AX2));
+                AY += (double)(lo2(AY2) + hi2(AY2));
                 __syncwarp();
             }
         }
