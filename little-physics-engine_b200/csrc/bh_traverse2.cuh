@@ -36,18 +36,27 @@ constexpr int T2_ABUF = 98;                 // A-list buffer (flushed at >= 64; 
 constexpr unsigned int T2_CLEAN = 0xFFFFu;
 constexpr float T2_MARGIN = 2e-5f;          // relative safety margin of the group classification
 
-struct T2Warp {
+struct __align__(16) APair {
+    float xh[2], yh[2];     // centre, high parts
+    float xl[2], yl[2];     // centre, low parts
+    float g[2];             // mass
+    unsigned int mask[2];   // lanes that reach the entry
+};
+struct __align__(16) MPair {
+    float xh[2], yh[2], xl[2], yl[2];
+    float g[2], lo[2];      // mass, lower edge of the opening threshold's guard band
+    float hi[2];            // upper edge
+    unsigned int mask[2];   // lanes that reach the node
+};
+
+struct __align__(16) T2Warp {
     uint2 q[T2_CAP];                        // FIFO ring of nodes to classify: {record slot, lanes (targets) that reach it}
-    // accept list, one array per component so that LDS.64 fetches the same component of two consecutive entries
-    float axh[T2_ABUF], ayh[T2_ABUF];       //   centre, high parts
-    float axl[T2_ABUF], ayl[T2_ABUF];       //   centre, low parts
-    float agm[T2_ABUF];                     //   mass
-    unsigned int amask[T2_ABUF];            //   lanes that reach the entry
+    // accept list: entries 2k and 2k+1 share one APair, each component of the two side by side, so that one
+    // LDS.128 fetches two packed-fp32 operands (three loads per pair of entries)
+    APair ap[T2_ABUF / 2];
     unsigned int aslot[T2_ABUF];            //   record slot (self test / stats only)
-    // mixed nodes of the current round, same one-array-per-component layout (evaluated in pairs as well)
-    float mxh[32], myh[32], mxl[32], myl[32];
-    float mgm[32], mlo[32], mhi[32];        //   mass, guard band of the opening threshold
-    unsigned int mmask[32];                 //   lanes that reach the node
+    // mixed nodes of the current round, same layout (evaluated in pairs as well)
+    MPair mp[16];
     unsigned int mslot[32];                 //   record slot
     unsigned int momask[32];                //   result: lanes that reached AND opened it
 };
@@ -90,12 +99,12 @@ struct LanePos2 {   // the lane's negated two-float position, each component dup
 template <bool STATS, bool SELF>
 __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, unsigned int lanebit, unsigned int self,
                                                const LanePos2& P, f32x2_t& AX2, f32x2_t& AY2, unsigned int& nacc) {
-    const f32x2_t xh = *reinterpret_cast<const f32x2_t*>(&W.axh[m]);
-    const f32x2_t yh = *reinterpret_cast<const f32x2_t*>(&W.ayh[m]);
-    const f32x2_t xl = *reinterpret_cast<const f32x2_t*>(&W.axl[m]);
-    const f32x2_t yl = *reinterpret_cast<const f32x2_t*>(&W.ayl[m]);
-    const float2 g = *reinterpret_cast<const float2*>(&W.agm[m]);
-    const uint2 mk = *reinterpret_cast<const uint2*>(&W.amask[m]);
+    const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(&W.ap[m >> 1]);
+    const ulonglong2 vh = ap[0], vl = ap[1];
+    const uint4 vg = *reinterpret_cast<const uint4*>(ap + 2);
+    const f32x2_t xh = vh.x, yh = vh.y, xl = vl.x, yl = vl.y;
+    const float2 g = make_float2(__uint_as_float(vg.x), __uint_as_float(vg.y));
+    const uint2 mk = make_uint2(vg.z, vg.w);
     const bool r0 = (mk.x & lanebit) != 0u, r1 = (mk.y & lanebit) != 0u;
     // a lane that accepted an ancestor of an entry gets nothing from it
     const float g0 = r0 ? g.x : 0.f, g1 = r1 ? g.y : 0.f;
@@ -227,9 +236,11 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 const unsigned int cntM = __popc(maskM);
                 if (toA) {
                     const unsigned int pos = nA + __popc(maskA & lt);
-                    W.axh[pos] = R.c.x; W.ayh[pos] = R.c.y; W.axl[pos] = R.c.z; W.ayl[pos] = R.c.w;
-                    W.agm[pos] = R.gm;
-                    W.amask[pos] = mask;
+                    APair& E = W.ap[pos >> 1];
+                    const unsigned int h = pos & 1u;
+                    E.xh[h] = R.c.x; E.yh[h] = R.c.y; E.xl[h] = R.c.z; E.yl[h] = R.c.w;
+                    E.g[h] = R.gm;
+                    E.mask[h] = mask;
                     if (SELF) W.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
                 }
                 nA += __popc(maskA);
@@ -240,29 +251,32 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                     kd[6] += 1; kd[7] += cnt;
                 }
                 if (toM) {
-                    W.mxh[posM] = R.c.x; W.myh[posM] = R.c.y; W.mxl[posM] = R.c.z; W.myl[posM] = R.c.w;
-                    W.mgm[posM] = R.gm; W.mlo[posM] = tlo; W.mhi[posM] = thi;
-                    W.mmask[posM] = mask;
+                    MPair& E = W.mp[posM >> 1];
+                    const unsigned int h = posM & 1u;
+                    E.xh[h] = R.c.x; E.yh[h] = R.c.y; E.xl[h] = R.c.z; E.yl[h] = R.c.w;
+                    E.g[h] = R.gm; E.lo[h] = tlo; E.hi[h] = thi;
+                    E.mask[h] = mask;
                     W.mslot[posM] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
                 }
                 if ((cntM & 1u) && lane == 0) {   // pad to an even count with an entry nobody reaches
-                    W.mxh[cntM] = 4.f; W.myh[cntM] = 4.f; W.mxl[cntM] = 0.f; W.myl[cntM] = 0.f;
-                    W.mgm[cntM] = 0.f; W.mlo[cntM] = -1.f; W.mhi[cntM] = -1.f;
-                    W.mmask[cntM] = 0u; W.mslot[cntM] = LPE_NONE;
+                    MPair& E = W.mp[cntM >> 1];
+                    E.xh[1] = 4.f; E.yh[1] = 4.f; E.xl[1] = 0.f; E.yl[1] = 0.f;
+                    E.g[1] = 0.f; E.lo[1] = -1.f; E.hi[1] = -1.f;
+                    E.mask[1] = 0u; W.mslot[cntM] = LPE_NONE;
                 }
                 __syncwarp();
                 f32x2_t AX2 = pack2(0.f, 0.f), AY2 = AX2;   // this round's partial sums, two lanes of fp32 per axis
 
                 // ---------------- phase 2a: the mixed nodes of this round, one body per lane ----------------
                 for (unsigned int m = 0; m < cntM; m += 2) {
-                    const f32x2_t xh = *reinterpret_cast<const f32x2_t*>(&W.mxh[m]);
-                    const f32x2_t yh = *reinterpret_cast<const f32x2_t*>(&W.myh[m]);
-                    const f32x2_t xl = *reinterpret_cast<const f32x2_t*>(&W.mxl[m]);
-                    const f32x2_t yl = *reinterpret_cast<const f32x2_t*>(&W.myl[m]);
-                    const float2 g = *reinterpret_cast<const float2*>(&W.mgm[m]);
-                    const float2 tl = *reinterpret_cast<const float2*>(&W.mlo[m]);
-                    const float2 th = *reinterpret_cast<const float2*>(&W.mhi[m]);
-                    const uint2 mk = *reinterpret_cast<const uint2*>(&W.mmask[m]);
+                    const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(&W.mp[m >> 1]);
+                    const ulonglong2 vh = mp[0], vl = mp[1];
+                    const float4 vg = *reinterpret_cast<const float4*>(mp + 2);
+                    const uint4 vm = *reinterpret_cast<const uint4*>(mp + 3);
+                    const f32x2_t xh = vh.x, yh = vh.y, xl = vl.x, yl = vl.y;
+                    const float2 g = make_float2(vg.x, vg.y), tl = make_float2(vg.z, vg.w);
+                    const float2 th = make_float2(__uint_as_float(vm.x), __uint_as_float(vm.y));
+                    const uint2 mk = make_uint2(vm.z, vm.w);
                     const f32x2_t dx = add2(add2(xh, LP.nphx), add2(xl, LP.nplx));
                     const f32x2_t dy = add2(add2(yh, LP.nphy), add2(yl, LP.nply));
                     const f32x2_t d2p = fma2(dx, dx, fma2(dy, dy, LP.eps2));
@@ -328,8 +342,9 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 // ---------------- phase 2b: the accept list, flushed when it is long enough ----------------
                 if (nA >= 64u || head == tail) {
                     if ((nA & 1u) && lane == 0) {   // pad to an even count with an entry nobody reaches
-                        W.axh[nA] = 4.f; W.ayh[nA] = 4.f; W.axl[nA] = 0.f; W.ayl[nA] = 0.f;   // outside the universe
-                        W.agm[nA] = 0.f; W.amask[nA] = 0u; W.aslot[nA] = LPE_NONE;
+                        APair& E = W.ap[nA >> 1];
+                        E.xh[1] = 4.f; E.yh[1] = 4.f; E.xl[1] = 0.f; E.yl[1] = 0.f;   // outside the universe
+                        E.g[1] = 0.f; E.mask[1] = 0u; W.aslot[nA] = LPE_NONE;
                     }
                     __syncwarp();
 #pragma unroll 2
