@@ -232,13 +232,18 @@ def our_arm(args, wl, rank, world, local_rank):
         send = torch.as_tensor(CudaArray(view.xchg_send, 4 * view.xchg_chunk), device="cuda")
         recv = torch.as_tensor(CudaArray(view.xchg_recv, 4 * view.xchg_chunk * world), device="cuda")
 
+    xe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # multi-GPU: allgather / scatter split
+
     def one_step():
         if world == 1:
             bh.step(params, 1)
         else:
             bh.step_begin(params)
+            xe[0].record(stream)
             dist.all_gather_into_tensor(recv, send)
+            xe[1].record(stream)
             bh.step_finish()
+            xe[2].record(stream)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -265,7 +270,8 @@ def our_arm(args, wl, rank, world, local_rank):
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
         st = bh.stats()
-        phases.append((st["ms_keygen"], st["ms_sort"], st["ms_build"], st["ms_traverse"]))
+        phases.append((st["ms_keygen"], st["ms_sort"], st["ms_build"], st["ms_traverse"]) +
+                      ((xe[0].elapsed_time(xe[1]), xe[1].elapsed_time(xe[2])) if world > 1 else (0.0, 0.0)))
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
@@ -321,7 +327,8 @@ def our_arm(args, wl, rank, world, local_rank):
                        "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events",
                        "parallelism": "single GPU" if world == 1 else
                        f"{world} GPUs: replicated tree, block-cyclic Morton-slice traversal, NCCL allgather of (x,y,vx,vy)"},
-            "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": trav_ms},
+            "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": trav_ms,
+                          "allgather": float(ph[4]), "scatter": float(ph[5])},
             "interactions_per_body": interactions / n,
             "roofline": {"bound": "fp32_fma", "kernel": "k_traverse2 (two-phase traversal)", "achieved": achieved,
                          "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak if fma_peak else None,

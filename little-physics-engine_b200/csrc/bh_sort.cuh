@@ -1,7 +1,9 @@
 // bh_sort.cuh — LSD radix sort (u64 key, u32 payload, 8-bit digits) and a device-wide exclusive scan.
 //
-// HBM-bound integer work: per pass the keys are read once for the per-tile digit histogram and keys+payload
-// are read and written once by the scatter (algorithmic 8 + 12 + 12 = 32 B per element per pass).
+// HBM-bound integer work. One histogram kernel reads the keys once and counts the digits of EVERY pass; each pass
+// is then a single kernel that reads keys + payload once and writes them once (algorithmic 8 + passes * 24 B per
+// element): a tile's position inside each digit's run comes from a decoupled look-back over the tiles before it
+// (status word = flag | count, one word per tile and digit), not from a separate count + scan launch pair.
 // Tiles are 2048 elements (256 threads x 8); a warp owns a contiguous 256-element run of its tile, so loads
 // are coalesced and the stable rank of an element is (warps before) + (earlier rounds of this warp) +
 // (lower lanes with the same digit), found with __match_any_sync — no per-element atomics.
@@ -14,78 +16,108 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_MAX_PASSES = 8;
+constexpr int SORT_HIST_STRIDE = 512;                 // words per pass in the histogram / base arrays
 
-// table[d * numTiles + tile] = number of elements of `tile` whose digit is d; totals[d] += the same.
-// `bins` is 256, or 512 for a 9-bit top digit (a 33-bit key then needs 4 passes instead of 5).
-__global__ void __launch_bounds__(SORT_THREADS)
-k_sort_count(const unsigned long long* __restrict__ keys, int n, int shift, int bins, int numTiles,
-             unsigned int* __restrict__ table, unsigned int* __restrict__ totals) {
-    __shared__ unsigned int hist[512];
-    const int tid = threadIdx.x;
-    hist[tid] = 0;
-    hist[tid + 256] = 0;
-    __syncthreads();
-    const unsigned int dmask = (unsigned int)bins - 1u;
-    const long long base = (long long)blockIdx.x * SORT_TILE;
+// ---- look-back status words: high half = epoch << 2 | state, low half = value -------------------------------
+// A word written in an earlier step carries an older epoch and reads as "not there yet", so the status array is
+// never cleared between steps.
+constexpr unsigned int LB_AGGREGATE = 1u, LB_INCLUSIVE = 2u;
+__device__ __forceinline__ unsigned long long lb_load(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void lb_store(unsigned long long* p, unsigned int epoch, unsigned int state, unsigned int value) {
+    const unsigned long long v = ((unsigned long long)((epoch << 2) | state) << 32) | value;
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Sum of the values published by the tiles before `tile` for one column (stride = words per tile). Tile ids are
+// handed out by an atomic counter, so every earlier tile is already running and never waits on a later one.
+__device__ __forceinline__ unsigned int lb_exclusive(const unsigned long long* column, size_t stride, unsigned int tile,
+                                                     unsigned int epoch, unsigned int* __restrict__ fault) {
+    // The walk looks at LB_WINDOW earlier tiles per round trip (independent loads in flight together) instead of
+    // one: when a whole wave of tiles publishes its counts at the same moment, the chain of dependent L2 round
+    // trips is what the tiles wait for, not the data.
+    constexpr int LB_WINDOW = 8;
+    unsigned int excl = 0;
+    unsigned int spins = 0;
+    unsigned int t = tile;   // tiles [t, tile) are already summed
+    while (t > 0u) {
+        unsigned long long w[LB_WINDOW];
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
-        const long long i = base + r * SORT_THREADS + tid;
-        if (i < n) atomicAdd(&hist[(unsigned int)(keys[i] >> shift) & dmask], 1u);
+        for (int k = 0; k < LB_WINDOW; ++k) {
+            const unsigned int idx = t - 1u - (unsigned int)k;
+            // before the first tile: an inclusive zero ends the walk
+            w[k] = (idx < t) ? lb_load(column + (size_t)idx * stride)
+                             : ((unsigned long long)((epoch << 2) | LB_INCLUSIVE) << 32);
+        }
+        bool done = false;
+        unsigned int used = 0;
+#pragma unroll
+        for (int k = 0; k < LB_WINDOW; ++k) {
+            const unsigned int hi = (unsigned int)(w[k] >> 32);
+            const bool ready = (hi >> 2) == epoch;
+            if (!done && used == (unsigned int)k && ready) {
+                excl += (unsigned int)w[k];
+                used = k + 1;
+                if ((hi & 3u) == LB_INCLUSIVE) done = true;
+            }
+        }
+        if (done) break;
+        t -= used;   // (used <= t: the entries past tile 0 are inclusive and end the walk)
+        if (used == 0u && ++spins > (1u << 22)) {   // a bounded wait turns a protocol bug into an error, not a hang
+            atomicExch(fault, 1u);
+            return excl;
+        }
+    }
+    return excl;
+}
+
+// hist[p * 512 + d] += number of keys whose digit in pass p is d, for every pass at once (keys read once).
+__global__ void __launch_bounds__(256)
+k_sort_hist(const unsigned long long* __restrict__ keys, int n, int passes, int lastBins, unsigned int* __restrict__ hist) {
+    extern __shared__ unsigned int sh_hist[];   // passes * 512
+    const int words = passes * SORT_HIST_STRIDE;
+    for (int k = threadIdx.x; k < words; k += blockDim.x) sh_hist[k] = 0;
+    __syncthreads();
+    const unsigned int lastMask = (unsigned int)lastBins - 1u;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long key = keys[i];
+        for (int p = 0; p < passes - 1; ++p)
+            atomicAdd(&sh_hist[p * SORT_HIST_STRIDE + ((unsigned int)(key >> (8 * p)) & 255u)], 1u);
+        atomicAdd(&sh_hist[(passes - 1) * SORT_HIST_STRIDE + ((unsigned int)(key >> (8 * (passes - 1))) & lastMask)], 1u);
     }
     __syncthreads();
-    for (int d = tid; d < bins; d += SORT_THREADS) {
-        const unsigned int c = hist[d];
-        table[(size_t)d * numTiles + blockIdx.x] = c;
-        if (c) atomicAdd(&totals[d], c);
+    for (int k = threadIdx.x; k < words; k += blockDim.x) {
+        const unsigned int c = sh_hist[k];
+        if (c) atomicAdd(&hist[k], c);
     }
 }
 
-// One block per digit: exclusive scan of that digit's row of the table, offset by the count of all smaller digits.
-__global__ void __launch_bounds__(256)
-k_sort_scan(unsigned int* __restrict__ table, const unsigned int* __restrict__ totals, int numTiles) {
-    __shared__ unsigned int sh[256];
-    __shared__ unsigned int s_base;
-    const int d = blockIdx.x;
+// One block per pass: hist row -> exclusive prefix (global start of each digit's run), in place.
+__global__ void __launch_bounds__(512) k_sort_bases(unsigned int* __restrict__ hist) {
+    __shared__ unsigned int sh[512];
+    unsigned int* row = hist + blockIdx.x * SORT_HIST_STRIDE;
     const int tid = threadIdx.x;
-    // base = sum of totals of smaller digits (up to 512 digits)
-    sh[tid] = ((tid < d) ? totals[tid] : 0u) + ((tid + 256 < d) ? totals[tid + 256] : 0u);
+    const unsigned int v = row[tid];
+    sh[tid] = v;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) sh[tid] += sh[tid + o];
+    for (int o = 1; o < 512; o <<= 1) {
+        const unsigned int t = (tid >= o) ? sh[tid - o] : 0u;
+        __syncthreads();
+        sh[tid] += t;
         __syncthreads();
     }
-    if (tid == 0) s_base = sh[0];
-    __syncthreads();
-    const unsigned int base = s_base;
-    unsigned int* row = table + (size_t)d * numTiles;
-    const int per = (numTiles + 255) / 256;
-    const int lo = tid * per;
-    const int hi = min(lo + per, numTiles);
-    unsigned int sum = 0;
-    for (int i = lo; i < hi; ++i) sum += row[i];
-    __syncthreads();
-    sh[tid] = sum;
-    __syncthreads();
-    // inclusive Hillis-Steele over 256 partial sums
-    for (int o = 1; o < 256; o <<= 1) {
-        unsigned int v = (tid >= o) ? sh[tid - o] : 0u;
-        __syncthreads();
-        sh[tid] += v;
-        __syncthreads();
-    }
-    unsigned int run = base + sh[tid] - sum;
-    for (int i = lo; i < hi; ++i) {
-        const unsigned int c = row[i];
-        row[i] = run;
-        run += c;
-    }
+    row[tid] = sh[tid] - v;
 }
 
 template <int BINS>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
-               unsigned long long* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
-               int numTiles, const unsigned int* __restrict__ table) {
+k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
+                unsigned long long* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
+                const unsigned int* __restrict__ digitBase, unsigned long long* __restrict__ status,
+                unsigned int epoch, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault) {
     // The tile is first sorted by digit INSIDE shared memory, then written out: consecutive threads then store
     // consecutive addresses within each digit's run, so every 32-byte sector written is fully used (a direct
     // scatter from registers wrote 8-byte keys and 4-byte payloads to 32 different sectors per instruction).
@@ -99,10 +131,13 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
     const int w = tid >> 5;
     const int lane = tid & 31;
     const unsigned int dmask = (unsigned int)bins - 1u;
+    __shared__ unsigned int s_tile;
+    if (tid == 0) s_tile = atomicAdd(tileCounter, 1u);   // tiles in start order: look-back never waits on a later block
     for (int k = tid; k < SORT_WARPS * BINS; k += SORT_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
+    const unsigned int tile = s_tile;
 
-    const long long tbase = (long long)blockIdx.x * SORT_TILE;
+    const long long tbase = (long long)tile * SORT_TILE;
     const long long wbase = tbase + (long long)w * (SORT_ITEMS * 32);
     unsigned long long key[SORT_ITEMS];
     unsigned int val[SORT_ITEMS];
@@ -143,7 +178,15 @@ k_sort_scatter(const unsigned long long* __restrict__ keysIn, const unsigned int
             run += c;
         }
         dbase[d] = run;   // digit total for now
-        gbase[d] = table[(size_t)d * numTiles + blockIdx.x];
+        // publish this tile's count, add up the tiles before it, publish the inclusive value for the tiles after it
+        unsigned long long* mine = status + (size_t)tile * BINS + d;
+        lb_store(mine, epoch, tile == 0u ? LB_INCLUSIVE : LB_AGGREGATE, run);
+        unsigned int excl = 0;
+        if (tile != 0u) {
+            excl = lb_exclusive(status + d, BINS, tile, epoch, fault);
+            lb_store(mine, epoch, LB_INCLUSIVE, excl + run);
+        }
+        gbase[d] = digitBase[d] + excl;
     }
     __syncthreads();
     // exclusive scan of the digit totals (bins <= 512, 256 threads: two per thread, Hillis-Steele over pair sums)

@@ -61,7 +61,10 @@ struct lpe_bh_ctx {
     // sort
     unsigned long long* keys[2] = {nullptr, nullptr};
     unsigned int* vals[2] = {nullptr, nullptr};
-    unsigned int *table = nullptr, *totals = nullptr;
+    unsigned int* totals = nullptr;            // per step: digit histograms / bases [8][512], tile counters [8], fault flag
+    unsigned long long* lbstatus = nullptr;    // look-back status words of the sort passes (epoch-tagged, never cleared)
+    unsigned int epoch = 0;
+    unsigned int* fault_host = nullptr;        // pinned copy of the sort's fault flag
     int sorted_sel = 0;
     // sorted copies
     SBody* sbody = nullptr;
@@ -140,7 +143,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) |
           dalloc(c, c->tmp, 5 * cap);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
-          dalloc(c, c->vals[1], cap) | dalloc(c, c->table, (size_t)512 * sortTiles) | dalloc(c, c->totals, 512 * 8);
+          dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512)) | dalloc(c, c->totals, 512 * 8 + 16);
     rc |= dalloc(c, c->sbody, cap) | dalloc(c, c->selfnode, cap) |
           dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
     rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
@@ -292,6 +295,22 @@ __global__ void __launch_bounds__(256) k_fma_peak(int iters, float a, float* __r
     if (s == 123.456f) sink[threadIdx.x] = s;
 }
 
+// The look-back of the sort gives up after a bounded wait and raises a flag instead of hanging the device; the flag
+// rides along with every synchronising call (no extra round trip).
+int fetch_fault(lpe_bh_ctx* c) {
+    if (!c->totals || !c->have_step || !c->fault_host) return 0;
+    CU_TRY(c, cudaMemcpyAsync(c->fault_host, c->totals + 512 * SORT_MAX_PASSES + SORT_MAX_PASSES, sizeof(unsigned int),
+                              cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+int check_fault(lpe_bh_ctx* c) {
+    if (c->fault_host && *c->fault_host) {
+        *c->fault_host = 0;
+        return fail(c, "radix sort look-back timed out (internal error): results of the last step are invalid");
+    }
+    return 0;
+}
+
 int choose_depth(const lpe_bh_params& p) {
     if (p.max_depth > 0) return p.max_depth > LPE_MAX_DEPTH ? LPE_MAX_DEPTH : p.max_depth;
     if (!(p.softening > 0.0) || !(p.theta > 0.0)) return LPE_MAX_DEPTH;
@@ -369,7 +388,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
 
     if (timing) cudaEventRecord(c->ev[0], st);
     CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), st));
-    CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * 512 * passes, st));
+    CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * (512 * SORT_MAX_PASSES + 16), st));
     CU_TRY(c, cudaMemsetAsync(c->mask, 0, sizeof(unsigned int) * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->levelMeta, 0, sizeof(unsigned int) * 3 * 32, st));
@@ -378,19 +397,33 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (timing) cudaEventRecord(c->ev[1], st);
 
     int sel = 0;
-    for (int ps = 0; ps < passes; ++ps) {
-        const int shift = 8 * ps;
-        const int bins = (ps == passes - 1) ? (1 << topBits) : 256;
-        unsigned int* totals = c->totals + 512 * ps;
-        k_sort_count<<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], n, shift, bins, sortTiles, c->table, totals);
-        k_sort_scan<<<bins, 256, 0, st>>>(c->table, totals, sortTiles);
-        if (bins == 512)
-            k_sort_scatter<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1],
-                                                                     c->vals[sel ^ 1], n, shift, sortTiles, c->table);
-        else
-            k_sort_scatter<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1],
-                                                                     c->vals[sel ^ 1], n, shift, sortTiles, c->table);
-        sel ^= 1;
+    {
+        // look-back words carry the step's epoch, so the status array is cleared only when the epoch wraps
+        if (c->epoch == 0u || c->epoch >= (1u << 30) - 1u) {
+            CU_TRY(c, cudaMemsetAsync(c->lbstatus, 0, sizeof(unsigned long long) * (size_t)cdiv((long long)c->cap, SORT_TILE) *
+                                                          (256 * (SORT_MAX_PASSES - 1) + 512), st));
+            c->epoch = 0u;
+        }
+        ++c->epoch;
+        unsigned int* hist = c->totals;
+        unsigned int* tileCounter = c->totals + 512 * SORT_MAX_PASSES;
+        unsigned int* fault = tileCounter + SORT_MAX_PASSES;
+        const int lastBins = 1 << topBits;
+        const int histBlocks = std::min(sortTiles, 148 * 8);
+        k_sort_hist<<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(c->keys[0], n, passes, lastBins, hist);
+        k_sort_bases<<<passes, 512, 0, st>>>(hist);
+        for (int ps = 0; ps < passes; ++ps) {
+            const int shift = 8 * ps;
+            unsigned long long* status = c->lbstatus + (size_t)ps * 256 * sortTiles;
+            const unsigned int* base = hist + 512 * ps;
+            if (ps == passes - 1 && lastBins == 512)
+                k_sort_onesweep<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
+                                                                          n, shift, base, status, c->epoch, tileCounter + ps, fault);
+            else
+                k_sort_onesweep<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
+                                                                          n, shift, base, status, c->epoch, tileCounter + ps, fault);
+            sel ^= 1;
+        }
     }
     c->sorted_sel = sel;
     const unsigned long long* skeys = c->keys[sel];
@@ -482,7 +515,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     CU_TRY(c, cudaGetLastError());
     // keygen, 3 per sort pass, gather, 2 scans of 3, terminals, witness, level_scan, topology,
     // one per level above Ltop, agg_top, traverse (+ overflow pass)
-    c->launches += 1 + 3 * (uint64_t)passes + 1 + 3 + 2 + 3 + 2 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
+    c->launches += 1 + 2 + (uint64_t)passes + 1 + 3 + 2 + 3 + 2 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
@@ -521,6 +554,8 @@ int lpe_bh_create(int device, lpe_bh_ctx** out) {
     }
     c->stream = c->own_stream;
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (cudaMallocHost(&c->fault_host, sizeof(unsigned int)) == cudaSuccess) *c->fault_host = 0;
+    else c->fault_host = nullptr;
     for (auto& ev : c->ev) cudaEventCreate(&ev);
     for (auto& ev : c->evc) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = c;
@@ -535,6 +570,7 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->evc) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->fault_host) cudaFreeHost(c->fault_host);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -638,17 +674,19 @@ int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy)
             if (vy) CU_TRY(c, cudaMemcpyAsync(vy, t3, bytes, cudaMemcpyDeviceToHost, st));
         }
     }
+    if (fetch_fault(c)) return 1;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaGetLastError());
-    return 0;
+    return check_fault(c);
 }
 
 int lpe_bh_synchronize(lpe_bh_ctx* c) {
     if (!c) return 1;
     CU_TRY(c, cudaSetDevice(c->device));
+    if (fetch_fault(c)) return 1;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaGetLastError());
-    return 0;
+    return check_fault(c);
 }
 
 int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
