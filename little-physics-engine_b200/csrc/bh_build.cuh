@@ -86,16 +86,33 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
     if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_in, cnt);
 }
 
+// optional re-ordering of the state arrays by k_gather (all null: the state stays in creation order)
+struct Reorder {
+    const double2* velIn;
+    const unsigned int* origIn;   // creation index of each state slot; null = identity
+    Body* bodyOut;
+    double2* velOut;
+    unsigned int* origOut;
+};
+
 // ---- 2. gather into Morton order: one 32-byte sector read and one written per body --------------------------
 __global__ void __launch_bounds__(256)
 k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ body,
          SBody* __restrict__ sbody, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot,
-         Scal* __restrict__ s) {
+         Scal* __restrict__ s, Reorder ro) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long mx = 0;
     if (i < n) {
-        const unsigned int b = sidx[i];
+        unsigned int b = sidx[i];
         const Body bd = body[b];
+        if (ro.bodyOut) {
+            // sharded runs keep the state itself in key order: the step's own writes and the exchange become
+            // sequential, and next step's gather reads almost in place (bodies move little per step)
+            ro.bodyOut[i] = bd;
+            ro.velOut[i] = ro.velIn[b];
+            ro.origOut[i] = ro.origIn ? ro.origIn[b] : b;
+            b = (unsigned int)i;
+        }
         SBody sb;
         sb.x = bd.x; sb.y = bd.y; sb.m = bd.m;
         sb.rankcomp = (bd.rank & 0x0FFFFFFFu) | (bd.comp << 28);

@@ -50,6 +50,12 @@ struct lpe_bh_ctx {
     // state
     Body* body = nullptr;
     double2* vel = nullptr;
+    // sharded runs: the state is re-ordered into key order every step (second set of buffers); orig[slot] is then
+    // the creation index of the body in that slot (orig_valid = false: the state is in creation order)
+    Body* body2 = nullptr;
+    double2* vel2 = nullptr;
+    unsigned int *orig = nullptr, *orig2 = nullptr;
+    bool orig_valid = false;
     unsigned int* rank_in = nullptr;   // staging of the caller's rank / component arrays
     unsigned char* comp_in = nullptr;
     // staging
@@ -160,11 +166,16 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     c->node_cap = ncap;
     c->xchg_send = c->xchg_recv = nullptr;
     c->xchg_chunk = 0;
+    c->body2 = nullptr; c->vel2 = nullptr; c->orig = c->orig2 = nullptr;
+    c->orig_valid = false;
     return 0;
 }
 
 int ensure_xchg(lpe_bh_ctx* c) {
     const uint64_t chunk = lpe_bh_shard_chunk(c->n, c->shard_n);
+    if (!c->body2 && (dalloc(c, c->body2, c->cap) || dalloc(c, c->vel2, c->cap) || dalloc(c, c->orig, c->cap) ||
+                      dalloc(c, c->orig2, c->cap)))
+        return 1;
     if (c->xchg_send && c->xchg_chunk == chunk) return 0;
     // (old exchange buffers, if any, stay in the allocation list and are released with the context)
     if (dalloc(c, c->xchg_send, chunk) || dalloc(c, c->xchg_recv, chunk * (uint64_t)c->shard_n)) return 1;
@@ -172,17 +183,29 @@ int ensure_xchg(lpe_bh_ctx* c) {
     return 0;
 }
 
-__global__ void k_pack2(int n, const double* __restrict__ a, const double* __restrict__ b, double2* __restrict__ out) {
+// host arrays are always in creation order; `orig` (null = identity) maps a state slot to its creation index
+__global__ void k_pack2(int n, const double* __restrict__ a, const double* __restrict__ b, double2* __restrict__ out,
+                        const unsigned int* __restrict__ orig) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = make_double2(a ? a[i] : 0.0, b ? b[i] : 0.0);
+    if (i < n) {
+        const unsigned int s = orig ? orig[i] : (unsigned int)i;
+        out[i] = make_double2(a ? a[s] : 0.0, b ? b[s] : 0.0);
+    }
 }
-__global__ void k_unpack2(int n, const double2* __restrict__ in, double* __restrict__ a, double* __restrict__ b) {
+__global__ void k_unpack2(int n, const double2* __restrict__ in, double* __restrict__ a, double* __restrict__ b,
+                          const unsigned int* __restrict__ orig) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const double2 v = in[i];
-        a[i] = v.x;
-        b[i] = v.y;
+        const unsigned int s = orig ? orig[i] : (unsigned int)i;
+        a[s] = v.x;
+        b[s] = v.y;
     }
+}
+__global__ void k_unpermute_u32(int n, const unsigned int* __restrict__ in, unsigned int* __restrict__ out,
+                                const unsigned int* __restrict__ orig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[orig[i]] = in[i];
 }
 // x, y, m (+ optional rank / component arrays) -> one 32-byte Body per entity
 __global__ void k_pack_body(int n, const double* __restrict__ x, const double* __restrict__ y,
@@ -212,20 +235,26 @@ __global__ void k_pack_mass(int n, const double* __restrict__ m, const unsigned 
     body[i].m = m[i];
     body[i].rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
 }
-__global__ void k_set_pos(int n, const double* __restrict__ x, const double* __restrict__ y, Body* __restrict__ body) {
+__global__ void k_set_pos(int n, const double* __restrict__ x, const double* __restrict__ y, Body* __restrict__ body,
+                          const unsigned int* __restrict__ orig) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) *reinterpret_cast<double2*>(&body[i].x) = make_double2(x[i], y[i]);
+    if (i < n) {
+        const unsigned int s = orig ? orig[i] : (unsigned int)i;
+        *reinterpret_cast<double2*>(&body[i].x) = make_double2(x[s], y[s]);
+    }
 }
-__global__ void k_get_pos(int n, const Body* __restrict__ body, double* __restrict__ x, double* __restrict__ y) {
+__global__ void k_get_pos(int n, const Body* __restrict__ body, double* __restrict__ x, double* __restrict__ y,
+                          const unsigned int* __restrict__ orig) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
         const double2 v = *reinterpret_cast<const double2*>(&body[i].x);
-        x[i] = v.x;
-        y[i] = v.y;
+        const unsigned int s = orig ? orig[i] : (unsigned int)i;
+        x[s] = v.x;
+        y[s] = v.y;
     }
 }
 
-// sharded mode: every rank's packed slice -> state arrays (creation order)
+// sharded mode: every rank's packed slice -> state arrays (sidx null: the state is in key order, slot = position)
 __global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, const unsigned int* __restrict__ sidx,
                                const double4* __restrict__ recv, Body* __restrict__ body,
                                double2* __restrict__ vel) {
@@ -235,7 +264,7 @@ __global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, cons
     const unsigned int r = gblock % (unsigned int)nranks, lblock = gblock / (unsigned int)nranks;
     const unsigned long long slot = (unsigned long long)lblock * LPE_SHARD_BLOCK + ((unsigned int)i % LPE_SHARD_BLOCK);
     const double4 v = recv[(unsigned long long)r * chunk + slot];
-    const unsigned int b = sidx[i];
+    const unsigned int b = sidx ? sidx[i] : (unsigned int)i;
     *reinterpret_cast<double2*>(&body[b].x) = make_double2(v.x, v.y);
     vel[b] = make_double2(v.z, v.w);
 }
@@ -435,7 +464,15 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         k_pack_mass<<<g256, 256, 0, st>>>(n, c->tmp + 2 * c->cap, c->pend_rank ? c->rank_in : nullptr, c->body);
         c->pend_mass = false;
     }
-    k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal);
+    Reorder ro{nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (c->shard_n > 1) ro = Reorder{c->vel, c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2};
+    k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal, ro);
+    if (c->shard_n > 1) {   // from here on the state IS in key order
+        std::swap(c->body, c->body2);
+        std::swap(c->vel, c->vel2);
+        std::swap(c->orig, c->orig2);
+        c->orig_valid = true;
+    }
     device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
     k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
@@ -464,7 +501,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (timing) cudaEventRecord(c->ev[3], st);
     if (c->pend_vel) {   // host path: velocities were uploaded behind the build; the kick is their first reader
         CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
-        k_pack2<<<g256, 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel);
+        k_pack2<<<g256, 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel, c->orig_valid ? c->orig : nullptr);
         c->pend_vel = false;
     }
 
@@ -601,6 +638,7 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
     if (ensure_capacity(c, n)) return 1;
     c->n = n;
     c->have_step = false;
+    c->orig_valid = false;
     if (n == 0) return 0;
     cudaStream_t st = c->stream;
     const size_t bytes = sizeof(double) * n;
@@ -614,7 +652,7 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
     k_pack_body<<<g, 256, 0, st>>>((int)n, t0, t1, t2, rank ? c->rank_in : nullptr, comp ? c->comp_in : nullptr, c->body);
     if (vx) CU_TRY(c, cudaMemcpyAsync(t0, vx, bytes, cudaMemcpyHostToDevice, st));
     if (vy) CU_TRY(c, cudaMemcpyAsync(t1, vy, bytes, cudaMemcpyHostToDevice, st));
-    k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t0 : nullptr, vy ? t1 : nullptr, c->vel);
+    k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t0 : nullptr, vy ? t1 : nullptr, c->vel, nullptr);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -627,7 +665,7 @@ int lpe_bh_upload_positions(lpe_bh_ctx* c, const double* x, const double* y) {
     double *t0 = c->tmp, *t1 = c->tmp + c->cap;
     CU_TRY(c, cudaMemcpyAsync(t0, x, bytes, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(t1, y, bytes, cudaMemcpyHostToDevice, c->stream));
-    k_set_pos<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t0, t1, c->body);
+    k_set_pos<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t0, t1, c->body, c->orig_valid ? c->orig : nullptr);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -640,7 +678,7 @@ int lpe_bh_upload_velocities(lpe_bh_ctx* c, const double* vx, const double* vy) 
     double *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
     CU_TRY(c, cudaMemcpyAsync(t2, vx, bytes, cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaMemcpyAsync(t3, vy, bytes, cudaMemcpyHostToDevice, c->stream));
-    k_pack2<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t2, t3, c->vel);
+    k_pack2<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, t2, t3, c->vel, c->orig_valid ? c->orig : nullptr);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -664,12 +702,12 @@ int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy)
         const int g = cdiv((long long)n, 256);
         double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
         if (x || y) {
-            k_get_pos<<<g, 256, 0, st>>>((int)n, c->body, t0, t1);
+            k_get_pos<<<g, 256, 0, st>>>((int)n, c->body, t0, t1, c->orig_valid ? c->orig : nullptr);
             if (x) CU_TRY(c, cudaMemcpyAsync(x, t0, bytes, cudaMemcpyDeviceToHost, st));
             if (y) CU_TRY(c, cudaMemcpyAsync(y, t1, bytes, cudaMemcpyDeviceToHost, st));
         }
         if (vx || vy) {
-            k_unpack2<<<g, 256, 0, st>>>((int)n, c->vel, t2, t3);
+            k_unpack2<<<g, 256, 0, st>>>((int)n, c->vel, t2, t3, c->orig_valid ? c->orig : nullptr);
             if (vx) CU_TRY(c, cudaMemcpyAsync(vx, t2, bytes, cudaMemcpyDeviceToHost, st));
             if (vy) CU_TRY(c, cudaMemcpyAsync(vy, t3, bytes, cudaMemcpyDeviceToHost, st));
         }
@@ -707,6 +745,7 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
     if (ensure_capacity(c, n)) return 1;
     c->n = n;
     c->have_step = false;
+    c->orig_valid = false;
     {
         cudaStream_t st = c->stream, cs = c->copy_stream;
         const size_t bytes = sizeof(double) * n;
@@ -780,7 +819,8 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     const size_t nn = (size_t)h.n_term + h.n_internal;
     if (o->sorted_keys) CU_TRY(c, cudaMemcpy(o->sorted_keys, c->keys[c->sorted_sel], 8 * n, cudaMemcpyDeviceToHost));
     std::vector<unsigned int> sidx(n);
-    CU_TRY(c, cudaMemcpy(sidx.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
+    // creation index of the body at each sorted position (a re-ordered state is in sorted order itself)
+    CU_TRY(c, cudaMemcpy(sidx.data(), c->orig_valid ? c->orig : c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
     if (o->sorted_index) std::memcpy(o->sorted_index, sidx.data(), 4 * n);
     if (nn == 0) return 0;
     std::vector<NodeMeta> mt(nn);
@@ -818,14 +858,25 @@ int lpe_bh_get_counts(lpe_bh_ctx* c, uint32_t* accepted, uint32_t* visited) {
     if (!(c->instr & 2)) return fail(c, "enable instrumentation bit1 before the step");
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
-    if (accepted) CU_TRY(c, cudaMemcpy(accepted, c->cntAcc, 4 * c->n, cudaMemcpyDeviceToHost));
-    if (visited) CU_TRY(c, cudaMemcpy(visited, c->cntVis, 4 * c->n, cudaMemcpyDeviceToHost));
+    for (int which = 0; which < 2; ++which) {
+        uint32_t* dst = which ? visited : accepted;
+        const unsigned int* src = which ? c->cntVis : c->cntAcc;
+        if (!dst || c->n == 0) continue;
+        if (c->orig_valid) {   // counters are per state slot: back to creation order
+            unsigned int* t = reinterpret_cast<unsigned int*>(c->tmp);
+            k_unpermute_u32<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, src, t, c->orig);
+            CU_TRY(c, cudaStreamSynchronize(c->stream));
+            src = t;
+        }
+        CU_TRY(c, cudaMemcpy(dst, src, 4 * c->n, cudaMemcpyDeviceToHost));
+    }
     return 0;
 }
 
 int lpe_bh_direct_accel(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t first, uint64_t count, double* ax, double* ay) {
     if (!c || !p || !ax || !ay) return 1;
     if (first + count > c->n) return fail(c, "target range out of bounds");
+    if (c->orig_valid) return fail(c, "direct sum is not available once a sharded step has re-ordered the state");
     if (count == 0) return 0;
     CU_TRY(c, cudaSetDevice(c->device));
     double *dax = c->tmp, *day = c->tmp + c->cap;
@@ -875,8 +926,8 @@ int lpe_bh_step_finish(lpe_bh_ctx* c) {
     if (!c->have_step) return fail(c, "lpe_bh_step_begin has not run");
     CU_TRY(c, cudaSetDevice(c->device));
     k_xchg_scatter<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->shard_n, c->xchg_chunk,
-                                                                       c->vals[c->sorted_sel], c->xchg_recv, c->body,
-                                                                       c->vel);
+                                                                       c->orig_valid ? nullptr : c->vals[c->sorted_sel],
+                                                                       c->xchg_recv, c->body, c->vel);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
