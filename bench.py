@@ -222,7 +222,8 @@ def our_arm(args, wl, rank, world, local_rank):
     interactions = bh.stats()["interactions"]
     fma_peak = bh.fma_peak_tflops()
 
-    send = recv = None
+    send = recv = token = None
+    p2p = False
     if world > 1:
         bh.set_shard(rank, world)
     bh.set_instrumentation(timing=True)
@@ -231,6 +232,25 @@ def our_arm(args, wl, rank, world, local_rank):
         view = bh.device_view()
         send = torch.as_tensor(CudaArray(view.xchg_send, 4 * view.xchg_chunk), device="cuda")
         recv = torch.as_tensor(CudaArray(view.xchg_recv, 4 * view.xchg_chunk * world), device="cuda")
+        # Direct exchange: every rank opens every other rank's receive buffer (CUDA IPC over NVLink peer memory) and
+        # the traversal kernel stores its results there itself. All ranks must agree, else the NCCL allgather is used.
+        ok = 0
+        if not args.no_p2p and world <= 8:
+            try:
+                handles = [None] * world
+                dist.all_gather_object(handles, bh.xchg_export())
+                for r, hnd in enumerate(handles):
+                    if r != rank:
+                        bh.xchg_import(r, hnd)
+                ok = 1 if bh.xchg_p2p_ready() else 0
+            except Exception as e:   # IPC not permitted on this box: fall back to the collective
+                log(rank, f"direct exchange unavailable: {e}")
+        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        p2p = bool(flag.item())
+        if not p2p and ok:
+            raise RuntimeError("ranks disagree on the direct exchange; rerun with --no-p2p")
+        token = torch.zeros(1, device="cuda", dtype=torch.int32)
 
     xe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # multi-GPU: allgather / scatter split
 
@@ -240,7 +260,10 @@ def our_arm(args, wl, rank, world, local_rank):
         else:
             bh.step_begin(params)
             xe[0].record(stream)
-            dist.all_gather_into_tensor(recv, send)
+            if p2p:
+                dist.all_reduce(token)      # stream-ordered barrier: every rank's stores have landed
+            else:
+                dist.all_gather_into_tensor(recv, send)
             xe[1].record(stream)
             bh.step_finish()
             xe[2].record(stream)
@@ -326,7 +349,9 @@ def our_arm(args, wl, rank, world, local_rank):
                        "quirk_mode": "reference", "precision": "fast",
                        "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events",
                        "parallelism": "single GPU" if world == 1 else
-                       f"{world} GPUs: replicated tree, block-cyclic Morton-slice traversal, NCCL allgather of (x,y,vx,vy)"},
+                       f"{world} GPUs: replicated tree, block-cyclic key-slice traversal, " +
+                       ("(x,y,vx,vy) stored into every rank's receive buffer by the traversal kernel itself (NVLink peer "
+                        "memory, CUDA IPC) + one-element allreduce as barrier" if p2p else "NCCL allgather of (x,y,vx,vy)")},
             "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": trav_ms,
                           "allgather": float(ph[4]), "scatter": float(ph[5])},
             "interactions_per_body": interactions / n,
@@ -360,6 +385,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL allgather instead of the fused peer-memory exchange")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -158,6 +158,18 @@ int  lpe_bh_get_device_view(lpe_bh_ctx* ctx, lpe_bh_device_view* out);
  * another rank's slice in; each is 4*xchg_chunk doubles. Synchronises. */
 int  lpe_bh_xchg_read_send(lpe_bh_ctx* ctx, double* host);
 int  lpe_bh_xchg_write_recv(lpe_bh_ctx* ctx, int src_rank, const double* host);
+/* Direct exchange over peer memory (NVLink / NVSwitch), 2..8 ranks of one node: once every rank's receive buffer is
+ * known to this context, the traversal kernel itself stores each new (x,y,vx,vy) into ALL ranks' receive buffers
+ * (the exchange overlaps the force computation) and the caller only needs a barrier between lpe_bh_step_begin and
+ * lpe_bh_step_finish instead of the allgather. One process per GPU: lpe_bh_xchg_export gives a 64-byte CUDA IPC
+ * handle of this rank's receive buffer (and registers the own buffer); ship it to the other ranks by any channel
+ * and lpe_bh_xchg_import it there. Same process (tests): lpe_bh_xchg_set_peer with the raw device pointer from
+ * lpe_bh_get_device_view. The receive buffer holds two generations (step parity), so one barrier per step is
+ * enough. A reallocation (different n) drops the peer table: exchange handles again. */
+int  lpe_bh_xchg_export(lpe_bh_ctx* ctx, void* handle64);
+int  lpe_bh_xchg_import(lpe_bh_ctx* ctx, int rank, const void* handle64);
+int  lpe_bh_xchg_set_peer(lpe_bh_ctx* ctx, int rank, void* recv_device_ptr);
+int  lpe_bh_xchg_p2p_ready(const lpe_bh_ctx* ctx);
 /* pure host helper (no GPU): which rank owns sorted position i, and where it sits in that rank's packed slice */
 int  lpe_bh_shard_owner(uint64_t sorted_pos, int nranks, int* rank_out, uint64_t* slot_out);
 uint64_t lpe_bh_shard_chunk(uint64_t n_bodies, int nranks);        /* elements per rank in the exchange buffers */

@@ -15,6 +15,9 @@
 
 namespace lpe {
 
+constexpr int LPE_MAX_P2P = 8;   // ranks of one NVSwitch domain that can exchange by direct peer stores
+
+
 // Scalars produced and consumed on the device inside one step (no host round trip).
 struct Scal {
     unsigned int n_in;          // sources inside [0,U)^2

@@ -41,6 +41,8 @@ struct TravArgs {
     Body* body;                     // state, creation order (positions are updated in place by the drift)
     double2* vel;
     double4* xchg_send;      // sharded mode: packed (x,y,vx,vy) of the own slice
+    double4* peer[LPE_MAX_P2P];   // direct exchange: this rank's slice inside every rank's receive buffer (NVLink peer
+    int npeer;                    //   memory); 0 = the caller runs a collective on xchg_send instead
     unsigned int* cntAcc;    // STATS only, creation order
     unsigned int* cntVis;
     Scal* s;
@@ -271,7 +273,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
             }
             if (c.shard_n > 1) {
                 const unsigned long long slot = (unsigned long long)lblock * 2048ull + within * 32ull + lane;
-                a.xchg_send[slot] = make_double4(p.x, p.y, v.x, v.y);
+                const double4 out = make_double4(p.x, p.y, v.x, v.y);
+                a.xchg_send[slot] = out;
+                for (int r = 0; r < a.npeer; ++r) a.peer[r][slot] = out;
             } else {
                 if (target) a.vel[b] = v;
                 if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;

@@ -381,7 +381,11 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
             }
             if (c.shard_n > 1) {
                 const unsigned long long slotx = (unsigned long long)lblock * 2048ull + within * 32ull + lane;
-                a.xchg_send[slotx] = make_double4(p.x, p.y, v.x, v.y);
+                // The exchange is fused into the kick: the new state goes straight into every rank's receive buffer
+                // (stores to NVLink peer memory overlap the rest of the traversal), no collective afterwards.
+                const double4 out = make_double4(p.x, p.y, v.x, v.y);
+                a.xchg_send[slotx] = out;
+                for (int r = 0; r < a.npeer; ++r) a.peer[r][slotx] = out;
             } else {
                 if (target) a.vel[b] = v;
                 if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;

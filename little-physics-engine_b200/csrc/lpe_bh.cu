@@ -91,7 +91,10 @@ struct lpe_bh_ctx {
     unsigned int *cntAcc = nullptr, *cntVis = nullptr;
     Scal* scal = nullptr;
     // exchange
-    double4 *xchg_send = nullptr, *xchg_recv = nullptr;
+    double4 *xchg_send = nullptr, *xchg_recv = nullptr;   // recv holds two generations (step parity) of nranks slices
+    double4* peer_recv[LPE_MAX_P2P] = {};                 // every rank's xchg_recv (own pointer, or opened through CUDA IPC)
+    void* peer_opened[LPE_MAX_P2P] = {};                  // IPC mappings to close
+    int xchg_parity = 0;
     // timing
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     lpe_bh_stats last{};
@@ -137,6 +140,8 @@ void free_all(lpe_bh_ctx* c) {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+void close_peers(lpe_bh_ctx* c);
+
 int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     if (n <= c->cap && c->cap != 0) return 0;
     cudaStreamSynchronize(c->stream);
@@ -166,9 +171,25 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     c->node_cap = ncap;
     c->xchg_send = c->xchg_recv = nullptr;
     c->xchg_chunk = 0;
+    close_peers(c);
     c->body2 = nullptr; c->vel2 = nullptr; c->orig = c->orig2 = nullptr;
     c->orig_valid = false;
     return 0;
+}
+
+void close_peers(lpe_bh_ctx* c) {
+    for (int r = 0; r < LPE_MAX_P2P; ++r) {
+        if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
+        c->peer_opened[r] = nullptr;
+        c->peer_recv[r] = nullptr;
+    }
+    c->xchg_parity = 0;
+}
+bool p2p_ready(const lpe_bh_ctx* c) {
+    if (c->shard_n <= 1 || c->shard_n > LPE_MAX_P2P || !c->xchg_recv) return false;
+    for (int r = 0; r < c->shard_n; ++r)
+        if (!c->peer_recv[r]) return false;
+    return true;
 }
 
 int ensure_xchg(lpe_bh_ctx* c) {
@@ -178,8 +199,9 @@ int ensure_xchg(lpe_bh_ctx* c) {
         return 1;
     if (c->xchg_send && c->xchg_chunk == chunk) return 0;
     // (old exchange buffers, if any, stay in the allocation list and are released with the context)
-    if (dalloc(c, c->xchg_send, chunk) || dalloc(c, c->xchg_recv, chunk * (uint64_t)c->shard_n)) return 1;
+    if (dalloc(c, c->xchg_send, chunk) || dalloc(c, c->xchg_recv, 2 * chunk * (uint64_t)c->shard_n)) return 1;
     c->xchg_chunk = chunk;
+    close_peers(c);   // the receive buffer moved: peers must exchange handles again
     return 0;
 }
 
@@ -509,6 +531,14 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta; ta.sbody = c->sbody;
     ta.selfnode = c->selfnode; ta.body = c->body; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
+    ta.npeer = 0;
+    if (sharded_begin && p2p_ready(c)) {
+        // this step's generation of every rank's receive buffer, at this rank's slice
+        c->xchg_parity ^= 1;
+        const size_t gen = (size_t)c->xchg_parity * c->xchg_chunk * (size_t)c->shard_n;
+        for (int r = 0; r < c->shard_n; ++r) ta.peer[r] = c->peer_recv[r] + gen + (size_t)c->shard_rank * c->xchg_chunk;
+        ta.npeer = c->shard_n;
+    }
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
     const unsigned int own = (nblocks + (unsigned int)c->shard_n - 1u - (unsigned int)c->shard_rank) / (unsigned int)c->shard_n;
     ta.n_chunks_local = own * (LPE_SHARD_BLOCK / 32u);
@@ -603,6 +633,7 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    close_peers(c);
     free_all(c);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->evc) if (ev) cudaEventDestroy(ev);
@@ -927,7 +958,8 @@ int lpe_bh_step_finish(lpe_bh_ctx* c) {
     CU_TRY(c, cudaSetDevice(c->device));
     k_xchg_scatter<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->shard_n, c->xchg_chunk,
                                                                        c->orig_valid ? nullptr : c->vals[c->sorted_sel],
-                                                                       c->xchg_recv, c->body, c->vel);
+                                                                       c->xchg_recv + (p2p_ready(c) ? (size_t)c->xchg_parity * c->xchg_chunk * (size_t)c->shard_n : 0),
+                                                                       c->body, c->vel);
     CU_TRY(c, cudaGetLastError());
     return 0;
 }
@@ -951,6 +983,46 @@ int lpe_bh_xchg_write_recv(lpe_bh_ctx* c, int src, const double* host) {
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
+
+// ---- direct exchange over peer memory (NVLink / NVSwitch): handles travel through the caller's own channel ----
+int lpe_bh_xchg_export(lpe_bh_ctx* c, void* handle64) {
+    if (!c || !handle64) return 1;
+    if (c->shard_n <= 1 || c->n == 0) return fail(c, "context is not sharded (set_shard + upload first)");
+    if (c->shard_n > LPE_MAX_P2P) return fail(c, "direct exchange supports at most 8 ranks");
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (ensure_xchg(c)) return 1;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
+    cudaIpcMemHandle_t hnd;
+    CU_TRY(c, cudaIpcGetMemHandle(&hnd, c->xchg_recv));
+    std::memcpy(handle64, &hnd, sizeof(hnd));
+    c->peer_recv[c->shard_rank] = c->xchg_recv;
+    return 0;
+}
+
+int lpe_bh_xchg_import(lpe_bh_ctx* c, int rank, const void* handle64) {
+    if (!c || !handle64) return 1;
+    if (c->shard_n <= 1 || c->shard_n > LPE_MAX_P2P) return fail(c, "direct exchange needs 2..8 ranks");
+    if (rank < 0 || rank >= c->shard_n || rank == c->shard_rank) return fail(c, "bad peer rank");
+    CU_TRY(c, cudaSetDevice(c->device));
+    cudaIpcMemHandle_t hnd;
+    std::memcpy(&hnd, handle64, sizeof(hnd));
+    void* ptr = nullptr;
+    CU_TRY(c, cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess));
+    if (c->peer_opened[rank]) cudaIpcCloseMemHandle(c->peer_opened[rank]);
+    c->peer_opened[rank] = ptr;
+    c->peer_recv[rank] = static_cast<double4*>(ptr);
+    return 0;
+}
+
+int lpe_bh_xchg_set_peer(lpe_bh_ctx* c, int rank, void* recv_device_ptr) {
+    if (!c) return 1;
+    if (c->shard_n <= 1 || c->shard_n > LPE_MAX_P2P) return fail(c, "direct exchange needs 2..8 ranks");
+    if (rank < 0 || rank >= c->shard_n) return fail(c, "bad peer rank");
+    c->peer_recv[rank] = static_cast<double4*>(recv_device_ptr);
+    return 0;
+}
+
+int lpe_bh_xchg_p2p_ready(const lpe_bh_ctx* c) { return (c && p2p_ready(c)) ? 1 : 0; }
 
 uint64_t lpe_bh_launch_count(const lpe_bh_ctx* c) { return c ? c->launches : 0; }
 

@@ -201,6 +201,21 @@ class BarnesHut:
         self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(n), C.c_void_p(x), C.c_void_p(y), C.c_void_p(vx),
                                          C.c_void_p(vy), C.c_void_p(m), None, None), "upload")
 
+    # ---- direct exchange over peer memory (include/lpe_bh.h) ----
+    def xchg_export(self):
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.lpe_bh_xchg_export(self.h, buf), "xchg_export")
+        return buf.raw
+
+    def xchg_import(self, rank, handle):
+        self._chk(self.lib.lpe_bh_xchg_import(self.h, C.c_int(rank), C.c_char_p(handle)), "xchg_import")
+
+    def xchg_set_peer(self, rank, recv_ptr):
+        self._chk(self.lib.lpe_bh_xchg_set_peer(self.h, C.c_int(rank), C.c_void_p(recv_ptr)), "xchg_set_peer")
+
+    def xchg_p2p_ready(self):
+        return bool(self.lib.lpe_bh_xchg_p2p_ready(self.h))
+
     def update_host_ptrs(self, params, n, x, y, vx, vy, m, rank=None, comp=None):
         """lpe_bh_update_host on raw host pointers (pinned memory makes the uploads overlap the step)."""
         self.n = n

@@ -240,3 +240,37 @@ def test_two_rank_sharded_step_on_one_gpu(port):
         for k in ("x", "y", "vx", "vy"):
             assert np.array_equal(got[k], ref[k]), k
         c.close()
+
+
+def test_two_rank_direct_exchange_on_one_gpu(port):
+    """Same two-context emulation, but the exchange is the fused one: each context's traversal kernel stores its
+    slice straight into BOTH contexts' receive buffers (lpe_bh_xchg_set_peer, the same-process form of the CUDA IPC
+    handles); no slice is copied by the host. Three steps so that both generations of the buffer are used."""
+    n = 5 * 2048 + 77
+    x, y, vx, vy, m = gen_uniform(n, 1024.0, 32)
+    pg = lpe_bh.make_params(1024.0, 0.25, dt_drift=0.004)
+    one = lpe_bh.BarnesHut(0)
+    one.upload(x, y, vx, vy, m); one.step(pg, 3); ref = one.download(); one.close()
+    ranks = [lpe_bh.BarnesHut(0) for _ in range(2)]
+    for r, c in enumerate(ranks):
+        c.set_shard(r, 2)
+        c.upload(x, y, vx, vy, m)
+    views = [c.device_view() for c in ranks]
+    for c in ranks:
+        assert not c.xchg_p2p_ready()
+        for r, v in enumerate(views):
+            c.xchg_set_peer(r, v.xchg_recv)
+        assert c.xchg_p2p_ready()
+    for _ in range(3):
+        for c in ranks:
+            c.step_begin(pg)
+        for c in ranks:
+            c.synchronize()          # the barrier a real run gets from a one-element allreduce
+        for c in ranks:
+            c.step_finish()
+    for c in ranks:
+        got = c.download()
+        for k in ("x", "y", "vx", "vy"):
+            assert np.array_equal(got[k], ref[k]), k
+        c.close()
+
