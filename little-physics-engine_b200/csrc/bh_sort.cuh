@@ -66,12 +66,42 @@ __device__ __forceinline__ unsigned int lb_exclusive(const unsigned long long* c
         }
         if (done) break;
         t -= used;   // (used <= t: the entries past tile 0 are inclusive and end the walk)
+        if (used == 0u) __nanosleep(64);   // nothing new: leave the L2 to the tiles we are waiting for
         if (used == 0u && ++spins > (1u << 22)) {   // a bounded wait turns a protocol bug into an error, not a hang
             atomicExch(fault, 1u);
             return excl;
         }
     }
     return excl;
+}
+
+// exclusive scan of one value per thread across a 256-thread block (warp shuffles + one word per warp)
+__device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v, unsigned int* sh, unsigned int* total) {
+    // sh: 8 words (one per warp) + 1
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = (lane < 8) ? sh[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < 8) sh[lane] = s;  // inclusive warp sums
+    }
+    __syncthreads();
+    const unsigned int wprefix = (w > 0) ? sh[w - 1] : 0u;
+    if (total) *total = sh[7];
+    const unsigned int ex = wprefix + inc - v;
+    __syncthreads();
+    return ex;
 }
 
 // hist[p * 512 + d] += number of keys whose digit in pass p is d, for every pass at once (keys read once).
@@ -168,8 +198,13 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
         __syncwarp();
     }
     __syncthreads();
-    // per digit: total in this tile, and the exclusive offsets of the warps inside the digit's run
-    for (int d = tid; d < bins; d += SORT_THREADS) {
+    // per digit: total in this tile, and the exclusive offsets of the warps inside the digit's run. The tile's counts
+    // are published at once (aggregate), the wait for the tiles before it comes after the local reordering.
+    constexpr int PER = BINS / SORT_THREADS;   // 1 or 2 digits per thread: tid * PER + k
+    unsigned int total[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int d = tid * PER + k;
         unsigned int run = 0;
 #pragma unroll
         for (int ww = 0; ww < SORT_WARPS; ++ww) {
@@ -177,37 +212,18 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
             cnt[ww][d] = run;
             run += c;
         }
-        dbase[d] = run;   // digit total for now
-        // publish this tile's count, add up the tiles before it, publish the inclusive value for the tiles after it
-        unsigned long long* mine = status + (size_t)tile * BINS + d;
-        lb_store(mine, epoch, tile == 0u ? LB_INCLUSIVE : LB_AGGREGATE, run);
-        unsigned int excl = 0;
-        if (tile != 0u) {
-            excl = lb_exclusive(status + d, BINS, tile, epoch, fault);
-            lb_store(mine, epoch, LB_INCLUSIVE, excl + run);
-        }
-        gbase[d] = digitBase[d] + excl;
+        total[k] = run;
+        lb_store(status + (size_t)tile * BINS + d, epoch, tile == 0u ? LB_INCLUSIVE : LB_AGGREGATE, run);
     }
-    __syncthreads();
-    // exclusive scan of the digit totals (bins <= 512, 256 threads: two per thread, Hillis-Steele over pair sums)
+    // exclusive scan of the digit totals -> start of each digit's run inside the tile
     {
-        __shared__ unsigned int pair[SORT_THREADS];
-        constexpr int PER = BINS / SORT_THREADS;   // 1 or 2
-        unsigned int v[PER];
+        __shared__ unsigned int sh_scan[9];
         unsigned int sum = 0;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { v[k] = dbase[tid * PER + k]; sum += v[k]; }
-        pair[tid] = sum;
-        __syncthreads();
-        for (int o = 1; o < SORT_THREADS; o <<= 1) {
-            const unsigned int t = (tid >= o) ? pair[tid - o] : 0u;
-            __syncthreads();
-            pair[tid] += t;
-            __syncthreads();
-        }
-        unsigned int run = pair[tid] - sum;
+        for (int k = 0; k < PER; ++k) sum += total[k];
+        unsigned int run = block_exclusive_scan_256(sum, sh_scan, nullptr);
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { dbase[tid * PER + k] = run; run += v[k]; }
+        for (int k = 0; k < PER; ++k) { dbase[tid * PER + k] = run; run += total[k]; }
     }
     __syncthreads();
 #pragma unroll
@@ -219,6 +235,17 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
             skey[lp] = key[r];
             sval[lp] = val[r];
         }
+    }
+    // now add up the tiles before this one and publish the inclusive value for the tiles after it
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        const int d = tid * PER + k;
+        unsigned int excl = 0;
+        if (tile != 0u) {
+            excl = lb_exclusive(status + d, BINS, tile, epoch, fault);
+            lb_store(status + (size_t)tile * BINS + d, epoch, LB_INCLUSIVE, excl + total[k]);
+        }
+        gbase[d] = digitBase[d] + excl;
     }
     __syncthreads();
     const int tileCount = (int)min((long long)SORT_TILE, (long long)n - tbase);
@@ -238,34 +265,6 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v, unsigned int* sh, unsigned int* total) {
-    // sh: 8 words (one per warp) + 1
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    unsigned int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) sh[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        unsigned int s = (lane < 8) ? sh[lane] : 0u;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-            if (lane >= o) s += t;
-        }
-        if (lane < 8) sh[lane] = s;  // inclusive warp sums
-    }
-    __syncthreads();
-    const unsigned int wprefix = (w > 0) ? sh[w - 1] : 0u;
-    if (total) *total = sh[7];
-    const unsigned int ex = wprefix + inc - v;
-    __syncthreads();
-    return ex;
-}
 
 template <class Load>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(Load load, int n, unsigned int* __restrict__ tileSums) {
