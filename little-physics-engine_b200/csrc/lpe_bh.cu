@@ -56,6 +56,7 @@ struct lpe_bh_ctx {
     double2* vel2 = nullptr;
     unsigned int *orig = nullptr, *orig2 = nullptr;
     bool orig_valid = false;
+    bool reorder_resident = true;   // resident runs (lpe_bh_step / sharded) keep the state in key order; the host tick does not
     unsigned int* rank_in = nullptr;   // staging of the caller's rank / component arrays
     unsigned char* comp_in = nullptr;
     // staging
@@ -294,12 +295,20 @@ __global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, cons
 // Direct O(N^2) sum in fp64 with the reference's force law (barnes_hut.cpp:257-282), tiled through shared memory.
 __global__ void __launch_bounds__(256)
 k_direct(int n, const Body* __restrict__ body, double U, double eps2, double G, int first, int count,
-         double* __restrict__ ax, double* __restrict__ ay) {
+         double* __restrict__ ax, double* __restrict__ ay, const unsigned int* __restrict__ orig) {
     __shared__ double sx[256], sy[256], sm[256];
+    // targets are the creation indices [first, first + count). With a re-ordered state (orig != null) every slot is
+    // looked at and the ones whose body falls into the range are computed.
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = first + k;
+    int i = first + k, out = k;
+    bool want = k < count;
+    if (orig) {
+        i = k;
+        out = (k < n) ? (int)orig[k] - first : -1;
+        want = k < n && out >= 0 && out < count;
+    }
     double2 p = make_double2(0.0, 0.0);
-    if (k < count) p = make_double2(body[i].x, body[i].y);
+    if (want) p = make_double2(body[i].x, body[i].y);
     double accx = 0.0, accy = 0.0;
     for (int base = 0; base < n; base += 256) {
         const int j = base + threadIdx.x;
@@ -325,9 +334,9 @@ k_direct(int n, const Body* __restrict__ body, double U, double eps2, double G, 
             accy += dy * f;
         }
     }
-    if (k < count) {
-        ax[k] = accx;
-        ay[k] = accy;
+    if (want) {
+        ax[out] = accx;
+        ay[out] = accy;
     }
 }
 
@@ -487,9 +496,13 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         c->pend_mass = false;
     }
     Reorder ro{nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (c->shard_n > 1) ro = Reorder{c->vel, c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2};
+    const bool reorder = c->shard_n > 1 || (c->reorder_resident && !c->pend_vel);
+    if (reorder && !c->body2 && (dalloc(c, c->body2, c->cap) || dalloc(c, c->vel2, c->cap) || dalloc(c, c->orig, c->cap) ||
+                                 dalloc(c, c->orig2, c->cap)))
+        return 1;
+    if (reorder) ro = Reorder{c->vel, c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2};
     k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal, ro);
-    if (c->shard_n > 1) {   // from here on the state IS in key order
+    if (reorder) {   // from here on the state IS in key order
         std::swap(c->body, c->body2);
         std::swap(c->vel, c->vel2);
         std::swap(c->orig, c->orig2);
@@ -907,13 +920,12 @@ int lpe_bh_get_counts(lpe_bh_ctx* c, uint32_t* accepted, uint32_t* visited) {
 int lpe_bh_direct_accel(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t first, uint64_t count, double* ax, double* ay) {
     if (!c || !p || !ax || !ay) return 1;
     if (first + count > c->n) return fail(c, "target range out of bounds");
-    if (c->orig_valid) return fail(c, "direct sum is not available once a sharded step has re-ordered the state");
     if (count == 0) return 0;
     CU_TRY(c, cudaSetDevice(c->device));
     double *dax = c->tmp, *day = c->tmp + c->cap;
-    k_direct<<<cdiv((long long)count, 256), 256, 0, c->stream>>>((int)c->n, c->body, p->universe_size,
-                                                                  p->softening * p->softening, p->G, (int)first,
-                                                                  (int)count, dax, day);
+    k_direct<<<cdiv((long long)(c->orig_valid ? c->n : count), 256), 256, 0, c->stream>>>(
+        (int)c->n, c->body, p->universe_size, p->softening * p->softening, p->G, (int)first, (int)count, dax, day,
+        c->orig_valid ? c->orig : nullptr);
     CU_TRY(c, cudaGetLastError());
     CU_TRY(c, cudaMemcpyAsync(ax, dax, 8 * count, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(ay, day, 8 * count, cudaMemcpyDeviceToHost, c->stream));

@@ -195,6 +195,17 @@ class BarnesHut:
         self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(self.n), _dp(x), _dp(y), _dp(vx), _dp(vy), _dp(m),
                                          _dp(rank), _dp(comp)), "upload")
 
+    def upload_positions(self, x, y):
+        """Replace the positions of the resident bodies (creation order), e.g. after a host-side MovementSystem."""
+        x, y = _f64(x), _f64(y)
+        assert len(x) == self.n and len(y) == self.n
+        self._chk(self.lib.lpe_bh_upload_positions(self.h, _dp(x), _dp(y)), "upload_positions")
+
+    def upload_velocities(self, vx, vy):
+        vx, vy = _f64(vx), _f64(vy)
+        assert len(vx) == self.n and len(vy) == self.n
+        self._chk(self.lib.lpe_bh_upload_velocities(self.h, _dp(vx), _dp(vy)), "upload_velocities")
+
     def upload_ptrs(self, n, x, y, vx, vy, m):
         """Raw host pointers (e.g. pinned torch tensors' data_ptr())."""
         self.n = n

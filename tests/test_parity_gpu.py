@@ -274,3 +274,32 @@ def test_two_rank_direct_exchange_on_one_gpu(port):
             assert np.array_equal(got[k], ref[k]), k
         c.close()
 
+
+def test_reordered_state_keeps_the_creation_order_interface(port):
+    """Resident steps keep the device state in key order; everything the ABI hands out stays in creation order:
+    download, per-body counts, the direct sum (kick only, so positions do not move and the sums must agree
+    before and after the steps), and partial uploads."""
+    n = 20000
+    x, y, vx, vy, m = gen_uniform(n, 1024.0, 77)
+    pg = lpe_bh.make_params(1024.0, 0.25, do_drift=False)
+    bh = lpe_bh.BarnesHut(0)
+    bh.set_instrumentation(counts=True)
+    bh.upload(x, y, vx, vy, m)
+    ax0, ay0 = bh.direct_accel(pg, 100, 5000)
+    bh.step(pg, 1)
+    acc1, _ = bh.counts()
+    bh.step(pg, 1)
+    acc2, _ = bh.counts()
+    ax1, ay1 = bh.direct_accel(pg, 100, 5000)
+    # (the sources are summed in state order, so the two sums differ by fp64 rounding only)
+    scale = np.abs(np.concatenate([ax0, ay0])).max()
+    assert np.abs(ax0 - ax1).max() <= 1e-12 * scale and np.abs(ay0 - ay1).max() <= 1e-12 * scale
+    assert np.array_equal(acc1, acc2)          # same positions -> same decisions, reported per creation index
+    got = bh.download()
+    assert np.array_equal(got["x"], x) and np.array_equal(got["y"], y)
+    # partial upload in creation order lands in the right slots
+    bh.upload_velocities(vx, vy)
+    back = bh.download()
+    assert np.array_equal(back["vx"], vx) and np.array_equal(back["vy"], vy)
+    bh.close()
+
