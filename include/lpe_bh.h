@@ -30,6 +30,7 @@ extern "C" {
 #define LPE_HAS_VELOCITY 2u /* Components::Velocity  -> target if it also has Mass (barnes_hut.cpp:89) */
 #define LPE_BOUNDARY     4u /* Components::Boundary  -> excluded from every view */
 #define LPE_LIQUID       8u /* ParticlePhase::Liquid -> not moved by MovementSystem (movement.cpp:25-29) */
+#define LPE_ASLEEP      16u /* Components::Sleep{asleep = true} -> skipped by BoundarySystem (boundary.cpp:29-31) */
 
 /* lpe_bh_params.precision */
 #define LPE_PREC_FAST   0 /* fp64 state + fp64 differences, fp32 interaction math, exact fp64 re-test of borderline theta decisions */
@@ -158,6 +159,21 @@ int  lpe_bh_get_device_view(lpe_bh_ctx* ctx, lpe_bh_device_view* out);
  * another rank's slice in; each is 4*xchg_chunk doubles. Synchronises. */
 int  lpe_bh_xchg_read_send(lpe_bh_ctx* ctx, double* host);
 int  lpe_bh_xchg_write_recv(lpe_bh_ctx* ctx, int src_rank, const double* host);
+/* ---- BoundarySystem as a device pass over the resident state -------------------------------
+ * Replaces Systems::BoundarySystem::update (reference src/systems/boundary.cpp:13-69, config
+ * include/systems/boundary.hpp:27-36) for resident runs, where it is the step right before BarnesHutSystem each
+ * tick (sim.cpp system order): bodies with LPE_HAS_VELOCITY and without LPE_ASLEEP are clamped to
+ * [margin, U - margin], the velocity component is reflected with damping, and after a bounce the speed is capped
+ * at max_speed. fp64, operation for operation as the reference (bit-exact against it). Asynchronous on the
+ * context's stream. */
+typedef struct lpe_bh_boundary_params {
+    double universe_size;    /* SharedSystemConfig::UniverseSizeMeters */
+    double margin;           /* BoundaryConfig::marginPixels * SharedSystemConfig::MetersPerPixel (metres) */
+    double bounce_damping;   /* BoundaryConfig::bounceDamping (default 0.7) */
+    double max_speed;        /* BoundaryConfig::maxSpeed (default 1.0) */
+} lpe_bh_boundary_params;
+int  lpe_bh_boundary(lpe_bh_ctx* ctx, const lpe_bh_boundary_params* p);
+
 /* Direct exchange over peer memory (NVLink / NVSwitch), 2..8 ranks of one node: once every rank's receive buffer is
  * known to this context, the traversal kernel itself stores each new (x,y,vx,vy) into ALL ranks' receive buffers
  * (the exchange overlaps the force computation) and the caller only needs a barrier between lpe_bh_step_begin and

@@ -292,6 +292,39 @@ __global__ void k_xchg_scatter(int n, int nranks, unsigned long long chunk, cons
     vel[b] = make_double2(v.z, v.w);
 }
 
+// BoundarySystem::update (reference src/systems/boundary.cpp:26-68) over the resident state, one body per thread.
+// Round-to-nearest intrinsics keep nvcc from contracting a*b+c into an FMA the reference (g++ -O2, x86-64) never uses.
+__global__ void __launch_bounds__(256)
+k_boundary(int n, Body* __restrict__ body, double2* __restrict__ vel, double marginM, double universeSizeM,
+           double bounceDamping, double maxSpeed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int cm = body[i].comp;
+    if (!(cm & LPE_HAS_VELOCITY) || (cm & LPE_ASLEEP)) return;   // view<Position, Velocity>, asleep skipped
+    double2 p = *reinterpret_cast<const double2*>(&body[i].x);
+    double2 v = vel[i];
+    const double hiEdge = __dsub_rn(universeSizeM, marginM);
+    bool bounced = false;
+    if (p.x < marginM) {
+        p.x = marginM; v.x = __dmul_rn(fabs(v.x), bounceDamping); bounced = true;
+    } else if (p.x > hiEdge) {
+        p.x = hiEdge; v.x = __dmul_rn(-fabs(v.x), bounceDamping); bounced = true;
+    }
+    if (p.y < marginM) {
+        p.y = marginM; v.y = __dmul_rn(fabs(v.y), bounceDamping); bounced = true;
+    } else if (p.y > hiEdge) {
+        p.y = hiEdge; v.y = __dmul_rn(-fabs(v.y), bounceDamping); bounced = true;
+    }
+    if (!bounced) return;
+    const double speed = __dsqrt_rn(__dadd_rn(__dmul_rn(v.x, v.x), __dmul_rn(v.y, v.y)));
+    if (speed > maxSpeed) {
+        v.x = __dmul_rn(__ddiv_rn(v.x, speed), maxSpeed);
+        v.y = __dmul_rn(__ddiv_rn(v.y, speed), maxSpeed);
+    }
+    *reinterpret_cast<double2*>(&body[i].x) = p;
+    vel[i] = v;
+}
+
 // Direct O(N^2) sum in fp64 with the reference's force law (barnes_hut.cpp:257-282), tiled through shared memory.
 __global__ void __launch_bounds__(256)
 k_direct(int n, const Body* __restrict__ body, double U, double eps2, double G, int first, int count,
@@ -993,6 +1026,19 @@ int lpe_bh_xchg_write_recv(lpe_bh_ctx* c, int src, const double* host) {
     CU_TRY(c, cudaMemcpyAsync(c->xchg_recv + (size_t)src * c->xchg_chunk, host, sizeof(double4) * c->xchg_chunk,
                               cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int lpe_bh_boundary(lpe_bh_ctx* c, const lpe_bh_boundary_params* p) {
+    if (!c || !p) return 1;
+    if (!(p->universe_size > 0.0) || !(p->margin >= 0.0)) return fail(c, "boundary: universe_size must be > 0 and margin >= 0");
+    if (c->n == 0) return 0;
+    CU_TRY(c, cudaSetDevice(c->device));
+    // the pass is per body and order-free: it runs on the state in whatever order it currently is
+    k_boundary<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->body, c->vel, p->margin, p->universe_size,
+                                                                   p->bounce_damping, p->max_speed);
+    CU_TRY(c, cudaGetLastError());
+    c->launches += 1;
     return 0;
 }
 

@@ -18,7 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liblpe_bh.so")
 
-HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID = 1, 2, 4, 8
+HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID, ASLEEP = 1, 2, 4, 8, 16
 PREC_FAST, PREC_STRICT = 0, 1
 KEYS_AUTO, KEYS_MORTON, KEYS_HILBERT = 0, 1, 2
 SHARD_BLOCK = 2048
@@ -49,6 +49,12 @@ class Stats(C.Structure):
         d = {k: getattr(self, k) for k, _ in self._fields_}
         d["t2_kinds"] = list(d["t2_kinds"])
         return d
+
+
+class BoundaryParams(C.Structure):
+    """lpe_bh_boundary_params: Systems::BoundaryConfig (include/systems/boundary.hpp:27-36), margin in metres."""
+    _fields_ = [("universe_size", C.c_double), ("margin", C.c_double), ("bounce_damping", C.c_double),
+                ("max_speed", C.c_double)]
 
 
 class TreeDump(C.Structure):
@@ -211,6 +217,11 @@ class BarnesHut:
         self.n = n
         self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(n), C.c_void_p(x), C.c_void_p(y), C.c_void_p(vx),
                                          C.c_void_p(vy), C.c_void_p(m), None, None), "upload")
+
+    def boundary(self, universe_size, margin=15.0, bounce_damping=0.7, max_speed=1.0):
+        """Systems::BoundarySystem::update as a device pass over the resident bodies (reference boundary.cpp:13-69)."""
+        bp = BoundaryParams(universe_size, margin, bounce_damping, max_speed)
+        self._chk(self.lib.lpe_bh_boundary(self.h, C.byref(bp)), "boundary")
 
     # ---- direct exchange over peer memory (include/lpe_bh.h) ----
     def xchg_export(self):

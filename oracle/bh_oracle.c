@@ -405,3 +405,47 @@ int orc_direct_accel(const orc_params* p, uint64_t n, const double* x, const dou
 const char* orc_bh_describe(void) {
     return "plain-C port of little-physics-engine src/systems/barnes_hut.cpp + movement.cpp (oracle/bh_oracle.c)";
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * BoundarySystem::update, reference src/systems/boundary.cpp:13-69 — clamp to [margin, U - margin], reflect the
+ * velocity component with damping, and after a bounce cap the speed at maxSpeed. View = Position + Velocity
+ * (boundary.cpp:22), asleep entities skipped (boundary.cpp:29-31).
+ * --------------------------------------------------------------------------------------------------------- */
+int orc_boundary(const orc_boundary_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
+                 const uint8_t* comp) {
+    if (!p || (n && (!x || !y || !vx || !vy))) return 1;
+    const double marginM = p->margin, universeSizeM = p->universe_size;
+    const double bounceDamping = p->bounce_damping, maxSpeed = p->max_speed;
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned cm = comp ? comp[i] : (ORC_HAS_MASS | ORC_HAS_VELOCITY);
+        if (!(cm & ORC_HAS_VELOCITY) || (cm & ORC_ASLEEP)) continue;
+        int bounced = 0;
+        if (x[i] < marginM) {                                   /* boundary.cpp:36-40 */
+            x[i] = marginM;
+            vx[i] = fabs(vx[i]) * bounceDamping;
+            bounced = 1;
+        } else if (x[i] > universeSizeM - marginM) {            /* boundary.cpp:42-46 */
+            x[i] = universeSizeM - marginM;
+            vx[i] = -fabs(vx[i]) * bounceDamping;
+            bounced = 1;
+        }
+        if (y[i] < marginM) {                                   /* boundary.cpp:49-53 */
+            y[i] = marginM;
+            vy[i] = fabs(vy[i]) * bounceDamping;
+            bounced = 1;
+        } else if (y[i] > universeSizeM - marginM) {            /* boundary.cpp:55-59 */
+            y[i] = universeSizeM - marginM;
+            vy[i] = -fabs(vy[i]) * bounceDamping;
+            bounced = 1;
+        }
+        if (bounced) {                                          /* boundary.cpp:62-68 */
+            const double speed = sqrt(vx[i] * vx[i] + vy[i] * vy[i]);
+            if (speed > maxSpeed) {
+                vx[i] = (vx[i] / speed) * maxSpeed;
+                vy[i] = (vy[i] / speed) * maxSpeed;
+            }
+        }
+    }
+    return 0;
+}
+

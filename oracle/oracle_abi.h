@@ -27,6 +27,15 @@ extern "C" {
 #define ORC_HAS_VELOCITY 2u  /* Components::Velocity */
 #define ORC_BOUNDARY     4u  /* Components::Boundary  (excluded from every view) */
 #define ORC_LIQUID       8u  /* ParticlePhase == Liquid (skipped by MovementSystem) */
+#define ORC_ASLEEP      16u  /* Components::Sleep with asleep == true (skipped by BoundarySystem, boundary.cpp:29-31) */
+
+/* BoundarySystem (reference include/systems/boundary.hpp:27-36, src/systems/boundary.cpp:16-19) */
+typedef struct {
+    double universe_size;    /* SharedSystemConfig::UniverseSizeMeters */
+    double margin;           /* BoundaryConfig::marginPixels * SharedSystemConfig::MetersPerPixel, in metres */
+    double bounce_damping;   /* BoundaryConfig::bounceDamping */
+    double max_speed;        /* BoundaryConfig::maxSpeed */
+} orc_boundary_params;
 
 typedef struct {
     double universe_size;          /* SharedSystemConfig::UniverseSizeMeters   (shared_system_config.hpp:11) */
@@ -63,6 +72,13 @@ typedef struct {
     double   force_seconds;
     double   total_seconds;
 } orc_stats;
+
+/* BoundarySystem::update on flat arrays, in place: bodies with ORC_HAS_VELOCITY and without ORC_ASLEEP are clamped
+ * to [margin, U - margin] and bounced (boundary.cpp:21-66). Same signature in both libraries. */
+int orc_boundary(const orc_boundary_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
+                 const uint8_t* comp);
+int ref_boundary(const orc_boundary_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
+                 const uint8_t* comp);
 
 #ifdef __cplusplus
 }

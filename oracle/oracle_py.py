@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libref_bh.so")
 PORT_SO = os.path.join(HERE, "liboracle_bh.so")
 
-HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID = 1, 2, 4, 8
+HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID, ASLEEP = 1, 2, 4, 8, 16
 
 
 class Params(C.Structure):
@@ -105,6 +105,23 @@ def build_ref():
     return REF_SO if os.path.exists(REF_SO) else None
 
 
+class BoundaryParams(C.Structure):
+    """orc_boundary_params (oracle_abi.h): BoundarySystem's configuration, margin in metres."""
+    _fields_ = [("universe_size", C.c_double), ("margin", C.c_double), ("bounce_damping", C.c_double),
+                ("max_speed", C.c_double)]
+
+
+def _boundary(fn, U, margin, damping, max_speed, x, y, vx, vy, comp):
+    out = [np.array(a, dtype=np.float64, copy=True) for a in (x, y, vx, vy)]
+    comp = None if comp is None else np.ascontiguousarray(comp, dtype=np.uint8)
+    bp = BoundaryParams(U, margin, damping, max_speed)
+    rc = fn(C.byref(bp), C.c_uint64(len(out[0])), *[_ptr(a, C.c_double) for a in out],
+            None if comp is None else _ptr(comp, C.c_uint8))
+    if rc:
+        raise RuntimeError("boundary failed")
+    return dict(x=out[0], y=out[1], vx=out[2], vy=out[3])
+
+
 class PortLib:
     kind = "port"
 
@@ -138,6 +155,10 @@ class PortLib:
             out["accepted"] = acc
             out["visited"] = vis
         return out
+
+    def boundary(self, U, x, y, vx, vy, comp=None, margin=15.0, damping=0.7, max_speed=1.0):
+        """BoundarySystem::update restated (bh_oracle.c: orc_boundary)."""
+        return _boundary(self.lib.orc_boundary, U, margin, damping, max_speed, x, y, vx, vy, comp)
 
     def tree(self, p, x, y, m, comp=None, rank=None):
         x, y, m = map(_f64, (x, y, m))
@@ -201,6 +222,10 @@ class RefLib:
         if rc:
             raise RuntimeError(f"ref_bh_run failed rc={rc} (2 = node pool grew: reference defect D1)")
         return dict(x=ox, y=oy, vx=ovx, vy=ovy, stats=st.as_dict())
+
+    def boundary(self, U, x, y, vx, vy, comp=None, margin=15.0, damping=0.7, max_speed=1.0):
+        """The reference's own BoundarySystem::update (ref_harness.cpp: ref_boundary)."""
+        return _boundary(self.lib.ref_boundary, U, margin, damping, max_speed, x, y, vx, vy, comp)
 
     def view_rank(self, n, comp=None):
         comp = None if comp is None else np.ascontiguousarray(comp, dtype=np.uint8)

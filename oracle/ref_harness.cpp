@@ -25,6 +25,7 @@
 #include "systems/barnes_hut.hpp"
 #undef private
 #include "systems/movement.hpp"
+#include "systems/boundary.hpp"
 #include "entities/entity_components.hpp"
 #include "entities/sim_components.hpp"
 
@@ -217,6 +218,47 @@ int ref_bh_tree(const orc_params* p, uint64_t n, const double* x, const double* 
 const char* ref_bh_describe(void) {
     return "reference sean-peters-au/little-physics-engine: src/systems/barnes_hut.cpp + movement.cpp, "
            "compiled unmodified (g++ -O2, ENTT_ID_TYPE=uint64), single thread";
+}
+
+/* The reference's own BoundarySystem::update (src/systems/boundary.cpp) on a registry filled from the arrays. */
+int ref_boundary(const orc_boundary_params* p, uint64_t n, double* x, double* y, double* vx, double* vy,
+                 const uint8_t* comp) {
+    if (!p || (n && (!x || !y || !vx || !vy))) return 1;
+    entt::registry reg;
+    std::vector<entt::entity> ents(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const unsigned cm = comp ? comp[i] : (ORC_HAS_MASS | ORC_HAS_VELOCITY);
+        const auto e = reg.create();
+        ents[i] = e;
+        reg.emplace<Components::Position>(e, x[i], y[i]);
+        if (cm & ORC_HAS_VELOCITY) reg.emplace<Components::Velocity>(e, vx[i], vy[i]);
+        if (cm & ORC_ASLEEP) {
+            Components::Sleep sl;
+            sl.asleep = true;
+            reg.emplace<Components::Sleep>(e, sl);
+        }
+    }
+    Systems::BoundarySystem bs;
+    SharedSystemConfig sc{};
+    sc.UniverseSizeMeters = p->universe_size;
+    sc.MetersPerPixel = 1.0;              // margin is handed over in metres
+    bs.setSharedSystemConfig(sc);
+    Systems::BoundaryConfig bc;
+    bc.marginPixels = p->margin;
+    bc.bounceDamping = p->bounce_damping;
+    bc.maxSpeed = p->max_speed;
+    bs.setSpecificConfig(bc);
+    bs.update(reg);
+    for (uint64_t i = 0; i < n; ++i) {
+        const auto& pos = reg.get<Components::Position>(ents[i]);
+        x[i] = pos.x;
+        y[i] = pos.y;
+        if (auto* v = reg.try_get<Components::Velocity>(ents[i])) {
+            vx[i] = v->x;
+            vy[i] = v->y;
+        }
+    }
+    return 0;
 }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
-"""Generates tests/golden/*.npz from the REFERENCE ITSELF (oracle/_ref/libref_bh.so = the reference's
-barnes_hut.cpp + movement.cpp compiled unmodified from /root/reference, see oracle/Makefile).
+"""Generates tests/golden/*.npz (and tests/golden/boundary/*.npz) from the REFERENCE ITSELF
+(oracle/_ref/libref_bh.so = the reference's barnes_hut.cpp + movement.cpp + boundary.cpp compiled unmodified from
+/root/reference, see oracle/Makefile).
 
 Run here (the container with /root/reference):   python tests/golden/make_golden.py
 The reference ships no golden vectors of its own, so these are the pinned known answers:
@@ -69,9 +70,42 @@ def cases():
     return out
 
 
+def boundary_cases():
+    """Inputs for BoundarySystem: bodies inside, outside each edge and exactly on the clamp
+    edges, fast and slow, with velocity-less and asleep entities mixed in."""
+    rng = np.random.default_rng(20261019)
+    out = {}
+    for name, n, U, margin, damping, vmax, vscale in (("default_cfg", 4000, 1000.0, 15.0, 0.7, 1.0, 3.0),
+                                                     ("no_damping_big_cap", 1500, 6e9, 2.5e7, 1.0, 1e4, 5e3),
+                                                     ("zero_margin", 1500, 1024.0, 0.0, 0.5, 0.25, 1.0)):
+        x = rng.uniform(-0.1 * U, 1.1 * U, n)
+        y = rng.uniform(-0.1 * U, 1.1 * U, n)
+        x[:8] = [margin, U - margin, np.nextafter(margin, -1), np.nextafter(U - margin, 2 * U), 0.0, U, -U, 2 * U]
+        y[4:12] = [margin, U - margin, np.nextafter(margin, -1), np.nextafter(U - margin, 2 * U), 0.0, U, -U, 2 * U]
+        vx = rng.standard_normal(n) * vscale
+        vy = rng.standard_normal(n) * vscale
+        vx[::37] = 0.0
+        vy[::41] = -0.0
+        comp = np.full(n, O.HAS_MASS | O.HAS_VELOCITY, np.uint8)
+        comp[3::7] = O.HAS_MASS                      # no Velocity: not in the view
+        comp[5::9] |= O.ASLEEP                       # asleep: skipped
+        out[name] = dict(x=x, y=y, vx=vx, vy=vy, comp=comp, U=U, margin=margin, damping=damping, vmax=vmax)
+    return out
+
+
 def main():
     ref = O.RefLib()
     print(ref.describe())
+    os.makedirs(os.path.join(HERE, "boundary"), exist_ok=True)
+    for name, c in boundary_cases().items():
+        r = ref.boundary(c["U"], c["x"], c["y"], c["vx"], c["vy"], comp=c["comp"], margin=c["margin"],
+                         damping=c["damping"], max_speed=c["vmax"])
+        path = os.path.join(HERE, "boundary", name + ".npz")
+        np.savez_compressed(path, x=c["x"], y=c["y"], vx=c["vx"], vy=c["vy"], comp=c["comp"],
+                            cfg=np.array([c["U"], c["margin"], c["damping"], c["vmax"]]),
+                            out_x=r["x"], out_y=r["y"], out_vx=r["vx"], out_vy=r["vy"])
+        moved = int(np.sum((r["x"] != c["x"]) | (r["y"] != c["y"])))
+        print(f"boundary/{name}: n={len(c['x'])} clamped={moved} -> {os.path.getsize(path)} B")
     for name, c in cases().items():
         p = O.make_params(c["U"], c["eps"], theta=c["theta"], thr=c["thr"], dt_kick=c["dt_kick"],
                           dt_drift=c["dt_drift"])
