@@ -103,6 +103,7 @@ struct StepConst {
     int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
     int test_overflow;        // tests only: pretend every two-phase frontier overflows
     int hilbert;              // sort key: 0 = Morton code, 1 = Hilbert index of the same depth-D cell
+    float eps2f;              // (float)eps2s, converted once on the host (the kernels would re-convert it in their loops)
 };
 
 // Mass and centre of mass of a node as the traversal sees it, in real units.

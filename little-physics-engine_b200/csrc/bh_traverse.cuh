@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
     TravRec* const frames = &sFrames[warp][0][0];
     const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
-    const float eps2f = (float)c.eps2s;
+    const float eps2f = c.eps2f;
     const double Us = c.U * c.invS;
     const float INF = __int_as_float(0x7f800000);
     constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
     const unsigned int lanebit = 1u << lane;
     const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
-    const float eps2f = (float)c.eps2s;
+    const float eps2f = c.eps2f;
     const double Us = c.U * c.invS;
     const float INF = __int_as_float(0x7f800000);
     const float FMAXV = 3.0e38f;

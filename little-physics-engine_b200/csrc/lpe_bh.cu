@@ -429,6 +429,7 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     k.eps = p.softening;
     const double es = p.softening * k.invS;
     k.eps2s = es * es;
+    k.eps2f = (float)k.eps2s;
     k.theta = p.theta;
     k.theta2 = p.theta * p.theta;
     k.thr = p.small_mass_threshold;
