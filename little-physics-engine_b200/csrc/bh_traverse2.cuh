@@ -180,19 +180,17 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
 
         const unsigned int tmask = __ballot_sync(0xFFFFFFFFu, target);
         if (tmask != 0u && n_nodes != 0u && !overflow) {
-            // ---- bounding box of the warp's targets (scaled units), as two-float edges ----
-            double bx0 = target ? pxs : 1e300, bx1 = target ? pxs : -1e300;
-            double by0 = target ? pys : 1e300, by1 = target ? pys : -1e300;
+            // ---- bounding box of the warp's targets (scaled units): fp32 edges rounded OUTWARD, so the box contains
+            // every fp64 position and the group classification stays conservative ----
+            float bx0 = target ? __double2float_rd(pxs) : INF, bx1 = target ? __double2float_ru(pxs) : -INF;
+            float by0 = target ? __double2float_rd(pys) : INF, by1 = target ? __double2float_ru(pys) : -INF;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                bx0 = fmin(bx0, __shfl_xor_sync(0xFFFFFFFFu, bx0, o));
-                bx1 = fmax(bx1, __shfl_xor_sync(0xFFFFFFFFu, bx1, o));
-                by0 = fmin(by0, __shfl_xor_sync(0xFFFFFFFFu, by0, o));
-                by1 = fmax(by1, __shfl_xor_sync(0xFFFFFFFFu, by1, o));
+                bx0 = fminf(bx0, __shfl_xor_sync(0xFFFFFFFFu, bx0, o));
+                bx1 = fmaxf(bx1, __shfl_xor_sync(0xFFFFFFFFu, bx1, o));
+                by0 = fminf(by0, __shfl_xor_sync(0xFFFFFFFFu, by0, o));
+                by1 = fmaxf(by1, __shfl_xor_sync(0xFFFFFFFFu, by1, o));
             }
-            const float x0h = (float)bx0, x1h = (float)bx1, y0h = (float)by0, y1h = (float)by1;
-            const float x0l = (float)(bx0 - (double)x0h), x1l = (float)(bx1 - (double)x1h);
-            const float y0l = (float)(by0 - (double)y0h), y1l = (float)(by1 - (double)y1h);
 
             unsigned int head = 0, tail = 1, nA = 0;
             if (lane == 0) W.q[0] = make_uint2(0u, tmask);   // the root, reached by every target
@@ -215,8 +213,8 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 }
                 head += cnt;
                 // distance bounds from the node centre to the targets' box
-                const float ax0 = (R.c.x - x0h) + (R.c.z - x0l), ax1 = (R.c.x - x1h) + (R.c.z - x1l);
-                const float ay0 = (R.c.y - y0h) + (R.c.w - y0l), ay1 = (R.c.y - y1h) + (R.c.w - y1l);
+                const float ax0 = (R.c.x - bx0) + R.c.z, ax1 = (R.c.x - bx1) + R.c.z;
+                const float ay0 = (R.c.y - by0) + R.c.w, ay1 = (R.c.y - by1) + R.c.w;
                 const float dxmin = fmaxf(fmaxf(-ax0, ax1), 0.f), dxmax = fmaxf(fabsf(ax0), fabsf(ax1));
                 const float dymin = fmaxf(fmaxf(-ay0, ay1), 0.f), dymax = fmaxf(fabsf(ay0), fabsf(ay1));
                 const float d2min = fmaf(dxmin, dxmin, fmaf(dymin, dymin, eps2f));
