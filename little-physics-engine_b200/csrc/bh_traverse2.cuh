@@ -23,6 +23,7 @@
 //
 // A warp whose frontier outgrows its shared-memory queue hands its chunk to the depth-first kernel (second launch).
 #pragma once
+#include <type_traits>
 #include "bh_common.cuh"
 #include "bh_traverse.cuh"
 
@@ -266,6 +267,13 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                 f32x2_t AX2 = pack2(0.f, 0.f), AY2 = AX2;   // this round's partial sums, two lanes of fp32 per axis
 
                 // ---------------- phase 2a: the mixed nodes of this round, one body per lane ----------------
+                // Run twice at most: the fast pass takes the fp32 decision everywhere and only REMEMBERS whether some
+                // lane came inside a guard band; if one did (about 1 round in 500) the round's mixed nodes are redone
+                // with the reference's fp64 test deciding those cases. No vote or branch per node in the fast pass.
+                auto mixed = [&](auto exactTag) -> bool {
+                constexpr bool EXACT = decltype(exactTag)::value;
+                bool bandAny = false;
+                AX2 = pack2(0.f, 0.f); AY2 = AX2;
                 for (unsigned int m = 0; m < cntM; m += 2) {
                     const ulonglong2* mp = reinterpret_cast<const ulonglong2*>(&W.mp[m >> 1]);
                     const ulonglong2 vh = mp[0], vl = mp[1];
@@ -283,13 +291,15 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                     const float d20 = reached0 ? lo2(d2p) : INF, d21 = reached1 ? hi2(d2p) : INF;
                     float lo0 = tl.x, lo1 = tl.y;
                     const bool band0 = d20 > lo0 && d20 < th.x, band1 = d21 > lo1 && d21 < th.y;
-                    if (__any_sync(0xFFFFFFFFu, band0 || band1)) {   // rare: guard band -> the reference's fp64 test decides
-                        if (band0)
+                    if (EXACT) {
+                        if (band0)   // guard band: the reference's fp64 test decides
                             lo0 = exact_open(a.agg, a.meta, a.recnode[W.mslot[m] & 0x7FFFFFFFu], c.quirk, c.invS, pxs,
                                              pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
                         if (band1)
                             lo1 = exact_open(a.agg, a.meta, a.recnode[W.mslot[m + 1] & 0x7FFFFFFFu], c.quirk, c.invS,
                                              pxs, pys, c.eps2s, Us, c.theta2) ? FMAXV : -1.f;
+                    } else {
+                        bandAny = bandAny || band0 || band1;
                     }
                     const bool open0 = d20 <= lo0, open1 = d21 <= lo1;
                     const unsigned int om0 = __ballot_sync(0xFFFFFFFFu, open0);
@@ -313,6 +323,11 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                     AX2 = fma2(dx, f, AX2);
                     AY2 = fma2(dy, f, AY2);
                 }
+                return bandAny;
+                };
+                bool redo = true;                       // counting runs take the exact pass only (counters tick once)
+                if (!STATS) redo = mixed(std::false_type{});
+                if (STATS || __any_sync(0xFFFFFFFFu, redo)) mixed(std::true_type{});
                 if (STATS) nwarp += cntM;
                 __syncwarp();
 
