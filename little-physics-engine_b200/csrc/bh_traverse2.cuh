@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravAr
                         E.g[1] = 0.f; E.mask[1] = 0u; W.aslot[nA] = LPE_NONE;
                     }
                     __syncwarp();
-#pragma unroll 2
+#pragma unroll 4
                     for (unsigned int m = 0; m < nA; m += 2)
                         t2_accept_pair<STATS, SELF>(W, m, lanebit, self, LP, AX2, AY2, nacc);
                     if (STATS) nwarp += nA;
