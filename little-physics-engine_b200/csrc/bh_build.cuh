@@ -59,9 +59,53 @@ __device__ __forceinline__ unsigned long long hilbert_index(unsigned int x, unsi
     return d;
 }
 
+// The same curve two levels per step: the walk above is a 4-state machine (state = swap | invert << 1 applied to the
+// remaining low bits), so a 64-entry table indexed by state and a nibble (2 bits of x, 2 bits of y) gives 4 index
+// bits and the next state. The table is filled from hilbert_index's own single-level rule, see hilbert_lut_entry.
+__device__ __forceinline__ unsigned int hilbert_level(unsigned int state, unsigned int xb, unsigned int yb,
+                                                      unsigned int& digit) {
+    const unsigned int sw = state & 1u, inv = state >> 1;
+    const unsigned int rx = (sw ? yb : xb) ^ inv, ry = (sw ? xb : yb) ^ inv;
+    digit = (3u * rx) ^ ry;
+    unsigned int nsw = sw, ninv = inv;
+    if (ry == 0u) {            // hilbert_index: (flip both if rx) then swap
+        if (rx == 1u) ninv ^= 1u;
+        nsw ^= 1u;
+    }
+    return nsw | (ninv << 1);
+}
+__device__ __forceinline__ unsigned char hilbert_lut_entry(unsigned int idx) {   // idx = state << 4 | y2 << 2 | x2
+    const unsigned int state = idx >> 4, x2 = idx & 3u, y2 = (idx >> 2) & 3u;
+    unsigned int d1, d0;
+    const unsigned int s1 = hilbert_level(state, x2 >> 1, y2 >> 1, d1);
+    const unsigned int s0 = hilbert_level(s1, x2 & 1u, y2 & 1u, d0);
+    return (unsigned char)((s0 << 4) | (d1 << 2) | d0);
+}
+__device__ __forceinline__ unsigned long long hilbert_index_lut(const unsigned char* lut, unsigned int x, unsigned int y, int D) {
+    unsigned long long d = 0;
+    unsigned int state = 0;
+    int b = D;
+    if (b & 1) {               // odd depth: one single level first
+        --b;
+        unsigned int dg;
+        state = hilbert_level(0u, (x >> b) & 1u, (y >> b) & 1u, dg);
+        d = dg;
+    }
+    for (b -= 2; b >= 0; b -= 2) {
+        const unsigned int nib = ((x >> b) & 3u) | (((y >> b) & 3u) << 2);
+        const unsigned int e = lut[(state << 4) | nib];
+        d = (d << 4) | (e & 15u);
+        state = e >> 4;
+    }
+    return d;
+}
+
 __global__ void __launch_bounds__(256)
 k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restrict__ keys,
          unsigned int* __restrict__ vals, Scal* __restrict__ s) {
+    __shared__ unsigned char lut[64];
+    if (threadIdx.x < 64) lut[threadIdx.x] = hilbert_lut_entry(threadIdx.x);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int in = 0;
     if (i < c.n) {
@@ -76,7 +120,7 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
             const unsigned int kmax = (1u << c.D) - 1u;
             const unsigned int ix = cell_index(p.x, c.h, c.invh, kmax);
             const unsigned int iy = cell_index(p.y, c.h, c.invh, kmax);
-            key = c.hilbert ? hilbert_index(ix, iy, c.D) : (spread_bits32(ix) | (spread_bits32(iy) << 1));
+            key = c.hilbert ? hilbert_index_lut(lut, ix, iy, c.D) : (spread_bits32(ix) | (spread_bits32(iy) << 1));
             in = 1;
         }
         keys[i] = key;
