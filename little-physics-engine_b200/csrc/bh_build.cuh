@@ -193,6 +193,33 @@ struct HeadFlag {
     }
 };
 
+// sinks of the single-pass scans
+struct TerminalSink {   // head-flag scan -> the terminal arrays (what k_terminals does from a stored prefix)
+    const unsigned long long* keys;
+    unsigned long long* tkey;
+    unsigned int* tfirst;
+    Scal* s;
+    int n;
+    __device__ __forceinline__ void operator()(int i, unsigned int excl, unsigned int head) const {
+        const unsigned int n_in = s->n_in;
+        if ((unsigned int)i < n_in) {
+            if (head) {
+                tkey[excl] = keys[i];
+                tfirst[excl] = (unsigned int)i;
+            }
+            if ((unsigned int)i == n_in - 1u) tfirst[excl + head] = n_in;
+        }
+        if (i == n) {
+            s->n_term = excl;   // grand total of the head flags
+            if (n_in == 0u) tfirst[0] = 0u;
+        }
+    }
+};
+struct StoreSink {      // plain exclusive prefix, out[0..n]
+    unsigned int* out;
+    __device__ __forceinline__ void operator()(int i, unsigned int excl, unsigned int) const { out[i] = excl; }
+};
+
 // ---- 3. terminals -----------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_terminals(int n, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ headExcl,

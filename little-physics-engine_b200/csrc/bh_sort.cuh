@@ -322,4 +322,79 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(Load load, int n, c
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Single-pass version of the same scan (decoupled look-back, one status word per tile): every element is loaded
+// once and handed to `sink(i, exclusive_prefix, value)` for i in [0, n] (i == n carries the grand total), so the
+// consumer of the scan is fused into it. One kernel instead of three + the consumer's own launch.
+// ------------------------------------------------------------------------------------------------
+// warp-wide look-back over one column: lane k inspects tile - 1 - k
+__device__ __forceinline__ unsigned int lb_exclusive_warp(const unsigned long long* status, unsigned int tile,
+                                                          unsigned int epoch, unsigned int* __restrict__ fault) {
+    const unsigned int lane = threadIdx.x & 31u;
+    unsigned int excl = 0, spins = 0;
+    unsigned int t = tile;   // tiles [t, tile) are already summed
+    while (t > 0u) {
+        const bool inrange = lane < t;
+        // before the first tile: an inclusive zero ends the walk
+        const unsigned long long w = inrange ? lb_load(status + (t - 1u - lane))
+                                             : ((unsigned long long)((epoch << 2) | LB_INCLUSIVE) << 32);
+        const unsigned int hi = (unsigned int)(w >> 32);
+        const bool ready = (hi >> 2) == epoch;
+        const unsigned int notReady = __ballot_sync(0xFFFFFFFFu, !ready);
+        const unsigned int usable = notReady ? ((1u << (__ffs(notReady) - 1)) - 1u) : 0xFFFFFFFFu;   // lanes before the first gap
+        const unsigned int incl = __ballot_sync(0xFFFFFFFFu, ready && (hi & 3u) == LB_INCLUSIVE) & usable;
+        const unsigned int take = incl ? ((2u << (__ffs(incl) - 1)) - 1u) : usable;                  // up to the first inclusive one
+        excl += __reduce_add_sync(0xFFFFFFFFu, ((take >> lane) & 1u) ? (unsigned int)w : 0u);
+        if (incl) break;
+        t -= __popc(usable);
+        if (usable == 0u) {
+            __nanosleep(64);
+            if (++spins > (1u << 22)) {   // bounded wait: a protocol bug becomes an error flag, not a hang
+                if (lane == 0) atomicExch(fault, 1u);
+                break;
+            }
+        }
+    }
+    return excl;
+}
+
+template <class Load, class Sink>
+__global__ void __launch_bounds__(SCAN_THREADS)
+k_scan_chained(Load load, Sink sink, int n, unsigned long long* __restrict__ status, unsigned int epoch,
+               unsigned int* __restrict__ ticket, unsigned int* __restrict__ fault) {
+    __shared__ unsigned int sh[9];
+    __shared__ unsigned int s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);   // tiles in start order
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const long long base = (long long)tile * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+    unsigned int v[SCAN_ITEMS];
+    unsigned int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const long long i = base + k;
+        v[k] = (i < n) ? load((int)i) : 0u;
+        sum += v[k];
+    }
+    unsigned int tot;
+    const unsigned int ex = block_exclusive_scan_256(sum, sh, &tot);
+    if (threadIdx.x == 0) lb_store(status + tile, epoch, tile == 0u ? LB_INCLUSIVE : LB_AGGREGATE, tot);
+    if (threadIdx.x < 32) {
+        unsigned int excl = 0;
+        if (tile != 0u) {
+            excl = lb_exclusive_warp(status, tile, epoch, fault);
+            if (threadIdx.x == 0) lb_store(status + tile, epoch, LB_INCLUSIVE, excl + tot);
+        }
+        if (threadIdx.x == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    unsigned int run = s_prefix + ex;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        const long long i = base + k;
+        if (i <= n) sink((int)i, run, v[k]);
+        run += v[k];
+    }
+}
+
 }  // namespace lpe

@@ -155,7 +155,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) |
           dalloc(c, c->tmp, 5 * cap);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
-          dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512)) | dalloc(c, c->totals, 512 * 8 + 16);
+          dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512) + 2 * ((size_t)scanTiles + 2)) | dalloc(c, c->totals, 512 * 8 + 16);
     rc |= dalloc(c, c->sbody, cap) | dalloc(c, c->selfnode, cap) |
           dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
     rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
@@ -494,8 +494,9 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     {
         // look-back words carry the step's epoch, so the status array is cleared only when the epoch wraps
         if (c->epoch == 0u || c->epoch >= (1u << 30) - 1u) {
-            CU_TRY(c, cudaMemsetAsync(c->lbstatus, 0, sizeof(unsigned long long) * (size_t)cdiv((long long)c->cap, SORT_TILE) *
-                                                          (256 * (SORT_MAX_PASSES - 1) + 512), st));
+            CU_TRY(c, cudaMemsetAsync(c->lbstatus, 0, sizeof(unsigned long long) *
+                                          ((size_t)cdiv((long long)c->cap, SORT_TILE) * (256 * (SORT_MAX_PASSES - 1) + 512) +
+                                           2 * ((size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 2)), st));
             c->epoch = 0u;
         }
         ++c->epoch;
@@ -542,11 +543,18 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         std::swap(c->orig, c->orig2);
         c->orig_valid = true;
     }
-    device_scan(c, HeadFlag{skeys, c->scal}, n, c->headExcl, nullptr);
-    k_terminals<<<g256, 256, 0, st>>>(n, skeys, c->headExcl, c->tkey, c->tfirst, c->scal);
+    // scans are single-pass (look-back over one status word per tile), each fused with its consumer
+    const int scanTiles = cdiv((long long)n + 1, SCAN_TILE);
+    unsigned int* scanTicket = c->totals + 512 * SORT_MAX_PASSES + SORT_MAX_PASSES + 1;
+    unsigned int* sortFault = c->totals + 512 * SORT_MAX_PASSES + SORT_MAX_PASSES;
+    unsigned long long* scanStatus = c->lbstatus + (size_t)cdiv((long long)c->cap, SORT_TILE) * (256 * (SORT_MAX_PASSES - 1) + 512);
+    k_scan_chained<<<scanTiles, SCAN_THREADS, 0, st>>>(HeadFlag{skeys, c->scal}, TerminalSink{skeys, c->tkey, c->tfirst, c->scal, n},
+                                                       n, scanStatus, c->epoch, scanTicket, sortFault);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
     k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->wstart, levelCount, c->scal);
-    device_scan(c, MaskPop{c->mask, c->scal}, n, c->P, nullptr);
+    k_scan_chained<<<scanTiles, SCAN_THREADS, 0, st>>>(MaskPop{c->mask, c->scal}, StoreSink{c->P}, n,
+                                                       scanStatus + (size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 1, c->epoch,
+                                                       scanTicket + 1, sortFault);
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
     Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
               c->selfnode, c->selfslot, c->rec, c->recnode};
@@ -629,7 +637,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     CU_TRY(c, cudaGetLastError());
     // keygen, 3 per sort pass, gather, 2 scans of 3, terminals, witness, level_scan, topology,
     // one per level above Ltop, agg_top, traverse (+ overflow pass)
-    c->launches += 1 + 2 + (uint64_t)passes + 1 + 3 + 2 + 3 + 2 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
+    c->launches += 1 + 2 + (uint64_t)passes + 1 + 1 + 1 + 1 + 2 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
