@@ -194,7 +194,8 @@ struct HeadFlag {
 };
 
 // sinks of the single-pass scans
-struct TerminalSink {   // head-flag scan -> the terminal arrays (what k_terminals does from a stored prefix)
+// ---- 3. terminals: the head-flag scan writes the terminal arrays itself ----------------------------------------
+struct TerminalSink {
     const unsigned long long* keys;
     unsigned long long* tkey;
     unsigned int* tfirst;
@@ -219,26 +220,6 @@ struct StoreSink {      // plain exclusive prefix, out[0..n]
     unsigned int* out;
     __device__ __forceinline__ void operator()(int i, unsigned int excl, unsigned int) const { out[i] = excl; }
 };
-
-// ---- 3. terminals -----------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_terminals(int n, const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ headExcl,
-            unsigned long long* __restrict__ tkey, unsigned int* __restrict__ tfirst, Scal* __restrict__ s) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int n_in = s->n_in;
-    if (i == 0) {
-        s->n_term = headExcl[n];  // grand total of the head flags
-        if (n_in == 0) tfirst[0] = 0;
-    }
-    if ((unsigned int)i >= n_in) return;
-    const bool head = (i == 0) || keys[i] != keys[i - 1];
-    const unsigned int t = headExcl[i];
-    if (head) {
-        tkey[t] = keys[i];
-        tfirst[t] = (unsigned int)i;
-    }
-    if ((unsigned int)i == n_in - 1) tfirst[t + (head ? 1u : 0u)] = n_in;
-}
 
 // ---- 4. witnesses: delta[], the per-terminal level masks, and the number of branching cells per level ------
 // wstart[t] = first terminal of the cell that t witnesses (the only galloping search of the whole build).

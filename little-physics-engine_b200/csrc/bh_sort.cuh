@@ -259,73 +259,16 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Device-wide exclusive scan of a u32 sequence produced on the fly by `Load` (reduce / spine / apply).
-// out[i] = sum_{j<i} load(j) for i in [0, n]; out[n] (= total) is also stored to *total when non-null.
+// Device-wide exclusive scan of a u32 sequence produced on the fly by `Load`.
 // ------------------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-template <class Load>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(Load load, int n, unsigned int* __restrict__ tileSums) {
-    __shared__ unsigned int sh[9];
-    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
-    unsigned int s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const long long i = base + k;
-        if (i < n) s += load((int)i);
-    }
-    unsigned int tot;
-    block_exclusive_scan_256(s, sh, &tot);
-    if (threadIdx.x == 0) tileSums[blockIdx.x] = tot;
-}
-
-// single block: exclusive scan of tileSums[0..numTiles) in place; total to tileSums[numTiles] and *total
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_spine(unsigned int* __restrict__ tileSums, int numTiles,
-                                                             unsigned int* __restrict__ total) {
-    __shared__ unsigned int sh[9];
-    unsigned int carry = 0;
-    for (int base = 0; base < numTiles; base += SCAN_THREADS) {
-        const int i = base + threadIdx.x;
-        const unsigned int v = (i < numTiles) ? tileSums[i] : 0u;
-        unsigned int tot;
-        const unsigned int ex = block_exclusive_scan_256(v, sh, &tot);
-        if (i < numTiles) tileSums[i] = carry + ex;
-        carry += tot;
-    }
-    if (threadIdx.x == 0) {
-        tileSums[numTiles] = carry;
-        if (total) *total = carry;
-    }
-}
-
-template <class Load>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(Load load, int n, const unsigned int* __restrict__ tileSums,
-                                                             unsigned int* __restrict__ out) {
-    __shared__ unsigned int sh[9];
-    const long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
-    unsigned int v[SCAN_ITEMS];
-    unsigned int s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const long long i = base + k;
-        v[k] = (i < n) ? load((int)i) : 0u;
-        s += v[k];
-    }
-    unsigned int run = tileSums[blockIdx.x] + block_exclusive_scan_256(s, sh, nullptr);
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        const long long i = base + k;
-        if (i <= n) out[i] = run;  // note: i == n stores the grand total
-        run += v[k];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
-// Single-pass version of the same scan (decoupled look-back, one status word per tile): every element is loaded
-// once and handed to `sink(i, exclusive_prefix, value)` for i in [0, n] (i == n carries the grand total), so the
-// consumer of the scan is fused into it. One kernel instead of three + the consumer's own launch.
+// Single pass (decoupled look-back, one status word per tile): every element is loaded once and handed to
+// `sink(i, exclusive_prefix, value)` for i in [0, n] (i == n carries the grand total), so the consumer of the scan
+// is fused into it. One kernel instead of reduce + spine + apply + the consumer's own launch.
 // ------------------------------------------------------------------------------------------------
 // warp-wide look-back over one column: lane k inspects tile - 1 - k
 __device__ __forceinline__ unsigned int lb_exclusive_warp(const unsigned long long* status, unsigned int tile,

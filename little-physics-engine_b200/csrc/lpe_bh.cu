@@ -77,7 +77,7 @@ struct lpe_bh_ctx {
     SBody* sbody = nullptr;
     unsigned int *selfnode = nullptr, *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
     // scans
-    unsigned int *tileSums = nullptr, *headExcl = nullptr, *P = nullptr;
+    unsigned int* P = nullptr;
     // terminals
     unsigned long long* tkey = nullptr;
     unsigned int *tfirst = nullptr, *mask = nullptr, *tnode = nullptr, *wstart = nullptr;
@@ -158,7 +158,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
           dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512) + 2 * ((size_t)scanTiles + 2)) | dalloc(c, c->totals, 512 * 8 + 16);
     rc |= dalloc(c, c->sbody, cap) | dalloc(c, c->selfnode, cap) |
           dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
-    rc |= dalloc(c, c->tileSums, (size_t)scanTiles + 2) | dalloc(c, c->headExcl, cap + 2) | dalloc(c, c->P, cap + 2);
+    rc |= dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
           dalloc(c, c->tnode, cap + 2) | dalloc(c, c->wstart, cap + 2) | dalloc(c, c->delta, cap + 2);
     rc |= dalloc(c, c->child, 4 * (cap + 8)) | dalloc(c, c->meta, ncap) | dalloc(c, c->levelList, cap + 8) |
@@ -451,15 +451,6 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     if (p.key_order < 0 || p.key_order > 2) return fail(c, "unknown key_order");
     k.hilbert = (p.key_order == LPE_KEYS_HILBERT || (p.key_order == LPE_KEYS_AUTO && p.precision == LPE_PREC_FAST)) ? 1 : 0;
     return 0;
-}
-
-template <class Load>
-void device_scan(lpe_bh_ctx* c, Load load, int n, unsigned int* out, unsigned int* total) {
-    // out[0..n] (n+1 entries): exclusive prefix, out[n] = total
-    const int tiles = cdiv((long long)n + 1, SCAN_TILE);
-    k_scan_reduce<<<tiles, SCAN_THREADS, 0, c->stream>>>(load, n, c->tileSums);
-    k_scan_spine<<<1, SCAN_THREADS, 0, c->stream>>>(c->tileSums, tiles, total);
-    k_scan_apply<<<tiles, SCAN_THREADS, 0, c->stream>>>(load, n, c->tileSums, out);
 }
 
 int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
