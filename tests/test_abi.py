@@ -22,7 +22,8 @@ def test_header_declares_the_expected_surface():
     syms = declared_symbols()
     for s in ("lpe_bh_create", "lpe_bh_destroy", "lpe_bh_upload", "lpe_bh_step", "lpe_bh_download",
               "lpe_bh_update_host", "lpe_bh_dump_tree", "lpe_bh_get_stats", "lpe_bh_last_error",
-              "lpe_bh_set_shard", "lpe_bh_step_begin", "lpe_bh_step_finish", "lpe_bh_workload"):
+              "lpe_bh_set_shard", "lpe_bh_step_begin", "lpe_bh_step_finish", "lpe_bh_workload", "lpe_bh_boundary",
+              "lpe_bh_xchg_export", "lpe_bh_xchg_import", "lpe_bh_xchg_set_peer", "lpe_bh_xchg_p2p_ready"):
         assert s in syms
 
 
@@ -37,6 +38,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(lpe_bh.Stats) == 16 * 8 + 4 * 4 + 5 * 4 + 4  # padded to 8
     assert C.sizeof(lpe_bh.TreeDump) == 10 * 8
     assert C.sizeof(lpe_bh.DeviceView) == 6 * 8
+    assert C.sizeof(lpe_bh.BoundaryParams) == 4 * 8
 
 
 def test_workloads_are_deterministic_and_in_bounds():
