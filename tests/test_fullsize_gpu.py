@@ -29,6 +29,36 @@ def test_c2_one_million_disk_vs_oracle(bh, port):
     bh.set_instrumentation()
 
 
+CLUSTERED = [
+    # kind, n, seed, U, eps, thr, dt_drift
+    ("plummer", 300_000, 43, U, EPS, 0.0, 1 / 120),
+    ("two_galaxies", 300_000, 44, U, EPS, 0.0, 1 / 120),
+    ("keplerian", 100_000, 5, 6e9, 2e7, 1e3, 6.756e-3),      # the scenario's own configuration (C1)
+]
+
+
+@pytest.mark.parametrize("kind,n,seed,Uw,eps,thr,dtd", CLUSTERED, ids=[c[0] for c in CLUSTERED])
+def test_clustered_workloads_vs_oracle(bh, port, kind, n, seed, Uw, eps, thr, dtd):
+    """The distributions of C3 / C4 / C1 (dense core, two clustered disks with heavy central bodies, Keplerian disk)
+    at sizes the oracle finishes in seconds: deep, unbalanced trees, mass ratios up to 1e6, every decision identical."""
+    x, y, vx, vy, m = lpe_bh.workload(kind, n, seed, Uw)
+    ref = port.run(O.make_params(Uw, eps, thr=thr, dt_drift=dtd), x, y, vx, vy, m, threads=8, per_body=True)
+    bh.set_instrumentation(counts=True)
+    bh.upload(x, y, vx, vy, m)
+    bh.step(lpe_bh.make_params(Uw, eps, thr=thr, dt_drift=dtd), 1)
+    got = bh.download()
+    acc, _ = bh.counts()
+    st = bh.stats()
+    bh.set_instrumentation()
+    assert np.array_equal(acc, ref["accepted"])
+    dv = rel_err((got["vx"] - vx, got["vy"] - vy), (ref["vx"] - vx, ref["vy"] - vy))
+    assert dv["max"] <= 1e-4 and dv["norm"] <= 1e-5, (kind, dv)
+    # positions: x' = x + v' dt, so the error is the velocity error times dt
+    dvmax = np.max(np.hypot(ref["vx"] - vx, ref["vy"] - vy))
+    assert np.max(np.hypot(got["x"] - ref["x"], got["y"] - ref["y"])) <= 1e-4 * dvmax * dtd + 1e-9 * Uw
+    assert st["overflow_chunks"] < max(1, n // 32)      # the overflow path may run, never for every chunk
+
+
 def test_c5_theta_sweep_interaction_counts(bh, port):
     """Accepted interactions per body fall with theta exactly as the oracle's do (subsample of C2 for the CPU side)."""
     x, y, vx, vy, m = lpe_bh.workload("disk", 1_000_000, 42, U)
