@@ -320,6 +320,12 @@ def our_arm(args, wl, rank, world, local_rank):
     ms_per_step = total_ms / args.steps
     value = n / (ms_per_step * 1e-3)
     ph = np.mean(np.array(phases), axis=0)
+    per_rank_traverse = None
+    if dist:   # load balance of the block-cyclic slices (C4 is the stress case): every rank's mean traversal time
+        mine = torch.tensor([float(ph[3])], device="cuda", dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank_traverse = [float(t.item()) for t in allr]
 
     # ---- end to end through host buffers (what Systems::BarnesHutSystem::update pays), N=1 path of the C ABI ----
     e2e = None
@@ -366,6 +372,7 @@ def our_arm(args, wl, rank, world, local_rank):
                         "memory, CUDA IPC) + one-element allreduce as barrier" if p2p else "NCCL allgather of (x,y,vx,vy)")},
             "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": trav_ms,
                           "allgather": float(ph[4]), "scatter": float(ph[5])},
+            "per_rank_traverse_ms": per_rank_traverse,
             "interactions_per_body": interactions / n,
             "roofline": {"bound": "fp32_fma", "kernel": "k_traverse2 (two-phase traversal)", "achieved": achieved,
                          "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak if fma_peak else None,
