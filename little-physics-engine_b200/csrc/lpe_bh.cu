@@ -64,6 +64,9 @@ struct lpe_bh_ctx {
     // lpe_bh_update_host: uploads run on a second stream, the step waits for each array only where it first reads it
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t evc[4] = {nullptr, nullptr, nullptr, nullptr};
+    // the gather into key order runs beside the terminal / witness / scan kernels (they only need the sorted keys)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t evs[2] = {nullptr, nullptr};
     bool pend_mass = false, pend_vel = false, pend_rank = false;
     // sort
     unsigned long long* keys[2] = {nullptr, nullptr};
@@ -516,9 +519,14 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     const unsigned int* sidx = c->vals[sel];
     if (timing) cudaEventRecord(c->ev[2], st);
 
+    // fork: the gather (and, in the host tick, the late mass / rank pack before it) runs on the side stream while
+    // this stream goes on with the kernels that only need the sorted keys; joined before k_topology
+    cudaStream_t sg = c->side_stream;
+    CU_TRY(c, cudaEventRecord(c->evs[0], st));
+    CU_TRY(c, cudaStreamWaitEvent(sg, c->evs[0], 0));
     if (c->pend_mass) {   // host path: masses and ranks were uploaded behind the key generation and the sort
-        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[2], 0));
-        k_pack_mass<<<g256, 256, 0, st>>>(n, c->tmp + 2 * c->cap, c->pend_rank ? c->rank_in : nullptr, c->body);
+        CU_TRY(c, cudaStreamWaitEvent(sg, c->evc[2], 0));
+        k_pack_mass<<<g256, 256, 0, sg>>>(n, c->tmp + 2 * c->cap, c->pend_rank ? c->rank_in : nullptr, c->body);
         c->pend_mass = false;
     }
     Reorder ro{nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -527,7 +535,8 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
                                  dalloc(c, c->orig2, c->cap)))
         return 1;
     if (reorder) ro = Reorder{c->vel, c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2};
-    k_gather<<<g256, 256, 0, st>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal, ro);
+    k_gather<<<g256, 256, 0, sg>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal, ro);
+    CU_TRY(c, cudaEventRecord(c->evs[1], sg));
     if (reorder) {   // from here on the state IS in key order
         std::swap(c->body, c->body2);
         std::swap(c->vel, c->vel2);
@@ -549,6 +558,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
     Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
               c->selfnode, c->selfslot, c->rec, c->recnode};
+    CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
     NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->sbody};
     // branching cells, deepest level first; the handful of cells of levels <= 5 share one single-block launch
@@ -667,6 +677,8 @@ int lpe_bh_create(int device, lpe_bh_ctx** out) {
     }
     c->stream = c->own_stream;
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
+    for (auto& ev : c->evs) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     if (cudaMallocHost(&c->fault_host, sizeof(unsigned int)) == cudaSuccess) *c->fault_host = 0;
     else c->fault_host = nullptr;
     for (auto& ev : c->ev) cudaEventCreate(&ev);
@@ -684,6 +696,8 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : c->evc) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto& ev : c->evs) if (ev) cudaEventDestroy(ev);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->fault_host) cudaFreeHost(c->fault_host);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
