@@ -29,6 +29,23 @@ def test_c2_one_million_disk_vs_oracle(bh, port):
     bh.set_instrumentation()
 
 
+@pytest.mark.parametrize("precision,tol", [(lpe_bh.PREC_STRICT, 1e-8), (lpe_bh.PREC_FAST, 1e-4)], ids=["strict", "fast"])
+def test_c1_keplerian_10k_hundred_steps(bh, port, precision, tol):
+    """BASELINE config C1: the reference's own galaxy scenario (Keplerian disk law, 10 000 bodies, its configuration,
+    fixed dt) for 100 resident ticks of kick + drift, against the oracle running the same 100 ticks."""
+    n, Uk, steps = 10_000, 6e9, 100
+    x, y, vx, vy, m = lpe_bh.workload("keplerian", n, 11, Uk)
+    kw = dict(theta=0.5, thr=1e3, dt_kick=1 / 120, dt_drift=6.756e-3)
+    ref = port.run(O.make_params(Uk, 2e7, **kw), x, y, vx, vy, m, nsteps=steps, threads=8)
+    bh.upload(x, y, vx, vy, m)
+    bh.step(lpe_bh.make_params(Uk, 2e7, precision=precision, **kw), steps)
+    got = bh.download()
+    dv = rel_err((got["vx"] - vx, got["vy"] - vy), (ref["vx"] - vx, ref["vy"] - vy))
+    assert dv["norm"] <= tol and dv["max"] <= 10 * tol, dv
+    disp = np.max(np.hypot(ref["x"] - x, ref["y"] - y))
+    assert np.max(np.hypot(got["x"] - ref["x"], got["y"] - ref["y"])) <= 10 * tol * disp + 1e-12 * Uk
+
+
 CLUSTERED = [
     # kind, n, seed, U, eps, thr, dt_drift
     ("plummer", 300_000, 43, U, EPS, 0.0, 1 / 120),
