@@ -131,7 +131,7 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
 }
 
 template <bool STATS, bool SELF>
-__global__ void __launch_bounds__(T2_THREADS, 6) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
+__global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;

@@ -571,7 +571,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         long long maxCells = (L < 15) ? (1ll << (2 * L)) : (long long)n;
         if (maxCells > n) maxCells = n;
         int grid = cdiv(maxCells * 4, 256);   // four lanes per cell
-        if (grid > sms * 8) grid = sms * 8;
+        if (grid > sms * 7) grid = sms * 7;
         k_agg_level<<<grid, 256, 0, st>>>(k, L, c->levelList, levelBase, levelCount, c->child, no, c->scal);
         ++levelLaunches;
     }
@@ -613,7 +613,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
             attr_set = true;
         }
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
-        if (grid > sms * 6) grid = sms * 6;
+        if (grid > sms * 7) grid = sms * 7;
         if (grid < 1) grid = 1;
         if (stats) k_traverse2<true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
         else if (selfT) k_traverse2<false, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
