@@ -327,6 +327,14 @@ def our_arm(args, wl, rank, world, local_rank):
         dist.all_gather(allr, mine)
         per_rank_traverse = [float(t.item()) for t in allr]
 
+    # clocks / throttle reasons sampled by nvidia-smi every 20 ms from the first warm-up step to the end of the
+    # device-timed region (which alone is only tens of milliseconds long). The sampler stops before the end-to-end
+    # loop: that one is host wall clock over ~55 CUDA API calls per tick, and a driver query every 20 ms stalls them
+    # (2.0 -> 2.3 ms per tick at 1 M bodies).
+    clocks = sampler.stop(t_busy0, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + device-timed region"
+
     # ---- end to end through host buffers (what Systems::BarnesHutSystem::update pays), N=1 path of the C ABI ----
     e2e = None
     if world == 1:
@@ -347,12 +355,7 @@ def our_arm(args, wl, rank, world, local_rank):
         e2e = {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "path": "multi-GPU runs keep bodies resident; host round trip measured at N=1 only"}
 
-    # clocks / throttle reasons sampled by nvidia-smi every 20 ms from the first warm-up step to the end of the
-    # end-to-end loop (the timed region alone is only tens of milliseconds long)
     log(rank, "timed region done")
-    clocks = sampler.stop(t_busy0, time.time()) if sampler else None
-    if clocks is not None:
-        clocks["window"] = "warm-up + timed region + e2e loop"
     if rank == 0:
         trav_ms = float(ph[3])
         flops = FLOPS_PER_INTERACTION * interactions / max(world, 1)    # this rank's share of the targets
