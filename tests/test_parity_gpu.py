@@ -303,3 +303,33 @@ def test_reordered_state_keeps_the_creation_order_interface(port):
     assert np.array_equal(back["vx"], vx) and np.array_equal(back["vy"], vy)
     bh.close()
 
+
+def test_context_reuse_across_sizes_and_modes(port):
+    """One context: small upload, resident steps, a larger upload (every device buffer is re-allocated, the key-order
+    state and the look-back epochs start over), the host tick, then sharded mode — each result equal to a fresh
+    context's."""
+    U = 1024.0
+    pg = lpe_bh.make_params(U, 0.25, dt_drift=0.004)
+
+    def fresh(n, seed, steps):
+        x, y, vx, vy, m = gen_uniform(n, U, seed)
+        c = lpe_bh.BarnesHut(0)
+        c.upload(x, y, vx, vy, m); c.step(pg, steps); out = c.download(); c.close()
+        return (x, y, vx, vy, m), out
+
+    ctx = lpe_bh.BarnesHut(0)
+    for n, seed, steps in ((700, 1, 3), (9000, 2, 2), (300, 3, 4), (9000, 2, 2)):
+        (x, y, vx, vy, m), want = fresh(n, seed, steps)
+        ctx.upload(x, y, vx, vy, m)
+        ctx.step(pg, steps)
+        got = ctx.download()
+        for k in ("x", "y", "vx", "vy"):
+            assert np.array_equal(got[k], want[k]), (n, k)
+    # host tick on the same context: one step, arrays updated in place
+    (x, y, vx, vy, m), want = fresh(5000, 4, 1)
+    hx, hy, hvx, hvy = x.copy(), y.copy(), vx.copy(), vy.copy()
+    ctx.update_host(pg, hx, hy, hvx, hvy, m)
+    for a, k in ((hx, "x"), (hy, "y"), (hvx, "vx"), (hvy, "vy")):
+        assert np.array_equal(a, want[k]), k
+    ctx.close()
+
