@@ -43,9 +43,9 @@ WORKLOADS = {
 }
 FLOPS_PER_INTERACTION = 20.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_traverse2 launch, from the committed ncu --set full capture
-# (profiles/r01_ncu_traverse2_c2_v16.txt: 145.35 MB read + 31.24 MB written); the kernel is not DRAM-bound, the
+# (profiles/r01_ncu_traverse2_c2_final.txt: 146.32 MB read + 32.57 MB written); the kernel is not DRAM-bound, the
 # figure only shows that nothing is re-read (the records alone are 52 MB, the bodies 64 MB).
-NCU_TRAFFIC_BYTES = {"c2": 176.6e6}
+NCU_TRAFFIC_BYTES = {"c2": 178.9e6}
 HBM_BYTES_PER_BODY = 340.0     # keygen + sort + gather + node arrays, 64-bit keys
 
 
