@@ -7,7 +7,8 @@
  *
  * TEST INFRASTRUCTURE ONLY. Built by oracle/Makefile (target `dropin`) against the reference headers and
  * vendored EnTT under /root/reference, into oracle/_ref/; run on the GPU box by tests/test_dropin_gpu.py.
- * Usage: dropin_check <n> <seed> [keplerian|uniform] [steps]   -> one JSON line on stdout, exit 0 on parity.
+ * Usage: dropin_check <n> <seed> [keplerian|uniform|boundary] [steps]   -> one JSON line on stdout, exit 0 on parity.
+ * kind "boundary" runs OUR Systems::BoundarySystem (host/systems/boundary.{hpp,cpp}) against the reference's.
  */
 #include <dlfcn.h>
 
@@ -20,9 +21,61 @@
 #include <vector>
 
 #include "systems/barnes_hut.hpp"  // ours (host/ precedes the reference include dir)
+#include "systems/boundary.hpp"    // ours as well
 #include "systems/movement.hpp"    // the reference's
 #include "lpe_bh.h"
 #include "oracle_abi.h"
+
+typedef int (*ref_boundary_fn)(const orc_boundary_params*, uint64_t, double*, double*, double*, double*, const uint8_t*);
+
+// kind "boundary": our Systems::BoundarySystem on a registry vs the reference's (ref_boundary), bit for bit
+static int boundary_check(void* h, uint64_t n, uint64_t seed) {
+    auto ref_boundary = reinterpret_cast<ref_boundary_fn>(dlsym(h, "ref_boundary"));
+    if (!ref_boundary) { std::printf("{\"error\": \"ref_boundary missing\"}\n"); return 2; }
+    const double U = 1000.0;
+    std::vector<double> x(n), y(n), vx(n), vy(n);
+    std::vector<uint8_t> comp(n);
+    uint64_t s = seed * 6364136223846793005ull + 1442695040888963407ull;
+    auto u = [&]() { s = s * 6364136223846793005ull + 1442695040888963407ull; return (double)(s >> 11) * (1.0 / 9007199254740992.0); };
+    for (uint64_t i = 0; i < n; ++i) {
+        x[i] = -100.0 + 1200.0 * u(); y[i] = -100.0 + 1200.0 * u();
+        vx[i] = 6.0 * (u() - 0.5); vy[i] = 6.0 * (u() - 0.5);
+        comp[i] = ORC_HAS_MASS | ORC_HAS_VELOCITY;
+        if (i % 7 == 3) comp[i] = ORC_HAS_MASS;          // no Velocity
+        if (i % 9 == 5) comp[i] |= ORC_ASLEEP;
+    }
+    SharedSystemConfig sc{};
+    sc.UniverseSizeMeters = U;
+    sc.MetersPerPixel = 0.5;
+    Systems::BoundaryConfig bc;   // defaults: 15 px, 0.7, 1.0
+    entt::registry reg;
+    std::vector<entt::entity> ents(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        auto e = reg.create();
+        ents[i] = e;
+        reg.emplace<Components::Position>(e, x[i], y[i]);
+        if (comp[i] & ORC_HAS_VELOCITY) reg.emplace<Components::Velocity>(e, vx[i], vy[i]);
+        if (comp[i] & ORC_ASLEEP) { Components::Sleep sl; sl.asleep = true; reg.emplace<Components::Sleep>(e, sl); }
+    }
+    Systems::BoundarySystem bs;
+    bs.setSharedSystemConfig(sc);
+    bs.setSpecificConfig(bc);
+    bs.update(reg);
+    orc_boundary_params bp{U, bc.marginPixels * sc.MetersPerPixel, bc.bounceDamping, bc.maxSpeed};
+    if (ref_boundary(&bp, n, x.data(), y.data(), vx.data(), vy.data(), comp.data())) return 2;
+    uint64_t bad = 0, moved = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const auto& q = reg.get<Components::Position>(ents[i]);
+        if (std::memcmp(&q.x, &x[i], 8) || std::memcmp(&q.y, &y[i], 8)) ++bad;
+        if (const auto* v = reg.try_get<Components::Velocity>(ents[i])) {
+            if (std::memcmp(&v->x, &vx[i], 8) || std::memcmp(&v->y, &vy[i], 8)) ++bad;
+        }
+        if (x[i] == bp.margin || x[i] == U - bp.margin) ++moved;
+    }
+    std::printf("{\"n\": %llu, \"kind\": \"boundary\", \"clamped_x\": %llu, \"mismatches\": %llu, \"ok\": %s}\n",
+                (unsigned long long)n, (unsigned long long)moved, (unsigned long long)bad, bad == 0 && moved > 0 ? "true" : "false");
+    return bad == 0 && moved > 0 ? 0 : 1;
+}
 
 typedef int (*ref_run_fn)(const orc_params*, uint64_t, const double*, const double*, const double*, const double*,
                           const double*, const uint8_t*, int, uint64_t, double*, double*, double*, double*, orc_stats*);
@@ -39,6 +92,7 @@ int main(int argc, char** argv) {
     const std::string dir = slash == std::string::npos ? "." : self.substr(0, slash);
     void* h = dlopen((dir + "/libref_bh.so").c_str(), RTLD_NOW | RTLD_LOCAL);
     if (!h) { std::printf("{\"error\": \"%s\"}\n", dlerror()); return 2; }
+    if (kind == "boundary") return boundary_check(h, n, seed);
     auto ref_run = reinterpret_cast<ref_run_fn>(dlsym(h, "ref_bh_run"));
     if (!ref_run) { std::printf("{\"error\": \"ref_bh_run missing\"}\n"); return 2; }
 

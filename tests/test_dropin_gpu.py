@@ -21,3 +21,18 @@ def test_registry_drop_in_matches_reference(n, kind, steps):
     rep = json.loads(line)
     assert r.returncode == 0 and rep.get("ok"), (rep, r.stderr[-500:])
     assert rep["dv_norm_rel"] <= 1e-4 and rep["dv_max_rel"] <= 1e-4
+
+
+@pytest.mark.parametrize("n,seed", [(1, 1), (4097, 2), (50000, 3)])
+def test_registry_boundary_drop_in_is_bit_exact(n, seed):
+    """OUR Systems::BoundarySystem (host/systems/boundary.{hpp,cpp} -> lpe_bh_boundary) on a real registry with
+    sleepers and velocity-less entities, against the reference's own BoundarySystem: identical bits."""
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/dropin_check not built (needs /root/reference at build time)")
+    r = subprocess.run([BIN, str(n), str(seed), "boundary"], capture_output=True, text=True, timeout=600)
+    line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else "{}"
+    rep = json.loads(line)
+    if n == 1:      # a single body may or may not be outside the margin: only the comparison matters
+        assert rep.get("mismatches") == 0, (rep, r.stderr[-500:])
+    else:
+        assert r.returncode == 0 and rep.get("ok") and rep["mismatches"] == 0 and rep["clamped_x"] > 0, (rep, r.stderr[-500:])
