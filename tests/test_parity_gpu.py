@@ -70,6 +70,8 @@ CASES = [
     ("theta10", 5000, 7, 14, 1.0, 0.0),
     ("eps_zero_depth30", 5000, 8, 0, 0.5, 0.0),
     ("eps_big_aggregated_terminals", 5000, 9, 6, 0.5, 0.0),
+    ("theta_zero_every_cell_opened", 2000, 10, 14, 0.0, 0.0),     # direct sum through the leaves; frontier overflow path
+    ("theta_huge_root_children_only", 2000, 11, 14, 50.0, 0.0),
 ]
 
 
