@@ -561,10 +561,10 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
     NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->sbody};
-    // branching cells, deepest level first; the handful of cells of levels <= 5 share one single-block launch
+    // branching cells, deepest level first; the handful of cells of levels <= 4 share one single-block launch
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-    const int Ltop = k.D - 1 < 5 ? k.D - 1 : 5;
+    const int Ltop = k.D - 1 < 4 ? k.D - 1 : 4;
     int levelLaunches = 0;
     for (int L = k.D - 1; L > Ltop; --L) {
         // a level holds at most min(4^L, n/2) cells
