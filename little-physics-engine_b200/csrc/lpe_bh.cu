@@ -605,13 +605,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         // two-phase kernel, then the depth-first kernel for the (normally zero) chunks whose frontier overflowed
         const size_t smem = sizeof(T2Warp) * T2_WARPS;
         const bool selfT = k.need_self != 0;
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_traverse2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            cudaFuncSetAttribute(k_traverse2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
-        }
+        static_assert(sizeof(T2Warp) * T2_WARPS <= 48 * 1024, "per-CTA work areas fit the default dynamic shared memory limit");
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
         if (grid > sms * 7) grid = sms * 7;
         if (grid < 1) grid = 1;
