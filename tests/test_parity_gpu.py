@@ -335,3 +335,35 @@ def test_context_reuse_across_sizes_and_modes(port):
         assert np.array_equal(a, want[k]), k
     ctx.close()
 
+
+def test_error_paths_report_and_leave_the_context_usable():
+    """Bad calls return an error with a message (lpe_bh_last_error) and never touch the state: the context keeps
+    working afterwards. (The reference's style: report and skip the update, barnes_hut.cpp:76-79.)"""
+    U = 1024.0
+    x, y, vx, vy, m = gen_uniform(500, U, 12)
+    c = lpe_bh.BarnesHut(0)
+    c.upload(x, y, vx, vy, m)
+    good = lpe_bh.make_params(U, 0.25)
+    for bad, word in ((lpe_bh.make_params(-1.0, 0.25), "universe_size"), (lpe_bh.make_params(U, 0.25, theta=-0.5), "theta"),
+                      (lpe_bh.make_params(U, 0.25, precision=7), "precision")):
+        with pytest.raises(RuntimeError, match=word):
+            c.step(bad, 1)
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        c.direct_accel(good, 400, 200)
+    with pytest.raises(RuntimeError, match="sharded"):
+        c.xchg_export()
+    with pytest.raises(RuntimeError):
+        c.dump_tree()                      # no step has run yet
+    c.step(good, 1)
+    got = c.download()
+    ref = lpe_bh.BarnesHut(0)
+    ref.upload(x, y, vx, vy, m); ref.step(good, 1); want = ref.download(); ref.close()
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(got[k], want[k]), k
+    # a sharded context refuses the unsharded entry points
+    c.set_shard(0, 2)
+    c.upload(x, y, vx, vy, m)
+    with pytest.raises(RuntimeError, match="sharded"):
+        c.step(good, 1)
+    c.close()
+
