@@ -386,6 +386,11 @@ def our_arm(args, wl, rank, world, local_rank):
                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
                              "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                              "algorithmic": f"{HBM_BYTES_PER_BODY:.0f} B/body x {n} bodies"},
+            # T_roof = N*B_alg/BW_HBM + N*F_alg/P_FP32 (phases are sequential; the replicated build
+            # is counted once per rank, the traversal divides by the ranks), against the measured step
+            "roofline_step": (lambda t_roof: {"t_roof_ms": t_roof, "t_measured_ms": ms_per_step, "frac": t_roof / ms_per_step})(
+                1e3 * (HBM_BYTES_PER_BODY * n / (peaks["hbm_gbs"] * 1e9) +
+                       (flops / (fma_peak * 1e12) if fma_peak else 0.0))),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
