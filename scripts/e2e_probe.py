@@ -14,7 +14,10 @@ ptrs = [t.data_ptr() for t in host]
 for rep in range(3):
     for it in range(3):
         bh.update_host_ptrs(p, n, *ptrs)
-    t0 = time.perf_counter()
+    ts = []
     for it in range(20):
+        t0 = time.perf_counter()
         bh.update_host_ptrs(p, n, *ptrs)
-    print("e2e ms/tick %.3f" % ((time.perf_counter() - t0) * 1e3 / 20))
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts.sort()
+    print("e2e ms/tick mean %.3f  min %.3f  median %.3f  max %.3f" % (sum(ts) / len(ts), ts[0], ts[len(ts) // 2], ts[-1]))
