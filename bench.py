@@ -248,20 +248,26 @@ def our_arm(args, wl, rank, world, local_rank):
         # the traversal kernel stores its results there itself. All ranks must agree, else the NCCL allgather is used.
         ok = 0
         if not args.no_p2p and world <= 8:
+            mine = None
             try:
-                handles = [None] * world
-                dist.all_gather_object(handles, bh.xchg_export())
-                for r, hnd in enumerate(handles):
-                    if r != rank:
-                        bh.xchg_import(r, hnd)
-                ok = 1 if bh.xchg_p2p_ready() else 0
-            except Exception as e:   # IPC not permitted on this box: fall back to the collective
-                log(rank, f"direct exchange unavailable: {e}")
+                mine = bh.xchg_export()
+            except Exception as e:
+                log(rank, f"direct exchange: export failed: {e}")
+            handles = [None] * world
+            dist.all_gather_object(handles, mine)          # every rank takes part, whatever happened above
+            if all(h is not None for h in handles):
+                try:
+                    for r, hnd in enumerate(handles):
+                        if r != rank:
+                            bh.xchg_import(r, hnd)
+                    ok = 1 if bh.xchg_p2p_ready() else 0
+                except Exception as e:   # IPC not permitted on this box: fall back to the collective
+                    log(rank, f"direct exchange unavailable: {e}")
         flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         p2p = bool(flag.item())
-        if not p2p and ok:
-            raise RuntimeError("ranks disagree on the direct exchange; rerun with --no-p2p")
+        if not p2p:
+            bh.xchg_reset()      # some rank could not open every handle: every rank goes back to the allgather
         token = torch.zeros(1, device="cuda", dtype=torch.int32)
 
     xe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # multi-GPU: allgather / scatter split

@@ -186,6 +186,9 @@ int  lpe_bh_xchg_export(lpe_bh_ctx* ctx, void* handle64);
 int  lpe_bh_xchg_import(lpe_bh_ctx* ctx, int rank, const void* handle64);
 int  lpe_bh_xchg_set_peer(lpe_bh_ctx* ctx, int rank, void* recv_device_ptr);
 int  lpe_bh_xchg_p2p_ready(const lpe_bh_ctx* ctx);
+/* forget every peer buffer (closes the IPC mappings): back to the collective exchange, e.g. when not every rank
+ * could open every handle */
+int  lpe_bh_xchg_reset(lpe_bh_ctx* ctx);
 /* pure host helper (no GPU): which rank owns sorted position i, and where it sits in that rank's packed slice */
 int  lpe_bh_shard_owner(uint64_t sorted_pos, int nranks, int* rank_out, uint64_t* slot_out);
 uint64_t lpe_bh_shard_chunk(uint64_t n_bodies, int nranks);        /* elements per rank in the exchange buffers */

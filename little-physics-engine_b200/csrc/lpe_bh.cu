@@ -1090,6 +1090,14 @@ int lpe_bh_xchg_set_peer(lpe_bh_ctx* c, int rank, void* recv_device_ptr) {
 
 int lpe_bh_xchg_p2p_ready(const lpe_bh_ctx* c) { return (c && p2p_ready(c)) ? 1 : 0; }
 
+int lpe_bh_xchg_reset(lpe_bh_ctx* c) {
+    if (!c) return 1;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    close_peers(c);
+    return 0;
+}
+
 uint64_t lpe_bh_launch_count(const lpe_bh_ctx* c) { return c ? c->launches : 0; }
 
 int lpe_bh_fma_peak(lpe_bh_ctx* c, double* tflops) {

@@ -238,6 +238,9 @@ class BarnesHut:
     def xchg_p2p_ready(self):
         return bool(self.lib.lpe_bh_xchg_p2p_ready(self.h))
 
+    def xchg_reset(self):
+        self._chk(self.lib.lpe_bh_xchg_reset(self.h), "xchg_reset")
+
     def update_host_ptrs(self, params, n, x, y, vx, vy, m, rank=None, comp=None):
         """lpe_bh_update_host on raw host pointers (pinned memory makes the uploads overlap the step)."""
         self.n = n

@@ -23,7 +23,7 @@ def test_header_declares_the_expected_surface():
     for s in ("lpe_bh_create", "lpe_bh_destroy", "lpe_bh_upload", "lpe_bh_step", "lpe_bh_download",
               "lpe_bh_update_host", "lpe_bh_dump_tree", "lpe_bh_get_stats", "lpe_bh_last_error",
               "lpe_bh_set_shard", "lpe_bh_step_begin", "lpe_bh_step_finish", "lpe_bh_workload", "lpe_bh_boundary",
-              "lpe_bh_xchg_export", "lpe_bh_xchg_import", "lpe_bh_xchg_set_peer", "lpe_bh_xchg_p2p_ready"):
+              "lpe_bh_xchg_export", "lpe_bh_xchg_import", "lpe_bh_xchg_set_peer", "lpe_bh_xchg_p2p_ready", "lpe_bh_xchg_reset"):
         assert s in syms
 
 

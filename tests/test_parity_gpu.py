@@ -263,13 +263,24 @@ def test_two_rank_direct_exchange_on_one_gpu(port):
         for r, v in enumerate(views):
             c.xchg_set_peer(r, v.xchg_recv)
         assert c.xchg_p2p_ready()
-    for _ in range(3):
+    for _ in range(2):
         for c in ranks:
             c.step_begin(pg)
         for c in ranks:
             c.synchronize()          # the barrier a real run gets from a one-element allreduce
         for c in ranks:
             c.step_finish()
+    # back to the collective exchange in mid-run (what a caller does when not every rank could open every handle)
+    for c in ranks:
+        c.xchg_reset()
+        assert not c.xchg_p2p_ready()
+    for c in ranks:
+        c.step_begin(pg)
+    slices = [c.xchg_read_send() for c in ranks]
+    for c in ranks:
+        for r, s in enumerate(slices):
+            c.xchg_write_recv(r, s)
+        c.step_finish()
     for c in ranks:
         got = c.download()
         for k in ("x", "y", "vx", "vy"):
