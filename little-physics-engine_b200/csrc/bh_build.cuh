@@ -280,7 +280,7 @@ struct Topo {
                               // position for a single-body leaf, or LPE_NONE
     NodeMeta* meta;           // [preorder]
     Agg* agg;                 // [preorder] written here only for aggregated terminals (>= 2 bodies in a depth-D cell)
-    unsigned int* levelList;  // cells grouped by level: levelList[levelBase[L] + i]
+    uint2* levelList;         // cells grouped by level: levelList[levelBase[L] + i] = {pre-order index, cell ordinal}
     const unsigned int* levelBase;
     unsigned int* levelCursor;
     const unsigned int* tfirst;
@@ -437,7 +437,7 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         const int L = __ffs(rest) - 1;
         rest &= rest - 1;
         const unsigned int local = atomicAdd(&cnt[L], 1u);
-        o.levelList[o.levelBase[L] + base[L] + local] = (unsigned int)t + Pt + i;
+        o.levelList[o.levelBase[L] + base[L] + local] = make_uint2((unsigned int)t + Pt + i, Pt + i);
         ++i;
     }
 }
@@ -457,12 +457,12 @@ struct NodeOut {
 // neighbouring lanes (one 128-byte line), and the sums are combined with two shuffle steps: (c0 + c1) + (c2 + c3),
 // deterministic. `p` is uniform across the quad; lanes of a quad must call this together.
 __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const NodeOut& o, unsigned int p,
+                                                    unsigned int qd, int cellLevel,
                                                     const unsigned int* __restrict__ child, double msi, int q,
                                                     unsigned int quadShift, bool live) {
     // every lane of the warp runs this (the ballot / shuffles use the full mask); quads past the end of the list
-    // carry live = false and neither read children nor store anything
-    const NodeMeta mp = o.meta[p];
-    const unsigned int qd = p - mp.start;
+    // carry live = false and neither read children nor store anything. The level list carries the cell's ordinal
+    // next to its pre-order index, so the child codes are fetched without a detour through the cell's own meta.
     const unsigned int ci = live ? child[(size_t)qd * 4 + q] : LPE_NONE;
     const bool valid = ci != LPE_NONE;
     Agg a;
@@ -535,7 +535,7 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         o.agg[p] = a;
         o.meta[p].skip = skip;
         if (p == 0) {   // the root has no parent to write its record
-            o.rec[0] = make_record(c, a, mp.level, skip, 1u, msi);
+            o.rec[0] = make_record(c, a, cellLevel, skip, 1u, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
             o.recnode[0] = 0u;
         }
@@ -544,7 +544,7 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
 
 // all branching cells of one level (children are at deeper levels: finished by earlier launches); 4 lanes per cell
 __global__ void __launch_bounds__(256)
-k_agg_level(StepConst c, int L, const unsigned int* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
+k_agg_level(StepConst c, int L, const uint2* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
             const unsigned int* __restrict__ levelCount, const unsigned int* __restrict__ child, NodeOut o,
             const Scal* __restrict__ s) {
     const unsigned int count = levelCount[L], base = levelBase[L];
@@ -557,14 +557,14 @@ k_agg_level(StepConst c, int L, const unsigned int* __restrict__ levelList, cons
     unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     for (unsigned int k = 0; k < rounds; ++k, i += quads) {
         const bool live = i < count;
-        const unsigned int p = levelList[base + (live ? i : 0u)];
-        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, p, child, msi, q, quadShift, live);
+        const uint2 e = levelList[base + (live ? i : 0u)];
+        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live);
     }
 }
 
 // the few cells of levels Ltop..0 in one block (a level has at most 4^L cells), one __syncthreads per level
 __global__ void __launch_bounds__(1024)
-k_agg_top(StepConst c, int Ltop, const unsigned int* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
+k_agg_top(StepConst c, int Ltop, const uint2* __restrict__ levelList, const unsigned int* __restrict__ levelBase,
           const unsigned int* __restrict__ levelCount, const unsigned int* __restrict__ child, NodeOut o,
           const Scal* __restrict__ s) {
     const double msi = mass_scale_inv(s->max_mass_bits);
@@ -577,8 +577,8 @@ k_agg_top(StepConst c, int Ltop, const unsigned int* __restrict__ levelList, con
         unsigned int i = threadIdx.x >> 2;
         for (unsigned int k = 0; k < rounds; ++k, i += quads) {
             const bool live = i < count;
-            const unsigned int p = levelList[base + (live ? i : 0u)];
-            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, p, child, msi, q, quadShift, live);
+            const uint2 e = levelList[base + (live ? i : 0u)];
+            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live);
         }
         __syncthreads();
     }

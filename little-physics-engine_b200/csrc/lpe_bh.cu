@@ -87,7 +87,8 @@ struct lpe_bh_ctx {
     signed char* delta = nullptr;
     // nodes (pre-order index), cells (ordinal), child blocks
     uint64_t node_cap = 0;
-    unsigned int *child = nullptr, *levelList = nullptr, *levelMeta = nullptr;
+    unsigned int *child = nullptr, *levelMeta = nullptr;
+    uint2* levelList = nullptr;
     NodeMeta* meta = nullptr;
     Agg* agg = nullptr;
     TravRec* rec = nullptr;
