@@ -2,26 +2,28 @@
 //
 // Same result as the depth-first walk in bh_traverse.cuh — every lane (body) takes the reference's own accept/open
 // decision for every node (barnes_hut.cpp:266-269) — but the work is organised so that the expensive part runs with
-// all 32 lanes busy and no per-node control flow:
+// all 32 lanes busy and no per-node control flow. One warp owns 32 key-consecutive targets and a FIFO ring of
+// {record slot, lane mask} entries in shared memory; the mask holds the targets that actually REACH the node (a
+// target that accepted an ancestor must never see it). Per round:
 //
-//   phase 1 (cooperative, one NODE per lane): the warp expands the tree breadth first. A lane loads one record and
-//     classifies its node against the bounding box of the warp's 32 targets, conservatively:
-//       A  every target accepts it      (d2_min >= s^2/theta^2 + margin, or the node is a leaf / terminal)
-//       O  every target opens it        (d2_max <= s^2/theta^2 - margin)
-//       M  mixed / too close to call    -> each lane will decide for itself in phase 2
-//     O and M nodes push their children on the next level's frontier. A node is "dirty" if some ancestor was M:
-//     a lane that ACCEPTED that ancestor must not see the node. Clean A nodes go to the A list; M nodes and every
-//     dirty node go to the M list together with the list slot of their parent.
-//   phase 2 (dense, one BODY per lane): every lane runs over the lists.
-//       A list: no test at all — two-float difference, rsqrt, three multiplies, two FMAs per interaction.
-//       M list: each entry carries the mask of lanes that reach it (= the lanes that opened its mixed parent, one
-//               ballot per mixed node, kept for the previous level only). A lane in the mask applies the per-lane
-//               theta test exactly as the depth-first kernel does (fp32 against two thresholds, the reference's fp64
-//               expression inside the guard band) and accumulates if it accepted; the ballot of the lanes that
-//               opened becomes the mask of the node's children. Children reached by every target are clean again
-//               (classified afresh); children reached by nobody are dropped with their whole subtree.
+//   phase 1 (cooperative, one NODE per lane): 32 ring entries are popped, their records gathered, and every node is
+//     classified against the bounding box of the warp's targets, conservatively:
+//       A  every target accepts it   (d2_min >= s^2/theta^2 + margin, or it is a leaf / terminal) -> accept list,
+//                                     with its mask
+//       O  every target opens it     (d2_max <= s^2/theta^2 - margin) -> its children inherit its mask
+//       M  mixed / too close to call -> mixed list of this round
+//   phase 2a (one BODY per lane, the round's mixed nodes, two per iteration with packed fp32): each lane that reaches
+//     the node takes the per-lane theta test (fp32 against the two edges of a guard band; if any lane lands inside
+//     a band the round's loop is redone with the reference's fp64 expression deciding those cases) and accumulates
+//     if it accepted. The ballot of the lanes that opened becomes the mask of the node's children; children nobody
+//     opened are dropped with their whole subtree.
+//   push: the children of O and M nodes are appended to the ring (positions from three ballots, one per bit of the
+//     child count).
+//   phase 2b (one BODY per lane, when >= 64 entries have gathered or the ring is empty): the accept list — no test at
+//     all, two entries per iteration: two-float difference, rsqrt, three multiplies, two FMAs per interaction, the
+//     mask only selects a zero mass.
 //
-// A warp whose frontier outgrows its shared-memory queue hands its chunk to the depth-first kernel (second launch).
+// A warp whose ring would overflow hands its chunk to the depth-first kernel (second launch).
 #pragma once
 #include <type_traits>
 #include "bh_common.cuh"
@@ -31,10 +33,8 @@ namespace lpe {
 
 constexpr int T2_THREADS = 128;
 constexpr int T2_WARPS = T2_THREADS / 32;
-constexpr int T2_CAP = 256;                 // frontier entries per level and warp
-constexpr int T2_ROUNDS = T2_CAP / 32;      // classification rounds per level
-constexpr int T2_ABUF = 98;                 // A-list buffer (flushed at >= 64; + 1 pad entry, even size)
-constexpr unsigned int T2_CLEAN = 0xFFFFu;
+constexpr int T2_CAP = 256;                 // ring entries per warp (power of two)
+constexpr int T2_ABUF = 98;                 // accept-list buffer (flushed at >= 64; + 1 pad entry, even size)
 constexpr float T2_MARGIN = 2e-5f;          // relative safety margin of the group classification
 
 struct __align__(16) APair {
