@@ -1,32 +1,36 @@
-// bh_build.cuh — Morton keys, terminals, path-compressed quadtree topology in pre-order, and the
-// bottom-up mass / centre-of-mass / first-occupant aggregation.
+// bh_build.cuh — sort keys (Hilbert or Morton index of the depth-D cell), terminals, path-compressed quadtree
+// topology in pre-order, and the bottom-up mass / centre-of-mass / first-occupant aggregation.
 //
 // What the reference builds by recursive insertion (barnes_hut.cpp:101-238) is rebuilt here from sorted
 // keys. Equivalences used (all verified against the compiled reference):
-//   Q10  child digit = (x >= mid) + 2*(y >= mid)  =>  reference DFS order == Morton order of the cells
+//   Q10  child digit = (x >= mid) + 2*(y >= mid)  =>  reference DFS order == Morton order of the cells; any other
+//        hierarchical curve (Hilbert) gives the same cells and the same tree, only another sibling order
 //   Q3   a chain of single-child cells carries one (M, COM); only its lowest cell's size matters
 //        => keep only branching cells (>= 2 non-empty children): a path-compressed tree
 //   Q4   cells smaller than theta*eps are always accepted => stop at depth D (terminals may aggregate)
 //   Q2   every internal cell counts its first occupant (minimum insertion rank) twice
 //
-// Topology without a level loop: for sorted terminals t (distinct depth-D cells), delta[t] = LCA level of
-// t and t+1. Every t is a "witness" of the branching cell at level delta[t] that contains t and t+1; that
-// cell is identified by (a, L) with a = its first terminal. A 32-bit level mask per terminal collects the
-// levels of the cells that start there (atomicOr), and
-//     ordinal(a, L)    = P[a] + popc(mask[a] & ((1<<L)-1))      P = exclusive scan of popc(mask)
-//     preorder(a, L)   = a + ordinal(a, L);   preorder(leaf t) = t + P[t] + popc(mask[t])
-//     skip(a..b)       = (b+1) + P[b+1]
-//     parent level     = max(delta[a-1], delta[b])
-// Aggregation is level-synchronous, deepest level first (one launch per level, nodes of a level listed by a
-// block-aggregated counting pass): a cell sums its <= 4 children in digit order (deterministic), and writes
-// their traversal records side by side into its CHILD BLOCK (one 128-byte line). The traversal always visits
-// all children of an opened cell, so every byte it fetches is used.
+// Topology without a level loop and without searches (one galloping search per witness aside): for sorted
+// terminals t (distinct depth-D cells), delta[t] = LCA level of t and t+1. Every t is a "witness" of the
+// branching cell at level delta[t] that contains t and t+1; that cell is identified by (a, L) with a = its first
+// terminal (kept in wstart[t]). A 32-bit level mask per terminal collects the levels of the cells that start
+// there (atomicOr), and with P = exclusive scan of popc(mask):
+//     ordinal(a, L)    = P[a] + popc(mask[a] & ((1<<L)-1))
+//     preorder(a, L)   = a + ordinal(a, L);   preorder(terminal t) = t + P[t] + popc(mask[t])
+//     first child of (a, L)  = the next deeper cell starting at a (preorder + 1), else terminal a
+//     other children         = for every witness t of the cell: the shallowest cell starting at t+1
+//                              ((t+1) + P[t+1]), else terminal t+1
+// Skip pointers are filled by the aggregation (a cell ends where its last child ends).
+// Aggregation is level-synchronous, deepest level first (one launch per level, cells of a level listed by a
+// block-aggregated counting pass in k_topology): a QUAD of lanes sums a cell's <= 4 children in the fixed order
+// (c0 + c1) + (c2 + c3) and writes their traversal records side by side into the cell's CHILD BLOCK (one 128-byte
+// line). The traversal always visits all children of an opened cell, so every byte it fetches is used.
 #pragma once
 #include "bh_common.cuh"
 
 namespace lpe {
 
-// ---- 1. Morton keys -------------------------------------------------------------------------------------
+// ---- 1. sort keys ---------------------------------------------------------------------------------------
 // Cell index along one axis at depth D, matching the reference's comparisons exactly: the reference descends with
 // `x < bx + 0.5*bs` tests on boundaries k*h that are exact in fp64, so the cell is the k with
 // k*h <= x < (k+1)*h; the quotient is only a first guess.

@@ -1,9 +1,11 @@
 // lpe_bh.cu — host side of the C ABI declared in include/lpe_bh.h: device buffers, staging, and the launch
 // sequence of one Barnes-Hut step. No CPU fallback: every entry point needs a CUDA device.
 //
-// One step, all on one stream, no host synchronisation (counts live in a device `Scal` block):
-//   keygen -> radix sort (u64 key, u32 index) -> gather -> head-flag scan -> terminals -> witnesses ->
-//   mask-popcount scan -> topology -> aggregate (walk-up) -> traverse + kick (+ drift)
+// One step, no host synchronisation (counts live in a device `Scal` block):
+//   keygen -> radix sort (u64 key, u32 index: histogram, bases, one look-back scatter per pass) ->
+//   [side stream: gather into key order] | head-flag scan that writes the terminals -> witnesses ->
+//   mask-popcount scan -> level offsets -> topology -> aggregation level by level -> traverse + kick (+ drift),
+//   then the depth-first kernel for the (normally zero) chunks whose frontier overflowed.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
