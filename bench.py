@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL)
 
-A "step" is one full pass of the hot path over all bodies: Morton keys, radix sort, quadtree build + aggregation,
+A "step" is one full pass of the hot path over all bodies: space-filling-curve keys, radix sort, quadtree build + aggregation,
 theta traversal, kick and drift. One JSON line is printed by rank 0.
 
   value      whole-job body-steps/s with the bodies resident in HBM (device-timed, CUDA events on the launching

@@ -78,10 +78,10 @@ typedef struct {
 
 /* tree dump for parity tests; every pointer may be NULL. Arrays are sized by the caller from lpe_bh_get_stats. */
 typedef struct {
-    uint64_t* sorted_keys;   /* [n_bodies] Morton keys in sorted order (bit 2D set = not in tree) */
+    uint64_t* sorted_keys;   /* [n_bodies] sort keys (Morton code or Hilbert index, see stats.hilbert) in sorted order (bit 2D set = not in tree) */
     uint32_t* sorted_index;  /* [n_bodies] creation index of the body at each sorted position */
     int32_t*  node_level;    /* [n_nodes] level of a branching cell; -1 single-body leaf; -2 aggregated cell at the depth bound */
-    uint64_t* node_key;      /* [n_nodes] Morton key (depth D) of the first body of the node */
+    uint64_t* node_key;      /* [n_nodes] sort key (depth D) of the first body of the node */
     uint32_t* node_skip;     /* [n_nodes] pre-order index of the first node after this node's subtree */
     uint32_t* node_first;    /* [n_nodes] creation index of the node's first occupant (minimum insertion rank) */
     uint32_t* node_count;    /* [n_nodes] bodies under the node */
@@ -147,7 +147,7 @@ int  lpe_bh_direct_accel(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t first
 
 /* ---- multi-GPU (one context per process/GPU; the collective itself is the caller's, e.g. NCCL allgather) ----
  * Every rank holds all bodies and builds the same tree; rank r traverses and integrates the sorted-order blocks
- * b with b % nranks == r (blocks of LPE_SHARD_BLOCK Morton-consecutive bodies), packs their new (x,y,vx,vy) into
+ * b with b % nranks == r (blocks of LPE_SHARD_BLOCK key-consecutive bodies), packs their new (x,y,vx,vy) into
  * xchg_send, and after the caller's allgather into xchg_recv, lpe_bh_step_finish scatters every rank's slice
  * back into the state arrays. nranks == 1 restores the single-GPU path. */
 #define LPE_SHARD_BLOCK 2048u

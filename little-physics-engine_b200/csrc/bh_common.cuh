@@ -2,7 +2,7 @@
 //
 // Data layout in HBM:
 //   state (creation order):  body Body[n] (32 B: x, y, m, rank, comp), vel double2[n]
-//   sorted (Morton order):   keys u64[n], sidx u32[n], sbody SBody[n] (32 B: x, y, m, rank|comp, creation index)
+//   sorted (key order):      keys u64[n], sidx u32[n], sbody SBody[n] (32 B: x, y, m, rank|comp, creation index)
 //   terminals (t < n_term):  tkey u64, tfirst u32, delta i8, mask u32, tnode u32
 //   nodes (pre-order index): meta NodeMeta (16 B), agg Agg (64 B)
 //   cells (ordinal):         child uint4;  records: rec TravRec[4 * (cells + 1)] in child blocks of 128 B
@@ -58,7 +58,7 @@ struct __align__(16) Body {
     unsigned int rank;    // insertion rank (position in the reference's view iteration)
     unsigned int comp;    // LPE_HAS_MASS | LPE_HAS_VELOCITY | LPE_BOUNDARY | LPE_LIQUID
 };
-struct __align__(16) SBody {   // the same body at its Morton-sorted position
+struct __align__(16) SBody {   // the same body at its key-sorted position
     double x, y, m;
     unsigned int rankcomp;   // rank | comp << 28
     unsigned int idx;        // creation index

@@ -3,7 +3,7 @@
 // Replaces BarnesHutSystem::calculateForce (reference barnes_hut.cpp:240-294) and, when do_drift is set,
 // MovementSystem::update (movement.cpp:13-39).
 //
-// One warp walks the tree for 32 Morton-consecutive targets, depth first in the reference's child order
+// One warp walks the tree for 32 key-consecutive targets, depth first in the reference's child order
 // (nw, ne, sw, se = Morton digit order), so nodes are met in pre-order. Each lane keeps its OWN accept/open
 // decision, as the reference does per body: a lane that accepted a node ignores that node's descendants by
 // remembering skipUntil = skip[node] (a pre-order index); the warp descends while any lane still opens.
