@@ -117,7 +117,8 @@ int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
 /* Stage bodies into device SoA buffers. rank[i] = position of body i in the iteration of
  * view<Position,Mass>(exclude<Boundary>) (the reference's insertion order); NULL = EnTT's default, newest
  * entity first. comp NULL = every body has Mass and Velocity. vx/vy NULL = zero. Asynchronous on the context's
- * stream when the host arrays are pinned. */
+ * stream when the host arrays are pinned. At most 2^28 bodies per context (32-bit record slots; about what fits
+ * in 180 GB of HBM at ~450 B/body). */
 int  lpe_bh_upload(lpe_bh_ctx* ctx, uint64_t n, const double* x, const double* y, const double* vx,
                    const double* vy, const double* m, const uint32_t* rank, const uint8_t* comp);
 /* Positions only (e.g. after other ECS systems moved bodies); n must match the last upload. */

@@ -24,6 +24,10 @@
 
 using namespace lpe;
 
+// Record slots and child codes are 32-bit (4 slots per cell, one flag bit): 2^28 bodies per context keeps every index
+// in range. At ~450 B/body that is also about what fits in 180 GB of HBM next to the sort buffers.
+static constexpr uint64_t LPE_MAX_BODIES = 1ull << 28;
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -720,7 +724,7 @@ int lpe_bh_set_instrumentation(lpe_bh_ctx* c, int flags) {
 int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, const double* vx, const double* vy,
                   const double* m, const uint32_t* rank, const uint8_t* comp) {
     if (!c) return 1;
-    if (n >= (1ull << 31) - 4096) return fail(c, "too many bodies (limit 2^31)");
+    if (n > LPE_MAX_BODIES) return fail(c, "too many bodies for one context (limit 2^28)");
     if (n && (!x || !y || !m)) return fail(c, "x, y and m are required");
     CU_TRY(c, cudaSetDevice(c->device));
     if (ensure_capacity(c, n)) return 1;
@@ -827,7 +831,7 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
     // Pipelined tick: the arrays go up on the copy stream in the order the step first reads them (positions and
     // components -> keys; masses and ranks -> gather; velocities -> kick) and the step waits per array, so only the
     // 17 B/body of the first group and the download sit on the critical path next to the kernels.
-    if (n >= (1ull << 31) - 4096) return fail(c, "too many bodies (limit 2^31)");
+    if (n > LPE_MAX_BODIES) return fail(c, "too many bodies for one context (limit 2^28)");
     if (!x || !y || !m) return fail(c, "x, y and m are required");
     CU_TRY(c, cudaSetDevice(c->device));
     if (ensure_capacity(c, n)) return 1;
