@@ -275,7 +275,13 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 const unsigned long long slot = (unsigned long long)lblock * 2048ull + within * 32ull + lane;
                 const double4 out = make_double4(p.x, p.y, v.x, v.y);
                 a.xchg_send[slot] = out;
-                for (int r = 0; r < a.npeer; ++r) a.peer[r][slot] = out;
+                for (int k = 1; k <= a.npeer; ++k) {   // rotating peer order, streaming stores (see bh_traverse2.cuh)
+                    int r = c.shard_rank + k;
+                    if (r >= a.npeer) r -= a.npeer;
+                    double2* dst = reinterpret_cast<double2*>(a.peer[r] + slot);
+                    __stcs(dst, make_double2(out.x, out.y));
+                    __stcs(dst + 1, make_double2(out.z, out.w));
+                }
             } else {
                 if (target) a.vel[b] = v;
                 if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;

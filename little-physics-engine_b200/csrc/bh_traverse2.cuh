@@ -399,7 +399,14 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                 // (stores to NVLink peer memory overlap the rest of the traversal), no collective afterwards.
                 const double4 out = make_double4(p.x, p.y, v.x, v.y);
                 a.xchg_send[slotx] = out;
-                for (int r = 0; r < a.npeer; ++r) a.peer[r][slotx] = out;
+                // peers in rotating order, starting after this rank: at any moment the ranks address different peers
+                for (int k = 1; k <= a.npeer; ++k) {
+                    int r = c.shard_rank + k;
+                    if (r >= a.npeer) r -= a.npeer;
+                    double2* dst = reinterpret_cast<double2*>(a.peer[r] + slotx);
+                    __stcs(dst, make_double2(out.x, out.y));       // streaming stores: nothing here is read again locally
+                    __stcs(dst + 1, make_double2(out.z, out.w));
+                }
             } else {
                 if (target) a.vel[b] = v;
                 if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;
