@@ -156,6 +156,8 @@ void close_peers(lpe_bh_ctx* c);
 int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     if (n <= c->cap && c->cap != 0) return 0;
     cudaStreamSynchronize(c->stream);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);   // (a step that failed half-way may not have joined them)
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     free_all(c);
     const uint64_t cap = n < 1024 ? 1024 : n;
     const uint64_t ncap = 2 * cap + 8;
@@ -692,6 +694,8 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     close_peers(c);
     free_all(c);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
