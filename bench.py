@@ -419,6 +419,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--bodies", type=int, default=None,
+                    help="TESTS ONLY: shrink the workload to this many bodies; the line is then marked reduced and is not a bench value")
     ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL allgather instead of the fused peer-memory exchange")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -430,7 +432,10 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
     # N=1: the configuration the metric is quoted on that the reference can also run (C2); N>1: the sharded 16M config
-    wl = WORKLOADS[args.workload or ("c2" if world == 1 else "c3")]
+    wl = dict(WORKLOADS[args.workload or ("c2" if world == 1 else "c3")])
+    if args.bodies:
+        wl["n"] = int(args.bodies)
+        wl["name"] = f"REDUCED to {wl['n']} bodies (contract test, not a bench value): " + wl["name"]
     if args.impl == "reference":
         reference_arm(args, wl, rank, world)
     else:
