@@ -31,3 +31,28 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
                         "--bodies", "20000", "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                        timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout[-500:], r.stderr[-500:])
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_own_arm_prints_one_contract_line():
+    """The own arm on a shrunk workload: one JSON line carrying every key of the contract, device and end-to-end
+    numbers both present, kernels actually launched."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--bodies", "100000", "--steps", "3",
+                        "--warmup", "3", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "roofline", "roofline_hbm", "roofline_step", "e2e",
+              "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["value"] > 0 and d["gpu_launches"] >= 3 * 20
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in d["roofline"], k
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 40 * 100000
+    assert d["e2e"]["d2h_bytes_per_step"] == 32 * 100000
+    assert 0 < d["roofline"]["frac"] < 1 and "REDUCED" in d["config"]["workload"]
