@@ -77,3 +77,18 @@ def test_no_gpu_means_loud_failure_not_fallback():
         pytest.skip("a CUDA device is present")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         lpe_bh.BarnesHut(0)
+
+
+def test_library_is_sm100a_with_packed_fp32_list_loops():
+    """The shipped library holds sm_100a SASS and the traversal's list loops really are packed fp32
+    (FADD2 / FMUL2 / FFMA2): a silent fall-back to scalar code or another arch would show here, without a GPU."""
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    lpe_bh.load_library()
+    out = subprocess.run(["cuobjdump", "-sass", lpe_bh.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    assert "sm_100a" in out
+    body = out[out.index("k_traverse2"):]
+    for op in ("FADD2", "FMUL2", "FFMA2", "MUFU.RSQ"):
+        assert op in body, op
