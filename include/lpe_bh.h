@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LPE_BH_ABI_VERSION 1
+#define LPE_BH_ABI_VERSION 2
 
 /* component mask bits (Position is implied) */
 #define LPE_HAS_MASS     1u /* Components::Mass      -> source if not Boundary (barnes_hut.cpp:117) */
@@ -90,14 +90,20 @@ typedef struct {
     double*   node_comy;     /* [n_nodes] */
 } lpe_bh_tree_dump;
 
-/* device-resident views for zero-copy interop (torch / NCCL plumbing); valid until the next upload or destroy */
+/* device-resident views for zero-copy interop (torch / NCCL plumbing). The pointers are valid until the next
+ * upload, STEP or destroy: every step re-orders the state into this step's key order in a second set of buffers and
+ * swaps the two sets. Slot i of body / vel holds the body whose creation index is orig[i] when key_ordered != 0;
+ * right after an upload (key_ordered == 0) slot i is body i and orig is not meaningful. */
 typedef struct {
-    void* body;       /* {double x, y, m; uint32 rank, comp}[n], 32 B per body, creation order */
+    void* body;       /* {double x, y, m; uint32 rank, comp}[n], 32 B per body */
     void* vel;        /* double2[n] */
+    void* orig;       /* uint32[n]: creation index of the body in each slot (key_ordered != 0) */
     void* xchg_send;  /* double4[xchg_chunk]  this rank's packed slice (x,y,vx,vy), see lpe_bh_set_shard */
     void* xchg_recv;  /* double4[xchg_chunk * nranks] */
     uint64_t n;
     uint64_t xchg_chunk; /* elements per rank in the exchange buffers */
+    int32_t key_ordered; /* 0: creation order (no step since the upload); 1: key order, see orig */
+    int32_t pad_;
 } lpe_bh_device_view;
 
 const char* lpe_bh_version(void);

@@ -134,46 +134,35 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
     if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_in, cnt);
 }
 
-// optional re-ordering of the state arrays by k_gather (all null: the state stays in creation order)
-struct Reorder {
-    const double2* velIn;
-    const unsigned int* origIn;   // creation index of each state slot; null = identity
-    Body* bodyOut;
-    double2* velOut;
-    unsigned int* origOut;
-};
-
-// ---- 2. gather into Morton order: one 32-byte sector read and one written per body --------------------------
+// ---- 2. gather: the state itself goes into key order (one 32-byte sector read and one written per body) ---------
+// Bodies move little per step, so next step's gather reads almost in place, the kick / drift writes of the traversal
+// are coalesced, and every later kernel reads bodies by sorted position. orig[] carries the creation index of each
+// slot (null on input = the state is still in creation order). velIn null: velocities are still on their way over
+// PCIe (host tick) and are packed straight into key order later.
 __global__ void __launch_bounds__(256)
-k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ body,
-         SBody* __restrict__ sbody, unsigned int* __restrict__ selfnode, unsigned int* __restrict__ selfslot,
-         Scal* __restrict__ s, Reorder ro) {
+k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ bodyIn,
+         const double2* __restrict__ velIn, const unsigned int* __restrict__ origIn, Body* __restrict__ bodyOut,
+         double2* __restrict__ velOut, unsigned int* __restrict__ origOut, unsigned int* __restrict__ selfnode,
+         unsigned int* __restrict__ selfslot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long mx = 0;
-    if (i < n) {
-        unsigned int b = sidx[i];
-        const Body bd = body[b];
-        if (ro.bodyOut) {
-            // sharded runs keep the state itself in key order: the step's own writes and the exchange become
-            // sequential, and next step's gather reads almost in place (bodies move little per step)
-            ro.bodyOut[i] = bd;
-            ro.velOut[i] = ro.velIn[b];
-            ro.origOut[i] = ro.origIn ? ro.origIn[b] : b;
-            b = (unsigned int)i;
-        }
-        SBody sb;
-        sb.x = bd.x; sb.y = bd.y; sb.m = bd.m;
-        sb.rankcomp = (bd.rank & 0x0FFFFFFFu) | (bd.comp << 28);
-        sb.idx = b;
-        sbody[i] = sb;
-        if (need_self) {
-            selfnode[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
-            selfslot[i] = LPE_NONE;
-        }
-        // largest source mass (bodies in the tree sort first): fixes the power-of-two mass unit of the records
-        if ((unsigned int)i < s->n_in && bd.m > 0.0) mx = (unsigned long long)__double_as_longlong(bd.m);
+    if (i >= n) return;
+    const unsigned int b = sidx[i];
+    bodyOut[i] = bodyIn[b];
+    if (velIn) velOut[i] = velIn[b];
+    origOut[i] = origIn ? origIn[b] : b;
+    if (need_self) {
+        selfnode[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
+        selfslot[i] = LPE_NONE;
     }
-    __shared__ unsigned long long shm[8];
+}
+
+// Largest source mass -> Scal::max_mass_bits (fixes the power-of-two mass unit of the traversal records). Runs with
+// the upload, not with the step: masses only change through an upload.
+__device__ __forceinline__ void block_max_mass(double m, unsigned int comp, Scal* __restrict__ s) {
+    unsigned long long mx = 0;
+    if ((comp & 1u) && !(comp & 4u) && m > 0.0 && m < __longlong_as_double(0x7FF0000000000000ll))
+        mx = (unsigned long long)__double_as_longlong(m);
+    __shared__ unsigned long long shm[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         const unsigned long long t = __shfl_xor_sync(0xFFFFFFFFu, mx, o);
@@ -182,7 +171,7 @@ k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body
     if ((threadIdx.x & 31) == 0) shm[threadIdx.x >> 5] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w) mx = shm[w] > mx ? shm[w] : mx;
+        for (unsigned int w = 1; w < (blockDim.x >> 5); ++w) mx = shm[w] > mx ? shm[w] : mx;
         if (mx) atomicMax(&s->max_mass_bits, mx);
     }
 }
@@ -288,7 +277,7 @@ struct Topo {
     const unsigned int* levelBase;
     unsigned int* levelCursor;
     const unsigned int* tfirst;
-    const SBody* sbody;
+    const Body* body;         // state in key order
     unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf
     unsigned int* selfslot;   // [sorted body] record slot of its own leaf (only written here for a one-terminal tree)
     TravRec* rec;
@@ -304,11 +293,11 @@ __device__ __forceinline__ double mass_scale_inv(unsigned long long max_mass_bit
 }
 
 // aggregate of one body
-__device__ __forceinline__ Agg body_agg(const SBody& sb, unsigned int pos, double thr) {
+__device__ __forceinline__ Agg body_agg(const Body& sb, unsigned int pos, double thr) {
     Agg a;
     a.m = sb.m; a.sx = sb.m * sb.x; a.sy = sb.m * sb.y;
     a.mf = sb.m; a.xf = sb.x; a.yf = sb.y;
-    a.frank = sb.rankcomp & 0x0FFFFFFFu; a.fidx = pos; a.count = 1u; a.small = (sb.m >= thr) ? 0u : 1u;
+    a.frank = sb.rank; a.fidx = pos; a.count = 1u; a.small = (sb.m >= thr) ? 0u : 1u;
     return a;
 }
 
@@ -377,21 +366,34 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         Agg a;
         if (single) {
             if (c.need_self) o.selfnode[first] = idx;
-            if (n_term == 1) a = body_agg(o.sbody[first], first, c.thr);
+            if (n_term == 1) a = body_agg(o.body[first], first, c.thr);
         } else {
             a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
             a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
-            for (unsigned int i = first; i < last; ++i) {
-                const SBody sb = o.sbody[i];
+            // Bodies that share a depth-D cell are summed in insertion-rank order, not in sorted-position order (which
+            // for equal keys is an accident of the previous permutation): the sums are then the same however the
+            // bodies reached this GPU (single GPU, or migrated between the ranks of a domain-decomposed run).
+            const bool canonical = (last - first) <= 64u;
+            unsigned int prev = 0u;
+            for (unsigned int k = first; k < last; ++k) {
+                unsigned int i = k;
+                if (canonical) {   // next larger rank (ranks are unique)
+                    unsigned int best = 0xFFFFFFFFu;
+                    for (unsigned int j = first; j < last; ++j) {
+                        const unsigned int r = o.body[j].rank;
+                        if ((k == first || r > prev) && r < best) { best = r; i = j; }
+                    }
+                    prev = best;
+                }
+                const Body sb = o.body[i];
                 a.m += sb.m; a.sx += sb.m * sb.x; a.sy += sb.m * sb.y;
-                const unsigned int r = sb.rankcomp & 0x0FFFFFFFu;
-                if (r < a.frank) { a.frank = r; a.fidx = i; a.mf = sb.m; a.xf = sb.x; a.yf = sb.y; }
+                if (sb.rank < a.frank) { a.frank = sb.rank; a.fidx = i; a.mf = sb.m; a.xf = sb.x; a.yf = sb.y; }
                 if (sb.m >= c.thr) a.small = 0u;
             }
             o.agg[idx] = a;
         }
         const unsigned int tcode = single ? (LPE_LEAF_FLAG | first) : idx;
-        if (n_term == 1) {   // a tree of one terminal: it is the root
+        if (n_term == 1 && !c.dd) {   // a tree of one terminal: it is the root
             const double msi = mass_scale_inv(s->max_mass_bits);
             o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
@@ -453,7 +455,7 @@ struct NodeOut {
     TravRec* rec;           // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
     unsigned int* recnode;  // [4 * block + slot] pre-order index of the cell stored in that slot (LPE_NONE for leaves)
     unsigned int* selfslot; // [sorted body] record slot of the body's own single-body leaf, LPE_NONE otherwise
-    const SBody* sbody;
+    const Body* body;       // state in key order
 };
 
 // One branching cell, handled by a QUAD of lanes: lane q owns child slot q. The four child reads are independent
@@ -478,11 +480,11 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         if (ci & LPE_LEAF_FLAG) {
             // a single-body leaf: read the body itself (one sector), no aggregate was ever stored for it
             leafpos = ci & ~LPE_LEAF_FLAG;
-            a = body_agg(o.sbody[leafpos], leafpos, c.thr);
+            a = body_agg(o.body[leafpos], leafpos, c.thr);
         } else {
             a = o.agg[ci];
             const NodeMeta mc = o.meta[ci];
-            level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + 1u;   // a deeper cell's skip is already final
+            level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + c.blockBase;   // a deeper cell's skip is already final
         }
     }
     const unsigned int vmask = (__ballot_sync(0xFFFFFFFFu, valid) >> quadShift) & 0xFu;
@@ -508,7 +510,7 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         }
         skip = start;   // every lane of the quad now holds the end of the whole cell
     }
-    const unsigned int slot = 4u * (qd + 1u) + r;
+    const unsigned int slot = 4u * (qd + c.blockBase) + r;
     if (valid) {
         o.rec[slot] = make_record(c, a, level, myskip, cbi, msi);
         o.recnode[slot] = (leafpos != LPE_NONE) ? LPE_NONE : ci;
@@ -538,8 +540,8 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         a.small |= (nvalid - 1u) << 1;   // children - 1, read back when this cell's own record is made
         o.agg[p] = a;
         o.meta[p].skip = skip;
-        if (p == 0) {   // the root has no parent to write its record
-            o.rec[0] = make_record(c, a, cellLevel, skip, 1u, msi);
+        if (p == 0 && !c.dd) {   // the root has no parent to write its record
+            o.rec[0] = make_record(c, a, cellLevel, skip, c.blockBase, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
             o.recnode[0] = 0u;
         }

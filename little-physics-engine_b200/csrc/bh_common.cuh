@@ -1,8 +1,9 @@
 // bh_common.cuh — shared device-side types for the B200 Barnes-Hut step.
 //
 // Data layout in HBM:
-//   state (creation order):  body Body[n] (32 B: x, y, m, rank, comp), vel double2[n]
-//   sorted (key order):      keys u64[n], sidx u32[n], sbody SBody[n] (32 B: x, y, m, rank|comp, creation index)
+//   state:                   body Body[n] (32 B: x, y, m, rank, comp), vel double2[n], orig u32[n] (creation index of a
+//                            slot) — creation order right after an upload, KEY ORDER after every step's gather
+//   sort:                    keys u64[n], sidx u32[n]
 //   terminals (t < n_term):  tkey u64, tfirst u32, delta i8, mask u32, tnode u32
 //   nodes (pre-order index): meta NodeMeta (16 B), agg Agg (64 B)
 //   cells (ordinal):         child uint4;  records: rec TravRec[4 * (cells + 1)] in child blocks of 128 B
@@ -20,11 +21,13 @@ constexpr int LPE_MAX_P2P = 8;   // ranks of one NVSwitch domain that can exchan
 
 // Scalars produced and consumed on the device inside one step (no host round trip).
 struct Scal {
+    // largest source mass as raw double bits (positive doubles order like integers). Set by the upload / pack kernels,
+    // NOT cleared per step (the per-step memset starts after this word): masses only change through an upload.
+    unsigned long long max_mass_bits;
     unsigned int n_in;          // sources inside [0,U)^2
     unsigned int n_term;        // distinct depth-D cells
     unsigned int n_internal;    // branching cells
     unsigned int work_counter;  // dynamic chunk dispenser of the traversal
-    unsigned long long max_mass_bits;  // max source mass as raw double bits (positive doubles order like integers)
     unsigned long long interactions;
     unsigned long long visits;
     unsigned long long warp_visits;    // node visits summed over warps (one per loop iteration)
@@ -58,12 +61,7 @@ struct __align__(16) Body {
     unsigned int rank;    // insertion rank (position in the reference's view iteration)
     unsigned int comp;    // LPE_HAS_MASS | LPE_HAS_VELOCITY | LPE_BOUNDARY | LPE_LIQUID
 };
-struct __align__(16) SBody {   // the same body at its key-sorted position
-    double x, y, m;
-    unsigned int rankcomp;   // rank | comp << 28
-    unsigned int idx;        // creation index
-};
-static_assert(sizeof(Body) == 32 && sizeof(SBody) == 32, "one sector per body");
+static_assert(sizeof(Body) == 32, "one sector per body");
 #define LPE_LEAF_FLAG 0x80000000u   // child[] entry of a single-body leaf: LPE_LEAF_FLAG | sorted position of the body
 
 // Per-node aggregate carried up the tree (exact sums; the quirk is applied only when a record is made). 64 bytes =
@@ -103,6 +101,8 @@ struct StepConst {
     int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
     int test_overflow;        // tests only: pretend every two-phase frontier overflows
     int hilbert;              // sort key: 0 = Morton code, 1 = Hilbert index of the same depth-D cell
+    int dd;                   // domain-decomposed rank: the local build leaves the root block and the top of the tree alone
+    unsigned int blockBase;   // child block of the cell with ordinal q is blockBase + q (1 on a single GPU: block 0 = root)
     float eps2f;              // (float)eps2s, converted once on the host (the kernels would re-convert it in their loops)
 };
 

@@ -33,12 +33,11 @@ struct TravArgs {
     const TravRec* rec;        // child blocks
     const Agg* agg;            // [preorder] exact sums: fp64 centre / mass for the rare exact test and STRICT mode
     const NodeMeta* meta;      // [preorder]
-    const SBody* sbody;             // [sorted body] position, mass, rank|comp, creation index
     const unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf (depth-first kernel)
     const unsigned int* selfslot;   // [sorted body] record slot of its own leaf (two-phase kernel)
     const unsigned int* recnode;    // [record slot] pre-order index
     const unsigned int* chunk_list; // depth-first kernel only: when set, process these chunks (two-phase overflow)
-    Body* body;                     // state, creation order (positions are updated in place by the drift)
+    Body* body;                     // state in key order (positions are updated in place by the drift)
     double2* vel;
     double4* xchg_send;      // sharded mode: packed (x,y,vx,vy) of the own slice
     double4* peer[LPE_MAX_P2P];   // direct exchange: this rank's slice inside every rank's receive buffer (NVLink peer
@@ -109,9 +108,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         double2 p = make_double2(0.0, 0.0);
         double bodyMass = 1.0;
         if (valid) {
-            const SBody sb = a.sbody[i];
-            b = sb.idx;
-            cm = sb.rankcomp >> 28;
+            const Body sb = a.body[i];
+            b = (unsigned int)i;
+            cm = sb.comp;
             p = make_double2(sb.x, sb.y);
             bodyMass = sb.m;
             if (c.need_self) self = a.selfnode[i];
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 const int level = mj.level;
                 double M, cx, cy;
                 if (level == -1) {   // single-body leaf: no aggregate is stored, the node is the body (meta.pad = its position)
-                    const SBody lb = a.sbody[mj.pad];
+                    const Body lb = a.body[mj.pad];
                     M = lb.m; cx = lb.x; cy = lb.y;
                 } else {
                     node_centre(a.agg[j], level, c.quirk, M, cx, cy);
@@ -266,7 +265,9 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         }
 
         if (valid) {
-            const bool mover = (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
+            // STRICT reads single-body leaves straight from the state (a.body), so positions must not move while the
+            // kernel runs: its drift is a separate elementwise pass (k_drift) after the traversal.
+            const bool mover = (PREC == 0 || c.shard_n > 1) && (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
             if (c.do_drift && mover) {
                 p.x += v.x * c.dtD;                                       // movement.cpp:32-33
                 p.y += v.y * c.dtD;

@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
         unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
         if (valid) {
-            const SBody sb = a.sbody[i];
-            b = sb.idx;
-            cm = sb.rankcomp >> 28;
+            const Body sb = a.body[i];
+            b = (unsigned int)i;
+            cm = sb.comp;
             p = make_double2(sb.x, sb.y);
             if (SELF) self = a.selfslot[i];
         }

@@ -56,13 +56,12 @@ struct lpe_bh_ctx {
     // state
     Body* body = nullptr;
     double2* vel = nullptr;
-    // sharded runs: the state is re-ordered into key order every step (second set of buffers); orig[slot] is then
-    // the creation index of the body in that slot (orig_valid = false: the state is in creation order)
+    // every step's gather re-orders the state into key order (second set of buffers); orig[slot] is then the creation
+    // index of the body in that slot (orig_valid = false: the state is in creation order, right after an upload)
     Body* body2 = nullptr;
     double2* vel2 = nullptr;
     unsigned int *orig = nullptr, *orig2 = nullptr;
     bool orig_valid = false;
-    bool reorder_resident = true;   // resident runs (lpe_bh_step / sharded) keep the state in key order; the host tick does not
     unsigned int* rank_in = nullptr;   // staging of the caller's rank / component arrays
     unsigned char* comp_in = nullptr;
     // staging
@@ -82,8 +81,6 @@ struct lpe_bh_ctx {
     unsigned int epoch = 0;
     unsigned int* fault_host = nullptr;        // pinned copy of the sort's fault flag
     int sorted_sel = 0;
-    // sorted copies
-    SBody* sbody = nullptr;
     unsigned int *selfnode = nullptr, *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
     // scans
     unsigned int* P = nullptr;
@@ -124,6 +121,19 @@ namespace {
             return 1;                                                                           \
         }                                                                                       \
     } while (0)
+
+// Every entry point runs on the context's device and puts the caller's current device back afterwards (the ECS
+// drop-in lives inside a host application that may use other devices).
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
 
 int fail(lpe_bh_ctx* c, const std::string& m) {
     if (c) c->err = m; else g_create_error = m;
@@ -166,10 +176,11 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     int rc = 0;
     rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) |
           dalloc(c, c->tmp, 5 * cap);
+    rc |= dalloc(c, c->body2, cap) | dalloc(c, c->vel2, cap) | dalloc(c, c->orig, cap) | dalloc(c, c->orig2, cap);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
           dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512) + 2 * ((size_t)scanTiles + 2)) | dalloc(c, c->totals, 512 * 8 + 16);
-    rc |= dalloc(c, c->sbody, cap) | dalloc(c, c->selfnode, cap) |
-          dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) | dalloc(c, c->ovf_list, cap / 32 + 8);
+    rc |= dalloc(c, c->selfnode, cap) | dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) |
+          dalloc(c, c->ovf_list, (size_t)cdiv((long long)cap, LPE_SHARD_BLOCK) * (LPE_SHARD_BLOCK / 32) + 8);
     rc |= dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
           dalloc(c, c->tnode, cap + 2) | dalloc(c, c->wstart, cap + 2) | dalloc(c, c->delta, cap + 2);
@@ -185,7 +196,6 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
     c->xchg_send = c->xchg_recv = nullptr;
     c->xchg_chunk = 0;
     close_peers(c);
-    c->body2 = nullptr; c->vel2 = nullptr; c->orig = c->orig2 = nullptr;
     c->orig_valid = false;
     return 0;
 }
@@ -207,9 +217,6 @@ bool p2p_ready(const lpe_bh_ctx* c) {
 
 int ensure_xchg(lpe_bh_ctx* c) {
     const uint64_t chunk = lpe_bh_shard_chunk(c->n, c->shard_n);
-    if (!c->body2 && (dalloc(c, c->body2, c->cap) || dalloc(c, c->vel2, c->cap) || dalloc(c, c->orig, c->cap) ||
-                      dalloc(c, c->orig2, c->cap)))
-        return 1;
     if (c->xchg_send && c->xchg_chunk == chunk) return 0;
     // (old exchange buffers, if any, stay in the allocation list and are released with the context)
     if (dalloc(c, c->xchg_send, chunk) || dalloc(c, c->xchg_recv, 2 * chunk * (uint64_t)c->shard_n)) return 1;
@@ -245,15 +252,18 @@ __global__ void k_unpermute_u32(int n, const unsigned int* __restrict__ in, unsi
 // x, y, m (+ optional rank / component arrays) -> one 32-byte Body per entity
 __global__ void k_pack_body(int n, const double* __restrict__ x, const double* __restrict__ y,
                             const double* __restrict__ m, const unsigned int* __restrict__ rank,
-                            const unsigned char* __restrict__ comp, Body* __restrict__ body) {
+                            const unsigned char* __restrict__ comp, Body* __restrict__ body, Scal* __restrict__ s) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     Body b;
-    b.x = x[i]; b.y = y[i]; b.m = m[i];
-    // EnTT iterates the leading pool back to front: newest entity is inserted first
-    b.rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
-    b.comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
-    body[i] = b;
+    b.m = 0.0; b.comp = 0u;
+    if (i < n) {
+        b.x = x[i]; b.y = y[i]; b.m = m[i];
+        // EnTT iterates the leading pool back to front: newest entity is inserted first
+        b.rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
+        b.comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+        body[i] = b;
+    }
+    block_max_mass(b.m, b.comp, s);
 }
 // the two halves of k_pack_body, for the pipelined host path: positions + components first, masses + ranks later
 __global__ void k_pack_pos(int n, const double* __restrict__ x, const double* __restrict__ y,
@@ -264,11 +274,31 @@ __global__ void k_pack_pos(int n, const double* __restrict__ x, const double* __
     body[i].comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
 }
 __global__ void k_pack_mass(int n, const double* __restrict__ m, const unsigned int* __restrict__ rank,
-                            Body* __restrict__ body) {
+                            Body* __restrict__ body, Scal* __restrict__ s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double mi = 0.0;
+    unsigned int cm = 0u;
+    if (i < n) {
+        mi = m[i];
+        cm = body[i].comp;   // written by k_pack_pos before the sort
+        body[i].m = mi;
+        body[i].rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
+    }
+    block_max_mass(mi, cm, s);
+}
+// MovementSystem::update as its own pass (STRICT precision: the traversal reads leaf bodies from the state, so the
+// positions must not move under it). Same expression as the fused drift of the traversal kernels.
+__global__ void __launch_bounds__(256) k_drift(int n, double dtD, Body* __restrict__ body, const double2* __restrict__ vel) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    body[i].m = m[i];
-    body[i].rank = rank ? rank[i] : (unsigned int)(n - 1 - i);
+    const unsigned int cm = body[i].comp;
+    const bool mover = (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
+    if (!mover) return;
+    double2 p = *reinterpret_cast<const double2*>(&body[i].x);
+    const double2 v = vel[i];
+    p.x += v.x * dtD;                                             // movement.cpp:32-33
+    p.y += v.y * dtD;
+    *reinterpret_cast<double2*>(&body[i].x) = p;
 }
 __global__ void k_set_pos(int n, const double* __restrict__ x, const double* __restrict__ y, Body* __restrict__ body,
                           const unsigned int* __restrict__ orig) {
@@ -462,6 +492,8 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     k.test_overflow = c->force_overflow ? 1 : 0;
     if (p.key_order < 0 || p.key_order > 2) return fail(c, "unknown key_order");
     k.hilbert = (p.key_order == LPE_KEYS_HILBERT || (p.key_order == LPE_KEYS_AUTO && p.precision == LPE_PREC_FAST)) ? 1 : 0;
+    k.dd = 0;
+    k.blockBase = 1u;
     return 0;
 }
 
@@ -484,7 +516,8 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     const int g256 = cdiv(n, 256);
 
     if (timing) cudaEventRecord(c->ev[0], st);
-    CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), st));
+    // (the first word, the mass scale, belongs to the upload)
+    CU_TRY(c, cudaMemsetAsync(reinterpret_cast<char*>(c->scal) + 8, 0, sizeof(Scal) - 8, st));
     CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * (512 * SORT_MAX_PASSES + 16), st));
     CU_TRY(c, cudaMemsetAsync(c->mask, 0, sizeof(unsigned int) * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * ((size_t)n + 1), st));
@@ -535,23 +568,18 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     CU_TRY(c, cudaStreamWaitEvent(sg, c->evs[0], 0));
     if (c->pend_mass) {   // host path: masses and ranks were uploaded behind the key generation and the sort
         CU_TRY(c, cudaStreamWaitEvent(sg, c->evc[2], 0));
-        k_pack_mass<<<g256, 256, 0, sg>>>(n, c->tmp + 2 * c->cap, c->pend_rank ? c->rank_in : nullptr, c->body);
+        k_pack_mass<<<g256, 256, 0, sg>>>(n, c->tmp + 2 * c->cap, c->pend_rank ? c->rank_in : nullptr, c->body, c->scal);
         c->pend_mass = false;
     }
-    Reorder ro{nullptr, nullptr, nullptr, nullptr, nullptr};
-    const bool reorder = c->shard_n > 1 || (c->reorder_resident && !c->pend_vel);
-    if (reorder && !c->body2 && (dalloc(c, c->body2, c->cap) || dalloc(c, c->vel2, c->cap) || dalloc(c, c->orig, c->cap) ||
-                                 dalloc(c, c->orig2, c->cap)))
-        return 1;
-    if (reorder) ro = Reorder{c->vel, c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2};
-    k_gather<<<g256, 256, 0, sg>>>(n, k.need_self, sidx, c->body, c->sbody, c->selfnode, c->selfslot, c->scal, ro);
+    // (host tick: the velocities are still on their way and are packed straight into key order before the kick)
+    k_gather<<<g256, 256, 0, sg>>>(n, k.need_self, sidx, c->body, c->pend_vel ? nullptr : c->vel,
+                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfnode, c->selfslot);
     CU_TRY(c, cudaEventRecord(c->evs[1], sg));
-    if (reorder) {   // from here on the state IS in key order
-        std::swap(c->body, c->body2);
-        std::swap(c->vel, c->vel2);
-        std::swap(c->orig, c->orig2);
-        c->orig_valid = true;
-    }
+    // from here on the state IS in key order
+    std::swap(c->body, c->body2);
+    std::swap(c->vel, c->vel2);
+    std::swap(c->orig, c->orig2);
+    c->orig_valid = true;
     // scans are single-pass (look-back over one status word per tile), each fused with its consumer
     const int scanTiles = cdiv((long long)n + 1, SCAN_TILE);
     unsigned int* scanTicket = c->totals + 512 * SORT_MAX_PASSES + SORT_MAX_PASSES + 1;
@@ -565,11 +593,11 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
                                                        scanStatus + (size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 1, c->epoch,
                                                        scanTicket + 1, sortFault);
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
-    Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->sbody,
+    Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->body,
               c->selfnode, c->selfslot, c->rec, c->recnode};
     CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
-    NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->sbody};
+    NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->body};
     // branching cells, deepest level first; the handful of cells of levels <= 4 share one single-block launch
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -593,7 +621,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     }
 
     TravArgs ta{};
-    ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta; ta.sbody = c->sbody;
+    ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta;
     ta.selfnode = c->selfnode; ta.body = c->body; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     ta.npeer = 0;
@@ -635,6 +663,10 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         } else {
             if (stats) k_traverse<1, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
             else k_traverse<1, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
+            if (k.do_drift && c->shard_n == 1) {   // STRICT: the drift is its own pass (see k_drift)
+                k_drift<<<g256, 256, 0, st>>>(n, k.dtD, c->body, c->vel);
+                ++travLaunches;
+            }
         }
     }
     if (timing) cudaEventRecord(c->ev[4], st);
@@ -655,7 +687,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
 
 extern "C" {
 
-const char* lpe_bh_version(void) { return "lpe_bh 0.1 (sm_100a, ABI 1)"; }
+const char* lpe_bh_version(void) { return "lpe_bh 0.2 (sm_100a, ABI 2)"; }
 
 int lpe_bh_device_count(void) {
     int n = 0;
@@ -671,29 +703,33 @@ int lpe_bh_create(int device, lpe_bh_ctx** out) {
     if (e != cudaSuccess || cnt == 0)
         return fail(nullptr, std::string("no CUDA device (this library has no CPU path): ") + cudaGetErrorString(e));
     if (device < 0 || device >= cnt) return fail(nullptr, "device index out of range");
-    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, cudaGetErrorString(e));
+    DevGuard _dg(device);
+    if ((e = cudaGetLastError()) != cudaSuccess) return fail(nullptr, cudaGetErrorString(e));
     lpe_bh_ctx* c = new lpe_bh_ctx();
     c->device = device;
-    if ((e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking)) != cudaSuccess) {
-        delete c;
-        return fail(nullptr, cudaGetErrorString(e));
+    bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& ev : c->evs) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    for (auto& ev : c->ev) ok = ok && cudaEventCreate(&ev) == cudaSuccess;
+    for (auto& ev : c->evc) ok = ok && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost(&c->fault_host, sizeof(unsigned int)) == cudaSuccess;
+    if (!ok) {
+        const std::string msg = std::string("cannot create streams / events / pinned flag: ") + cudaGetErrorString(cudaGetLastError());
+        c->stream = c->own_stream;
+        lpe_bh_destroy(c);
+        return fail(nullptr, msg);
     }
+    *c->fault_host = 0;
     c->stream = c->own_stream;
-    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking);
-    for (auto& ev : c->evs) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (cudaMallocHost(&c->fault_host, sizeof(unsigned int)) == cudaSuccess) *c->fault_host = 0;
-    else c->fault_host = nullptr;
-    for (auto& ev : c->ev) cudaEventCreate(&ev);
-    for (auto& ev : c->evc) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
     *out = c;
     return 0;
 }
 
 void lpe_bh_destroy(lpe_bh_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    DevGuard _dg(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     close_peers(c);
@@ -730,7 +766,7 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
     if (!c) return 1;
     if (n > LPE_MAX_BODIES) return fail(c, "too many bodies for one context (limit 2^28)");
     if (n && (!x || !y || !m)) return fail(c, "x, y and m are required");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     if (ensure_capacity(c, n)) return 1;
     c->n = n;
     c->have_step = false;
@@ -745,7 +781,8 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
     CU_TRY(c, cudaMemcpyAsync(t2, m, bytes, cudaMemcpyHostToDevice, st));
     if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank_in, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
     if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp_in, comp, n, cudaMemcpyHostToDevice, st));
-    k_pack_body<<<g, 256, 0, st>>>((int)n, t0, t1, t2, rank ? c->rank_in : nullptr, comp ? c->comp_in : nullptr, c->body);
+    CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), st));
+    k_pack_body<<<g, 256, 0, st>>>((int)n, t0, t1, t2, rank ? c->rank_in : nullptr, comp ? c->comp_in : nullptr, c->body, c->scal);
     if (vx) CU_TRY(c, cudaMemcpyAsync(t0, vx, bytes, cudaMemcpyHostToDevice, st));
     if (vy) CU_TRY(c, cudaMemcpyAsync(t1, vy, bytes, cudaMemcpyHostToDevice, st));
     k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t0 : nullptr, vy ? t1 : nullptr, c->vel, nullptr);
@@ -756,7 +793,7 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
 int lpe_bh_upload_positions(lpe_bh_ctx* c, const double* x, const double* y) {
     if (!c || !x || !y) return 1;
     if (c->n == 0) return 0;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     const size_t bytes = sizeof(double) * c->n;
     double *t0 = c->tmp, *t1 = c->tmp + c->cap;
     CU_TRY(c, cudaMemcpyAsync(t0, x, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -769,7 +806,7 @@ int lpe_bh_upload_positions(lpe_bh_ctx* c, const double* x, const double* y) {
 int lpe_bh_upload_velocities(lpe_bh_ctx* c, const double* vx, const double* vy) {
     if (!c || !vx || !vy) return 1;
     if (c->n == 0) return 0;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     const size_t bytes = sizeof(double) * c->n;
     double *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
     CU_TRY(c, cudaMemcpyAsync(t2, vx, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -782,7 +819,7 @@ int lpe_bh_upload_velocities(lpe_bh_ctx* c, const double* vx, const double* vy) 
 int lpe_bh_step(lpe_bh_ctx* c, const lpe_bh_params* p, int nsteps) {
     if (!c || !p) return 1;
     if (c->shard_n > 1) return fail(c, "sharded context: use lpe_bh_step_begin / lpe_bh_step_finish");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     for (int s = 0; s < nsteps; ++s)
         if (run_step(c, *p, false)) return 1;
     return 0;
@@ -790,7 +827,7 @@ int lpe_bh_step(lpe_bh_ctx* c, const lpe_bh_params* p, int nsteps) {
 
 int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy) {
     if (!c) return 1;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     const uint64_t n = c->n;
     if (n) {
         cudaStream_t st = c->stream;
@@ -816,7 +853,7 @@ int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy)
 
 int lpe_bh_synchronize(lpe_bh_ctx* c) {
     if (!c) return 1;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     if (fetch_fault(c)) return 1;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaGetLastError());
@@ -837,7 +874,7 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
     // 17 B/body of the first group and the download sit on the critical path next to the kernels.
     if (n > LPE_MAX_BODIES) return fail(c, "too many bodies for one context (limit 2^28)");
     if (!x || !y || !m) return fail(c, "x, y and m are required");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     if (ensure_capacity(c, n)) return 1;
     c->n = n;
     c->have_step = false;
@@ -860,6 +897,7 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
         CU_TRY(c, cudaMemcpyAsync(t + 4 * cap, vy, bytes, cudaMemcpyHostToDevice, cs));
         CU_TRY(c, cudaEventRecord(c->evc[3], cs));
         CU_TRY(c, cudaStreamWaitEvent(st, c->evc[1], 0));
+        CU_TRY(c, cudaMemsetAsync(c->scal, 0, 8, st));   // the mass scale is rebuilt by k_pack_mass (side stream, after the sort)
         k_pack_pos<<<cdiv((long long)n, 256), 256, 0, st>>>((int)n, t, t + cap, comp ? c->comp_in : nullptr, c->body);
         c->pend_mass = true;
         c->pend_rank = rank != nullptr;
@@ -877,7 +915,7 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
 
 int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
     if (!c || !out) return 1;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     lpe_bh_stats s = c->last;
     s.n_bodies = c->n;
@@ -907,7 +945,7 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
 int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     if (!c || !o) return 1;
     if (!c->have_step) return fail(c, "no step has been run since the last upload");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     const size_t n = c->n;
     Scal h;
@@ -915,25 +953,33 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     const size_t nn = (size_t)h.n_term + h.n_internal;
     if (o->sorted_keys) CU_TRY(c, cudaMemcpy(o->sorted_keys, c->keys[c->sorted_sel], 8 * n, cudaMemcpyDeviceToHost));
     std::vector<unsigned int> sidx(n);
-    // creation index of the body at each sorted position (a re-ordered state is in sorted order itself)
-    CU_TRY(c, cudaMemcpy(sidx.data(), c->orig_valid ? c->orig : c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
+    // creation index of the body at each sorted position (after a step the state is in sorted order itself)
+    CU_TRY(c, cudaMemcpy(sidx.data(), c->orig, 4 * n, cudaMemcpyDeviceToHost));
     if (o->sorted_index) std::memcpy(o->sorted_index, sidx.data(), 4 * n);
     if (nn == 0) return 0;
     std::vector<NodeMeta> mt(nn);
     std::vector<Agg> ag(nn);
     std::vector<unsigned long long> tk(h.n_term);
-    std::vector<SBody> sb(n);
+    std::vector<Body> sb(n);
     CU_TRY(c, cudaMemcpy(mt.data(), c->meta, sizeof(NodeMeta) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(ag.data(), c->agg, sizeof(Agg) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(tk.data(), c->tkey, 8 * (size_t)h.n_term, cudaMemcpyDeviceToHost));
-    CU_TRY(c, cudaMemcpy(sb.data(), c->sbody, sizeof(SBody) * n, cudaMemcpyDeviceToHost));
+    // the bodies as the tree saw them: the step's drift has moved the key-ordered state since, but the buffer the gather
+    // read from (now body2) still holds the pre-step bodies, and the sort's payload maps sorted position -> old slot
+    {
+        std::vector<Body> old(n);
+        std::vector<unsigned int> perm(n);
+        CU_TRY(c, cudaMemcpy(old.data(), c->body2, sizeof(Body) * n, cudaMemcpyDeviceToHost));
+        CU_TRY(c, cudaMemcpy(perm.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; ++i) sb[i] = old[perm[i]];
+    }
     for (size_t i = 0; i < nn; ++i) {
         Agg a = ag[i];
         if (mt[i].level == -1) {   // single-body leaves keep no aggregate on the device: rebuild it from the body
             const unsigned int pos = mt[i].pad;
-            const SBody& s0 = sb[pos];
+            const Body& s0 = sb[pos];
             a.m = s0.m; a.sx = s0.m * s0.x; a.sy = s0.m * s0.y; a.mf = s0.m; a.xf = s0.x; a.yf = s0.y;
-            a.frank = s0.rankcomp & 0x0FFFFFFFu; a.fidx = pos; a.count = 1; a.small = 0;
+            a.frank = s0.rank; a.fidx = pos; a.count = 1; a.small = 0;
         }
         double M, cx, cy;
         node_centre(a, mt[i].level, c->last_c.quirk, M, cx, cy);
@@ -952,7 +998,7 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
 int lpe_bh_get_counts(lpe_bh_ctx* c, uint32_t* accepted, uint32_t* visited) {
     if (!c) return 1;
     if (!(c->instr & 2)) return fail(c, "enable instrumentation bit1 before the step");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     for (int which = 0; which < 2; ++which) {
         uint32_t* dst = which ? visited : accepted;
@@ -973,7 +1019,7 @@ int lpe_bh_direct_accel(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t first, u
     if (!c || !p || !ax || !ay) return 1;
     if (first + count > c->n) return fail(c, "target range out of bounds");
     if (count == 0) return 0;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     double *dax = c->tmp, *day = c->tmp + c->cap;
     k_direct<<<cdiv((long long)(c->orig_valid ? c->n : count), 256), 256, 0, c->stream>>>(
         (int)c->n, c->body, p->universe_size, p->softening * p->softening, p->G, (int)first, (int)count, dax, day,
@@ -1011,7 +1057,7 @@ int lpe_bh_set_shard(lpe_bh_ctx* c, int rank, int nranks) {
 
 int lpe_bh_step_begin(lpe_bh_ctx* c, const lpe_bh_params* p) {
     if (!c || !p) return 1;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     return run_step(c, *p, true);
 }
 
@@ -1019,9 +1065,9 @@ int lpe_bh_step_finish(lpe_bh_ctx* c) {
     if (!c) return 1;
     if (c->shard_n <= 1 || c->n == 0) return 0;
     if (!c->have_step) return fail(c, "lpe_bh_step_begin has not run");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     k_xchg_scatter<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->shard_n, c->xchg_chunk,
-                                                                       c->orig_valid ? nullptr : c->vals[c->sorted_sel],
+                                                                       nullptr,
                                                                        c->xchg_recv + (p2p_ready(c) ? (size_t)c->xchg_parity * c->xchg_chunk * (size_t)c->shard_n : 0),
                                                                        c->body, c->vel);
     CU_TRY(c, cudaGetLastError());
@@ -1031,7 +1077,7 @@ int lpe_bh_step_finish(lpe_bh_ctx* c) {
 int lpe_bh_xchg_read_send(lpe_bh_ctx* c, double* host) {
     if (!c || !host) return 1;
     if (c->shard_n <= 1 || !c->xchg_send) return fail(c, "context is not sharded");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     CU_TRY(c, cudaMemcpyAsync(host, c->xchg_send, sizeof(double4) * c->xchg_chunk, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -1041,7 +1087,7 @@ int lpe_bh_xchg_write_recv(lpe_bh_ctx* c, int src, const double* host) {
     if (!c || !host) return 1;
     if (c->shard_n <= 1 || !c->xchg_recv) return fail(c, "context is not sharded");
     if (src < 0 || src >= c->shard_n) return fail(c, "source rank out of range");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     CU_TRY(c, cudaMemcpyAsync(c->xchg_recv + (size_t)src * c->xchg_chunk, host, sizeof(double4) * c->xchg_chunk,
                               cudaMemcpyHostToDevice, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1052,7 +1098,7 @@ int lpe_bh_boundary(lpe_bh_ctx* c, const lpe_bh_boundary_params* p) {
     if (!c || !p) return 1;
     if (!(p->universe_size > 0.0) || !(p->margin >= 0.0)) return fail(c, "boundary: universe_size must be > 0 and margin >= 0");
     if (c->n == 0) return 0;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     // the pass is per body and order-free: it runs on the state in whatever order it currently is
     k_boundary<<<cdiv((long long)c->n, 256), 256, 0, c->stream>>>((int)c->n, c->body, c->vel, p->margin, p->universe_size,
                                                                    p->bounce_damping, p->max_speed);
@@ -1066,7 +1112,7 @@ int lpe_bh_xchg_export(lpe_bh_ctx* c, void* handle64) {
     if (!c || !handle64) return 1;
     if (c->shard_n <= 1 || c->n == 0) return fail(c, "context is not sharded (set_shard + upload first)");
     if (c->shard_n > LPE_MAX_P2P) return fail(c, "direct exchange supports at most 8 ranks");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     if (ensure_xchg(c)) return 1;
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size is part of the ABI");
     cudaIpcMemHandle_t hnd;
@@ -1080,7 +1126,7 @@ int lpe_bh_xchg_import(lpe_bh_ctx* c, int rank, const void* handle64) {
     if (!c || !handle64) return 1;
     if (c->shard_n <= 1 || c->shard_n > LPE_MAX_P2P) return fail(c, "direct exchange needs 2..8 ranks");
     if (rank < 0 || rank >= c->shard_n || rank == c->shard_rank) return fail(c, "bad peer rank");
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     cudaIpcMemHandle_t hnd;
     std::memcpy(&hnd, handle64, sizeof(hnd));
     void* ptr = nullptr;
@@ -1103,7 +1149,7 @@ int lpe_bh_xchg_p2p_ready(const lpe_bh_ctx* c) { return (c && p2p_ready(c)) ? 1 
 
 int lpe_bh_xchg_reset(lpe_bh_ctx* c) {
     if (!c) return 1;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     close_peers(c);
     return 0;
@@ -1113,7 +1159,7 @@ uint64_t lpe_bh_launch_count(const lpe_bh_ctx* c) { return c ? c->launches : 0; 
 
 int lpe_bh_fma_peak(lpe_bh_ctx* c, double* tflops) {
     if (!c || !tflops) return 1;
-    CU_TRY(c, cudaSetDevice(c->device));
+    DevGuard _dg(c->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
     float* sink = nullptr;
@@ -1157,6 +1203,9 @@ int lpe_bh_get_device_view(lpe_bh_ctx* c, lpe_bh_device_view* o) {
     if (c->shard_n > 1 && c->n && ensure_xchg(c)) return 1;
     o->body = c->body;
     o->vel = c->vel;
+    o->orig = c->orig;
+    o->key_ordered = c->orig_valid ? 1 : 0;
+    o->pad_ = 0;
     o->xchg_send = c->xchg_send;
     o->xchg_recv = c->xchg_recv;
     o->n = c->n;

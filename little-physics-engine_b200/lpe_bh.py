@@ -68,8 +68,9 @@ class TreeDump(C.Structure):
 
 class DeviceView(C.Structure):
     _fields_ = [
-        ("body", C.c_void_p), ("vel", C.c_void_p), ("xchg_send", C.c_void_p),
-        ("xchg_recv", C.c_void_p), ("n", C.c_uint64), ("xchg_chunk", C.c_uint64),
+        ("body", C.c_void_p), ("vel", C.c_void_p), ("orig", C.c_void_p), ("xchg_send", C.c_void_p),
+        ("xchg_recv", C.c_void_p), ("n", C.c_uint64), ("xchg_chunk", C.c_uint64), ("key_ordered", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 

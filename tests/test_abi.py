@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(lpe_bh.Params) == 7 * 8 + 6 * 4
     assert C.sizeof(lpe_bh.Stats) == 16 * 8 + 4 * 4 + 5 * 4 + 4  # padded to 8
     assert C.sizeof(lpe_bh.TreeDump) == 10 * 8
-    assert C.sizeof(lpe_bh.DeviceView) == 6 * 8
+    assert C.sizeof(lpe_bh.DeviceView) == 8 * 8
     assert C.sizeof(lpe_bh.BoundaryParams) == 4 * 8
 
 
