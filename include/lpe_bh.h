@@ -200,6 +200,61 @@ int  lpe_bh_xchg_reset(lpe_bh_ctx* ctx);
 int  lpe_bh_shard_owner(uint64_t sorted_pos, int nranks, int* rank_out, uint64_t* slot_out);
 uint64_t lpe_bh_shard_chunk(uint64_t n_bodies, int nranks);        /* elements per rank in the exchange buffers */
 
+/* ---- multi-GPU, domain-decomposed (contiguous key ranges per GPU, per-GPU sort + build, one exchange
+ * of tree nodes) ------------------------------------------------------------------------------------------------
+ * Nothing is replicated: rank r owns the bodies whose sort key lies in [K_r, K_r+1) (splitters = arbitrary keys),
+ * sorts and builds only those, publishes the roots of its part of the tree to every rank and stores into rank d's
+ * record array the child blocks of the cells that a body of d's key range could open (a conservative box test: the
+ * locally essential tree). Every rank then builds the few cells that straddle a splitter from the published roots
+ * — same child order, same sums as the single-GPU build — and traverses for its own bodies: per-body accept / open
+ * decisions are those of the single-GPU tree (= the reference's). Bodies that leave a key range are stored straight
+ * into their new owner's state arrays. All traffic is plain stores to NVLink peer memory inside the step's own
+ * kernels plus two in-stream flag barriers per step; there is no collective call. FAST precision only.
+ *
+ * Setup (every rank, same capacity / import_blocks / nranks):
+ *   lpe_bh_dd_init -> exchange windows (same process: lpe_bh_dd_window + lpe_bh_dd_set_peer; one process per GPU:
+ *   lpe_bh_dd_export + lpe_bh_dd_import, handles shipped by any channel) -> lpe_bh_dd_upload (the WHOLE input on every
+ *   rank; each keeps its share) -> a host barrier across the ranks -> lpe_bh_dd_step in lockstep.
+ * lpe_bh_dd_phase runs one of the step's three phases without relying on concurrently running peers (tests that play
+ * several ranks on one GPU: phase p on every context, synchronise all, next phase). */
+typedef struct {
+    uint64_t capacity;        /* body slots of this rank */
+    uint64_t n_live;          /* bodies this rank owns after the last step */
+    uint64_t n_in_tree, n_terminals, n_cells;   /* of the rank's own part of the tree */
+    uint64_t n_roots;         /* roots published by all ranks (leaves of the top of the tree) */
+    uint64_t exported_blocks[8]; /* child blocks (128 B records + 128 B fp64 side records) stored into each rank */
+    uint64_t interactions;    /* accepted interactions of the rank's targets (stats only) */
+    uint64_t work_cost;       /* list entries evaluated by the rank's traversal */
+    uint64_t overflow_chunks;
+    uint32_t import_blocks;   /* capacity of one sender's import region */
+    uint32_t fault;           /* device fault bits since the last check */
+    int32_t  rank, nranks, depth, pad_;
+    /* last step, CUDA events, only when timing is enabled: keys + migration | wait for every rank's migrants |
+     * inbox keys + sort | build | flags + publish + export | wait for every rank's export | top of the tree | traversal */
+    float ms_keygen, ms_wait_a, ms_sort, ms_build, ms_export, ms_wait_b, ms_top, ms_traverse, ms_total, pad2_;
+} lpe_bh_dd_stats;
+
+int  lpe_bh_dd_init(lpe_bh_ctx* ctx, int rank, int nranks, uint64_t capacity, uint32_t import_blocks /* 0 = default */);
+int  lpe_bh_dd_export(lpe_bh_ctx* ctx, void* handle64);                    /* CUDA IPC handle of this rank's window */
+int  lpe_bh_dd_import(lpe_bh_ctx* ctx, int rank, const void* handle64);
+void* lpe_bh_dd_window(lpe_bh_ctx* ctx);                                   /* same-process form: raw device pointer */
+int  lpe_bh_dd_set_peer(lpe_bh_ctx* ctx, int rank, void* window, int peer_device /* -1: same device */);
+int  lpe_bh_dd_ready(const lpe_bh_ctx* ctx);
+int  lpe_bh_dd_upload(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n, const double* x, const double* y,
+                      const double* vx, const double* vy, const double* m, const uint32_t* rank, const uint8_t* comp);
+int  lpe_bh_dd_step(lpe_bh_ctx* ctx, const lpe_bh_params* p, int nsteps);  /* all ranks in lockstep; asynchronous */
+int  lpe_bh_dd_phase(lpe_bh_ctx* ctx, const lpe_bh_params* p, int phase);  /* 0, 1, 2 */
+/* this rank's bodies with their creation indices; arrays of >= capacity elements, any may be NULL; synchronises */
+int  lpe_bh_dd_download(lpe_bh_ctx* ctx, uint64_t* n_out, uint32_t* index, double* x, double* y, double* vx,
+                        double* vy, uint32_t* accepted);
+int  lpe_bh_dd_get_stats(lpe_bh_ctx* ctx, lpe_bh_dd_stats* out);
+/* splitters as depth-30 keys, nranks + 1 values (first 0, last 2^60); set: same values on every rank before the same step */
+int  lpe_bh_dd_get_splitters(lpe_bh_ctx* ctx, uint64_t* split30);
+int  lpe_bh_dd_set_splitters(lpe_bh_ctx* ctx, const uint64_t* split30);
+/* pure host helpers (no GPU): the sort key of cell (ix, iy) at a level and its inverse */
+uint64_t lpe_bh_cell_key(uint32_t ix, uint32_t iy, int level, int hilbert);
+void lpe_bh_key_cell(uint64_t key, int level, int hilbert, uint32_t* ix, uint32_t* iy);
+
 /* cumulative number of this library's kernels launched by the context (bench.py's gpu_launches) */
 uint64_t lpe_bh_launch_count(const lpe_bh_ctx* ctx);
 /* FP32 FMA peak of the device by a register-resident FMA loop, TFLOP/s (2 flops per FMA): the roofline denominator

@@ -47,7 +47,7 @@ __device__ __forceinline__ unsigned int cell_index(double x, double h, double in
 // every cell stay contiguous, so the same tree falls out of the sorted keys), but consecutive indices are always
 // edge-adjacent cells: 32 consecutive bodies form a compact blob instead of straddling a Z-curve jump, which is what
 // the traversal's per-warp grouping wants.
-__device__ __forceinline__ unsigned long long hilbert_index(unsigned int x, unsigned int y, int D) {
+__host__ __device__ __forceinline__ unsigned long long hilbert_index(unsigned int x, unsigned int y, int D) {
     unsigned long long d = 0;
     const unsigned int n1 = (1u << D) - 1u;
     for (int b = D - 1; b >= 0; --b) {
@@ -142,18 +142,14 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
 __global__ void __launch_bounds__(256)
 k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ bodyIn,
          const double2* __restrict__ velIn, const unsigned int* __restrict__ origIn, Body* __restrict__ bodyOut,
-         double2* __restrict__ velOut, unsigned int* __restrict__ origOut, unsigned int* __restrict__ selfnode,
-         unsigned int* __restrict__ selfslot) {
+         double2* __restrict__ velOut, unsigned int* __restrict__ origOut, unsigned int* __restrict__ selfslot) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned int b = sidx[i];
     bodyOut[i] = bodyIn[b];
     if (velIn) velOut[i] = velIn[b];
     origOut[i] = origIn ? origIn[b] : b;
-    if (need_self) {
-        selfnode[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
-        selfslot[i] = LPE_NONE;
-    }
+    if (need_self) selfslot[i] = LPE_NONE;   // set for bodies that end up alone in their depth-D cell
 }
 
 // Largest source mass -> Scal::max_mass_bits (fixes the power-of-two mass unit of the traversal records). Runs with
@@ -278,7 +274,6 @@ struct Topo {
     unsigned int* levelCursor;
     const unsigned int* tfirst;
     const Body* body;         // state in key order
-    unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf
     unsigned int* selfslot;   // [sorted body] record slot of its own leaf (only written here for a one-terminal tree)
     TravRec* rec;
     unsigned int* recnode;
@@ -365,7 +360,6 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         o.meta[idx] = mt;
         Agg a;
         if (single) {
-            if (c.need_self) o.selfnode[first] = idx;
             if (n_term == 1) a = body_agg(o.body[first], first, c.thr);
         } else {
             a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
@@ -397,7 +391,7 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
             const double msi = mass_scale_inv(s->max_mass_bits);
             o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
-            o.recnode[0] = idx;
+            o.recnode[0] = single ? (LPE_LEAF_FLAG | first) : idx;
             if (single && c.need_self) o.selfslot[first] = 0u;
         }
         // branching cells whose first terminal is t, shallow to deep: ordinal Pt + i, pre-order t + Pt + i
@@ -513,7 +507,7 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
     const unsigned int slot = 4u * (qd + c.blockBase) + r;
     if (valid) {
         o.rec[slot] = make_record(c, a, level, myskip, cbi, msi);
-        o.recnode[slot] = (leafpos != LPE_NONE) ? LPE_NONE : ci;
+        o.recnode[slot] = (leafpos != LPE_NONE) ? (LPE_LEAF_FLAG | leafpos) : ci;
         if (leafpos != LPE_NONE && c.need_self) o.selfslot[leafpos] = slot;
     } else if (live) {
         o.rec[slot] = invalid_record();

@@ -34,6 +34,13 @@ struct Scal {
     unsigned int ovf_count;     // chunks the two-phase traversal handed to the depth-first kernel (frontier overflow)
     unsigned int work_counter2; // dispenser of that second launch
     unsigned long long t2[8];   // two-phase diagnostics (STATS only): entries by kind
+    // domain-decomposed runs (bh_dd.cuh)
+    unsigned int n_live;        // bodies this rank owns in this step (slots [0, n_live) after the gather)
+    unsigned int dd_nroots;     // roots of the top tree (0 = empty tree)
+    unsigned int exp_list_count;
+    unsigned int exp_count[8];  // child blocks exported to each rank
+    unsigned int pad_dd;
+    unsigned long long work_cost;   // list entries evaluated by this rank's traversal (load-balance weight)
 };
 
 // Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.

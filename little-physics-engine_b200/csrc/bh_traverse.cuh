@@ -5,8 +5,10 @@
 //
 // One warp walks the tree for 32 key-consecutive targets, depth first in the reference's child order
 // (nw, ne, sw, se = Morton digit order), so nodes are met in pre-order. Each lane keeps its OWN accept/open
-// decision, as the reference does per body: a lane that accepted a node ignores that node's descendants by
-// remembering skipUntil = skip[node] (a pre-order index); the warp descends while any lane still opens.
+// decision, as the reference does per body: a lane that accepted a node at depth d ignores everything the walk meets
+// below depth d until it is back at depth <= d; the warp descends while any lane still opens. Nodes are addressed by
+// record slot only (no pre-order index), so the walk also runs over the record array of a domain-decomposed rank,
+// whose top blocks and imported blocks have no place in the rank's own pre-order.
 //
 // Memory: the children of a cell sit side by side in one 128-byte CHILD BLOCK (4 x TravRec). Opening a cell is one
 // coalesced 128-byte load by 8 lanes into the warp's frame stack in shared memory; every visit then reads its
@@ -33,9 +35,8 @@ struct TravArgs {
     const TravRec* rec;        // child blocks
     const Agg* agg;            // [preorder] exact sums: fp64 centre / mass for the rare exact test and STRICT mode
     const NodeMeta* meta;      // [preorder]
-    const unsigned int* selfnode;   // [sorted body] pre-order index of its own leaf (depth-first kernel)
-    const unsigned int* selfslot;   // [sorted body] record slot of its own leaf (two-phase kernel)
-    const unsigned int* recnode;    // [record slot] pre-order index
+    const unsigned int* selfslot;   // [sorted body] record slot of its own single-body leaf
+    const unsigned int* recnode;    // [record slot] pre-order index of the node, or LPE_LEAF_FLAG | sorted position of a leaf's body
     const unsigned int* chunk_list; // depth-first kernel only: when set, process these chunks (two-phase overflow)
     Body* body;                     // state in key order (positions are updated in place by the drift)
     double2* vel;
@@ -46,6 +47,11 @@ struct TravArgs {
     unsigned int* cntVis;
     Scal* s;
     unsigned int n_chunks_local;  // 32-body chunks this rank owns
+    // domain-decomposed runs: record slots outside [localLo, localHi) belong to the top of the tree or were imported
+    // from another rank; their exact centre / level come from xrec[slot] = {cx, cy, M, level} instead of agg / meta
+    const double4* xrec;
+    unsigned int localLo, localHi;
+    unsigned int* chunk_cost;     // [chunk] list entries evaluated for the chunk (load-balance weight); may be null
 };
 
 // The reference's test, barnes_hut.cpp:261-269, on exactly scaled operands (power-of-two scaling commutes
@@ -63,6 +69,21 @@ __device__ __noinline__ bool exact_open(const Agg* __restrict__ agg, const NodeM
     return !(__ddiv_rn(sizeSq, distSq) < theta2);
 }
 
+// The same test for a record slot of the two-phase kernel, wherever the node came from.
+__device__ __noinline__ bool exact_open_slot(const Agg* __restrict__ agg, const NodeMeta* __restrict__ meta,
+                                             const unsigned int* __restrict__ recnode, const double4* __restrict__ xrec,
+                                             unsigned int localLo, unsigned int localHi, unsigned int slot, int quirk,
+                                             double invS, double pxs, double pys, double eps2s, double Us, double theta2) {
+    if (slot >= localLo && slot < localHi)
+        return exact_open(agg, meta, recnode[slot], quirk, invS, pxs, pys, eps2s, Us, theta2);
+    const double4 x = xrec[slot];
+    const double dxs = x.x * invS - pxs, dys = x.y * invS - pys;
+    const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dxs, dxs), __dmul_rn(dys, dys)), eps2s);
+    const double size = ldexp(Us, -(int)x.w);
+    const double sizeSq = __dmul_rn(size, size);
+    return !(__ddiv_rn(sizeSq, distSq) < theta2);
+}
+
 // 8 lanes copy one 128-byte child block into a frame of the warp's stack
 __device__ __forceinline__ void load_block(const TravRec* __restrict__ rec, unsigned int block, TravRec* frame, int lane) {
     __syncwarp();
@@ -76,15 +97,19 @@ __device__ __forceinline__ void load_block(const TravRec* __restrict__ rec, unsi
 template <int PREC, bool STATS>
 __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravArgs a) {
     __shared__ TravRec sFrames[TRAV_WARPS][TRAV_FRAMES][4];
+    __shared__ unsigned int sBlock[TRAV_WARPS][TRAV_FRAMES];   // child block held by each frame (record slot = 4 * block + k)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     TravRec* const frames = &sFrames[warp][0][0];
-    const unsigned int n_nodes = a.s->n_term + a.s->n_internal;
+    unsigned int* const fblock = &sBlock[warp][0];
+    const unsigned int n_nodes = c.dd ? a.s->dd_nroots : a.s->n_term + a.s->n_internal;
+    const long long n_bodies = c.dd ? (long long)a.s->n_live : (long long)c.n;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = c.eps2f;
     const double Us = c.U * c.invS;
     const float INF = __int_as_float(0x7f800000);
     constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32
+    constexpr int ACTIVE = 1 << 20;   // accDepth of a lane that has accepted none of the current node's ancestors
 
     while (true) {
         unsigned int q = 0;
@@ -102,7 +127,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         const unsigned int lblock = q / CHUNKS_PER_BLOCK, within = q % CHUNKS_PER_BLOCK;
         const unsigned int gblock = lblock * (unsigned int)c.shard_n + (unsigned int)c.shard_rank;
         const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
-        const bool valid = i < c.n;
+        const bool valid = i < n_bodies;
+        if (c.dd && (long long)q * 32 >= n_bodies) continue;   // tail slots of a domain-decomposed rank hold no bodies
 
         unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
@@ -113,23 +139,28 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
             cm = sb.comp;
             p = make_double2(sb.x, sb.y);
             bodyMass = sb.m;
-            if (c.need_self) self = a.selfnode[i];
+            if (c.need_self) self = a.selfslot[i];
         }
         // bodyView of update(): Position + Velocity + Mass, not Boundary (barnes_hut.cpp:89)
         const bool target = valid && (cm & 1u) && (cm & 2u) && !(cm & 4u);
         const double pxs = p.x * c.invS, pys = p.y * c.invS;
-        unsigned int skipUntil = target ? 0u : 0xFFFFFFFFu;
+        // Per-lane decisions without a per-lane stack: a lane that ACCEPTED a node at depth d ignores every node met
+        // at a greater depth until the walk is back at depth <= d (the node's next sibling or an ancestor's).
+        int accDepth = target ? ACTIVE : -1;
         unsigned int nacc = 0, nvis = 0, nwarp = 0;
         double2 v = make_double2(0.0, 0.0);
         if (valid) v = a.vel[b];
 
-        // ---- depth-first walk over child blocks; d, k, j are warp-uniform ----
+        // ---- depth-first walk over child blocks; d, k are warp-uniform ----
         int d = 0, k = 0;
-        unsigned int j = 0;              // pre-order index of the node at frame d, slot k
         unsigned long long kstack = 0;   // 2 bits per depth: slot being processed there
         unsigned long long cstack = 0;   // 2 bits per depth: (number of children in that frame) - 1
         const bool alive = n_nodes != 0;
-        if (alive) load_block(a.rec, 0u, frames, lane);
+        if (alive) {
+            load_block(a.rec, 0u, frames, lane);
+            if (lane == 0) fblock[0] = 0u;
+            __syncwarp();
+        }
 
         if constexpr (PREC == 0) {
             // two-float lane position, negated once: d = (c_hi - p_hi) + (c_lo - p_lo)
@@ -143,12 +174,6 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
             double AX = 0.0, AY = 0.0;
             float ax = 0.f, ay = 0.f;
             while (alive) {
-                const TravRec* R = frames + (d * 4 + k);
-                const float4 C = R->c;
-                const float4 Bq = *reinterpret_cast<const float4*>(&R->gm);   // gm, open_t, skip, cblock
-                const unsigned int cb = __float_as_uint(Bq.w);
-                // a childless node (leaf / terminal) is followed in pre-order by the next index
-                const unsigned int skip = cb ? __float_as_uint(Bq.z) : j + 1u;
                 if (k > (int)((cstack >> (2 * d)) & 3ull)) {
                     // child block finished: flush the fp32 partial sums and return to the parent's next slot
                     AX += (double)ax; AY += (double)ay;
@@ -158,40 +183,45 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     k = (int)((kstack >> (2 * d)) & 3ull) + 1;
                     continue;
                 }
+                const TravRec* R = frames + (d * 4 + k);
+                const float4 C = R->c;
+                const float4 Bq = *reinterpret_cast<const float4*>(&R->gm);   // gm, open_t, skip, cblock
+                const unsigned int cb = __float_as_uint(Bq.w);
+                const unsigned int slot = 4u * fblock[d] + (unsigned int)k;
+                const bool active = d <= accDepth;
+                if (active) accDepth = ACTIVE;
                 const float dx = (C.x + nphx) + (C.z + nplx);
                 const float dy = (C.y + nphy) + (C.w + nply);
                 float d2 = fmaf(dx, dx, fmaf(dy, dy, eps2f));
                 // a lane that accepted an ancestor sees the node infinitely far away: never opens, contributes 0
-                d2 = (j >= skipUntil) ? d2 : INF;
+                d2 = active ? d2 : INF;
                 float lo = Bq.y * bandLo;
                 if (d2 > lo && d2 < Bq.y * bandHi)   // rare: inside the guard band -> the reference's fp64 test decides
-                    lo = exact_open(a.agg, a.meta, j, c.quirk, c.invS, pxs, pys, c.eps2s, Us, c.theta2) ? INF : -1.f;
+                    lo = exact_open_slot(a.agg, a.meta, a.recnode, a.xrec, a.localLo, a.localHi, slot, c.quirk, c.invS, pxs,
+                                         pys, c.eps2s, Us, c.theta2) ? INF : -1.f;
                 const bool open = d2 <= lo;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
-                // accepted (or already skipping): descendants are ignored up to skip; max() keeps an earlier,
-                // larger skip of a lane that accepted an ancestor
-                if (!open) skipUntil = max(skipUntil, skip);
+                if (active && !open) accDepth = d;   // accepted: the subtree below is ignored
                 float rinv;
                 asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(open ? INF : d2));
                 float f = (Bq.x * rinv) * (rinv * rinv);
-                if (selfTest && j == self) f = 0.f;
+                if (selfTest && slot == self) f = 0.f;
                 ax = fmaf(dx, f, ax);
                 ay = fmaf(dy, f, ay);
                 if (STATS) {
                     nwarp++;
-                    const bool active = d2 != INF;
                     nvis += active ? 1u : 0u;
-                    nacc += (active && !open && j != self && Bq.y != -2.0f) ? 1u : 0u;
+                    nacc += (active && !open && slot != self && Bq.y != -2.0f) ? 1u : 0u;
                 }
                 if (anyopen) {
                     kstack = (kstack & ~(3ull << (2 * d))) | ((unsigned long long)k << (2 * d));
                     ++d;
                     cstack = (cstack & ~(3ull << (2 * d))) | ((unsigned long long)(cb & 3u) << (2 * d));
                     k = 0;
-                    ++j;   // first child follows its parent in pre-order
                     load_block(a.rec, cb >> 2, frames + d * 4, lane);
+                    if (lane == 0) fblock[d] = cb >> 2;
+                    __syncwarp();
                 } else {
-                    j = skip;
                     ++k;
                 }
             }
@@ -203,32 +233,42 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
             }
         } else {
             // STRICT: the reference's arithmetic, operation for operation (barnes_hut.cpp:257-286), in real units.
-            // Pre-order == the reference's nw,ne,sw,se recursion order, so the velocity sum has the same order too.
+            // The walk visits the children of a cell in key order; with Morton keys that is the reference's
+            // nw,ne,sw,se recursion order, so the velocity sum has the same order too.
             const double m = bodyMass;
             const double eps2 = __dmul_rn(c.eps, c.eps);
             while (alive) {
-                const TravRec* R = frames + (d * 4 + k);
-                const float open_t = R->open_t;
-                const unsigned int cblock = R->cblock;
-                const unsigned int skip = cblock ? R->skip : j + 1u;
                 if (k > (int)((cstack >> (2 * d)) & 3ull)) {
                     if (d == 0) break;
                     --d;
                     k = (int)((kstack >> (2 * d)) & 3ull) + 1;
                     continue;
                 }
-                const NodeMeta mj = a.meta[j];
-                const int level = mj.level;
+                const TravRec* R = frames + (d * 4 + k);
+                const float open_t = R->open_t;
+                const unsigned int cblock = R->cblock;
+                const unsigned int slot = 4u * fblock[d] + (unsigned int)k;
+                // exact mass / centre / level of the node: from the rank's own aggregates, or (top of a decomposed tree,
+                // imported cells) from the fp64 side record that travelled with the record
+                int level;
                 double M, cx, cy;
-                if (level == -1) {   // single-body leaf: no aggregate is stored, the node is the body (meta.pad = its position)
-                    const Body lb = a.body[mj.pad];
-                    M = lb.m; cx = lb.x; cy = lb.y;
+                if (slot >= a.localLo && slot < a.localHi) {
+                    const unsigned int rn = a.recnode[slot];
+                    if (rn & LPE_LEAF_FLAG) {   // single-body leaf: no aggregate is stored, the node is the body
+                        const Body lb = a.body[rn & ~LPE_LEAF_FLAG];
+                        M = lb.m; cx = lb.x; cy = lb.y; level = -1;
+                    } else {
+                        level = a.meta[rn].level;
+                        node_centre(a.agg[rn], level, c.quirk, M, cx, cy);
+                    }
                 } else {
-                    node_centre(a.agg[j], level, c.quirk, M, cx, cy);
+                    const double4 x = a.xrec[slot];
+                    cx = x.x; cy = x.y; M = x.z; level = (int)x.w;
                 }
                 const double dx = (cx * c.invS - pxs) * c.S, dy = (cy * c.invS - pys) * c.S;   // exact: S is a power of two
                 const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), eps2);
-                const bool active = j >= skipUntil;
+                const bool active = d <= accDepth;
+                if (active) accDepth = ACTIVE;
                 bool open = false;
                 if (level >= 0 && open_t != -2.0f) {
                     const double size = ldexp(c.U, -level);
@@ -237,8 +277,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 open = open && active;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
                 const bool acc = active && !open;
-                if (acc) skipUntil = skip;
-                if (acc && j != self && open_t != -2.0f) {
+                if (acc) accDepth = d;
+                if (acc && slot != self && open_t != -2.0f) {
                     const double dist = sqrt(distSq);
                     const double force = __ddiv_rn(__dmul_rn(__dmul_rn(c.G, M), m), distSq);
                     const double invDistMass = __ddiv_rn(force, __dmul_rn(m, dist));
@@ -255,10 +295,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     ++d;
                     cstack = (cstack & ~(3ull << (2 * d))) | ((unsigned long long)(cblock & 3u) << (2 * d));
                     k = 0;
-                    ++j;
                     load_block(a.rec, cblock >> 2, frames + d * 4, lane);
+                    if (lane == 0) fblock[d] = cblock >> 2;
+                    __syncwarp();
                 } else {
-                    j = skip;
                     ++k;
                 }
             }

@@ -6,6 +6,7 @@
 //   [side stream: gather into key order] | head-flag scan that writes the terminals -> witnesses ->
 //   mask-popcount scan -> level offsets -> topology -> aggregation level by level -> traverse + kick (+ drift),
 //   then the depth-first kernel for the (normally zero) chunks whose frontier overflowed.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -21,6 +22,7 @@
 #include "bh_build.cuh"
 #include "bh_traverse.cuh"
 #include "bh_traverse2.cuh"
+#include "bh_dd.cuh"
 
 using namespace lpe;
 
@@ -81,7 +83,7 @@ struct lpe_bh_ctx {
     unsigned int epoch = 0;
     unsigned int* fault_host = nullptr;        // pinned copy of the sort's fault flag
     int sorted_sel = 0;
-    unsigned int *selfnode = nullptr, *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
+    unsigned int *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
     // scans
     unsigned int* P = nullptr;
     // terminals
@@ -103,6 +105,33 @@ struct lpe_bh_ctx {
     double4* peer_recv[LPE_MAX_P2P] = {};                 // every rank's xchg_recv (own pointer, or opened through CUDA IPC)
     void* peer_opened[LPE_MAX_P2P] = {};                  // IPC mappings to close
     int xchg_parity = 0;
+    int sms = 148;
+    // domain decomposition (lpe_bh_dd.inl)
+    bool dd = false;
+    int dd_rank = 0, dd_R = 1;
+    unsigned int dd_icap = 0;                 // import blocks per sender
+    char* dd_win = nullptr;                   // own window (peer-visible): header, root tables, state x2, records
+    size_t dd_win_bytes = 0;
+    char* dd_peer_win[LPE_MAX_P2P] = {};      // every rank's window (own pointer, raw peer pointer, or an IPC mapping)
+    void* dd_peer_opened[LPE_MAX_P2P] = {};   // IPC mappings to close
+    int dd_cur = 0;                           // which of the two state buffer sets of the window is current
+    unsigned long long dd_epoch = 0;          // step number: the value the barrier flags carry
+    unsigned long long dd_split30[LPE_MAX_P2P + 1] = {};   // splitters as depth-30 keys
+    int dd_hilbert = -1;                      // key order the splitters were made for
+    int dd_dom_depth = -1;                    // depth the device copy of the domain table was built for
+    uint64_t dd_n_total = 0;                  // bodies of the whole input
+    double dd_U = 0.0;
+    DDDomain* dd_dom = nullptr;
+    std::vector<char> dd_dom_host;
+    unsigned int* dd_eidx = nullptr;
+    uint4* dd_list = nullptr;
+    unsigned int dd_list_cap = 0;
+    unsigned long long* dd_oob = nullptr;     // ordered-encoded box of the out-of-tree targets seen by phase A
+    double* dd_payload = nullptr;             // 2 x 6 doubles: this step's mail of the two barrier points
+    double4* dd_xrec = nullptr;
+    unsigned int* dd_chunk_cost = nullptr;
+    DDTop dd_top{};
+    cudaEvent_t dd_ev[10] = {};
     // timing
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     lpe_bh_stats last{};
@@ -163,29 +192,37 @@ inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 void close_peers(lpe_bh_ctx* c);
 
-int ensure_capacity(lpe_bh_ctx* c, uint64_t n) {
-    if (n <= c->cap && c->cap != 0) return 0;
+void dd_release(lpe_bh_ctx* c);
+int dd_check_fault(lpe_bh_ctx* c);
+
+// dd: the context becomes one rank of a domain-decomposed run with n slots; the state arrays and the records then live
+// in the rank's peer-visible window (lpe_bh_dd.inl) instead of being allocated here
+int ensure_capacity(lpe_bh_ctx* c, uint64_t n, bool dd = false) {
+    if (!dd && !c->dd && n <= c->cap && c->cap != 0) return 0;
     cudaStreamSynchronize(c->stream);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);   // (a step that failed half-way may not have joined them)
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     free_all(c);
+    dd_release(c);
     const uint64_t cap = n < 1024 ? 1024 : n;
     const uint64_t ncap = 2 * cap + 8;
+    const uint64_t recSlots = 4 * (cap + 8 + (dd ? DD_TOPCAP : 0));
     const int sortTiles = cdiv((long long)cap, SORT_TILE);
     const int scanTiles = cdiv((long long)cap + 1, SCAN_TILE);
     int rc = 0;
-    rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) |
-          dalloc(c, c->tmp, 5 * cap);
-    rc |= dalloc(c, c->body2, cap) | dalloc(c, c->vel2, cap) | dalloc(c, c->orig, cap) | dalloc(c, c->orig2, cap);
+    rc |= dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) | dalloc(c, c->tmp, 5 * cap);
+    if (!dd)
+        rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->body2, cap) | dalloc(c, c->vel2, cap) |
+              dalloc(c, c->orig, cap) | dalloc(c, c->orig2, cap) | dalloc(c, c->rec, recSlots);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
           dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512) + 2 * ((size_t)scanTiles + 2)) | dalloc(c, c->totals, 512 * 8 + 16);
-    rc |= dalloc(c, c->selfnode, cap) | dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, 4 * (cap + 8)) |
+    rc |= dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, recSlots) |
           dalloc(c, c->ovf_list, (size_t)cdiv((long long)cap, LPE_SHARD_BLOCK) * (LPE_SHARD_BLOCK / 32) + 8);
     rc |= dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
           dalloc(c, c->tnode, cap + 2) | dalloc(c, c->wstart, cap + 2) | dalloc(c, c->delta, cap + 2);
     rc |= dalloc(c, c->child, 4 * (cap + 8)) | dalloc(c, c->meta, ncap) | dalloc(c, c->levelList, cap + 8) |
-          dalloc(c, c->levelMeta, 3 * 32) | dalloc(c, c->agg, ncap) | dalloc(c, c->rec, 4 * (cap + 8));
+          dalloc(c, c->levelMeta, 3 * 32) | dalloc(c, c->agg, ncap);
     rc |= dalloc(c, c->cntAcc, cap) | dalloc(c, c->cntVis, cap) | dalloc(c, c->scal, 1);
     if (rc) {
         free_all(c);
@@ -288,9 +325,10 @@ __global__ void k_pack_mass(int n, const double* __restrict__ m, const unsigned 
 }
 // MovementSystem::update as its own pass (STRICT precision: the traversal reads leaf bodies from the state, so the
 // positions must not move under it). Same expression as the fused drift of the traversal kernels.
-__global__ void __launch_bounds__(256) k_drift(int n, double dtD, Body* __restrict__ body, const double2* __restrict__ vel) {
+__global__ void __launch_bounds__(256) k_drift(int n, double dtD, Body* __restrict__ body, const double2* __restrict__ vel,
+                                               const Scal* __restrict__ live) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || (live && (unsigned int)i >= live->n_live)) return;
     const unsigned int cm = body[i].comp;
     const bool mover = (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
     if (!mover) return;
@@ -497,70 +535,76 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     return 0;
 }
 
-int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
-    StepConst k;
-    if (make_const(c, p, k)) return 1;
-    const int n = (int)c->n;
-    if (n == 0) return 0;
-    if (c->shard_n > 1 && ensure_xchg(c)) return 1;
-    cudaStream_t st = c->stream;
-    const bool timing = c->instr & 1;
-    const bool stats = c->instr & 2;
+// ---- one step, in the pieces the single-GPU step and the domain-decomposed phases are assembled from ------------------
+struct SortPlan { int passes, topBits; };
+SortPlan sort_plan(const StepConst& k) {
     // 8-bit digits; a key of 8p+1 bits (33 for D = 16) gets a 9-bit top digit instead of one more pass
     const int keyBits = 2 * k.D + 1;
-    int passes = (keyBits + 7) / 8;
-    int topBits = keyBits - 8 * (passes - 1);
-    if (passes > 1 && topBits == 1) { --passes; topBits = 9; }
-    if (topBits < 8) topBits = 8;
-    const int sortTiles = cdiv(n, SORT_TILE);
-    const int g256 = cdiv(n, 256);
+    SortPlan sp;
+    sp.passes = (keyBits + 7) / 8;
+    sp.topBits = keyBits - 8 * (sp.passes - 1);
+    if (sp.passes > 1 && sp.topBits == 1) { --sp.passes; sp.topBits = 9; }
+    if (sp.topBits < 8) sp.topBits = 8;
+    return sp;
+}
 
-    if (timing) cudaEventRecord(c->ev[0], st);
+int step_prologue(lpe_bh_ctx* c, int n) {
+    cudaStream_t st = c->stream;
     // (the first word, the mass scale, belongs to the upload)
     CU_TRY(c, cudaMemsetAsync(reinterpret_cast<char*>(c->scal) + 8, 0, sizeof(Scal) - 8, st));
     CU_TRY(c, cudaMemsetAsync(c->totals, 0, sizeof(unsigned int) * (512 * SORT_MAX_PASSES + 16), st));
     CU_TRY(c, cudaMemsetAsync(c->mask, 0, sizeof(unsigned int) * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->child, 0xFF, sizeof(unsigned int) * 4 * ((size_t)n + 1), st));
     CU_TRY(c, cudaMemsetAsync(c->levelMeta, 0, sizeof(unsigned int) * 3 * 32, st));
+    return 0;
+}
 
-    k_keygen<<<g256, 256, 0, st>>>(k, c->body, c->keys[0], c->vals[0], c->scal);
-    if (timing) cudaEventRecord(c->ev[1], st);
-
+// keys[0] / vals[0] -> sorted keys / payload in keys[sorted_sel] / vals[sorted_sel]
+int step_sort(lpe_bh_ctx* c, const StepConst& k, int n) {
+    cudaStream_t st = c->stream;
+    const SortPlan plan = sort_plan(k);
+    const int passes = plan.passes, topBits = plan.topBits;
+    const int sortTiles = cdiv(n, SORT_TILE);
     int sel = 0;
-    {
-        // look-back words carry the step's epoch, so the status array is cleared only when the epoch wraps
-        if (c->epoch == 0u || c->epoch >= (1u << 30) - 1u) {
-            CU_TRY(c, cudaMemsetAsync(c->lbstatus, 0, sizeof(unsigned long long) *
-                                          ((size_t)cdiv((long long)c->cap, SORT_TILE) * (256 * (SORT_MAX_PASSES - 1) + 512) +
-                                           2 * ((size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 2)), st));
-            c->epoch = 0u;
-        }
-        ++c->epoch;
-        unsigned int* hist = c->totals;
-        unsigned int* tileCounter = c->totals + 512 * SORT_MAX_PASSES;
-        unsigned int* fault = tileCounter + SORT_MAX_PASSES;
-        const int lastBins = 1 << topBits;
-        const int histBlocks = std::min(sortTiles, 148 * 8);
-        k_sort_hist<<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(c->keys[0], n, passes, lastBins, hist);
-        k_sort_bases<<<passes, 512, 0, st>>>(hist);
-        for (int ps = 0; ps < passes; ++ps) {
-            const int shift = 8 * ps;
-            unsigned long long* status = c->lbstatus + (size_t)ps * 256 * sortTiles;
-            const unsigned int* base = hist + 512 * ps;
-            if (ps == passes - 1 && lastBins == 512)
-                k_sort_onesweep<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                                          n, shift, base, status, c->epoch, tileCounter + ps, fault);
-            else
-                k_sort_onesweep<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                                          n, shift, base, status, c->epoch, tileCounter + ps, fault);
-            sel ^= 1;
-        }
+    // look-back words carry the step's epoch, so the status array is cleared only when the epoch wraps
+    if (c->epoch == 0u || c->epoch >= (1u << 30) - 1u) {
+        CU_TRY(c, cudaMemsetAsync(c->lbstatus, 0, sizeof(unsigned long long) *
+                                      ((size_t)cdiv((long long)c->cap, SORT_TILE) * (256 * (SORT_MAX_PASSES - 1) + 512) +
+                                       2 * ((size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 2)), st));
+        c->epoch = 0u;
+    }
+    ++c->epoch;
+    unsigned int* hist = c->totals;
+    unsigned int* tileCounter = c->totals + 512 * SORT_MAX_PASSES;
+    unsigned int* fault = tileCounter + SORT_MAX_PASSES;
+    const int lastBins = 1 << topBits;
+    const int histBlocks = std::min(sortTiles, 148 * 8);
+    k_sort_hist<<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(c->keys[0], n, passes, lastBins, hist);
+    k_sort_bases<<<passes, 512, 0, st>>>(hist);
+    for (int ps = 0; ps < passes; ++ps) {
+        const int shift = 8 * ps;
+        unsigned long long* status = c->lbstatus + (size_t)ps * 256 * sortTiles;
+        const unsigned int* base = hist + 512 * ps;
+        if (ps == passes - 1 && lastBins == 512)
+            k_sort_onesweep<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
+                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault);
+        else
+            k_sort_onesweep<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
+                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault);
+        sel ^= 1;
     }
     c->sorted_sel = sel;
-    const unsigned long long* skeys = c->keys[sel];
-    const unsigned int* sidx = c->vals[sel];
-    if (timing) cudaEventRecord(c->ev[2], st);
+    c->launches += 2 + (uint64_t)passes;
+    c->last.sort_passes = passes;
+    return 0;
+}
 
+// gather into key order (side stream) | terminals -> witnesses -> ordinals -> topology -> aggregation, deepest level first
+int step_build(lpe_bh_ctx* c, const StepConst& k, int n) {
+    cudaStream_t st = c->stream;
+    const int g256 = cdiv(n, 256);
+    const unsigned long long* skeys = c->keys[c->sorted_sel];
+    const unsigned int* sidx = c->vals[c->sorted_sel];
     // fork: the gather (and, in the host tick, the late mass / rank pack before it) runs on the side stream while
     // this stream goes on with the kernels that only need the sorted keys; joined before k_topology
     cudaStream_t sg = c->side_stream;
@@ -573,7 +617,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     }
     // (host tick: the velocities are still on their way and are packed straight into key order before the kick)
     k_gather<<<g256, 256, 0, sg>>>(n, k.need_self, sidx, c->body, c->pend_vel ? nullptr : c->vel,
-                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfnode, c->selfslot);
+                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfslot);
     CU_TRY(c, cudaEventRecord(c->evs[1], sg));
     // from here on the state IS in key order
     std::swap(c->body, c->body2);
@@ -594,13 +638,12 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
                                                        scanTicket + 1, sortFault);
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
     Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->body,
-              c->selfnode, c->selfslot, c->rec, c->recnode};
+              c->selfslot, c->rec, c->recnode};
     CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
     NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->body};
     // branching cells, deepest level first; the handful of cells of levels <= 4 share one single-block launch
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    const int sms = c->sms;
     const int Ltop = k.D - 1 < 4 ? k.D - 1 : 4;
     int levelLaunches = 0;
     for (int L = k.D - 1; L > Ltop; --L) {
@@ -613,18 +656,27 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         ++levelLaunches;
     }
     k_agg_top<<<1, 1024, 0, st>>>(k, Ltop, c->levelList, levelBase, levelCount, c->child, no, c->scal);
-    if (timing) cudaEventRecord(c->ev[3], st);
-    if (c->pend_vel) {   // host path: velocities were uploaded behind the build; the kick is their first reader
-        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
-        k_pack2<<<g256, 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel, c->orig_valid ? c->orig : nullptr);
-        c->pend_vel = false;
-    }
+    // gather, 2 scans, witness, level_scan, topology, one launch per level above Ltop, agg_top
+    c->launches += 1 + 2 + 1 + 1 + 1 + (uint64_t)levelLaunches + 1;
+    return 0;
+}
 
+int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int n, bool sharded_begin) {
+    cudaStream_t st = c->stream;
+    const bool stats = c->instr & 2;
+    const int g256 = cdiv(n, 256);
+    const int sms = c->sms;
     TravArgs ta{};
     ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta;
-    ta.selfnode = c->selfnode; ta.body = c->body; ta.vel = c->vel;
+    ta.body = c->body; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     ta.npeer = 0;
+    ta.xrec = c->dd_xrec; ta.localLo = 0u; ta.localHi = 0xFFFFFFFFu; ta.chunk_cost = nullptr;
+    if (k.dd) {
+        ta.localLo = 4u * k.blockBase;
+        ta.localHi = 4u * (k.blockBase + (unsigned int)c->cap + 8u);
+        ta.chunk_cost = c->dd_chunk_cost;
+    }
     if (sharded_begin && p2p_ready(c)) {
         // this step's generation of every rank's receive buffer, at this rank's slice
         c->xchg_parity ^= 1;
@@ -633,7 +685,7 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
         ta.npeer = c->shard_n;
     }
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
-    const unsigned int own = (nblocks + (unsigned int)c->shard_n - 1u - (unsigned int)c->shard_rank) / (unsigned int)c->shard_n;
+    const unsigned int own = (nblocks + (unsigned int)k.shard_n - 1u - (unsigned int)k.shard_rank) / (unsigned int)k.shard_n;
     ta.n_chunks_local = own * (LPE_SHARD_BLOCK / 32u);
     ta.selfslot = c->selfslot; ta.recnode = c->recnode; ta.chunk_list = nullptr;
     const int maxGridCtas = sms * 8;
@@ -664,22 +716,45 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
             if (stats) k_traverse<1, true><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
             else k_traverse<1, false><<<grid, TRAV_THREADS, 0, st>>>(k, ta);
             if (k.do_drift && c->shard_n == 1) {   // STRICT: the drift is its own pass (see k_drift)
-                k_drift<<<g256, 256, 0, st>>>(n, k.dtD, c->body, c->vel);
+                k_drift<<<g256, 256, 0, st>>>(n, k.dtD, c->body, c->vel, k.dd ? c->scal : nullptr);
                 ++travLaunches;
             }
         }
     }
+    c->launches += (uint64_t)travLaunches;
+    return 0;
+}
+
+int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
+    if (c->dd) return fail(c, "context is in domain-decomposed mode: use lpe_bh_dd_step / lpe_bh_dd_phase");
+    StepConst k;
+    if (make_const(c, p, k)) return 1;
+    const int n = (int)c->n;
+    if (n == 0) return 0;
+    if (c->shard_n > 1 && ensure_xchg(c)) return 1;
+    cudaStream_t st = c->stream;
+    const bool timing = c->instr & 1;
+    if (timing) cudaEventRecord(c->ev[0], st);
+    if (step_prologue(c, n)) return 1;
+    k_keygen<<<cdiv(n, 256), 256, 0, st>>>(k, c->body, c->keys[0], c->vals[0], c->scal);
+    c->launches += 1;
+    if (timing) cudaEventRecord(c->ev[1], st);
+    if (step_sort(c, k, n)) return 1;
+    if (timing) cudaEventRecord(c->ev[2], st);
+    if (step_build(c, k, n)) return 1;
+    if (timing) cudaEventRecord(c->ev[3], st);
+    if (c->pend_vel) {   // host path: velocities were uploaded behind the build; the kick is their first reader
+        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
+        k_pack2<<<cdiv(n, 256), 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel, c->orig_valid ? c->orig : nullptr);
+        c->pend_vel = false;
+    }
+    if (step_traverse(c, k, p, n, sharded_begin)) return 1;
     if (timing) cudaEventRecord(c->ev[4], st);
     CU_TRY(c, cudaGetLastError());
-    // keygen, 3 per sort pass, gather, 2 scans of 3, terminals, witness, level_scan, topology,
-    // one per level above Ltop, agg_top, traverse (+ overflow pass)
-    c->launches += 1 + 2 + (uint64_t)passes + 1 + 1 + 1 + 1 + 2 + (uint64_t)levelLaunches + 1 + (uint64_t)travLaunches;
     c->last_c = k;
     c->have_step = true;
     c->last.depth = k.D;
-    c->last.sort_passes = passes;
     c->last.hilbert = k.hilbert;
-    (void)sharded_begin;
     return 0;
 }
 
@@ -722,6 +797,8 @@ int lpe_bh_create(int device, lpe_bh_ctx** out) {
     }
     *c->fault_host = 0;
     c->stream = c->own_stream;
+    cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+    if (c->sms <= 0) c->sms = 148;
     *out = c;
     return 0;
 }
@@ -730,6 +807,8 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     if (!c) return;
     DevGuard _dg(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    dd_release(c);
+    for (auto& ev : c->dd_ev) if (ev) cudaEventDestroy(ev);
     if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     close_peers(c);
@@ -857,6 +936,7 @@ int lpe_bh_synchronize(lpe_bh_ctx* c) {
     if (fetch_fault(c)) return 1;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     CU_TRY(c, cudaGetLastError());
+    if (c->dd && dd_check_fault(c)) return 1;
     return check_fault(c);
 }
 
@@ -1214,3 +1294,5 @@ int lpe_bh_get_device_view(lpe_bh_ctx* c, lpe_bh_device_view* o) {
 }
 
 }  // extern "C"
+
+#include "lpe_bh_dd.inl"

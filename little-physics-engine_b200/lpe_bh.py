@@ -74,6 +74,25 @@ class DeviceView(C.Structure):
     ]
 
 
+class DDStats(C.Structure):
+    """lpe_bh_dd_stats"""
+    _fields_ = [
+        ("capacity", C.c_uint64), ("n_live", C.c_uint64), ("n_in_tree", C.c_uint64), ("n_terminals", C.c_uint64),
+        ("n_cells", C.c_uint64), ("n_roots", C.c_uint64), ("exported_blocks", C.c_uint64 * 8),
+        ("interactions", C.c_uint64), ("work_cost", C.c_uint64), ("overflow_chunks", C.c_uint64),
+        ("import_blocks", C.c_uint32), ("fault", C.c_uint32), ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("depth", C.c_int32), ("pad_", C.c_int32),
+        ("ms_keygen", C.c_float), ("ms_wait_a", C.c_float), ("ms_sort", C.c_float), ("ms_build", C.c_float),
+        ("ms_export", C.c_float), ("ms_wait_b", C.c_float), ("ms_top", C.c_float), ("ms_traverse", C.c_float),
+        ("ms_total", C.c_float), ("pad2_", C.c_float),
+    ]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["exported_blocks"] = list(d["exported_blocks"])
+        return d
+
+
 def make_params(U, eps, theta=0.5, dt_kick=1.0 / 120, dt_drift=None, thr=0.0, quirk=True, precision=PREC_FAST,
                 do_drift=True, max_depth=0, G=G_REAL, key_order=KEYS_AUTO):
     p = Params()
@@ -124,6 +143,12 @@ def load_library():
     lib.lpe_bh_free_pinned.argtypes = [C.c_void_p]
     lib.lpe_bh_shard_chunk.restype = C.c_uint64
     lib.lpe_bh_shard_chunk.argtypes = [C.c_uint64, C.c_int]
+    lib.lpe_bh_dd_window.restype = C.c_void_p
+    lib.lpe_bh_dd_window.argtypes = [C.c_void_p]
+    lib.lpe_bh_cell_key.restype = C.c_uint64
+    lib.lpe_bh_cell_key.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int]
+    lib.lpe_bh_key_cell.restype = None
+    lib.lpe_bh_key_cell.argtypes = [C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -155,6 +180,17 @@ def shard_owner(pos, nranks):
     r, s = C.c_int(0), C.c_uint64(0)
     load_library().lpe_bh_shard_owner(C.c_uint64(pos), C.c_int(nranks), C.byref(r), C.byref(s))
     return r.value, s.value
+
+
+def cell_key(ix, iy, level, hilbert=True):
+    """Sort key of cell (ix, iy) of a quadtree level (host helper, no GPU)."""
+    return int(load_library().lpe_bh_cell_key(ix, iy, level, 1 if hilbert else 0))
+
+
+def key_cell(key, level, hilbert=True):
+    x, y = C.c_uint32(0), C.c_uint32(0)
+    load_library().lpe_bh_key_cell(C.c_uint64(key), level, 1 if hilbert else 0, C.byref(x), C.byref(y))
+    return x.value, y.value
 
 
 class BarnesHut:
@@ -255,6 +291,10 @@ class BarnesHut:
     def synchronize(self):
         self._chk(self.lib.lpe_bh_synchronize(self.h), "synchronize")
 
+    def synchronize_quiet(self):
+        if self.h:
+            self.lib.lpe_bh_synchronize(self.h)
+
     def download(self):
         out = [np.empty(self.n, np.float64) for _ in range(4)]
         self._chk(self.lib.lpe_bh_download(self.h, *[_dp(a) for a in out]), "download")
@@ -336,3 +376,135 @@ class BarnesHut:
         v = DeviceView()
         self._chk(self.lib.lpe_bh_get_device_view(self.h, C.byref(v)), "get_device_view")
         return v
+
+    # ---- multi-GPU, domain-decomposed (include/lpe_bh.h) ----
+    def dd_init(self, rank, nranks, capacity, import_blocks=0):
+        self._chk(self.lib.lpe_bh_dd_init(self.h, C.c_int(rank), C.c_int(nranks), C.c_uint64(capacity),
+                                          C.c_uint32(import_blocks)), "dd_init")
+        self._rank, self._nranks, self._capacity = rank, nranks, max(int(capacity), 1024)
+
+    def dd_window(self):
+        return self.lib.lpe_bh_dd_window(self.h)
+
+    def dd_set_peer(self, rank, window, peer_device=-1):
+        self._chk(self.lib.lpe_bh_dd_set_peer(self.h, C.c_int(rank), C.c_void_p(window), C.c_int(peer_device)), "dd_set_peer")
+
+    def dd_export(self):
+        buf = C.create_string_buffer(64)
+        self._chk(self.lib.lpe_bh_dd_export(self.h, buf), "dd_export")
+        return buf.raw
+
+    def dd_import(self, rank, handle):
+        self._chk(self.lib.lpe_bh_dd_import(self.h, C.c_int(rank), C.c_char_p(handle)), "dd_import")
+
+    def dd_ready(self):
+        return bool(self.lib.lpe_bh_dd_ready(self.h))
+
+    def dd_upload(self, params, x, y, vx, vy, m, rank=None, comp=None):
+        """Every rank is given the whole input and keeps the bodies of its own key range."""
+        x, y, vx, vy, m = map(_f64, (x, y, vx, vy, m))
+        rank = None if rank is None else np.ascontiguousarray(rank, dtype=np.uint32)
+        comp = None if comp is None else np.ascontiguousarray(comp, dtype=np.uint8)
+        self.n = len(x)
+        self._chk(self.lib.lpe_bh_dd_upload(self.h, C.byref(params), C.c_uint64(self.n), _dp(x), _dp(y), _dp(vx), _dp(vy),
+                                            _dp(m), _dp(rank), _dp(comp)), "dd_upload")
+
+    def dd_phase(self, params, phase):
+        self._chk(self.lib.lpe_bh_dd_phase(self.h, C.byref(params), C.c_int(phase)), "dd_phase")
+
+    def dd_step(self, params, nsteps=1):
+        self._chk(self.lib.lpe_bh_dd_step(self.h, C.byref(params), C.c_int(nsteps)), "dd_step")
+
+    def dd_download(self, counts=False):
+        cap = self._capacity
+        idx = np.empty(cap, np.uint32)
+        out = [np.empty(cap, np.float64) for _ in range(4)]
+        acc = np.empty(cap, np.uint32) if counts else None
+        n = C.c_uint64(0)
+        self._chk(self.lib.lpe_bh_dd_download(self.h, C.byref(n), _dp(idx), *[_dp(a) for a in out], _dp(acc)), "dd_download")
+        k = n.value
+        d = dict(index=idx[:k], x=out[0][:k], y=out[1][:k], vx=out[2][:k], vy=out[3][:k])
+        if counts:
+            d["accepted"] = acc[:k]
+        return d
+
+    def dd_stats(self):
+        s = DDStats()
+        self._chk(self.lib.lpe_bh_dd_get_stats(self.h, C.byref(s)), "dd_get_stats")
+        return s.as_dict()
+
+    def dd_get_splitters(self):
+        a = (C.c_uint64 * (self._nranks + 1))()
+        self._chk(self.lib.lpe_bh_dd_get_splitters(self.h, a), "dd_get_splitters")
+        return [int(v) for v in a]
+
+    def dd_set_splitters(self, split30):
+        a = (C.c_uint64 * (self._nranks + 1))(*[int(v) for v in split30])
+        self._chk(self.lib.lpe_bh_dd_set_splitters(self.h, a), "dd_set_splitters")
+
+
+class DDGroup:
+    """All ranks of a domain-decomposed run driven by ONE host thread (SURVEY.md 8(b) "Threading").
+
+    devices = one CUDA device index per rank. Distinct devices: every rank's phases are queued on its own GPU and the
+    in-stream flag barriers make the GPUs wait for each other (peer access between the devices). The same device for
+    every rank (tests on a one-GPU box): the phases are run rank after rank with a host synchronisation in between,
+    since kernels of one GPU must not wait for each other.
+    """
+
+    def __init__(self, devices, capacity, import_blocks=0):
+        self.devices = list(devices)
+        self.R = len(self.devices)
+        self.lockstep = len(set(self.devices)) == self.R
+        if not self.lockstep and len(set(self.devices)) != 1:
+            raise ValueError("either one device per rank or the same device for all ranks")
+        self.ranks = [BarnesHut(d) for d in self.devices]
+        for r, c in enumerate(self.ranks):
+            c.dd_init(r, self.R, capacity, import_blocks)
+        wins = [c.dd_window() for c in self.ranks]
+        for c in self.ranks:
+            for r, w in enumerate(wins):
+                c.dd_set_peer(r, w, self.devices[r] if self.lockstep else -1)
+        self.n = 0
+
+    def close(self):
+        for c in self.ranks:
+            c.synchronize_quiet()
+        for c in self.ranks:
+            c.close()
+
+    def upload(self, params, x, y, vx, vy, m, rank=None, comp=None):
+        self.n = len(x)
+        for c in self.ranks:
+            c.dd_upload(params, x, y, vx, vy, m, rank=rank, comp=comp)
+
+    def step(self, params, nsteps=1):
+        for _ in range(nsteps):
+            if self.lockstep:
+                for c in self.ranks:
+                    c.dd_step(params, 1)
+            else:
+                for ph in range(3):
+                    for c in self.ranks:
+                        c.dd_phase(params, ph)
+                    for c in self.ranks:
+                        c.synchronize()
+
+    def download(self, counts=False):
+        """State of all ranks assembled in creation order."""
+        out = {k: np.full(self.n, np.nan) for k in ("x", "y", "vx", "vy")}
+        if counts:
+            out["accepted"] = np.zeros(self.n, np.uint32)
+        seen = np.zeros(self.n, np.int32)
+        for c in self.ranks:
+            d = c.dd_download(counts=counts)
+            i = d["index"]
+            seen[i] += 1
+            for k in out:
+                out[k][i] = d[k]
+        if not np.all(seen == 1):
+            raise RuntimeError(f"domain decomposition lost or duplicated bodies: {np.count_nonzero(seen != 1)} of {self.n}")
+        return out
+
+    def stats(self):
+        return [c.dd_stats() for c in self.ranks]
