@@ -1,23 +1,31 @@
 #!/usr/bin/env python
 """bench.py — Barnes-Hut body-steps/s (theta = 0.5) on B200, the metric of BASELINE.json.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c4]
-    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU, NCCL)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload c1|c2|c3|c4|c5] [--precision fast|strict] [--mgpu dd|replicated]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (one rank per GPU)
 
-A "step" is one full pass of the hot path over all bodies: space-filling-curve keys, radix sort, quadtree build + aggregation,
-theta traversal, kick and drift. One JSON line is printed by rank 0.
+A "step" is one full pass of the hot path over all bodies: space-filling-curve keys, radix sort, quadtree build +
+aggregation, theta traversal, kick and drift. One JSON line is printed by rank 0.
+
+Workload: C3 (16 M-body Plummer sphere) at EVERY N, so that the driver's 1 -> 8 GPU series is one problem (strong
+scaling). At N = 1 the line also carries a "c2" object: the 1 M-body disk (BASELINE config 2) measured the same way.
 
   value      whole-job body-steps/s with the bodies resident in HBM (device-timed, CUDA events on the launching
              stream, max over ranks); L2 is flushed between timed steps.
-  e2e        the same metric through the call the ECS drop-in makes (lpe_bh_update_host semantics): pinned host
-             buffers -> upload -> step -> download, every step, copies inside the timed region.
-  roofline   the dominant kernel (k_traverse): FP32-pipe bound, algorithmic flops = 20 per
-             accepted interaction, against the FP32 FMA peak measured on this GPU by lpe_bh_fma_peak.
+  e2e        the same metric through the call the ECS drop-in makes (lpe_bh_update_host): pinned host buffers ->
+             upload -> step -> download, every step, copies inside the timed region (N = 1).
+  roofline   the dominant kernel (k_traverse2): FP32-pipe bound, algorithmic flops = 20 per accepted
+             interaction, against the FP32 FMA peak measured on this GPU by lpe_bh_fma_peak.
   roofline_hbm  the HBM-bound phases (keygen + sort + build) against MEASURED_PEAKS.json's copy bandwidth.
   cpu_baseline  the reference's own barnes_hut.cpp + movement.cpp (oracle/_ref, compiled unmodified) on the host.
+  parity_check  N > 1: one extra counted step of the decomposed run against the unsharded step on rank 0's GPU.
 
---impl reference times that CPU code (all it can use: it is single-threaded) on bounded samples.
-The oracle is only ever the baseline / checker here; the measured product path is the CUDA library.
+N > 1 (--mgpu dd, default): domain decomposition — every rank owns a key range, sorts and builds only its bodies,
+exchanges the top of the tree and the locally essential cells through NVLink peer memory (include/lpe_bh.h,
+lpe_bh_dd_*); --mgpu replicated keeps round 1's replicated-tree variant for comparison.
+--impl reference times the reference's CPU code (single-threaded) on bounded samples; that process
+never loads the CUDA library.
 """
 import argparse
 import json
@@ -37,16 +45,34 @@ EPS = U / 2 ** 14
 THETA = 0.5
 DT = 1.0 / 120.0
 WORKLOADS = {
+    # C1: the reference's own Keplerian-disk scenario configuration (keplerian_disk.cpp:16-29) at 10 k bodies
+    "c1": dict(kind="keplerian", n=10_000, seed=5, U=6e9, eps=2e7, thr=1e3, dt_drift=6.756e-3,
+               name="C1: 10k-body Keplerian disk (reference scenario config: U=6e9, eps=2e7, threshold 1e3), theta=0.5"),
     "c2": dict(kind="disk", n=1_000_000, seed=42, name="C2: 1M-body uniform disk, theta=0.5, U=2^20, eps=U/2^14"),
     "c3": dict(kind="plummer", n=16_000_000, seed=43, name="C3: 16M-body Plummer sphere, theta=0.5, U=2^20, eps=U/2^14"),
     "c4": dict(kind="two_galaxies", n=4_000_000, seed=44, name="C4: 4M-body two-galaxy collision, theta=0.5, U=2^20, eps=U/2^14"),
+    "c5": dict(kind="disk", n=1_000_000, seed=42, name="C5: theta sweep 0.3-1.0 on the 1M-body disk + direct O(N^2) at 256k bodies"),
 }
 FLOPS_PER_INTERACTION = 20.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_traverse2 launch, from the committed ncu --set full capture
-# (profiles/r01_ncu_traverse2_c2_final.txt: 146.32 MB read + 32.57 MB written); the kernel is not DRAM-bound, the
-# figure only shows that nothing is re-read (the records alone are 52 MB, the bodies 64 MB).
-NCU_TRAFFIC_BYTES = {"c2": 178.9e6}
-HBM_BYTES_PER_BODY = 340.0     # keygen + sort + gather + node arrays, 64-bit keys
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_traverse2 launch, from the committed ncu --set full captures
+NCU_TRAFFIC = {"c2": (178.9e6, "profiles/r01_ncu_traverse2_c2_final.txt (ncu --set full, one launch)")}
+# SURVEY.md §8(d) algorithmic bytes of the HBM phases: state 40 B read + 32 B written, key + index 12 B, 24 B per sort
+# pass, sorted gather 24 B, node arrays 85 B  ->  193 + 24 * passes (4 passes for the 33-bit keys of depth 16)
+def hbm_bytes_per_body(passes):
+    return 193.0 + 24.0 * passes
+
+
+def wl_params(wl):
+    return dict(U=wl.get("U", U), eps=wl.get("eps", EPS), thr=wl.get("thr", 0.0), dt_kick=DT, dt_drift=wl.get("dt_drift", DT))
+
+
+def config_for(wl, world, precision, mgpu):
+    """Identical in both arms (the driver compares the two config objects)."""
+    p = wl_params(wl)
+    return {"workload": wl["name"], "bodies": wl["n"], "theta": THETA, "softening": p["eps"], "universe": p["U"],
+            "quirk_mode": "reference", "precision": precision, "n_gpus": world,
+            "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events",
+            "parallelism": "single GPU" if world == 1 else f"{world} GPUs, {mgpu}"}
 
 
 def measured_peaks():
@@ -107,84 +133,73 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
-def reference_arm(args, wl, rank, world):
-    """The reference's own CPU implementation on this box's host cores. Bounded sample per step: the full tree is
-    built over all N bodies (every body is a source) and the force loop runs over every `stride`-th body — done by
-    giving only those bodies a Velocity component, so it is still the unmodified reference code path
-    (barnes_hut.cpp:89 iterates view<Position,Velocity,Mass>). A step's time is scaled to all N targets:
-    t_step = t_build + (t_sample - t_build) * stride, with t_build from a build-only call."""
-    if rank != 0:
-        return
+def reference_sample(wl, steps, warmup):
+    """The reference's own CPU implementation on this box's host cores, on a bounded sample of the workload.
+
+    Sample: every `sub`-th body of the workload (all of it up to 2 M bodies; about 1 M bodies of C3 / C4, where one CPU
+    step of the whole thing would take minutes and a 5 GB node pool); per step the full tree is built over those
+    bodies and the force loop runs over every `stride`-th of them — done by giving only those a Velocity component, so
+    it is still the unmodified code path (barnes_hut.cpp:89 iterates view<Position,Velocity,Mass>).
+    Reported separately: what was MEASURED (seconds per sample step) and what is derived from it (a full step's time
+    = build + force time scaled to all targets; the reference gets slower per body as N grows, so running it on a
+    subsample flatters the reference, not us)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
-    import lpe_bh
+    import workloads
+    p = wl_params(wl)
     n_full = wl["n"]
-    x, y, vx, vy, m = lpe_bh.workload(wl["kind"], n_full, wl["seed"], U)
-    # Workloads above 2 M bodies (C3: 16 M would be minutes and 5 GB of node pool per CPU step): the reference runs on
-    # every k-th body of the same workload (about 1 M bodies); its per-body throughput on that sample is reported
-    # (the reference gets slower per body as N grows, so this flatters the reference, not us).
+    x, y, vx, vy, m = workloads.workload(wl["kind"], n_full, wl["seed"], p["U"])
     sub = max(1, n_full // 1_000_000) if n_full > 2_000_000 else 1
     if sub > 1:
         x, y, vx, vy, m = (np.ascontiguousarray(a[::sub]) for a in (x, y, vx, vy, m))
     n = len(x)
-    p = O.make_params(U, EPS, theta=THETA, dt_kick=DT, dt_drift=DT)
+    po = O.make_params(p["U"], p["eps"], theta=THETA, thr=p["thr"], dt_kick=p["dt_kick"], dt_drift=p["dt_drift"])
     stride = max(1, n // 50_000)          # ~50k targets per sample: ~1-2 s of force work per step
     comp = np.full(n, O.HAS_MASS, np.uint8)
     comp[::stride] |= O.HAS_VELOCITY
     ntargets = int(np.count_nonzero(comp & O.HAS_VELOCITY))
     if O.RefLib.available():
         lib, kind = O.RefLib(), "reference"
-        run = lambda: lib.run(p, x, y, vx, vy, m, comp=comp, nsteps=1, pool_nodes=4 * n + 4096)["stats"]["total_seconds"]
-        build = lambda: lib.tree(p, x, y, m, pool_nodes=4 * n + 4096)[1]["build_seconds"]
+        run = lambda: lib.run(po, x, y, vx, vy, m, comp=comp, nsteps=1, pool_nodes=4 * n + 4096)["stats"]["total_seconds"]
+        build = lambda: lib.tree(po, x, y, m, pool_nodes=4 * n + 4096)[1]["build_seconds"]
     else:
         lib, kind = O.PortLib(), "port"
-        run = lambda: lib.run(p, x, y, vx, vy, m, comp=comp, nsteps=1, threads=1)["stats"]["total_seconds"]
-        build = lambda: lib.tree(p, x, y, m)[1]["build_seconds"]
+        run = lambda: lib.run(po, x, y, vx, vy, m, comp=comp, nsteps=1, threads=1)["stats"]["total_seconds"]
+        build = lambda: lib.tree(po, x, y, m)[1]["build_seconds"]
     t_build = build()
-    times = []
-    for s in range(args.warmup + args.steps):
+    measured, full = [], []
+    for s in range(warmup + steps):
         t = run()
-        if s >= args.warmup:
-            times.append(t_build + max(t - t_build, 0.0) * (n / ntargets))
-    ms = 1e3 * float(np.mean(times))
-    value = n / (ms * 1e-3)
-    ms = ms * (n_full / n)                # time of one step of the full workload at the measured per-body rate
-    sample = (f"per step: full tree build over all {n} bodies + force loop over every {stride}th body "
-              f"({ntargets} targets), scaled to {n} targets; {lib.describe()}")
-    if sub > 1:
-        sample = (f"every {sub}th body of the {n_full}-body workload ({n} bodies); " + sample +
-                  f"; ms_per_step = {n_full} bodies at the measured per-body rate")
+        if s >= warmup:
+            measured.append(t)
+            full.append(t_build + max(t - t_build, 0.0) * (n / ntargets))
+    t_meas, t_full = float(np.mean(measured)), float(np.mean(full))
+    value = n / t_full
+    return {
+        "value": value, "unit": "body-steps/s", "cores": 1, "kind": kind, "host_cores_available": os.cpu_count(),
+        "measured_seconds_per_sample_step": t_meas, "build_seconds": t_build, "sample_bodies": n, "sample_targets": ntargets,
+        "extrapolation": f"full step of the {n}-body sample = build + (sample step - build) x {n / ntargets:.1f} "
+                         f"= {t_full:.3f} s; value = {n} bodies / that",
+        "sample": (f"every {sub}th body of the workload ({n} bodies): per step a full tree build over them + the force "
+                   f"loop over every {stride}th ({ntargets} targets); {lib.describe()}"),
+    }, t_meas
+
+
+def reference_arm(args, wl, rank, world):
+    if rank != 0:
+        return
+    base, t_meas = reference_sample(wl, args.steps, args.warmup)
     line = {
-        "impl": "reference", "metric": "barnes_hut_body_steps_per_sec", "value": value, "unit": "body-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "bodies": n_full, "theta": THETA},
-        "cpu_baseline": {"value": value, "unit": "body-steps/s", "cores": 1, "kind": kind, "sample": sample,
-                         "host_cores_available": os.cpu_count()},
-        "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": "barnes_hut_body_steps_per_sec", "value": base["value"], "unit": "body-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_meas,       # MEASURED: one bounded sample step (see cpu_baseline.extrapolation for `value`)
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_for(wl, max(args.gpus, 1), args.precision, args.mgpu),
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def cpu_baseline_n1(wl):
-    """Rank 0, N=1 only: ONE full, unsampled step of the reference on the same bodies (about 20 s for C2)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_py as O
-    import lpe_bh
-    n = min(wl["n"], 1_000_000)            # C3/C4: the first 1M bodies of the same distribution (bounded sample)
-    x, y, vx, vy, m = lpe_bh.workload(wl["kind"], wl["n"], wl["seed"], U)
-    x, y, vx, vy, m = (a[:n] for a in (x, y, vx, vy, m))
-    p = O.make_params(U, EPS, theta=THETA, dt_kick=DT, dt_drift=DT)
-    if O.RefLib.available():
-        lib, kind = O.RefLib(), "reference"
-        t = lib.run(p, x, y, vx, vy, m, nsteps=1, pool_nodes=4 * n + 4096)["stats"]["total_seconds"]
-    else:
-        lib, kind = O.PortLib(), "port"
-        t = lib.run(p, x, y, vx, vy, m, nsteps=1, threads=1)["stats"]["total_seconds"]
-    return {"value": n / t, "unit": "body-steps/s", "cores": 1, "kind": kind, "seconds_per_step": t,
-            "sample": f"one full step (tree build + all {n} targets + movement) of {n} bodies of the workload; "
-                      f"{lib.describe()}; host has {os.cpu_count()} cores, the reference can use 1"}
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
@@ -199,7 +214,134 @@ def log(rank, msg):
     print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
 
 
-def our_arm(args, wl, rank, world, local_rank):
+def make_gpu_params(lpe_bh, wl, precision="fast", theta=THETA, quirk=True):
+    p = wl_params(wl)
+    return lpe_bh.make_params(p["U"], p["eps"], theta=theta, thr=p["thr"], dt_kick=p["dt_kick"], dt_drift=p["dt_drift"],
+                              quirk=quirk, precision=lpe_bh.PREC_STRICT if precision == "strict" else lpe_bh.PREC_FAST)
+
+
+def measure_single(torch, lpe_bh, bh, stream, wl, bodies, params, steps, warmup, flush, precision):
+    """Device-resident single-GPU steps: per-step CUDA events, L2 flushed in between. Returns a dict of measurements."""
+    x, y, vx, vy, m = bodies
+    n = len(x)
+    bh.set_instrumentation(counts=True)
+    bh.upload(x, y, vx, vy, m)
+    bh.step(params, 1)
+    st = bh.stats()
+    interactions, passes = st["interactions"], st["sort_passes"]
+    bh.set_instrumentation(timing=True)
+    bh.upload(x, y, vx, vy, m)
+    for _ in range(warmup):
+        bh.step(params, 1)
+    torch.cuda.synchronize()
+    launches0 = bh.launch_count()
+    step_ms, phases = [], []
+    for _ in range(steps):
+        flush.zero_()                       # evict L2 between timed steps (not timed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        bh.step(params, 1)
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        s = bh.stats()
+        phases.append((s["ms_keygen"], s["ms_sort"], s["ms_build"], s["ms_traverse"]))
+    launches = bh.launch_count() - launches0
+    ph = np.mean(np.array(phases), axis=0)
+    ms = float(np.mean(step_ms))
+    return dict(n=n, ms_per_step=ms, value=n / (ms * 1e-3), interactions=interactions, passes=passes,
+                phases={"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": float(ph[3])},
+                launches=int(launches), kernel="k_traverse2 (two-phase traversal)" if precision == "fast" else "k_traverse<STRICT> (depth-first, fp64)")
+
+
+def measure_e2e(torch, bh, bodies, params, steps):
+    """Through host buffers, as Systems::BarnesHutSystem::update pays it: lpe_bh_update_host on pinned SoA arrays."""
+    x, y, vx, vy, m = bodies
+    n = len(x)
+    hx, hy, hvx, hvy, hm = (torch.from_numpy(a.copy()).pin_memory() for a in (x, y, vx, vy, m))
+    ptrs = [t.data_ptr() for t in (hx, hy, hvx, hvy, hm)]
+    e2e_steps = max(3, min(steps, 20))
+    bh.set_instrumentation()              # no phase events in the host-clocked loop
+    for it in range(2 + e2e_steps):
+        if it == 2:
+            torch.cuda.synchronize()
+            te0 = time.perf_counter()
+        bh.update_host_ptrs(params, n, *ptrs)   # synchronises; the result lands in the pinned host arrays
+    e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
+    return {"value": n / (e2e_ms * 1e-3), "unit": "body-steps/s", "ms_per_step": e2e_ms,
+            "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 32 * n,
+            "path": "pinned host SoA -> lpe_bh_update_host (uploads on a copy stream behind the step, kick + drift, "
+                    "x/y/vx/vy downloaded; host wall clock incl. sync)"}
+
+
+def rooflines(meas, fma_peak, peaks, peak_kind, workload_key, world=1):
+    n, trav_ms = meas["n"], meas["phases"]["traverse"]
+    flops = FLOPS_PER_INTERACTION * meas["interactions"] / max(world, 1)
+    achieved = flops / (trav_ms * 1e-3) / 1e12
+    bpb = hbm_bytes_per_body(meas["passes"])
+    hbm_ms = meas["phases"]["keygen"] + meas["phases"]["sort"] + meas["phases"]["build"]
+    hbm_ach = bpb * n / max(world, 1) / (hbm_ms * 1e-3) / 1e9
+    traffic, tsrc = NCU_TRAFFIC.get(workload_key, (None, None))
+    t_roof = 1e3 * (bpb * n / max(world, 1) / (peaks["hbm_gbs"] * 1e9) + (flops / (fma_peak * 1e12) if fma_peak else 0.0))
+    return {
+        "roofline": {"bound": "fp32_fma", "kernel": meas["kernel"], "achieved": achieved, "peak": fma_peak,
+                     "unit": "TFLOP/s", "frac": achieved / fma_peak if fma_peak else None, "traffic": traffic,
+                     "traffic_source": tsrc,
+                     "peak_source": "lpe_bh_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                     "algorithmic": f"{FLOPS_PER_INTERACTION:.0f} flop x {meas['interactions']} accepted interactions / step"
+                                    + (f" / {world} ranks" if world > 1 else "")},
+        "roofline_hbm": {"bound": "hbm", "kernels": "k_keygen + k_sort_* + build kernels", "achieved": hbm_ach,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                         "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                         "algorithmic": f"{bpb:.0f} B/body ({meas['passes']} sort passes) x {n} bodies"
+                                        + (f" / {world} ranks" if world > 1 else "")},
+        # SURVEY.md 8(d): T_roof = N*B_alg/BW_HBM + N*F_alg/P_FP32 (phases are sequential), against the measured step
+        "roofline_step": {"t_roof_ms": t_roof, "t_measured_ms": meas["ms_per_step"], "frac": t_roof / meas["ms_per_step"]},
+    }
+
+
+def cpu_baseline_n1(wl):
+    base, _ = reference_sample(wl, 1, 0)
+    return base
+
+
+def c5_lines(torch, lpe_bh, bh, stream, wl, bodies, flush):
+    """theta sweep on the 1 M-body disk and the direct O(N^2) sum on its first 262 144 bodies."""
+    x, y, vx, vy, m = bodies
+    n = len(x)
+    sweep = []
+    for theta in (0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0):
+        p = make_gpu_params(lpe_bh, wl, theta=theta)
+        r = measure_single(torch, lpe_bh, bh, stream, wl, bodies, p, 5, 3, flush, "fast")
+        sweep.append({"theta": theta, "ms_per_step": r["ms_per_step"], "value": r["value"],
+                      "interactions_per_body": r["interactions"] / n, "traverse_ms": r["phases"]["traverse"]})
+    nd = 262_144
+    sub = tuple(a[:nd] for a in bodies)
+    pq = make_gpu_params(lpe_bh, wl, quirk=False)
+    bh.set_instrumentation()
+    bh.upload(*sub)
+    bh.direct_accel(pq, 0, 1024)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    ax, ay = bh.direct_accel(pq, 0, nd)
+    direct_s = time.perf_counter() - t0
+    # Barnes-Hut on the same bodies, textbook tree (no first-occupant double count), against the direct sum
+    one = lpe_bh.make_params(U, EPS, theta=THETA, dt_kick=1.0, dt_drift=1.0, quirk=False, do_drift=False)
+    bh.upload(sub[0], sub[1], np.zeros(nd), np.zeros(nd), sub[4])
+    bh.step(one, 1)
+    got = bh.download()
+    G = 6.674e-11
+    mag = np.hypot(ax, ay)
+    err = np.hypot(got["vx"] - ax, got["vy"] - ay) / np.maximum(mag, 1e-3 * np.median(mag))
+    return {"theta_sweep": sweep,
+            "direct": {"bodies": nd, "seconds": direct_s, "pair_interactions_per_s": nd * (nd - 1) / direct_s,
+                       "value": nd / direct_s, "note": "fp64 direct sum (lpe_bh_direct_accel), host wall clock incl. download",
+                       "bh_textbook_vs_direct_median_rel_err": float(np.median(err)),
+                       "bh_textbook_vs_direct_p99_rel_err": float(np.percentile(err, 99))}}
+
+
+def our_arm(args, wl, key, rank, world, local_rank):
     import torch
     import lpe_bh
     log(rank, f"start world={world} local_rank={local_rank} workload={wl['name']}")
@@ -215,9 +357,10 @@ def our_arm(args, wl, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n = wl["n"]
-    x, y, vx, vy, m = lpe_bh.workload(wl["kind"], n, wl["seed"], U)
+    wp = wl_params(wl)
+    bodies = lpe_bh.workload(wl["kind"], n, wl["seed"], wp["U"])
     log(rank, "workload generated")
-    params = lpe_bh.make_params(U, EPS, theta=THETA, dt_kick=DT, dt_drift=DT)
+    params = make_gpu_params(lpe_bh, wl, args.precision)
     bh = lpe_bh.BarnesHut(local_rank)
     # a real (non-default) stream shared by torch and the library, so torch.cuda.Event brackets the library's kernels
     stream = torch.cuda.Stream()
@@ -226,182 +369,55 @@ def our_arm(args, wl, rank, world, local_rank):
     bh.set_stream(stream.cuda_stream)
     peaks, peak_kind = measured_peaks()
     warmup = max(args.warmup, 3)
-
-    # one counting step on a scratch copy of the bodies: interactions per step for the flop roofline
-    bh.set_instrumentation(counts=True)
-    bh.upload(x, y, vx, vy, m)
-    bh.step(params, 1)
-    interactions = bh.stats()["interactions"]
-    fma_peak = bh.fma_peak_tflops()
-
-    send = recv = token = None
-    p2p = False
-    if world > 1:
-        bh.set_shard(rank, world)
-    bh.set_instrumentation(timing=True)
-    bh.upload(x, y, vx, vy, m)
-    if world > 1:
-        view = bh.device_view()
-        send = torch.as_tensor(CudaArray(view.xchg_send, 4 * view.xchg_chunk), device="cuda")
-        recv = torch.as_tensor(CudaArray(view.xchg_recv, 4 * view.xchg_chunk * world), device="cuda")
-        # Direct exchange: every rank opens every other rank's receive buffer (CUDA IPC over NVLink peer memory) and
-        # the traversal kernel stores its results there itself. All ranks must agree, else the NCCL allgather is used.
-        ok = 0
-        if not args.no_p2p and world <= 8:
-            mine = None
-            try:
-                mine = bh.xchg_export()
-            except Exception as e:
-                log(rank, f"direct exchange: export failed: {e}")
-            handles = [None] * world
-            dist.all_gather_object(handles, mine)          # every rank takes part, whatever happened above
-            if all(h is not None for h in handles):
-                try:
-                    for r, hnd in enumerate(handles):
-                        if r != rank:
-                            bh.xchg_import(r, hnd)
-                    ok = 1 if bh.xchg_p2p_ready() else 0
-                except Exception as e:   # IPC not permitted on this box: fall back to the collective
-                    log(rank, f"direct exchange unavailable: {e}")
-        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        p2p = bool(flag.item())
-        if not p2p:
-            bh.xchg_reset()      # some rank could not open every handle: every rank goes back to the allgather
-        token = torch.zeros(1, device="cuda", dtype=torch.int32)
-
-    xe = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # multi-GPU: allgather / scatter split
-
-    def one_step():
-        if world == 1:
-            bh.step(params, 1)
-        else:
-            bh.step_begin(params)
-            xe[0].record(stream)
-            if p2p:
-                dist.all_reduce(token)      # stream-ordered barrier: every rank's stores have landed
-            else:
-                dist.all_gather_into_tensor(recv, send)
-            xe[1].record(stream)
-            bh.step_finish()
-            xe[2].record(stream)
-
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    fma_peak = bh.fma_peak_tflops()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.wait_first()
     t_busy0 = time.time()
-    for _ in range(warmup):
-        one_step()
-    torch.cuda.synchronize()
-    log(rank, "warm-up done")
+    line = None
 
-    launches0 = bh.launch_count()
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall0 = time.time()
-    step_ms, phases = [], []
-    for _ in range(args.steps):
-        flush.zero_()                       # evict L2 between timed steps (not timed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        one_step()
-        e1.record(stream)
-        e1.synchronize()
-        step_ms.append(e0.elapsed_time(e1))
-        st = bh.stats()
-        phases.append((st["ms_keygen"], st["ms_sort"], st["ms_build"], st["ms_traverse"]) +
-                      ((xe[0].elapsed_time(xe[1]), xe[1].elapsed_time(xe[2])) if world > 1 else (0.0, 0.0)))
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    t_wall1 = time.time()
-    launches = bh.launch_count() - launches0
-    total_ms = float(np.sum(step_ms))
-    if dist:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = n / (ms_per_step * 1e-3)
-    ph = np.mean(np.array(phases), axis=0)
-    per_rank_traverse = None
-    if dist:   # load balance of the block-cyclic slices (C4 is the stress case): every rank's mean traversal time
-        mine = torch.tensor([float(ph[3])], device="cuda", dtype=torch.float64)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        per_rank_traverse = [float(t.item()) for t in allr]
-
-    # clocks / throttle reasons sampled by nvidia-smi every 20 ms from the first warm-up step to the end of the
-    # device-timed region (which alone is only tens of milliseconds long). The sampler stops before the end-to-end
-    # loop: that one is host wall clock over ~55 CUDA API calls per tick, and a driver query every 20 ms stalls them
-    # (2.0 -> 2.3 ms per tick at 1 M bodies).
-    clocks = sampler.stop(t_busy0, time.time()) if sampler else None
-    if clocks is not None:
-        clocks["window"] = "warm-up + device-timed region"
-
-    # ---- end to end through host buffers (what Systems::BarnesHutSystem::update pays), N=1 path of the C ABI ----
-    e2e = None
     if world == 1:
-        hx, hy, hvx, hvy, hm = (torch.from_numpy(a.copy()).pin_memory() for a in (x, y, vx, vy, m))
-        ptrs = [t.data_ptr() for t in (hx, hy, hvx, hvy, hm)]
-        e2e_steps = max(3, min(args.steps, 20))
-        bh.set_instrumentation()              # no phase events in the host-clocked loop
-        for it in range(2 + e2e_steps):
-            if it == 2:
-                torch.cuda.synchronize()
-                te0 = time.perf_counter()
-            bh.update_host_ptrs(params, n, *ptrs)   # synchronises; the result lands in the pinned host arrays
-        e2e_ms = (time.perf_counter() - te0) * 1e3 / e2e_steps
-        e2e = {"value": n / (e2e_ms * 1e-3), "unit": "body-steps/s", "ms_per_step": e2e_ms,
-               "h2d_bytes_per_step": 40 * n, "d2h_bytes_per_step": 32 * n,
-               "path": "pinned host SoA -> lpe_bh_update_host (uploads on a copy stream behind the step, kick + drift, "
-                       "x/y/vx/vy downloaded; host wall clock incl. sync)"}
-    else:
-        e2e = {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "path": "multi-GPU runs keep bodies resident; host round trip measured at N=1 only"}
-
-    log(rank, "timed region done")
-    if rank == 0:
-        trav_ms = float(ph[3])
-        flops = FLOPS_PER_INTERACTION * interactions / max(world, 1)    # this rank's share of the targets
-        achieved = flops / (trav_ms * 1e-3) / 1e12
-        hbm_ms = float(ph[0] + ph[1] + ph[2])
-        hbm_ach = HBM_BYTES_PER_BODY * n / (hbm_ms * 1e-3) / 1e9
+        meas = measure_single(torch, lpe_bh, bh, stream, wl, bodies, params, args.steps, warmup, flush, args.precision)
+        clocks = sampler.stop(t_busy0, time.time()) if sampler else None
+        if clocks is not None:
+            clocks["window"] = "warm-up + device-timed region"
+        e2e = measure_e2e(torch, bh, bodies, params, args.steps)
+        log(rank, "timed region done")
         line = {
-            "metric": "barnes_hut_body_steps_per_sec", "value": value, "unit": "body-steps/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64 state, f32 interaction math", "data": "synthetic",
-            "config": {"workload": wl["name"], "bodies": n, "theta": THETA, "softening": EPS, "universe": U,
-                       "quirk_mode": "reference", "precision": "fast",
-                       "l2": "256 MB buffer written between timed steps (L2 flush); per-step CUDA events",
-                       "parallelism": "single GPU" if world == 1 else
-                       f"{world} GPUs: replicated tree, block-cyclic key-slice traversal, " +
-                       ("(x,y,vx,vy) stored into every rank's receive buffer by the traversal kernel itself (NVLink peer "
-                        "memory, CUDA IPC) + one-element allreduce as barrier" if p2p else "NCCL allgather of (x,y,vx,vy)")},
-            "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": trav_ms,
-                          "allgather": float(ph[4]), "scatter": float(ph[5])},
-            "per_rank_traverse_ms": per_rank_traverse,
-            "interactions_per_body": interactions / n,
-            "roofline": {"bound": "fp32_fma", "kernel": "k_traverse2 (two-phase traversal)", "achieved": achieved,
-                         "peak": fma_peak, "unit": "TFLOP/s", "frac": achieved / fma_peak if fma_peak else None,
-                         "traffic": NCU_TRAFFIC_BYTES.get(args.workload or ("c2" if world == 1 else "c3")),
-                         "peak_source": "lpe_bh_fma_peak measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
-                         "algorithmic": f"{FLOPS_PER_INTERACTION:.0f} flop x {interactions} accepted interactions / launch"},
-            "roofline_hbm": {"bound": "hbm", "kernels": "k_keygen + k_sort_* + build kernels", "achieved": hbm_ach,
-                             "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                             "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                             "algorithmic": f"{HBM_BYTES_PER_BODY:.0f} B/body x {n} bodies"},
-            # T_roof = N*B_alg/BW_HBM + N*F_alg/P_FP32 (phases are sequential; the replicated build
-            # is counted once per rank, the traversal divides by the ranks), against the measured step
-            "roofline_step": (lambda t_roof: {"t_roof_ms": t_roof, "t_measured_ms": ms_per_step, "frac": t_roof / ms_per_step})(
-                1e3 * (HBM_BYTES_PER_BODY * n / (peaks["hbm_gbs"] * 1e9) +
-                       (flops / (fma_peak * 1e12) if fma_peak else 0.0))),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "metric": "barnes_hut_body_steps_per_sec", "value": meas["value"], "unit": "body-steps/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": meas["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64 state, f32 interaction math" if args.precision == "fast" else "f64", "data": "synthetic",
+            "config": config_for(wl, 1, args.precision, args.mgpu), "phases_ms": meas["phases"],
+            "interactions_per_body": meas["interactions"] / n,
+            **rooflines(meas, fma_peak, peaks, peak_kind, key),
+            "e2e": e2e, "gpu_launches": meas["launches"], "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if key == "c5":
+            line.update(c5_lines(torch, lpe_bh, bh, stream, wl, bodies, flush))
+        if args.workload is None and not args.bodies:
+            # the 1 M-body configuration of BASELINE.json in the same run
+            w2 = dict(WORKLOADS["c2"])
+            b2 = lpe_bh.workload(w2["kind"], w2["n"], w2["seed"], U)
+            p2 = make_gpu_params(lpe_bh, w2, args.precision)
+            m2 = measure_single(torch, lpe_bh, bh, stream, w2, b2, p2, args.steps, warmup, flush, args.precision)
+            c2 = {"config": config_for(w2, 1, args.precision, args.mgpu), "value": m2["value"], "unit": "body-steps/s",
+                  "ms_per_step": m2["ms_per_step"], "phases_ms": m2["phases"], "interactions_per_body": m2["interactions"] / w2["n"],
+                  **rooflines(m2, fma_peak, peaks, peak_kind, "c2"), "e2e": measure_e2e(torch, bh, b2, p2, args.steps),
+                  "gpu_launches": m2["launches"]}
+            if not args.no_cpu_baseline:
+                c2["cpu_baseline"] = cpu_baseline_n1(w2)
+            line["c2"] = c2
+        if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_n1(wl)
+    elif args.mgpu == "dd":
+        line = dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank, world, local_rank, warmup, flush,
+                      fma_peak, peaks, peak_kind, sampler, t_busy0)
+    else:
+        line = replicated_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank, world, warmup, flush,
+                              fma_peak, peaks, peak_kind, sampler, t_busy0)
+    if rank == 0:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
@@ -411,6 +427,262 @@ def our_arm(args, wl, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank, world, local_rank, warmup, flush,
+           fma_peak, peaks, peak_kind, sampler, t_busy0):
+    """Domain-decomposed run: one process per GPU, windows exchanged once as CUDA IPC handles, then lockstep steps whose
+    only synchronisation is the library's own in-stream flag barriers."""
+    x, y, vx, vy, m = bodies
+    n = len(x)
+    capacity = int(n / world * 1.5) + 65536
+    bh.dd_init(rank, world, capacity)
+    handles = [None] * world
+    dist.all_gather_object(handles, bh.dd_export())
+    for r, hnd in enumerate(handles):
+        if r != rank:
+            bh.dd_import(r, hnd)
+    bh.dd_upload(params, x, y, vx, vy, m)
+    torch.cuda.synchronize()
+    dist.barrier()
+    log(rank, "bodies distributed")
+
+    def gather_costs():
+        mine = bh.dd_chunk_costs()
+        allc = [None] * world
+        dist.all_gather_object(allc, mine)
+        return allc
+
+    def rebalance():
+        st = bh.dd_stats()
+        local = st["ms_keygen"] + st["ms_sort"] + st["ms_build"] + st["ms_export"]
+        allc = gather_costs()
+        mean_cost = float(np.mean(np.concatenate([c for _, c in allc]))) if sum(len(c) for _, c in allc) else 1.0
+        t = torch.tensor([local, st["ms_traverse"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        beta = mean_cost * float(t[0].item()) / max(float(t[1].item()), 1e-9)     # sort + build share of a chunk, in list entries
+        new = lpe_bh.balanced_splitters(allc, world, beta)
+        bh.dd_set_splitters(new)
+        return beta
+
+    # settle: a few steps, re-balance on the measured per-chunk cost, a few more (the bodies move to their new owners)
+    bh.set_instrumentation(timing=True)
+    balance_log = []
+    for it in range(3):
+        bh.dd_step(params, 2)
+        bh.synchronize()
+        balance_log.append({"traverse_ms": bh.dd_stats()["ms_traverse"], "n_live": bh.dd_stats()["n_live"]})
+        beta = rebalance()
+        dist.barrier()
+    for _ in range(warmup):
+        bh.dd_step(params, 1)
+    bh.synchronize()
+    torch.cuda.synchronize()
+    log(rank, "warm-up done")
+    launches0 = bh.launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    step_ms, phases = [], []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        bh.dd_step(params, 1)
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        s = bh.dd_stats()
+        phases.append([s[k] for k in ("ms_keygen", "ms_wait_a", "ms_sort", "ms_build", "ms_export", "ms_wait_b", "ms_top", "ms_traverse")])
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = bh.launch_count() - launches0
+    t = torch.tensor([float(np.sum(step_ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    ph = np.mean(np.array(phases), axis=0)
+    allph = [None] * world
+    dist.all_gather_object(allph, [float(v) for v in ph])
+    st = bh.dd_stats()
+    allst = [None] * world
+    dist.all_gather_object(allst, {"n_live": st["n_live"], "n_cells": st["n_cells"], "exported_blocks": sum(st["exported_blocks"]),
+                                   "n_roots": st["n_roots"]})
+    clocks = sampler.stop(t_busy0, time.time()) if sampler else None
+    if clocks is not None:
+        clocks["window"] = "settling + warm-up + device-timed region"
+
+    # ---- parity: one counted step of the decomposed run against the unsharded step on rank 0's GPU ----
+    parity = dd_parity_check(torch, dist, lpe_bh, bh, bodies, params, rank, world, local_rank, capacity)
+    log(rank, "timed region done")
+    if rank != 0:
+        return None
+    names = ("keygen", "wait_migrants", "sort", "build", "export", "wait_export", "top", "traverse")
+    arr = np.array(allph)
+    imax = arr.max(axis=0)
+    interactions = parity["interactions"]
+    meas = dict(n=n, ms_per_step=ms_per_step, interactions=interactions, passes=bh.stats()["sort_passes"],
+                phases={"keygen": float(imax[0]), "sort": float(imax[2]), "build": float(imax[3] + imax[4]),
+                        "traverse": float(imax[7])}, kernel="k_traverse2 (two-phase traversal)")
+    return {
+        "metric": "barnes_hut_body_steps_per_sec", "value": n / (ms_per_step * 1e-3), "unit": "body-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64 state, f32 interaction math", "data": "synthetic",
+        "config": config_for(wl, world, args.precision, args.mgpu),
+        "parallelism_detail": "domain decomposition by key range: per-rank sort + build, published roots + locally essential "
+                              "child blocks stored into peer memory (CUDA IPC over NVLink) by the step's own kernels, two "
+                              "in-stream flag barriers per step, no collective in the data path",
+        "phases_ms_max_over_ranks": dict(zip(names, (float(v) for v in imax))),
+        "phases_ms_per_rank": {nm: [float(v) for v in arr[:, i]] for i, nm in enumerate(names)},
+        "per_rank": allst, "balance": {"beta_list_entries_per_chunk": beta, "settling": balance_log},
+        "interactions_per_body": interactions / n, "parity_check": parity,
+        **rooflines(meas, fma_peak, peaks, peak_kind, key, world),
+        "e2e": {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "path": "multi-GPU runs keep the bodies resident on their owners; the host round trip is measured at N=1"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
+def dd_parity_check(torch, dist, lpe_bh, bh, bodies, params, rank, world, local_rank, capacity):
+    """Re-distribute the ORIGINAL bodies, run one counted step on all ranks, gather on rank 0 and compare with one
+    unsharded step of the same bodies on rank 0's GPU: identical per-body accepted-interaction counts (every theta
+    decision), velocities within fp32 summation noise."""
+    x, y, vx, vy, m = bodies
+    n = len(x)
+    bh.set_instrumentation(counts=True)
+    bh.dd_upload(params, x, y, vx, vy, m)
+    torch.cuda.synchronize()
+    dist.barrier()
+    bh.dd_step(params, 1)
+    d = bh.dd_download(counts=True)
+    nl = torch.tensor([len(d["index"])], device="cuda", dtype=torch.int64)
+    counts = [torch.zeros_like(nl) for _ in range(world)]
+    dist.all_gather(counts, nl)
+    pad = lambda a, dt: torch.from_numpy(np.concatenate([a, np.zeros(capacity - len(a), a.dtype)]).astype(dt)).cuda()
+    mine = {"index": pad(d["index"], np.int64), "vx": pad(d["vx"], np.float64), "vy": pad(d["vy"], np.float64),
+            "acc": pad(d["accepted"], np.int64)}
+    got = {}
+    for k, t in mine.items():
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, parts, dst=0)
+        if rank == 0:
+            got[k] = np.concatenate([p[:int(c.item())].cpu().numpy() for p, c in zip(parts, counts)])
+    bh.set_instrumentation(timing=True)
+    out = None
+    if rank == 0:
+        one = lpe_bh.BarnesHut(local_rank)
+        one.set_instrumentation(counts=True)
+        one.upload(x, y, vx, vy, m)
+        one.step(params, 1)
+        ref = one.download()
+        racc, _ = one.counts()
+        interactions = one.stats()["interactions"]
+        one.close()
+        idx = got["index"]
+        seen = np.bincount(idx, minlength=n)
+        dvx, dvy = got["vx"] - vx[idx], got["vy"] - vy[idx]
+        rvx, rvy = ref["vx"][idx] - vx[idx], ref["vy"][idx] - vy[idx]
+        mag = np.hypot(rvx, rvy)
+        err = np.hypot(dvx - rvx, dvy - rvy) / np.maximum(mag, 1e-3 * np.median(mag))
+        out = {"what": "one counted step of the decomposed run vs the unsharded step on one GPU, all bodies",
+               "bodies": n, "every_body_owned_once": bool(np.all(seen == 1)),
+               "accepted_counts_identical": bool(np.array_equal(got["acc"], racc[idx])),
+               "max_rel_dv_diff": float(err.max()), "interactions": int(interactions)}
+    dist.barrier()
+    return out
+
+
+def replicated_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank, world, warmup, flush, fma_peak,
+                   peaks, peak_kind, sampler, t_busy0):
+    """Round 1's variant: every rank holds all bodies and builds the same tree, traversal by block-cyclic key slices,
+    new state stored into every rank's receive buffer by the traversal kernel itself."""
+    x, y, vx, vy, m = bodies
+    n = len(x)
+    bh.set_instrumentation(counts=True)
+    bh.upload(x, y, vx, vy, m)
+    bh.step(params, 1)
+    interactions = bh.stats()["interactions"]
+    bh.set_shard(rank, world)
+    bh.set_instrumentation(timing=True)
+    bh.upload(x, y, vx, vy, m)
+    view = bh.device_view()
+    send = torch.as_tensor(CudaArray(view.xchg_send, 4 * view.xchg_chunk), device="cuda")
+    recv = torch.as_tensor(CudaArray(view.xchg_recv, 4 * view.xchg_chunk * world), device="cuda")
+    ok = 0
+    if not args.no_p2p and world <= 8:
+        mine = None
+        try:
+            mine = bh.xchg_export()
+        except Exception as e:
+            log(rank, f"direct exchange: export failed: {e}")
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        if all(h is not None for h in handles):
+            try:
+                for r, hnd in enumerate(handles):
+                    if r != rank:
+                        bh.xchg_import(r, hnd)
+                ok = 1 if bh.xchg_p2p_ready() else 0
+            except Exception as e:
+                log(rank, f"direct exchange unavailable: {e}")
+    flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    p2p = bool(flag.item())
+    if not p2p:
+        bh.xchg_reset()
+    token = torch.zeros(1, device="cuda", dtype=torch.int32)
+
+    def one_step():
+        bh.step_begin(params)
+        if p2p:
+            dist.all_reduce(token)      # stream-ordered barrier: every rank's stores have landed
+        else:
+            dist.all_gather_into_tensor(recv, send)
+        bh.step_finish()
+
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize()
+    launches0 = bh.launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    step_ms, phases = [], []
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        one_step()
+        e1.record(stream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        s = bh.stats()
+        phases.append((s["ms_keygen"], s["ms_sort"], s["ms_build"], s["ms_traverse"]))
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = bh.launch_count() - launches0
+    t = torch.tensor([float(np.sum(step_ms))], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    ph = np.mean(np.array(phases), axis=0)
+    clocks = sampler.stop(t_busy0, time.time()) if sampler else None
+    if rank != 0:
+        return None
+    meas = dict(n=n, ms_per_step=ms_per_step, interactions=interactions, passes=bh.stats()["sort_passes"],
+                phases={"keygen": float(ph[0]) * world, "sort": float(ph[1]) * world, "build": float(ph[2]) * world,
+                        "traverse": float(ph[3])}, kernel="k_traverse2 (two-phase traversal)")
+    return {
+        "metric": "barnes_hut_body_steps_per_sec", "value": n / (ms_per_step * 1e-3), "unit": "body-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64 state, f32 interaction math", "data": "synthetic",
+        "config": config_for(wl, world, args.precision, args.mgpu),
+        "parallelism_detail": "replicated tree, block-cyclic key-slice traversal, " +
+                              ("(x,y,vx,vy) stored into every rank's receive buffer by the traversal kernel (NVLink peer memory)"
+                               if p2p else "NCCL allgather of (x,y,vx,vy)"),
+        "phases_ms": {"keygen": float(ph[0]), "sort": float(ph[1]), "build": float(ph[2]), "traverse": float(ph[3])},
+        "interactions_per_body": interactions / n,
+        **rooflines(meas, fma_peak, peaks, peak_kind, key, world),
+        "e2e": {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "path": "multi-GPU runs keep bodies resident; host round trip measured at N=1 only"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -418,10 +690,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--mgpu", default="dd", choices=["dd", "replicated"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bodies", type=int, default=None,
                     help="TESTS ONLY: shrink the workload to this many bodies; the line is then marked reduced and is not a bench value")
-    ap.add_argument("--no-p2p", action="store_true", help="multi-GPU: NCCL allgather instead of the fused peer-memory exchange")
+    ap.add_argument("--no-p2p", action="store_true", help="--mgpu replicated: NCCL allgather instead of the fused peer-memory exchange")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -431,15 +705,16 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
-    # N=1: the configuration the metric is quoted on that the reference can also run (C2); N>1: the sharded 16M config
-    wl = dict(WORKLOADS[args.workload or ("c2" if world == 1 else "c3")])
+    # ONE workload at every N (the driver's scaling series must be one problem): C3, the sharded 16 M-body configuration
+    key = args.workload or "c3"
+    wl = dict(WORKLOADS[key])
     if args.bodies:
         wl["n"] = int(args.bodies)
         wl["name"] = f"REDUCED to {wl['n']} bodies (contract test, not a bench value): " + wl["name"]
     if args.impl == "reference":
         reference_arm(args, wl, rank, world)
     else:
-        our_arm(args, wl, rank, world, local_rank)
+        our_arm(args, wl, key, rank, world, local_rank)
 
 
 if __name__ == "__main__":

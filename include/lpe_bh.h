@@ -248,6 +248,9 @@ int  lpe_bh_dd_phase(lpe_bh_ctx* ctx, const lpe_bh_params* p, int phase);  /* 0,
 int  lpe_bh_dd_download(lpe_bh_ctx* ctx, uint64_t* n_out, uint32_t* index, double* x, double* y, double* vx,
                         double* vy, uint32_t* accepted);
 int  lpe_bh_dd_get_stats(lpe_bh_ctx* ctx, lpe_bh_dd_stats* out);
+/* load-balance input: per 32-body chunk of this rank's sorted bodies, the depth-30 key of its first body and the list
+ * entries its warp evaluated in the last traversal; arrays of >= capacity / 32 + 1 elements; synchronises */
+int  lpe_bh_dd_chunk_costs(lpe_bh_ctx* ctx, uint64_t* n_chunks, uint64_t* first_key30, uint32_t* cost);
 /* splitters as depth-30 keys, nranks + 1 values (first 0, last 2^60); set: same values on every rank before the same step */
 int  lpe_bh_dd_get_splitters(lpe_bh_ctx* ctx, uint64_t* split30);
 int  lpe_bh_dd_set_splitters(lpe_bh_ctx* ctx, const uint64_t* split30);

@@ -8,3 +8,6 @@ OUT="$HERE/liblpe_bh.so"
   -Xcompiler -fPIC,-O3,-Wall -Xptxas -v --shared \
   -o "$OUT" "$HERE/csrc/lpe_bh.cu" "$HERE/csrc/workloads.cpp" -lcudart 2> "$HERE/build.log" || { cat "$HERE/build.log"; exit 1; }
 echo "built $OUT"
+# the synthetic workload generators alone (no CUDA): what bench.py --impl reference loads instead of the product library
+"${CXX:-g++}" -std=c++17 -O3 -fPIC -shared -Wall -o "$HERE/libworkloads.so" "$HERE/csrc/workloads.cpp"
+echo "built $HERE/libworkloads.so"

@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
             continue;
         }
 
-        if (a.chunk_cost && lane == 0) a.chunk_cost[q] = cost + 32u;   // (+ the per-body share of sort and build)
+        if (a.chunk_cost && lane == 0) a.chunk_cost[q] = cost;
         double2 v = make_double2(0.0, 0.0);
         if (valid) v = a.vel[b];
         const double accScale = c.G * massScale * c.invS * c.invS;   // a = G*sum M d/r^3; scaled units M/Ms, d/S

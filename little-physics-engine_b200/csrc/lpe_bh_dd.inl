@@ -607,6 +607,33 @@ int lpe_bh_dd_get_stats(lpe_bh_ctx* c, lpe_bh_dd_stats* o) {
     return 0;
 }
 
+// Load-balance input: for every 32-body chunk of this rank's sorted bodies, the depth-30 key of its first body and the
+// number of list entries its warp evaluated in the last step's traversal. The caller concatenates the ranks' arrays
+// (they are globally key-ordered), weighs them and picks new splitters. Synchronises.
+int lpe_bh_dd_chunk_costs(lpe_bh_ctx* c, uint64_t* n_chunks, uint64_t* first_key30, uint32_t* cost) {
+    if (!c || !n_chunks) return 1;
+    if (!c->dd || !c->have_step) return fail(c, "no domain-decomposed step has run");
+    DevGuard _dg(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned int nl = 0;
+    CU_TRY(c, cudaMemcpy(&nl, &dd_hdr(c)->n_live, sizeof(nl), cudaMemcpyDeviceToHost));
+    const uint64_t nc = ((uint64_t)nl + 31) / 32;
+    *n_chunks = nc;
+    if (!nc) return 0;
+    if (cost) CU_TRY(c, cudaMemcpy(cost, c->dd_chunk_cost, 4 * nc, cudaMemcpyDeviceToHost));
+    if (first_key30) {
+        // every 32nd sorted key (strided copy: 8 bytes out of every 256)
+        CU_TRY(c, cudaMemcpy2D(first_key30, 8, c->keys[c->sorted_sel], 256, 8, nc, cudaMemcpyDeviceToHost));
+        const int sh = 2 * (LPE_MAX_DEPTH - c->last_c.D);
+        const uint64_t top = 1ull << (2 * LPE_MAX_DEPTH);
+        for (uint64_t i = 0; i < nc; ++i) {
+            const uint64_t k = first_key30[i];
+            first_key30[i] = (k >> (2 * c->last_c.D)) ? top : (k << sh);   // a chunk of bodies outside the tree sorts last
+        }
+    }
+    return 0;
+}
+
 int lpe_bh_dd_get_splitters(lpe_bh_ctx* c, uint64_t* split30) {
     if (!c || !split30) return 1;
     if (!c->dd) return fail(c, "context is not in domain-decomposed mode");

@@ -433,6 +433,13 @@ class BarnesHut:
         self._chk(self.lib.lpe_bh_dd_get_stats(self.h, C.byref(s)), "dd_get_stats")
         return s.as_dict()
 
+    def dd_chunk_costs(self):
+        cap = self._capacity // 32 + 2
+        keys, cost = np.empty(cap, np.uint64), np.empty(cap, np.uint32)
+        n = C.c_uint64(0)
+        self._chk(self.lib.lpe_bh_dd_chunk_costs(self.h, C.byref(n), _dp(keys), _dp(cost)), "dd_chunk_costs")
+        return keys[:n.value].copy(), cost[:n.value].copy()
+
     def dd_get_splitters(self):
         a = (C.c_uint64 * (self._nranks + 1))()
         self._chk(self.lib.lpe_bh_dd_get_splitters(self.h, a), "dd_get_splitters")
@@ -508,3 +515,30 @@ class DDGroup:
 
     def stats(self):
         return [c.dd_stats() for c in self.ranks]
+
+    def rebalance(self, beta=240.0):
+        """New splitters from the last step's per-chunk traversal cost (+ beta per chunk for sort and build)."""
+        new = balanced_splitters([c.dd_chunk_costs() for c in self.ranks], self.R, beta)
+        for c in self.ranks:
+            c.dd_set_splitters(new)
+        return new
+
+
+def balanced_splitters(per_rank, nranks, beta=240.0):
+    """Splitters (depth-30 keys) that give every rank the same share of sum(cost + beta) over the 32-body chunks.
+    per_rank = [(first_key30, cost)] in rank order: the ranks' key ranges are disjoint and ascending, so the
+    concatenation is globally key-ordered. Pure host arithmetic, the same on every rank."""
+    keys = np.concatenate([k for k, _ in per_rank])
+    w = np.concatenate([c for _, c in per_rank]).astype(np.float64) + float(beta)
+    top = 1 << 60
+    split = [0]
+    if len(keys):
+        cum = np.cumsum(w)
+        for r in range(1, nranks):
+            i = int(np.searchsorted(cum, cum[-1] * r / nranks))
+            k = int(keys[min(i, len(keys) - 1)])
+            split.append(max(k, split[-1]))
+    else:
+        split += [top * r // nranks for r in range(1, nranks)]
+    split.append(top)
+    return split

@@ -56,3 +56,16 @@ def test_own_arm_prints_one_contract_line():
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 40 * 100000
     assert d["e2e"]["d2h_bytes_per_step"] == 32 * 100000
     assert 0 < d["roofline"]["frac"] < 1 and "REDUCED" in d["config"]["workload"]
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """The reference arm's process loads oracle/ and the workload generators only — not liblpe_bh.so."""
+    code = ("import sys, json; sys.argv=['bench.py']; import bench; "
+            "w=dict(bench.WORKLOADS['c2']); w['n']=5000; bench.reference_sample(w, 1, 0); "
+            "maps=open('/proc/self/maps').read(); "
+            "print(json.dumps({'product': 'liblpe_bh.so' in maps, 'workloads': 'libworkloads.so' in maps, "
+            "'oracle': ('libref_bh.so' in maps) or ('liboracle_bh.so' in maps)}))")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1500:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d == {"product": False, "workloads": True, "oracle": True}, d

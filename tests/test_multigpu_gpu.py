@@ -29,3 +29,29 @@ def test_sharded_step_across_processes_matches_unsharded():
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("bit for bit") == 2 * world, r.stdout[-2000:]
+
+
+@pytest.mark.gpu
+def test_domain_decomposed_step_across_processes():
+    """scripts/check_dd.py under torchrun: CUDA IPC windows, in-stream flag barriers, migration, a re-balance in the
+    middle; FAST = identical decisions, STRICT = bit for bit against one GPU."""
+    if _gpu_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "scripts", "check_dd.py"),
+           "200000", "4"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("] OK") == 2 * world and "FAIL" not in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.gpu
+def test_domain_decomposed_step_one_host_thread_two_gpus():
+    """One host thread queues every rank's phases on its own GPU (peer access instead of IPC)."""
+    if _gpu_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "check_dd.py"), "--one-process", "2", "200000", "4"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("] OK") == 4 and "FAIL" not in r.stdout, r.stdout[-2000:]
