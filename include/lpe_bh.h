@@ -228,7 +228,8 @@ typedef struct {
     uint64_t overflow_chunks;
     uint32_t import_blocks;   /* capacity of one sender's import region */
     uint32_t fault;           /* device fault bits since the last check */
-    int32_t  rank, nranks, depth, pad_;
+    int32_t  rank, nranks, depth;
+    int32_t  export_rounds;   /* generations of the exporter's breadth-first walk (its critical path) */
     /* last step, CUDA events, only when timing is enabled: keys + migration | wait for every rank's migrants |
      * inbox keys + sort | build | flags + publish + export | wait for every rank's export | top of the tree | traversal */
     float ms_keygen, ms_wait_a, ms_sort, ms_build, ms_export, ms_wait_b, ms_top, ms_traverse, ms_total, pad2_;

@@ -142,8 +142,10 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
 __global__ void __launch_bounds__(256)
 k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ bodyIn,
          const double2* __restrict__ velIn, const unsigned int* __restrict__ origIn, Body* __restrict__ bodyOut,
-         double2* __restrict__ velOut, unsigned int* __restrict__ origOut, unsigned int* __restrict__ selfslot) {
+         double2* __restrict__ velOut, unsigned int* __restrict__ origOut, unsigned int* __restrict__ selfslot,
+         const unsigned int* __restrict__ n_dev) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_dev) n = (int)*n_dev;
     if (i >= n) return;
     const unsigned int b = sidx[i];
     bodyOut[i] = bodyIn[b];

@@ -37,10 +37,12 @@ struct Scal {
     // domain-decomposed runs (bh_dd.cuh)
     unsigned int n_live;        // bodies this rank owns in this step (slots [0, n_live) after the gather)
     unsigned int dd_nroots;     // roots of the top tree (0 = empty tree)
-    unsigned int exp_list_count;
+    unsigned int dd_myroots;    // roots this rank publishes
     unsigned int exp_count[8];  // child blocks exported to each rank
-    unsigned int pad_dd;
+    unsigned int n_sort;        // slots holding this step's keys: last step's bodies + the migrants that arrived
     unsigned long long work_cost;   // list entries evaluated by this rank's traversal (load-balance weight)
+    unsigned int dd_rounds;     // generations of the exporter's breadth-first walk (longest destination)
+    unsigned int pad_dd2;
 };
 
 // Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.

@@ -39,10 +39,15 @@ struct DDQuad {                 // one maximal aligned quadrant of a rank's key 
     int pad;
     double x0, y0, x1, y1;      // [x0, x1) x [y0, y1): every in-tree body of the quadrant lies inside (keygen's own bounds)
 };
+constexpr int DD_BVH_LEAVES = 256;                      // >= DD_MAXQ, power of two
 struct DDDomain {               // identical on every rank; rebuilt on the host when the splitters or the depth change
     int nq[LPE_MAX_P2P];
     double box[LPE_MAX_P2P][4];                 // bounding box of the rank's quadrants: x0, y0, x1, y1
     DDQuad q[LPE_MAX_P2P][DD_MAXQ];
+    // The same quadrants as a binary tree of boxes (heap order: node k has children 2k and 2k+1, leaf j is node
+    // DD_BVH_LEAVES + j), in scaled units (x / S) as floats rounded OUTWARD; x0 > x1 marks an empty node. The quadrants
+    // are in key order, so neighbours in the list are neighbours in space and the inner boxes are tight.
+    float4 bvh[LPE_MAX_P2P][2 * DD_BVH_LEAVES];
 };
 struct DDSplit {                // depth-D splitters: rank r owns keys in [k[r], k[r+1]); k[R] = all ones
     unsigned long long k[LPE_MAX_P2P + 1];
@@ -159,48 +164,48 @@ __device__ __forceinline__ unsigned long long dd_body_key(const StepConst& c, co
 }
 __device__ __forceinline__ unsigned long long dd_dead_key(int D) { return (1ull << (2 * D)) | 1ull; }   // sorts last
 
-// ---- phase A: keys of the own bodies; leavers go straight into their new owner's tail slots -------------------------
-// c.n = S (slots). Slots [0, n_live) hold bodies; the tail belongs to the peers in this phase (they store migrants
-// there) and is NOT read here: its keys are written by k_dd_keygen_inbox after the barrier.
+// ---- phase A: keys of the own bodies; leavers go straight into their new owner's state arrays ----------------------
+// Slots [0, n_live) hold the rank's bodies. A body whose key left the rank's range is stored right behind the live
+// bodies of its new owner (slot = the owner's n_live + a ticket from the owner's counter): the owner then sorts
+// n_live + arrivals slots, whatever the capacity. The slots behind n_live belong to the peers during this phase and are
+// not touched here; their keys are made by k_dd_keygen_inbox after the barrier.
 __global__ void __launch_bounds__(256)
 k_dd_keygen(StepConst c, DDSplit sp, const Body* __restrict__ body, const double2* __restrict__ vel,
             const unsigned int* __restrict__ orig, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
-            Scal* __restrict__ s, DDHeader* __restrict__ hdr, DDPeers peers, unsigned long long* __restrict__ oob, int icap) {
+            Scal* __restrict__ s, DDHeader* __restrict__ hdr, DDPeers peers, unsigned long long* __restrict__ oob) {
     __shared__ unsigned char lut[64];
     if (threadIdx.x < 64) lut[threadIdx.x] = hilbert_lut_entry(threadIdx.x);
     __syncthreads();
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int n_prev = hdr->n_live;
+    if (blockIdx.x * blockDim.x >= n_prev) return;
     unsigned int in = 0, live = 0;
-    if (i < c.n) {
-        unsigned long long key = dd_dead_key(c.D);
-        if ((unsigned int)i < n_prev) {
-            const Body b = body[i];
-            bool inside;
-            key = dd_body_key(c, lut, make_double2(b.x, b.y), b.comp, inside);
-            const int owner = dd_owner(sp, key);
-            const bool target = (b.comp & 1u) && (b.comp & 2u) && !(b.comp & 4u);
-            if (!inside && target) {   // a target outside the tree: the last rank's domain must cover it
-                atomicMin(&oob[0], ordered_bits(b.x)); atomicMin(&oob[1], ordered_bits(b.y));
-                atomicMax(&oob[2], ordered_bits(b.x)); atomicMax(&oob[3], ordered_bits(b.y));
-            }
-            if (owner == sp.me) {
-                live = 1; in = inside ? 1u : 0u;
+    if (i < n_prev) {
+        const Body b = body[i];
+        bool inside;
+        unsigned long long key = dd_body_key(c, lut, make_double2(b.x, b.y), b.comp, inside);
+        const int owner = dd_owner(sp, key);
+        const bool target = (b.comp & 1u) && (b.comp & 2u) && !(b.comp & 4u);
+        if (!inside && target) {   // a target outside the tree: the last rank's domain must cover it
+            atomicMin(&oob[0], ordered_bits(b.x)); atomicMin(&oob[1], ordered_bits(b.y));
+            atomicMax(&oob[2], ordered_bits(b.x)); atomicMax(&oob[3], ordered_bits(b.y));
+        }
+        if (owner == sp.me) {
+            live = 1; in = inside ? 1u : 0u;
+        } else {
+            DDHeader* oh = peers.hdr[owner];
+            const unsigned int slot = oh->n_live + atomicAdd(&oh->inbox_count, 1u);
+            if (slot < (unsigned int)c.n) {
+                peers.body[owner][slot] = b;
+                peers.vel[owner][slot] = vel[i];
+                peers.orig[owner][slot] = orig[i];
             } else {
-                const unsigned int k = atomicAdd(&peers.hdr[owner]->inbox_count, 1u);
-                if (k < (unsigned int)icap) {
-                    const unsigned int slot = (unsigned int)c.n - 1u - k;
-                    peers.body[owner][slot] = b;
-                    peers.vel[owner][slot] = vel[i];
-                    peers.orig[owner][slot] = orig[i];
-                } else {
-                    atomicOr(&hdr->fault, 1u);
-                }
-                key = dd_dead_key(c.D);
+                atomicOr(&hdr->fault, 1u);
             }
+            key = dd_dead_key(c.D);   // sorts behind everything: the slot is free again after the gather
         }
         keys[i] = key;
-        vals[i] = (unsigned int)i;
+        vals[i] = i;
     }
     const unsigned int cin = __syncthreads_count(in);
     const unsigned int clive = __syncthreads_count(live);
@@ -210,7 +215,7 @@ k_dd_keygen(StepConst c, DDSplit sp, const Body* __restrict__ body, const double
     }
 }
 
-// ---- phase B, first kernel: keys of the bodies that arrived in the tail slots ---------------------------------------
+// ---- phase B, first kernel: keys of the bodies that arrived behind the live ones; how many slots the sort covers -----
 __global__ void __launch_bounds__(256)
 k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, unsigned long long* __restrict__ keys,
                   unsigned int* __restrict__ vals, Scal* __restrict__ s, DDHeader* __restrict__ hdr) {
@@ -218,14 +223,16 @@ k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, unsign
     if (threadIdx.x < 64) lut[threadIdx.x] = hilbert_lut_entry(threadIdx.x);
     __syncthreads();
     unsigned int cnt = hdr->inbox_count;
-    const unsigned int room = (unsigned int)c.n - hdr->n_live;
+    const unsigned int n_prev = hdr->n_live;
+    const unsigned int room = (unsigned int)c.n - n_prev;
     if (cnt > room) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&hdr->fault, 1u);
         cnt = room;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) s->n_sort = n_prev + cnt;
     unsigned int in = 0, live = 0;
     for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < cnt; k += gridDim.x * blockDim.x) {
-        const unsigned int slot = (unsigned int)c.n - 1u - k;
+        const unsigned int slot = n_prev + k;
         const Body b = body[slot];
         bool inside;
         unsigned long long key = dd_body_key(c, lut, make_double2(b.x, b.y), b.comp, inside);
@@ -236,9 +243,9 @@ k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, unsign
             ++live;
             in += inside ? 1u : 0u;
         }
-        keys[slot] = key;   // (vals[slot] = slot was written by phase A)
+        keys[slot] = key;
+        vals[slot] = slot;
     }
-    (void)vals;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         in += __shfl_xor_sync(0xFFFFFFFFu, in, o);
@@ -254,83 +261,12 @@ k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, unsign
 // Conservative: the reference opens a cell for a body at p when !(size^2 / (|com - p|^2 + eps^2) < theta^2)
 // (barnes_hut.cpp:261-269). For every p inside a box, |com - p|^2 >= dmin^2 (distance from com to the box), so if
 // size^2 < theta^2 * (dmin^2 + eps^2) * (1 - 1e-9) no body of the box opens the cell and its children are never
-// visited from there. A flagged cell gets an export index per destination (any unique index will do: the layout of the
-// imported blocks does not change any result).
+// visited from there.
 __device__ __forceinline__ bool dd_box_may_open(double cx, double cy, double sizeSq, double eps2, double theta2,
                                                 double x0, double y0, double x1, double y1) {
     const double dx = fmax(fmax(x0 - cx, cx - x1), 0.0), dy = fmax(fmax(y0 - cy, cy - y1), 0.0);
     const double d2 = dx * dx + dy * dy + eps2;
     return !(sizeSq < theta2 * d2 * (1.0 - 1e-9));
-}
-
-struct DDExport {
-    const uint2* levelList;         // every local cell: {pre-order index, ordinal}
-    const NodeMeta* meta;
-    const Agg* agg;
-    const unsigned long long* tkey;
-    unsigned int* eidx;             // [dest][cellCap] export index of the cell's child block, LPE_NONE = not exported
-    uint4* list;                    // {ordinal, dest, export index, -}
-    unsigned int cellCap;
-    unsigned int icap;              // import blocks per sender on every rank
-    unsigned int listCap;
-};
-
-__global__ void __launch_bounds__(256)
-k_dd_export_flags(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDExport e, Scal* __restrict__ s,
-                  DDHeader* __restrict__ hdr) {
-    const unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= s->n_internal) return;
-    const uint2 pq = e.levelList[idx];
-    const NodeMeta mt = e.meta[pq.x];
-    const int L = mt.level;
-    const int shift = 2 * (c.D - L);
-    // a cell is complete (and a cell of the global tree) iff its whole key interval lies inside this rank's range
-    const unsigned long long kstart = (e.tkey[mt.start] >> shift) << shift;
-    const unsigned long long kend = kstart + (1ull << shift);
-    const bool inner = kstart >= sp.k[sp.me] && kend <= sp.k[sp.me + 1] && kend != 0ull;
-    double cx = 0.0, cy = 0.0, sizeSq = 0.0;
-    if (inner) {
-        double M;
-        node_centre(e.agg[pq.x], L, c.quirk, M, cx, cy);
-        const double size = ldexp(c.U, -L);
-        sizeSq = size * size;
-    }
-    const double eps2 = c.eps * c.eps;
-    for (int d = 0; d < sp.R; ++d) {
-        if (d == sp.me) continue;
-        bool open = false;
-        if (inner) {
-            const int nq = dom->nq[d];
-            if (nq > 0 && dd_box_may_open(cx, cy, sizeSq, eps2, c.theta2, dom->box[d][0], dom->box[d][1], dom->box[d][2], dom->box[d][3])) {
-                for (int k = 0; k < nq && !open; ++k) {
-                    const DDQuad& q = dom->q[d][k];
-                    open = dd_box_may_open(cx, cy, sizeSq, eps2, c.theta2, q.x0, q.y0, q.x1, q.y1);
-                }
-            }
-            if (!open && d == sp.R - 1) {
-                // targets outside the universe live on the last rank: union of every rank's box of such bodies
-                double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-                bool any = false;
-                for (int r = 0; r < sp.R; ++r) {
-                    const double* pl = hdr->mail[0][r].payload;
-                    if (pl[0] <= pl[2]) { any = true; x0 = fmin(x0, pl[0]); y0 = fmin(y0, pl[1]); x1 = fmax(x1, pl[2]); y1 = fmax(y1, pl[3]); }
-                }
-                if (any) open = dd_box_may_open(cx, cy, sizeSq, eps2, c.theta2, x0, y0, x1, y1);
-            }
-        }
-        unsigned int ex = LPE_NONE;
-        if (open) {
-            ex = atomicAdd(&s->exp_count[d], 1u);
-            if (ex >= e.icap) {
-                atomicOr(&hdr->fault, 2u);
-                ex = LPE_NONE;
-            } else {
-                const unsigned int li = atomicAdd(&s->exp_list_count, 1u);
-                if (li < e.listCap) e.list[li] = make_uint4(pq.y, (unsigned int)d, ex, 0u);
-            }
-        }
-        e.eidx[(size_t)d * e.cellCap + pq.y] = ex;
-    }
 }
 
 // fp64 side record of a non-local slot: {centre x, centre y, mass, level} as the traversal's exact test wants them
@@ -340,20 +276,6 @@ __device__ __forceinline__ double4 dd_xrec(const Agg& a, int level, int quirk) {
     return make_double4(cx, cy, M, (double)level);
 }
 
-// ---- phase B: roots of the non-empty inner quadrants -> every rank's root table ----------------------------------------
-struct DDPublish {
-    const unsigned long long* tkey;
-    const unsigned int* tfirst;
-    const unsigned int* tnode;
-    const unsigned int* mask;
-    const unsigned int* P;
-    const Agg* agg;
-    const Body* body;
-    const unsigned int* eidx;
-    unsigned int cellCap;
-    unsigned int icap;
-    unsigned int importBase;   // first import block on every rank; sender s owns [importBase + s * icap, + icap)
-};
 __device__ __forceinline__ unsigned int dd_lower_bound(const unsigned long long* __restrict__ a, unsigned int n, unsigned long long v) {
     unsigned int lo = 0, hi = n;
     while (lo < hi) {
@@ -362,9 +284,22 @@ __device__ __forceinline__ unsigned int dd_lower_bound(const unsigned long long*
     }
     return lo;
 }
+
+// ---- phase B: the roots of the rank's non-empty inner quadrants (one block) ---------------------------------------------
+struct DDRootsIn {
+    const unsigned long long* tkey;
+    const unsigned int* tfirst;
+    const unsigned int* tnode;
+    const unsigned int* mask;
+    const unsigned int* P;
+    const Agg* agg;
+    const Body* body;
+};
+// myroots[i].cblock = ORDINAL of the root cell (LPE_NONE for a leaf / aggregated terminal); the exporter turns it into
+// the child block index each destination will see
 __global__ void __launch_bounds__(256)
-k_dd_publish(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDPublish a, DDPeers peers, Scal* __restrict__ s,
-             DDHeader* __restrict__ hdr) {
+k_dd_roots(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDRootsIn a, DDRoot* __restrict__ myroots,
+           Scal* __restrict__ s, DDHeader* __restrict__ hdr) {
     __shared__ unsigned int sh[9];
     const int j = threadIdx.x;
     const int nq = dom->nq[sp.me];
@@ -383,8 +318,7 @@ k_dd_publish(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDPublis
     const unsigned int pos = block_exclusive_scan_256(nonempty ? 1u : 0u, sh, &total);
     if (nonempty) {
         DDRoot r;
-        r.key = q.key; r.owner = (unsigned int)sp.me; r.leafpos = LPE_NONE; r.pad[0] = r.pad[1] = 0u;
-        unsigned int ordinal = LPE_NONE;
+        r.key = q.key; r.owner = (unsigned int)sp.me; r.leafpos = LPE_NONE; r.pad[0] = r.pad[1] = 0u; r.cblock = LPE_NONE;
         if (t1 - t0 == 1u) {   // one terminal: a single-body leaf or an aggregated depth-D cell
             const unsigned int first = a.tfirst[t0], last = a.tfirst[t0 + 1];
             if (last - first == 1u) {
@@ -394,86 +328,206 @@ k_dd_publish(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDPublis
             }
         } else {               // the lowest cell that holds every body of the quadrant
             const int L = lca_level(a.tkey[t0], a.tkey[t1 - 1], c.D);
-            ordinal = a.P[t0] + (unsigned int)__popc(a.mask[t0] & ((1u << L) - 1u));
-            r.level = L; r.agg = a.agg[t0 + ordinal];
+            const unsigned int ordinal = a.P[t0] + (unsigned int)__popc(a.mask[t0] & ((1u << L) - 1u));
+            r.level = L; r.agg = a.agg[t0 + ordinal]; r.cblock = ordinal;
         }
-        if (pos < (unsigned int)DD_MAXROOTS) {
-            for (int d = 0; d < sp.R; ++d) {
-                r.cblock = 0u;
-                if (ordinal != LPE_NONE) {
-                    if (d == sp.me) r.cblock = c.blockBase + ordinal;
-                    else {
-                        const unsigned int ex = a.eidx[(size_t)d * a.cellCap + ordinal];
-                        r.cblock = (ex == LPE_NONE) ? DD_POISON_BLOCK : a.importBase + (unsigned int)sp.me * a.icap + ex;
-                    }
-                }
-                peers.roots[d][(size_t)sp.me * DD_MAXROOTS + pos] = r;
-            }
-        } else {
-            atomicOr(&hdr->fault, 4u);
-        }
+        if (pos < (unsigned int)DD_MAXROOTS) myroots[pos] = r;
+        else atomicOr(&hdr->fault, 4u);
     }
     if (j == 0) {
-        const unsigned int cnt = total < (unsigned int)DD_MAXROOTS ? total : (unsigned int)DD_MAXROOTS;
-        for (int d = 0; d < sp.R; ++d) peers.hdr[d]->root_count[sp.me] = cnt;
+        s->dd_myroots = total < (unsigned int)DD_MAXROOTS ? total : (unsigned int)DD_MAXROOTS;
         hdr->n_live = s->n_live;     // the state is compact again: next step's phase A reads slots [0, n_live)
         hdr->inbox_count = 0u;       // consumed; the peers touch it again only after the barrier that follows
     }
 }
 
-// ---- phase B: the flagged child blocks -> the destination's record array (peer stores) ----------------------------
-struct DDWrite {
-    const uint4* list;
-    const unsigned int* eidx;
+// ---- phase B: publish the roots to rank d and export the child blocks rank d can reach ----------------------------------
+// Breadth first from the roots: a cell's child block goes to rank d only if some body of d's key range could open the
+// cell AND all its ancestors — exactly the records d's traversal can reach, never the rest of this rank's tree (the
+// work is proportional to the exported part, a few thousand cells, not to the rank's million cells). The queue lives in
+// global memory and doubles as the numbering: the cell at queue position e is exported as block e of this rank's
+// import region on d, so a parent knows its children's block numbers the moment it pushes them.
+// The reachability test below the roots is the traversal's own group classification (bh_traverse2.cuh, phase 1) against
+// d's quadrants instead of a warp's bounding box: fp32 from the record alone, box edges rounded outward, the same
+// safety margins — if it says "every body of the box accepts", every warp of rank d (whose box lies inside) says so
+// too and never asks for the children. The quadrants are searched through a small tree of boxes (DDDomain::bvh).
+// One thread-block CLUSTER per destination: the generations of the breadth-first walk are separated by cluster
+// barriers, four lanes work on one exported cell (one per child record).
+struct DDExportArgs {
+    const DDRoot* myroots;
     const unsigned int* child;      // [4 * ordinal + digit]
     const TravRec* rec;             // own records (local blocks)
     const NodeMeta* meta;
     const Agg* agg;
     const Body* body;
-    unsigned int cellCap, icap, importBase, listCap;
+    unsigned int* queue;            // [dest][icap] ordinals of the exported cells
+    unsigned int* pushed;           // [dest][DD_EXPORT_ROUNDS] "somebody pushed in this round"
+    unsigned int icap, importBase;
 };
-__global__ void __launch_bounds__(256)
-k_dd_export_write(StepConst c, int me, DDWrite w, DDPeers peers, const Scal* __restrict__ s) {
-    unsigned int count = s->exp_list_count;
-    if (count > w.listCap) count = w.listCap;
-    const unsigned int quads = (gridDim.x * blockDim.x) >> 2;
-    const int r = threadIdx.x & 3;
-    for (unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2; i < count; i += quads) {
-        const uint4 e = w.list[i];
-        const unsigned int q = e.x, d = e.y, ex = e.z;
-        TravRec R = w.rec[4u * (c.blockBase + q) + r];
-        // the r-th valid child in digit order sits in slot r
-        unsigned int code = LPE_NONE, seen = 0;
-#pragma unroll
-        for (int dg = 0; dg < 4; ++dg) {
-            const unsigned int cd = w.child[(size_t)q * 4 + dg];
-            if (cd != LPE_NONE) {
-                if (seen == (unsigned int)r) code = cd;
-                ++seen;
+constexpr int DD_EXPORT_ROUNDS = 2 * LPE_MAX_DEPTH + 4;   // (a round handles at least one generation of the walk)
+constexpr int DD_EXPORT_THREADS = 1024;
+constexpr int DD_EXPORT_CLUSTER = 8;
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __launch_bounds__(DD_EXPORT_THREADS)
+k_dd_export(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDExportArgs a, DDPeers peers, Scal* __restrict__ s,
+            DDHeader* __restrict__ hdr) {
+    __shared__ float4 bvh[2 * DD_BVH_LEAVES];
+    __shared__ float4 oboxf;
+    __shared__ int haveOob;
+    const int d = blockIdx.y;
+    const int crank = blockIdx.x;                 // rank of this block inside its cluster
+    const int tid = threadIdx.x;
+    const unsigned int nroots = s->dd_myroots;
+    const bool remote = d != sp.me;
+    if (!remote && crank != 0) return;            // the own table is written by one block; nobody waits for the others
+    if (tid == 0) {
+        // targets outside the universe live on the last rank: union of every rank's box of such bodies
+        double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+        bool any = false;
+        if (d == sp.R - 1)
+            for (int r = 0; r < sp.R; ++r) {
+                const double* pl = hdr->mail[0][r].payload;
+                if (pl[0] <= pl[2]) { any = true; x0 = fmin(x0, pl[0]); y0 = fmin(y0, pl[1]); x1 = fmax(x1, pl[2]); y1 = fmax(y1, pl[3]); }
+            }
+        oboxf = make_float4(__double2float_rd(x0 * c.invS), __double2float_rd(y0 * c.invS),
+                            __double2float_ru(x1 * c.invS), __double2float_ru(y1 * c.invS));
+        haveOob = any ? 1 : 0;
+    }
+    for (int k = tid; k < 2 * DD_BVH_LEAVES; k += blockDim.x) bvh[k] = dom->bvh[d][k];
+    __syncthreads();
+    const float eps2f = c.eps2f;
+    auto boxAccepts = [&](const TravRec& R, const float4 bx) -> bool {   // every point of the box accepts the node
+        const float ax0 = (R.c.x - bx.x) + R.c.z, ax1 = (R.c.x - bx.z) + R.c.z;
+        const float ay0 = (R.c.y - bx.y) + R.c.w, ay1 = (R.c.y - bx.w) + R.c.w;
+        const float dxmin = fmaxf(fmaxf(-ax0, ax1), 0.f), dymin = fmaxf(fmaxf(-ay0, ay1), 0.f);
+        const float d2min = fmaf(dxmin, dxmin, fmaf(dymin, dymin, eps2f));
+        return d2min * (1.0f - T2_MARGIN) >= R.open_t * (1.0f + OPEN_BAND);
+    };
+    auto mayOpen32 = [&](const TravRec& R) -> bool {
+        if (haveOob && !boxAccepts(R, oboxf)) return true;
+        // depth-first over the heap-ordered tree without a stack: leaving node k = climb while k is a right child,
+        // then step to the sibling
+        unsigned int k = 1u;
+        while (k) {
+            const float4 bx = bvh[k];
+            if (bx.x > bx.z || boxAccepts(R, bx)) {   // empty, or the whole group of quadrants accepts
+                k >>= __ffs(~k) - 1;
+                k = (k > 1u) ? k + 1u : 0u;
+            } else if (k >= (unsigned int)DD_BVH_LEAVES) {
+                return true;                          // a quadrant the node may be opened from
+            } else {
+                k <<= 1;
             }
         }
+        return false;
+    };
+    unsigned int* queue = a.queue + (size_t)d * a.icap;
+    unsigned int* tailNext = &s->exp_count[d];     // zeroed with the step's scalars
+    const unsigned int regionBase = a.importBase + (unsigned int)sp.me * a.icap;   // this rank's import region on every rank
+    // a cell that may be opened from d: next queue position = its export index; returns the child block index d will see
+    auto pushCell = [&](unsigned int ordinal) -> unsigned int {
+        const unsigned int e = atomicAdd(tailNext, 1u);
+        if (e >= a.icap) {
+            atomicOr(&hdr->fault, 2u);
+            return DD_POISON_BLOCK;
+        }
+        queue[e] = ordinal;
+        return regionBase + e;
+    };
+    // ---- the roots: published to d whatever they are; root CELLS that d may open start the queue ----
+    if (crank == 0) {
+        for (unsigned int i = tid; i < nroots; i += blockDim.x) {
+            DDRoot r = a.myroots[i];
+            const unsigned int ordinal = r.cblock;
+            r.cblock = 0u;
+            if (ordinal != LPE_NONE) {
+                if (!remote) r.cblock = c.blockBase + ordinal;
+                else {   // (a root has no record on this rank: make the one the top builders will make)
+                    const TravRec R = make_record(c, r.agg, r.level, 1u, 0u, mass_scale_inv(s->max_mass_bits));
+                    r.cblock = (R.open_t >= 0.f && mayOpen32(R)) ? pushCell(ordinal) : DD_POISON_BLOCK;
+                }
+            }
+            peers.roots[d][(size_t)sp.me * DD_MAXROOTS + i] = r;
+        }
+        if (tid == 0) peers.hdr[d]->root_count[sp.me] = nroots;
+    }
+    if (!remote) return;
+    cluster_sync_all();
+    // ---- breadth first, one generation per round; a quad of lanes per exported cell ----
+    // Queue position e is always handled by quad (e mod quads), so it does not matter that the lanes read the tail at
+    // slightly different moments (a lane that sees entries pushed in the current round just handles them early).
+    // What must be uniform is the decision to stop: round g's pushers raise pushed[g], which is only read after the
+    // barrier that ends the round. One cluster barrier per generation.
+    unsigned int head = 0;
+    const int r4 = tid & 3;
+    const unsigned int quadsPerBlock = blockDim.x >> 2;
+    const unsigned int quads = quadsPerBlock * DD_EXPORT_CLUSTER;
+    const unsigned int myQuad = (unsigned int)crank * quadsPerBlock + ((unsigned int)tid >> 2);
+    unsigned int* pushed = a.pushed + (size_t)d * DD_EXPORT_ROUNDS;   // zeroed with the step's scratch
+    for (int round = 0; round < DD_EXPORT_ROUNDS - 1; ++round) {
+        unsigned int tail = __ldcg(tailNext);
+        if (tail > a.icap) tail = a.icap;
+        bool any = false;
+        for (unsigned int e = head + ((myQuad + quads - head % quads) % quads); e < tail; e += quads) {
+            const unsigned int q = __ldcg(queue + e);
+            const uint4* src = reinterpret_cast<const uint4*>(a.rec + 4u * (c.blockBase + q) + r4);
+            uint4 v0 = src[0], v1 = src[1];
+            TravRec R;
+            R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
+            R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
+            if (R.cblock != 0u) {   // a cell: its own child block as numbered on d, if d can open it at all
+                const bool open = R.open_t >= 0.f && mayOpen32(R);   // (open_t = -2: skipped by the small-mass rule, never opened)
+                const unsigned int blk = open ? pushCell((R.cblock >> 2) - c.blockBase) : DD_POISON_BLOCK;
+                any = any || open;
+                v1.w = (blk << 2) | (R.cblock & 3u);
+            }
+            uint4* o = reinterpret_cast<uint4*>(peers.rec[d] + 4u * ((size_t)regionBase + e) + r4);
+            __stcs(o, v0);
+            __stcs(o + 1, v1);
+        }
+        if (any) pushed[round] = 1u;
+        head = tail;
+        cluster_sync_all();   // this round's pushes (queue entries, the tail, the flag) are visible to the whole cluster
+        if (__ldcg(pushed + round) == 0u) {
+            if (tid == 0 && crank == 0) atomicMax(&s->dd_rounds, (unsigned int)round + 1u);
+            break;
+        }
+    }
+}
+
+// the fp64 side records of the exported blocks (exact centre / mass / level of every child: guard-band re-tests and
+// STRICT precision on the receiving rank) — one thread per exported record, off the breadth-first critical path
+__global__ void __launch_bounds__(256)
+k_dd_export_x(StepConst c, int me, DDExportArgs a, DDPeers peers, const Scal* __restrict__ s) {
+    const int d = blockIdx.y;
+    if (d == me) return;
+    const unsigned int count = min(s->exp_count[d], a.icap);
+    const unsigned int* queue = a.queue + (size_t)d * a.icap;
+    const unsigned int regionBase = a.importBase + (unsigned int)me * a.icap;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4u * count; i += gridDim.x * blockDim.x) {
+        const unsigned int e = i >> 2, r4 = i & 3u;
+        const unsigned int q = queue[e];
+        const uint4 cd4 = *reinterpret_cast<const uint4*>(a.child + (size_t)q * 4);
+        const unsigned int cds[4] = {cd4.x, cd4.y, cd4.z, cd4.w};
+        unsigned int code = LPE_NONE, seen = 0;   // the r-th valid child in digit order sits in slot r
+#pragma unroll
+        for (int dg = 0; dg < 4; ++dg)
+            if (cds[dg] != LPE_NONE) {
+                if (seen == r4) code = cds[dg];
+                ++seen;
+            }
         double4 X = make_double4(0.0, 0.0, 0.0, -1.0);
         if (code != LPE_NONE) {
             if (code & LPE_LEAF_FLAG) {
-                const Body b = w.body[code & ~LPE_LEAF_FLAG];
+                const Body b = a.body[code & ~LPE_LEAF_FLAG];
                 X = make_double4(b.x, b.y, b.m, -1.0);
             } else {
-                const int level = w.meta[code].level;
-                X = dd_xrec(w.agg[code], level, c.quirk);
-                if (level >= 0) {   // a cell: its own child block, as numbered on the destination
-                    const unsigned int qc = (R.cblock >> 2) - c.blockBase;
-                    const unsigned int exc = w.eidx[(size_t)d * w.cellCap + qc];
-                    const unsigned int blk = (exc == LPE_NONE) ? DD_POISON_BLOCK : w.importBase + (unsigned int)me * w.icap + exc;
-                    R.cblock = (blk << 2) | (R.cblock & 3u);
-                }
+                X = dd_xrec(a.agg[code], a.meta[code].level, c.quirk);
             }
         }
-        const size_t dst = 4u * ((size_t)w.importBase + (size_t)me * w.icap + ex) + r;
-        uint4* o = reinterpret_cast<uint4*>(peers.rec[d] + dst);
-        const uint4* src = reinterpret_cast<const uint4*>(&R);
-        __stcs(o, src[0]);
-        __stcs(o + 1, src[1]);
-        double2* ox = reinterpret_cast<double2*>(peers.xrec[d] + dst);
+        double2* ox = reinterpret_cast<double2*>(peers.xrec[d] + 4u * ((size_t)regionBase + e) + r4);
         __stcs(ox, make_double2(X.x, X.y));
         __stcs(ox + 1, make_double2(X.z, X.w));
     }
@@ -495,9 +549,12 @@ struct DDTop {
     signed char* delta;     // [DD_TOPROOTS]
 };
 #define DD_CELL_FLAG 0x40000000u
+constexpr int DD_TOP_SMEM_ROOTS = 640;   // up to this many roots the whole construction runs out of shared memory
+constexpr size_t DD_TOP_SMEM_BYTES = (size_t)DD_TOP_SMEM_ROOTS * (sizeof(DDRoot) + sizeof(Agg) + 16 + 4 * 4 + 4);
 __global__ void __launch_bounds__(1024)
 k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDRoot* __restrict__ roots, DDTop t,
          TravRec* __restrict__ rec, double4* __restrict__ xrec, unsigned int* __restrict__ selfslot, Scal* __restrict__ s) {
+    extern __shared__ __align__(16) unsigned char dsm[];
     __shared__ unsigned int base[LPE_MAX_P2P + 1];
     __shared__ unsigned long long key[DD_TOPROOTS];
     __shared__ unsigned int levelsMask, ncellsSh;
@@ -510,7 +567,18 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
     }
     __syncthreads();
     const int N = (int)base[R];
-    auto rootAt = [&](int i) -> const DDRoot& {
+    // work arrays: shared memory when the roots fit (the usual case: a few dozen roots per rank), else global scratch.
+    // Generic pointers, one code path.
+    const bool inShared = N <= DD_TOP_SMEM_ROOTS;
+    DDRoot* sroots = reinterpret_cast<DDRoot*>(dsm);
+    Agg* cagg = inShared ? reinterpret_cast<Agg*>(dsm + (size_t)DD_TOP_SMEM_ROOTS * sizeof(DDRoot)) : t.agg;
+    unsigned int* child = inShared ? reinterpret_cast<unsigned int*>(dsm + (size_t)DD_TOP_SMEM_ROOTS * (sizeof(DDRoot) + sizeof(Agg))) : t.child;
+    unsigned int* mask = inShared ? child + 4 * DD_TOP_SMEM_ROOTS : t.mask;
+    unsigned int* P = inShared ? mask + DD_TOP_SMEM_ROOTS : t.P;          // (P[N] lives in ncellsSh)
+    unsigned int* wstart = inShared ? P + DD_TOP_SMEM_ROOTS : t.wstart;
+    int* cellLevel = inShared ? reinterpret_cast<int*>(wstart + DD_TOP_SMEM_ROOTS) : t.cellLevel;
+    signed char* delta = inShared ? reinterpret_cast<signed char*>(cellLevel + DD_TOP_SMEM_ROOTS) : t.delta;
+    auto globalRoot = [&](int i) -> const DDRoot& {
         int r = 0;
         while (r + 1 < R && (unsigned int)i >= base[r + 1]) ++r;
         return roots[(size_t)r * DD_MAXROOTS + ((unsigned int)i - base[r])];
@@ -518,9 +586,18 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
     const double msi = mass_scale_inv(s->max_mass_bits);
     if (tid == 0) s->dd_nroots = (unsigned int)N;
     if (N == 0) return;
+    if (inShared) {   // the published roots, rank after rank = in key order
+        const int words = (int)(sizeof(DDRoot) / 16);
+        for (int k = tid; k < N * words; k += blockDim.x) {
+            const int i = k / words, w = k % words;
+            reinterpret_cast<uint4*>(sroots + i)[w] = reinterpret_cast<const uint4*>(&globalRoot(i))[w];
+        }
+        __syncthreads();
+    }
+    auto rootAt = [&](int i) -> const DDRoot& { return inShared ? sroots[i] : globalRoot(i); };
     auto writeChild = [&](unsigned int slot, const Agg& a, int level, unsigned int cblockIndex, const DDRoot* root) {
         rec[slot] = make_record(c, a, level, 1u, cblockIndex, msi);
-        xrec[slot] = dd_xrec(a, level, c.quirk);
+        xrec[slot] = dd_xrec(a, level, c.quirk);   // (node_centre is inlined in both: the divisions are shared)
         if (root && root->owner == (unsigned int)me && root->leafpos != LPE_NONE && c.need_self) selfslot[root->leafpos] = slot;
     };
     if (N == 1) {   // one root: it is the root of the tree
@@ -531,16 +608,16 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
         }
         return;
     }
-    for (int i = tid; i < N; i += blockDim.x) { key[i] = rootAt(i).key; t.mask[i] = 0u; }
+    for (int i = tid; i < N; i += blockDim.x) { key[i] = rootAt(i).key; mask[i] = 0u; }
     __syncthreads();
     for (int i = tid; i < N - 1; i += blockDim.x) {
         const int L = lca_level(key[i], key[i + 1], c.D);
         const int shift = 2 * (c.D - L);
         int a = i;
         while (a > 0 && (key[a - 1] >> shift) == (key[i] >> shift)) --a;
-        t.delta[i] = (signed char)L;
-        t.wstart[i] = (unsigned int)a;
-        atomicOr(&t.mask[a], 1u << L);
+        delta[i] = (signed char)L;
+        wstart[i] = (unsigned int)a;
+        atomicOr(&mask[a], 1u << L);
         atomicOr(&levelsMask, 1u << L);
     }
     __syncthreads();
@@ -548,79 +625,75 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
         unsigned int run = 0;
         for (int b0 = 0; b0 < N; b0 += 32) {
             const int i = b0 + tid;
-            const unsigned int v = (i < N) ? (unsigned int)__popc(t.mask[i]) : 0u;
+            const unsigned int v = (i < N) ? (unsigned int)__popc(mask[i]) : 0u;
             unsigned int inc = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const unsigned int u = __shfl_up_sync(0xFFFFFFFFu, inc, o);
                 if (tid >= o) inc += u;
             }
-            if (i < N) t.P[i] = run + inc - v;
+            if (i < N) P[i] = run + inc - v;
             run += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
-        if (tid == 0) { t.P[N] = run; ncellsSh = run; }
+        if (tid == 0) ncellsSh = run;
     }
     __syncthreads();
-    const int ncells = (int)ncellsSh;
-    for (int k = tid; k < 4 * ncells; k += blockDim.x) t.child[k] = LPE_NONE;
+    const int ncells = (int)ncellsSh;   // <= N - 1
+    for (int k = tid; k < 4 * ncells; k += blockDim.x) child[k] = LPE_NONE;
     __syncthreads();
     for (int i = tid; i < N; i += blockDim.x) {
-        const unsigned int mk = t.mask[i], Pi = t.P[i];
+        const unsigned int mk = mask[i], Pi = P[i];
         unsigned int rest = mk, j = 0;
         while (rest) {   // cells that start at root i, shallow to deep
             const int L = __ffs(rest) - 1;
             rest &= rest - 1;
             const unsigned int ord = Pi + j;
-            t.cellLevel[ord] = L;
+            cellLevel[ord] = L;
             const unsigned int digit = (unsigned int)(key[i] >> (2 * (c.D - L - 1))) & 3u;
-            t.child[(size_t)ord * 4 + digit] = rest ? (DD_CELL_FLAG | (ord + 1u)) : (unsigned int)i;
+            child[(size_t)ord * 4 + digit] = rest ? (DD_CELL_FLAG | (ord + 1u)) : (unsigned int)i;
             ++j;
         }
         if (i < N - 1) {   // as the witness of the cell at level delta[i]: the child that starts at root i + 1
-            const int L = (int)t.delta[i];
-            const unsigned int a0 = t.wstart[i];
-            const unsigned int q = t.P[a0] + (unsigned int)__popc(t.mask[a0] & ((1u << L) - 1u));
-            const unsigned int code = t.mask[i + 1] ? (DD_CELL_FLAG | t.P[i + 1]) : (unsigned int)(i + 1);
+            const int L = (int)delta[i];
+            const unsigned int a0 = wstart[i];
+            const unsigned int q = P[a0] + (unsigned int)__popc(mask[a0] & ((1u << L) - 1u));
+            const unsigned int code = mask[i + 1] ? (DD_CELL_FLAG | P[i + 1]) : (unsigned int)(i + 1);
             const unsigned int digit = (unsigned int)(key[i + 1] >> (2 * (c.D - L - 1))) & 3u;
-            t.child[(size_t)q * 4 + digit] = code;
+            child[(size_t)q * 4 + digit] = code;
         }
     }
     __syncthreads();
+    // aggregates, deepest level first (sums only: no division on this serial path)
+    auto childAgg = [&](unsigned int code, int& level, unsigned int& cb, const DDRoot*& root) -> Agg {
+        Agg a;
+        a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
+        a.frank = 0xFFFFFFFFu; a.fidx = 0; a.count = 0; a.small = 1u;
+        level = -3; cb = 0u; root = nullptr;
+        if (code != LPE_NONE) {
+            if (code & DD_CELL_FLAG) {
+                const unsigned int o2 = code & ~DD_CELL_FLAG;
+                a = cagg[o2]; level = cellLevel[o2]; cb = DD_TOPB + o2;
+            } else {
+                const DDRoot& r0 = rootAt((int)code);
+                a = r0.agg; level = r0.level; cb = r0.cblock; root = &r0;
+            }
+        }
+        return a;
+    };
     unsigned int levels = levelsMask;
-    while (levels) {   // deepest level first
+    while (levels) {
         const int L = 31 - __clz(levels);
         levels &= ~(1u << L);
         for (int ord = tid; ord < ncells; ord += blockDim.x) {
-            if (t.cellLevel[ord] != L) continue;
+            if (cellLevel[ord] != L) continue;
             Agg ch[4];
-            int lvl[4];
-            unsigned int cb[4];
-            const DDRoot* rt[4];
             unsigned int nvalid = 0;
 #pragma unroll
             for (int dg = 0; dg < 4; ++dg) {
-                const unsigned int code = t.child[(size_t)ord * 4 + dg];
-                Agg a;
-                a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
-                a.frank = 0xFFFFFFFFu; a.fidx = 0; a.count = 0; a.small = 1u;
-                lvl[dg] = -3; cb[dg] = 0u; rt[dg] = nullptr;
-                if (code != LPE_NONE) {
-                    ++nvalid;
-                    if (code & DD_CELL_FLAG) {
-                        const unsigned int o2 = code & ~DD_CELL_FLAG;
-                        a = t.agg[o2]; lvl[dg] = t.cellLevel[o2]; cb[dg] = DD_TOPB + o2;
-                    } else {
-                        const DDRoot& r0 = rootAt((int)code);
-                        a = r0.agg; lvl[dg] = r0.level; cb[dg] = r0.cblock; rt[dg] = &r0;
-                    }
-                }
-                ch[dg] = a;
+                int lv; unsigned int cb; const DDRoot* rt;
+                ch[dg] = childAgg(child[(size_t)ord * 4 + dg], lv, cb, rt);
+                nvalid += lv != -3 ? 1u : 0u;
             }
-            unsigned int slot = 4u * (DD_TOPB + (unsigned int)ord);
-#pragma unroll
-            for (int dg = 0; dg < 4; ++dg)
-                if (lvl[dg] != -3) writeChild(slot++, ch[dg], lvl[dg], cb[dg], rt[dg]);
-            for (; slot < 4u * (DD_TOPB + (unsigned int)ord) + 4u; ++slot) rec[slot] = invalid_record();
             // (c0 + c1) + (c2 + c3); first occupant = minimum insertion rank
             Agg r;
             r.m = (ch[0].m + ch[1].m) + (ch[2].m + ch[3].m);
@@ -633,12 +706,28 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
             r.mf = ch[best].mf; r.xf = ch[best].xf; r.yf = ch[best].yf; r.frank = ch[best].frank; r.fidx = ch[best].fidx;
             r.count = ch[0].count + ch[1].count + ch[2].count + ch[3].count;
             r.small = (ch[0].small & ch[1].small & ch[2].small & ch[3].small & 1u) | ((nvalid - 1u) << 1);
-            t.agg[ord] = r;
+            cagg[ord] = r;
         }
         __syncthreads();
     }
+    // the records: one thread per (cell, child digit); the valid children of a cell fill its block in digit order
+    for (int k = tid; k < 4 * ncells; k += blockDim.x) {
+        const int ord = k >> 2, dg = k & 3;
+        unsigned int before = 0, nvalid = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const bool v = child[(size_t)ord * 4 + j] != LPE_NONE;
+            nvalid += v ? 1u : 0u;
+            before += (v && j < dg) ? 1u : 0u;
+        }
+        int lv; unsigned int cb; const DDRoot* rt;
+        const Agg a = childAgg(child[(size_t)ord * 4 + dg], lv, cb, rt);
+        const unsigned int blockSlot = 4u * (DD_TOPB + (unsigned int)ord);
+        if (lv != -3) writeChild(blockSlot + before, a, lv, cb, rt);
+        else rec[blockSlot + nvalid + ((unsigned int)dg - before)] = invalid_record();   // the unused slots behind them
+    }
     if (tid == 0) {   // the root: the shallowest cell that starts at root 0
-        writeChild(0u, t.agg[0], t.cellLevel[0], DD_TOPB, nullptr);
+        writeChild(0u, cagg[0], cellLevel[0], DD_TOPB, nullptr);
         rec[1] = rec[2] = rec[3] = invalid_record();
     }
 }

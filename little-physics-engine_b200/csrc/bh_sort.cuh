@@ -106,8 +106,10 @@ __device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v,
 
 // hist[p * 512 + d] += number of keys whose digit in pass p is d, for every pass at once (keys read once).
 __global__ void __launch_bounds__(256)
-k_sort_hist(const unsigned long long* __restrict__ keys, int n, int passes, int lastBins, unsigned int* __restrict__ hist) {
+k_sort_hist(const unsigned long long* __restrict__ keys, int n, int passes, int lastBins, unsigned int* __restrict__ hist,
+            const unsigned int* __restrict__ n_dev) {
     extern __shared__ unsigned int sh_hist[];   // passes * 512
+    if (n_dev) n = (int)*n_dev;   // element count known only on the device (domain-decomposed ranks)
     const int words = passes * SORT_HIST_STRIDE;
     for (int k = threadIdx.x; k < words; k += blockDim.x) sh_hist[k] = 0;
     __syncthreads();
@@ -147,7 +149,9 @@ __global__ void __launch_bounds__(SORT_THREADS)
 k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
                 unsigned long long* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
                 const unsigned int* __restrict__ digitBase, unsigned long long* __restrict__ status,
-                unsigned int epoch, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault) {
+                unsigned int epoch, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault,
+                const unsigned int* __restrict__ n_dev) {
+    if (n_dev) n = (int)*n_dev;   // tiles past the device-side element count take a ticket and leave
     // The tile is first sorted by digit INSIDE shared memory, then written out: consecutive threads then store
     // consecutive addresses within each digit's run, so every 32-byte sector written is fully used (a direct
     // scatter from registers wrote 8-byte keys and 4-byte payloads to 32 different sectors per instruction).
@@ -166,6 +170,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
     for (int k = tid; k < SORT_WARPS * BINS; k += SORT_THREADS) (&cnt[0][0])[k] = 0;
     __syncthreads();
     const unsigned int tile = s_tile;
+    if ((long long)tile * SORT_TILE >= n) return;
 
     const long long tbase = (long long)tile * SORT_TILE;
     const long long wbase = tbase + (long long)w * (SORT_ITEMS * 32);

@@ -123,10 +123,10 @@ struct lpe_bh_ctx {
     double dd_U = 0.0;
     DDDomain* dd_dom = nullptr;
     std::vector<char> dd_dom_host;
-    unsigned int* dd_eidx = nullptr;
-    uint4* dd_list = nullptr;
-    unsigned int dd_list_cap = 0;
+    DDRoot* dd_myroots = nullptr;             // roots of this rank's inner quadrants (k_dd_roots -> k_dd_export)
+    unsigned int* dd_queue = nullptr;         // [dest][icap] breadth-first queues of the exporter
     unsigned long long* dd_oob = nullptr;     // ordered-encoded box of the out-of-tree targets seen by phase A
+    unsigned int* dd_pushed = nullptr;        // round flags of the exporter (behind dd_oob)
     double* dd_payload = nullptr;             // 2 x 6 doubles: this step's mail of the two barrier points
     double4* dd_xrec = nullptr;
     unsigned int* dd_chunk_cost = nullptr;
@@ -560,7 +560,7 @@ int step_prologue(lpe_bh_ctx* c, int n) {
 }
 
 // keys[0] / vals[0] -> sorted keys / payload in keys[sorted_sel] / vals[sorted_sel]
-int step_sort(lpe_bh_ctx* c, const StepConst& k, int n) {
+int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_dev = nullptr) {
     cudaStream_t st = c->stream;
     const SortPlan plan = sort_plan(k);
     const int passes = plan.passes, topBits = plan.topBits;
@@ -579,7 +579,7 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n) {
     unsigned int* fault = tileCounter + SORT_MAX_PASSES;
     const int lastBins = 1 << topBits;
     const int histBlocks = std::min(sortTiles, 148 * 8);
-    k_sort_hist<<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(c->keys[0], n, passes, lastBins, hist);
+    k_sort_hist<<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(c->keys[0], n, passes, lastBins, hist, n_dev);
     k_sort_bases<<<passes, 512, 0, st>>>(hist);
     for (int ps = 0; ps < passes; ++ps) {
         const int shift = 8 * ps;
@@ -587,10 +587,10 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n) {
         const unsigned int* base = hist + 512 * ps;
         if (ps == passes - 1 && lastBins == 512)
             k_sort_onesweep<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault);
+                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault, n_dev);
         else
             k_sort_onesweep<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault);
+                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault, n_dev);
         sel ^= 1;
     }
     c->sorted_sel = sel;
@@ -600,7 +600,7 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n) {
 }
 
 // gather into key order (side stream) | terminals -> witnesses -> ordinals -> topology -> aggregation, deepest level first
-int step_build(lpe_bh_ctx* c, const StepConst& k, int n) {
+int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_dev = nullptr) {
     cudaStream_t st = c->stream;
     const int g256 = cdiv(n, 256);
     const unsigned long long* skeys = c->keys[c->sorted_sel];
@@ -617,7 +617,7 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n) {
     }
     // (host tick: the velocities are still on their way and are packed straight into key order before the kick)
     k_gather<<<g256, 256, 0, sg>>>(n, k.need_self, sidx, c->body, c->pend_vel ? nullptr : c->vel,
-                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfslot);
+                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfslot, n_dev);
     CU_TRY(c, cudaEventRecord(c->evs[1], sg));
     // from here on the state IS in key order
     std::swap(c->body, c->body2);

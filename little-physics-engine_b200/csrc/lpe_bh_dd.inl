@@ -49,7 +49,7 @@ void dd_release(lpe_bh_ctx* c) {
     c->dd_R = 1; c->dd_rank = 0;
     c->body = c->body2 = nullptr; c->vel = c->vel2 = nullptr; c->orig = c->orig2 = nullptr;
     c->rec = nullptr; c->dd_xrec = nullptr;
-    c->dd_dom = nullptr; c->dd_eidx = nullptr; c->dd_list = nullptr; c->dd_oob = nullptr; c->dd_payload = nullptr;
+    c->dd_dom = nullptr; c->dd_myroots = nullptr; c->dd_queue = nullptr; c->dd_oob = nullptr; c->dd_payload = nullptr;
     c->dd_chunk_cost = nullptr; c->dd_top = DDTop{};
     c->dd_dom_depth = -1;
     c->n = 0;
@@ -181,6 +181,24 @@ int dd_build_domain(lpe_bh_ctx* c, const StepConst& k) {
         }
         H->nq[r] = nq;
         H->box[r][0] = bx0; H->box[r][1] = by0; H->box[r][2] = bx1; H->box[r][3] = by1;
+        // tree of boxes over the quadrants (scaled units, floats rounded outward)
+        auto down = [](double v) { float f = (float)v; return ((double)f > v) ? std::nextafterf(f, -INFINITY) : f; };
+        auto up = [](double v) { float f = (float)v; return ((double)f < v) ? std::nextafterf(f, INFINITY) : f; };
+        float4* B = H->bvh[r];
+        for (int j = 0; j < DD_BVH_LEAVES; ++j) {
+            if (j < nq) {
+                const DDQuad& q = H->q[r][j];
+                B[DD_BVH_LEAVES + j] = make_float4(down(q.x0 * k.invS), down(q.y0 * k.invS), up(q.x1 * k.invS), up(q.y1 * k.invS));
+            } else {
+                B[DD_BVH_LEAVES + j] = make_float4(1.f, 1.f, 0.f, 0.f);   // empty
+            }
+        }
+        for (int n = DD_BVH_LEAVES - 1; n >= 1; --n) {
+            const float4 l = B[2 * n], rr = B[2 * n + 1];
+            const bool le = l.x > l.z, re = rr.x > rr.z;
+            B[n] = le ? rr : re ? l : make_float4(std::min(l.x, rr.x), std::min(l.y, rr.y), std::max(l.z, rr.z), std::max(l.w, rr.w));
+        }
+        B[0] = make_float4(1.f, 1.f, 0.f, 0.f);
     }
     // (pageable source: the copy is staged before the call returns, so the host table may be rebuilt right away)
     CU_TRY(c, cudaMemcpyAsync(c->dd_dom, H, sizeof(DDDomain), cudaMemcpyHostToDevice, c->stream));
@@ -200,8 +218,8 @@ __global__ void k_dd_payload(int point, const unsigned long long* __restrict__ o
         p[3] = any ? ordered_value(oob[3]) : 0.0;
         p[4] = p[5] = 0.0;
     } else {
-        p[0] = (double)s->n_live; p[1] = (double)s->n_in; p[2] = (double)s->exp_list_count;
-        p[3] = p[4] = p[5] = 0.0;
+        p[0] = (double)s->n_live; p[1] = (double)s->n_in;
+        p[2] = p[3] = p[4] = p[5] = 0.0;
     }
 }
 
@@ -234,10 +252,10 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
         if (timing) cudaEventRecord(c->dd_ev[0], st);
         if (step_prologue(c, S)) return 1;
         CU_TRY(c, cudaMemsetAsync(c->dd_oob, 0xFF, 16, st));
-        CU_TRY(c, cudaMemsetAsync(c->dd_oob + 2, 0, 16, st));
+        CU_TRY(c, cudaMemsetAsync(c->dd_oob + 2, 0, 16 + sizeof(unsigned int) * LPE_MAX_P2P * DD_EXPORT_ROUNDS, st));   // + the exporter's round flags
         const DDPeers peers = dd_peers(c, c->dd_cur);
         k_dd_keygen<<<cdiv(S, 256), 256, 0, st>>>(k, sp, c->body, c->vel, c->orig, c->keys[0], c->vals[0], c->scal, hdr,
-                                                  peers, c->dd_oob, S);
+                                                  peers, c->dd_oob);
         k_dd_payload<<<1, 32, 0, st>>>(0, c->dd_oob, c->scal, c->dd_payload);
         if (timing) cudaEventRecord(c->dd_ev[1], st);
         k_dd_signal<<<1, 32, 0, st>>>(0, c->dd_epoch, c->dd_rank, c->dd_R, peers, c->dd_payload);
@@ -246,19 +264,31 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
         k_dd_wait<<<1, 32, 0, st>>>(0, c->dd_epoch, c->dd_R, hdr);
         if (timing) cudaEventRecord(c->dd_ev[2], st);
         k_dd_keygen_inbox<<<64, 256, 0, st>>>(k, sp, c->body, c->keys[0], c->vals[0], c->scal, hdr);
-        if (step_sort(c, k, S)) return 1;
+        if (step_sort(c, k, S, &c->scal->n_sort)) return 1;
         if (timing) cudaEventRecord(c->dd_ev[3], st);
-        if (step_build(c, k, S)) return 1;
+        if (step_build(c, k, S, &c->scal->n_sort)) return 1;
         c->dd_cur ^= 1;
         if (timing) cudaEventRecord(c->dd_ev[4], st);
         const DDLayout L = dd_layout(c->cap, c->dd_R, c->dd_icap);
         const DDPeers peers = dd_peers(c, c->dd_cur);
-        DDExport ex{c->levelList, c->meta, c->agg, c->tkey, c->dd_eidx, c->dd_list, (unsigned int)c->cap, c->dd_icap, c->dd_list_cap};
-        k_dd_export_flags<<<cdiv(S, 256), 256, 0, st>>>(k, sp, c->dd_dom, ex, c->scal, hdr);
-        DDPublish pb{c->tkey, c->tfirst, c->tnode, c->mask, c->P, c->agg, c->body, c->dd_eidx, (unsigned int)c->cap, c->dd_icap, L.importBase};
-        k_dd_publish<<<1, 256, 0, st>>>(k, sp, c->dd_dom, pb, peers, c->scal, hdr);
-        DDWrite wr{c->dd_list, c->dd_eidx, c->child, c->rec, c->meta, c->agg, c->body, (unsigned int)c->cap, c->dd_icap, L.importBase, c->dd_list_cap};
-        k_dd_export_write<<<c->sms * 4, 256, 0, st>>>(k, c->dd_rank, wr, peers, c->scal);
+        DDRootsIn ri{c->tkey, c->tfirst, c->tnode, c->mask, c->P, c->agg, c->body};
+        k_dd_roots<<<1, 256, 0, st>>>(k, sp, c->dd_dom, ri, c->dd_myroots, c->scal, hdr);
+        DDExportArgs ea{c->dd_myroots, c->child, c->rec, c->meta, c->agg, c->body, c->dd_queue, c->dd_pushed, c->dd_icap, L.importBase};
+        {   // one cluster of DD_EXPORT_CLUSTER blocks per destination
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(DD_EXPORT_CLUSTER, c->dd_R);
+            cfg.blockDim = dim3(DD_EXPORT_THREADS);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = DD_EXPORT_CLUSTER; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            const DDDomain* domc = c->dd_dom;
+            CU_TRY(c, cudaLaunchKernelEx(&cfg, k_dd_export, k, sp, domc, ea, peers, c->scal, hdr));
+        }
+        if (c->dd_R > 1) k_dd_export_x<<<dim3(16, c->dd_R), 256, 0, st>>>(k, c->dd_rank, ea, peers, c->scal);
         k_dd_payload<<<1, 32, 0, st>>>(1, c->dd_oob, c->scal, c->dd_payload);
         if (timing) cudaEventRecord(c->dd_ev[5], st);
         k_dd_signal<<<1, 32, 0, st>>>(1, c->dd_epoch, c->dd_rank, c->dd_R, peers, c->dd_payload + 6);
@@ -267,7 +297,7 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
         k_dd_wait<<<1, 32, 0, st>>>(1, c->dd_epoch, c->dd_R, hdr);
         if (timing) cudaEventRecord(c->dd_ev[6], st);
         const DDLayout L = dd_layout(c->cap, c->dd_R, c->dd_icap);
-        k_dd_top<<<1, 1024, 0, st>>>(k, c->dd_rank, c->dd_R, hdr, reinterpret_cast<const DDRoot*>(c->dd_win + L.roots), c->dd_top,
+        k_dd_top<<<1, 1024, DD_TOP_SMEM_BYTES, st>>>(k, c->dd_rank, c->dd_R, hdr, reinterpret_cast<const DDRoot*>(c->dd_win + L.roots), c->dd_top,
                                      c->rec, c->dd_xrec, c->selfslot, c->scal);
         if (timing) cudaEventRecord(c->dd_ev[7], st);
         if (step_traverse(c, k, p, S, false)) return 1;
@@ -338,10 +368,12 @@ int lpe_bh_dd_init(lpe_bh_ctx* c, int rank, int nranks, uint64_t capacity, uint3
     c->orig2 = reinterpret_cast<unsigned int*>(c->dd_win + L.orig[1]);
     c->rec = reinterpret_cast<TravRec*>(c->dd_win + L.rec);
     c->dd_xrec = reinterpret_cast<double4*>(c->dd_win + L.xrec);
-    c->dd_list_cap = (unsigned int)std::max(1, nranks - 1) * c->dd_icap;
     int rc = 0;
-    rc |= dalloc(c, c->dd_dom, 1) | dalloc(c, c->dd_eidx, (size_t)nranks * S) | dalloc(c, c->dd_list, c->dd_list_cap) |
-          dalloc(c, c->dd_oob, 4) | dalloc(c, c->dd_payload, 12) | dalloc(c, c->dd_chunk_cost, S / 32 + 64);
+    rc |= dalloc(c, c->dd_dom, 1) | dalloc(c, c->dd_myroots, DD_MAXROOTS) | dalloc(c, c->dd_queue, (size_t)nranks * c->dd_icap) |
+          dalloc(c, c->dd_oob, 4 + LPE_MAX_P2P * DD_EXPORT_ROUNDS / 2 + 2) | dalloc(c, c->dd_payload, 12) | dalloc(c, c->dd_chunk_cost, S / 32 + 64);
+    // (set on every init: the attribute is kept per device)
+    if (cudaFuncSetAttribute(k_dd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_TOP_SMEM_BYTES) != cudaSuccess) rc = 1;
+    c->dd_pushed = reinterpret_cast<unsigned int*>(c->dd_oob + 4);
     rc |= dalloc(c, c->dd_top.mask, DD_TOPROOTS) | dalloc(c, c->dd_top.P, DD_TOPROOTS + 1) |
           dalloc(c, c->dd_top.wstart, DD_TOPROOTS) | dalloc(c, c->dd_top.child, 4 * DD_TOPROOTS) |
           dalloc(c, c->dd_top.cellLevel, DD_TOPROOTS) | dalloc(c, c->dd_top.agg, DD_TOPROOTS) |
@@ -592,6 +624,7 @@ int lpe_bh_dd_get_stats(lpe_bh_ctx* c, lpe_bh_dd_stats* o) {
         o->interactions = s.interactions; o->work_cost = s.work_cost; o->overflow_chunks = s.ovf_count;
         for (int r = 0; r < c->dd_R; ++r) o->exported_blocks[r] = s.exp_count[r];
         o->depth = c->last_c.D;
+        o->export_rounds = (int32_t)s.dd_rounds;
         if (c->instr & 1) {
             cudaEventElapsedTime(&o->ms_keygen, c->dd_ev[0], c->dd_ev[1]);
             cudaEventElapsedTime(&o->ms_wait_a, c->dd_ev[1], c->dd_ev[2]);

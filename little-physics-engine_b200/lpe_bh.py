@@ -81,7 +81,7 @@ class DDStats(C.Structure):
         ("n_cells", C.c_uint64), ("n_roots", C.c_uint64), ("exported_blocks", C.c_uint64 * 8),
         ("interactions", C.c_uint64), ("work_cost", C.c_uint64), ("overflow_chunks", C.c_uint64),
         ("import_blocks", C.c_uint32), ("fault", C.c_uint32), ("rank", C.c_int32), ("nranks", C.c_int32),
-        ("depth", C.c_int32), ("pad_", C.c_int32),
+        ("depth", C.c_int32), ("export_rounds", C.c_int32),
         ("ms_keygen", C.c_float), ("ms_wait_a", C.c_float), ("ms_sort", C.c_float), ("ms_build", C.c_float),
         ("ms_export", C.c_float), ("ms_wait_b", C.c_float), ("ms_top", C.c_float), ("ms_traverse", C.c_float),
         ("ms_total", C.c_float), ("pad2_", C.c_float),

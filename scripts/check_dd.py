@@ -28,7 +28,7 @@ def bodies(n):
 
 
 def params(U, precision):
-    return lpe_bh.make_params(U, U / 2 ** 14, theta=0.5, dt_kick=1 / 120, dt_drift=0.05, precision=precision)
+    return lpe_bh.make_params(U, U / 2 ** 14, theta=0.5, dt_kick=1e5, dt_drift=0.05, precision=precision)   # (a long kick: dv stays resolvable next to |v| ~ 2e3)
 
 
 def reference(device, p, b, steps, counts):
