@@ -138,7 +138,6 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
     const unsigned int lt = (1u << lane) - 1u;
     const unsigned int lanebit = 1u << lane;
     const unsigned int n_nodes = c.dd ? a.s->dd_nroots : a.s->n_term + a.s->n_internal;
-    const long long n_bodies = c.dd ? (long long)a.s->n_live : (long long)c.n;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = c.eps2f;
     const double Us = c.U * c.invS;
@@ -155,8 +154,10 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
         const unsigned int lblock = q / CHUNKS_PER_BLOCK, within = q % CHUNKS_PER_BLOCK;
         const unsigned int gblock = lblock * (unsigned int)c.shard_n + (unsigned int)c.shard_rank;
         const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
+        // (a domain-decomposed rank knows its body count only on the device; the tail slots hold no bodies)
+        const long long n_bodies = c.dd ? (long long)a.s->n_live : (long long)c.n;
         const bool valid = i < n_bodies;
-        if (c.dd && (long long)q * 32 >= n_bodies) continue;   // tail slots of a domain-decomposed rank hold no bodies
+        if (c.dd && (long long)q * 32 >= n_bodies) continue;
 
         unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
         LP.nphx = pack2(nphx, nphx); LP.nphy = pack2(nphy, nphy);
         LP.nplx = pack2(nplx, nplx); LP.nply = pack2(nply, nply);
         LP.eps2 = pack2(eps2f, eps2f);
-        unsigned int nacc = 0, nwarp = 0, cost = 0;
+        unsigned int nacc = 0, nwarp = 0, cost = 0;   // cost: nodes the warp classified (load-balance weight)
         unsigned int kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // STATS: A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes
         double AX = 0.0, AY = 0.0;
         bool overflow = c.test_overflow != 0;
@@ -333,7 +334,6 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                 if (!STATS) redo = mixed(std::false_type{});
                 if (STATS || __any_sync(0xFFFFFFFFu, redo)) mixed(std::true_type{});
                 if (STATS) nwarp += cntM;
-                cost += cntM;
                 __syncwarp();
 
                 // ---------------- children of opened nodes join the queue with the mask of the lanes that opened ----------------
@@ -370,7 +370,6 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                     for (unsigned int m = 0; m < nA; m += 2)
                         t2_accept_pair<STATS, SELF>(W, m, lanebit, self, LP, AX2, AY2, nacc);
                     if (STATS) nwarp += nA;
-                    cost += nA;
                     nA = 0;
                 }
                 // fp32 partial sums go to fp64 every round
@@ -378,6 +377,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                 AY += (double)(lo2(AY2) + hi2(AY2));
                 __syncwarp();
             }
+            cost = tail;   // every node that entered the ring was classified once
         }
 
         if (overflow) {
