@@ -274,6 +274,27 @@ def measure_e2e(torch, bh, bodies, params, steps):
                     "x/y/vx/vy downloaded; host wall clock incl. sync)"}
 
 
+def e2e_registry(n, ticks):
+    """Wall clock of Systems::BarnesHutSystem::update(entt::registry&) itself — the drop-in class on a real EnTT
+    registry (host/dropin_bench.cpp, compiled against the reference's headers where they exist; the binary travels)."""
+    exe = os.path.join(ROOT, "little-physics-engine_b200", "host", "_build", "dropin_bench")
+    if not os.path.exists(exe):
+        return {"value": None, "note": "host/_build/dropin_bench not built (needs the reference headers at build time)"}
+    out = {}
+    for mode in ("pagewise", "per_entity"):
+        r = subprocess.run([exe, str(n), str(ticks), mode], capture_output=True, text=True, timeout=900)
+        if r.returncode != 0 or not r.stdout.strip():
+            return {"value": None, "note": f"dropin_bench failed: {r.stderr[-300:]}"}
+        out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    pw = out["pagewise"]
+    return {"value": pw["body_steps_per_s"], "unit": "body-steps/s", "ms_per_step": pw["ms_per_update"],
+            "h2d_bytes_per_step": pw["h2d_bytes_per_tick"], "d2h_bytes_per_step": pw["d2h_bytes_per_tick"],
+            "staging_path_taken": pw["staging_path_taken"],
+            "ms_per_step_entity_by_entity_staging": out["per_entity"]["ms_per_update"],
+            "path": "entt::registry -> Systems::BarnesHutSystem::update (pool pages copied into page-locked {x,y} buffers by "
+                    "4 worker threads -> lpe_bh_update_host_aos -> velocities copied back into the pool pages); host wall clock"}
+
+
 def rooflines(meas, fma_peak, peaks, peak_kind, workload_key, world=1):
     n, trav_ms = meas["n"], meas["phases"]["traverse"]
     flops = FLOPS_PER_INTERACTION * meas["interactions"] / max(world, 1)
@@ -396,6 +417,8 @@ def our_arm(args, wl, key, rank, world, local_rank):
         }
         if key == "c5":
             line.update(c5_lines(torch, lpe_bh, bh, stream, wl, bodies, flush))
+        if key == "c2" and not args.bodies:
+            line["e2e_registry"] = e2e_registry(n, 10)
         if args.workload is None and not args.bodies:
             # the 1 M-body configuration of BASELINE.json in the same run
             w2 = dict(WORKLOADS["c2"])
@@ -405,7 +428,7 @@ def our_arm(args, wl, key, rank, world, local_rank):
             c2 = {"config": config_for(w2, 1, args.precision, args.mgpu), "value": m2["value"], "unit": "body-steps/s",
                   "ms_per_step": m2["ms_per_step"], "phases_ms": m2["phases"], "interactions_per_body": m2["interactions"] / w2["n"],
                   **rooflines(m2, fma_peak, peaks, peak_kind, "c2"), "e2e": measure_e2e(torch, bh, b2, p2, args.steps),
-                  "gpu_launches": m2["launches"]}
+                  "e2e_registry": e2e_registry(w2["n"], 10), "gpu_launches": m2["launches"]}
             if not args.no_cpu_baseline:
                 c2["cpu_baseline"] = cpu_baseline_n1(w2)
             line["c2"] = c2

@@ -142,6 +142,22 @@ int  lpe_bh_synchronize(lpe_bh_ctx* ctx);
 int  lpe_bh_update_host(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n, double* x, double* y, double* vx,
                         double* vy, const double* m, const uint32_t* rank, const uint8_t* comp);
 
+/* The same tick for callers that keep {x, y} records (EnTT's Position / Velocity pools: reference
+ * include/math/vector_math.hpp:46-49,120-123): pos and vel are 2n doubles each, updated in place. */
+int  lpe_bh_update_host_aos(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n, double* pos, double* vel,
+                            const double* m, const uint32_t* rank, const uint8_t* comp);
+
+/* The same tick in three calls for a caller that first has to gather its components (the ECS drop-in): each call
+ * queues the device work its array unlocks and returns, so the next array is gathered while the GPU runs.
+ *   lpe_bh_tick_begin   positions ({x,y} records) [+ component masks]  -> keys, sort          (asynchronous)
+ *   lpe_bh_tick_mass    masses [+ insertion ranks]                       -> gather, tree build  (asynchronous)
+ *   lpe_bh_tick_finish  velocities ({vx,vy} records, updated in place)   -> traversal + kick [+ drift: pos updated in
+ *                       place when do_drift]; synchronises
+ * Host arrays should be page-locked (lpe_bh_alloc_pinned) and must stay untouched until lpe_bh_tick_finish returns. */
+int  lpe_bh_tick_begin(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n, const double* pos, const uint8_t* comp);
+int  lpe_bh_tick_mass(lpe_bh_ctx* ctx, const double* m, const uint32_t* rank);
+int  lpe_bh_tick_finish(lpe_bh_ctx* ctx, double* pos, double* vel);
+
 int  lpe_bh_get_stats(lpe_bh_ctx* ctx, lpe_bh_stats* out);          /* synchronises */
 int  lpe_bh_dump_tree(lpe_bh_ctx* ctx, lpe_bh_tree_dump* out);      /* tree of the last step; synchronises */
 /* per-body accepted / visited counts of the last step in creation order (instrumentation bit1 must be on) */

@@ -74,7 +74,10 @@ struct lpe_bh_ctx {
     // the gather into key order runs beside the terminal / witness / scan kernels (they only need the sorted keys)
     cudaStream_t side_stream = nullptr;
     cudaEvent_t evs[2] = {nullptr, nullptr};
-    bool pend_mass = false, pend_vel = false, pend_rank = false;
+    bool pend_mass = false, pend_vel = false, pend_rank = false, pend_vel_aos = false;
+    int tick_stage = 0;           // lpe_bh_tick_begin / _mass / _finish: which call comes next
+    StepConst tick_k{};
+    lpe_bh_params tick_p{};
     // sort
     unsigned long long* keys[2] = {nullptr, nullptr};
     unsigned int* vals[2] = {nullptr, nullptr};
@@ -337,6 +340,26 @@ __global__ void __launch_bounds__(256) k_drift(int n, double dtD, Body* __restri
     p.x += v.x * dtD;                                             // movement.cpp:32-33
     p.y += v.y * dtD;
     *reinterpret_cast<double2*>(&body[i].x) = p;
+}
+// array-of-structs forms for the ECS drop-in: EnTT keeps Position / Velocity as {double x, y} records, so its pool pages
+// can be copied as they are (lpe_bh_update_host_aos)
+__global__ void k_pack_pos_aos(int n, const double2* __restrict__ pos, const unsigned char* __restrict__ comp, Body* __restrict__ body) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    *reinterpret_cast<double2*>(&body[i].x) = pos[i];
+    body[i].comp = comp ? (unsigned int)comp[i] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+}
+__global__ void k_pack_vel_aos(int n, const double2* __restrict__ v, double2* __restrict__ out, const unsigned int* __restrict__ orig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v[orig ? orig[i] : (unsigned int)i];
+}
+__global__ void k_unpack_vel_aos(int n, const double2* __restrict__ in, double2* __restrict__ out, const unsigned int* __restrict__ orig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[orig ? orig[i] : (unsigned int)i] = in[i];
+}
+__global__ void k_get_pos_aos(int n, const Body* __restrict__ body, double2* __restrict__ out, const unsigned int* __restrict__ orig) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[orig ? orig[i] : (unsigned int)i] = *reinterpret_cast<const double2*>(&body[i].x);
 }
 __global__ void k_set_pos(int n, const double* __restrict__ x, const double* __restrict__ y, Body* __restrict__ body,
                           const unsigned int* __restrict__ orig) {
@@ -745,8 +768,13 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (timing) cudaEventRecord(c->ev[3], st);
     if (c->pend_vel) {   // host path: velocities were uploaded behind the build; the kick is their first reader
         CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
-        k_pack2<<<cdiv(n, 256), 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel, c->orig_valid ? c->orig : nullptr);
+        if (c->pend_vel_aos)
+            k_pack_vel_aos<<<cdiv(n, 256), 256, 0, st>>>(n, reinterpret_cast<const double2*>(c->tmp + 3 * c->cap), c->vel,
+                                                         c->orig_valid ? c->orig : nullptr);
+        else
+            k_pack2<<<cdiv(n, 256), 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel, c->orig_valid ? c->orig : nullptr);
         c->pend_vel = false;
+        c->pend_vel_aos = false;
     }
     if (step_traverse(c, k, p, n, sharded_begin)) return 1;
     if (timing) cudaEventRecord(c->ev[4], st);
@@ -991,6 +1019,149 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
     }
     // BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
     return lpe_bh_download(c, p->do_drift ? x : nullptr, p->do_drift ? y : nullptr, vx, vy);
+}
+
+// The same tick for callers whose components are {x, y} records (EnTT pools): pos / vel are 2n doubles each.
+int lpe_bh_update_host_aos(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double* pos, double* vel, const double* m,
+                           const uint32_t* rank, const uint8_t* comp) {
+    if (!c || !p) return 1;
+    if (c->dd) return fail(c, "context is in domain-decomposed mode");
+    if (c->shard_n > 1) return fail(c, "sharded context: use lpe_bh_step_begin / lpe_bh_step_finish");
+    if (n == 0) return 0;
+    if (n > LPE_MAX_BODIES) return fail(c, "too many bodies for one context (limit 2^28)");
+    if (!pos || !vel || !m) return fail(c, "pos, vel and m are required");
+    DevGuard _dg(c->device);
+    if (ensure_capacity(c, n)) return 1;
+    c->n = n;
+    c->have_step = false;
+    c->orig_valid = false;
+    cudaStream_t st = c->stream, cs = c->copy_stream;
+    double* t = c->tmp;
+    const size_t cap = c->cap;
+    const int g = cdiv((long long)n, 256);
+    CU_TRY(c, cudaEventRecord(c->evc[0], st));           // the staging buffers are free once earlier work is done
+    CU_TRY(c, cudaStreamWaitEvent(cs, c->evc[0], 0));
+    CU_TRY(c, cudaMemcpyAsync(t, pos, 16 * n, cudaMemcpyHostToDevice, cs));
+    if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp_in, comp, n, cudaMemcpyHostToDevice, cs));
+    CU_TRY(c, cudaEventRecord(c->evc[1], cs));
+    CU_TRY(c, cudaMemcpyAsync(t + 2 * cap, m, 8 * n, cudaMemcpyHostToDevice, cs));
+    if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank_in, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, cs));
+    CU_TRY(c, cudaEventRecord(c->evc[2], cs));
+    CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vel, 16 * n, cudaMemcpyHostToDevice, cs));
+    CU_TRY(c, cudaEventRecord(c->evc[3], cs));
+    CU_TRY(c, cudaStreamWaitEvent(st, c->evc[1], 0));
+    CU_TRY(c, cudaMemsetAsync(c->scal, 0, 8, st));   // the mass scale is rebuilt by k_pack_mass (side stream, after the sort)
+    k_pack_pos_aos<<<g, 256, 0, st>>>((int)n, reinterpret_cast<const double2*>(t), comp ? c->comp_in : nullptr, c->body);
+    c->pend_mass = true;
+    c->pend_rank = rank != nullptr;
+    c->pend_vel = true;
+    c->pend_vel_aos = true;
+    const int rc = run_step(c, *p, false);
+    if (rc || c->pend_mass || c->pend_vel) {   // a failed step must not leave waits dangling for the next one
+        c->pend_mass = c->pend_vel = c->pend_vel_aos = false;
+        cudaStreamSynchronize(cs);
+        if (rc) return 1;
+    }
+    // BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
+    const unsigned int* orig = c->orig_valid ? c->orig : nullptr;
+    if (p->do_drift) {
+        k_get_pos_aos<<<g, 256, 0, st>>>((int)n, c->body, reinterpret_cast<double2*>(t), orig);
+        CU_TRY(c, cudaMemcpyAsync(pos, t, 16 * n, cudaMemcpyDeviceToHost, st));
+    }
+    k_unpack_vel_aos<<<g, 256, 0, st>>>((int)n, c->vel, reinterpret_cast<double2*>(t + 3 * cap), orig);
+    CU_TRY(c, cudaMemcpyAsync(vel, t + 3 * cap, 16 * n, cudaMemcpyDeviceToHost, st));
+    if (fetch_fault(c)) return 1;
+    CU_TRY(c, cudaStreamSynchronize(st));
+    CU_TRY(c, cudaGetLastError());
+    return check_fault(c);
+}
+
+// ---- the same tick in three calls, so that a caller that has to GATHER its components first (the ECS drop-in) can
+// overlap that with the device: positions -> keys + sort are queued; masses -> the build; velocities -> kick, result.
+int lpe_bh_tick_begin(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, const double* pos, const uint8_t* comp) {
+    if (!c || !p) return 1;
+    if (c->dd) return fail(c, "context is in domain-decomposed mode");
+    if (c->shard_n > 1) return fail(c, "sharded context: use lpe_bh_step_begin / lpe_bh_step_finish");
+    if (n == 0 || n > LPE_MAX_BODIES) return fail(c, "tick: 1 .. 2^28 bodies");
+    if (!pos) return fail(c, "pos is required");
+    DevGuard _dg(c->device);
+    if (ensure_capacity(c, n)) return 1;
+    c->n = n;
+    c->have_step = false;
+    c->orig_valid = false;
+    c->tick_stage = 0;
+    if (make_const(c, *p, c->tick_k)) return 1;
+    c->tick_p = *p;
+    cudaStream_t st = c->stream;
+    const int g = cdiv((long long)n, 256);
+    if (c->instr & 1) cudaEventRecord(c->ev[0], st);
+    CU_TRY(c, cudaMemcpyAsync(c->tmp, pos, 16 * n, cudaMemcpyHostToDevice, st));
+    if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp_in, comp, n, cudaMemcpyHostToDevice, st));
+    CU_TRY(c, cudaMemsetAsync(c->scal, 0, 8, st));   // the mass scale is rebuilt by lpe_bh_tick_mass
+    k_pack_pos_aos<<<g, 256, 0, st>>>((int)n, reinterpret_cast<const double2*>(c->tmp), comp ? c->comp_in : nullptr, c->body);
+    if (step_prologue(c, (int)n)) return 1;
+    k_keygen<<<g, 256, 0, st>>>(c->tick_k, c->body, c->keys[0], c->vals[0], c->scal);
+    c->launches += 2;
+    if (c->instr & 1) cudaEventRecord(c->ev[1], st);
+    if (step_sort(c, c->tick_k, (int)n)) return 1;
+    if (c->instr & 1) cudaEventRecord(c->ev[2], st);
+    CU_TRY(c, cudaGetLastError());
+    c->tick_stage = 1;
+    return 0;
+}
+
+int lpe_bh_tick_mass(lpe_bh_ctx* c, const double* m, const uint32_t* rank) {
+    if (!c) return 1;
+    if (c->tick_stage != 1) return fail(c, "lpe_bh_tick_mass: call lpe_bh_tick_begin first");
+    if (!m) return fail(c, "m is required");
+    DevGuard _dg(c->device);
+    cudaStream_t st = c->stream;
+    const uint64_t n = c->n;
+    CU_TRY(c, cudaMemcpyAsync(c->tmp + 2 * c->cap, m, 8 * n, cudaMemcpyHostToDevice, st));
+    if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank_in, rank, 4 * n, cudaMemcpyHostToDevice, st));
+    k_pack_mass<<<cdiv((long long)n, 256), 256, 0, st>>>((int)n, c->tmp + 2 * c->cap, rank ? c->rank_in : nullptr, c->body, c->scal);
+    c->pend_vel = true;    // the gather leaves the velocities alone: they arrive with lpe_bh_tick_finish
+    const int rc = step_build(c, c->tick_k, (int)n);
+    c->pend_vel = false;
+    if (rc) return 1;
+    if (c->instr & 1) cudaEventRecord(c->ev[3], st);
+    CU_TRY(c, cudaGetLastError());
+    c->launches += 1;
+    c->tick_stage = 2;
+    return 0;
+}
+
+int lpe_bh_tick_finish(lpe_bh_ctx* c, double* pos, double* vel) {
+    if (!c) return 1;
+    if (c->tick_stage != 2) return fail(c, "lpe_bh_tick_finish: call lpe_bh_tick_begin and lpe_bh_tick_mass first");
+    if (!vel) return fail(c, "vel is required");
+    c->tick_stage = 0;
+    DevGuard _dg(c->device);
+    cudaStream_t st = c->stream;
+    const uint64_t n = c->n;
+    const int g = cdiv((long long)n, 256);
+    double* t = c->tmp;
+    const size_t cap = c->cap;
+    const unsigned int* orig = c->orig_valid ? c->orig : nullptr;
+    CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vel, 16 * n, cudaMemcpyHostToDevice, st));
+    k_pack_vel_aos<<<g, 256, 0, st>>>((int)n, reinterpret_cast<const double2*>(t + 3 * cap), c->vel, orig);
+    if (step_traverse(c, c->tick_k, c->tick_p, (int)n, false)) return 1;
+    if (c->instr & 1) cudaEventRecord(c->ev[4], st);
+    c->last_c = c->tick_k;
+    c->have_step = true;
+    c->last.depth = c->tick_k.D;
+    c->last.hilbert = c->tick_k.hilbert;
+    if (c->tick_p.do_drift && pos) {
+        k_get_pos_aos<<<g, 256, 0, st>>>((int)n, c->body, reinterpret_cast<double2*>(t), orig);
+        CU_TRY(c, cudaMemcpyAsync(pos, t, 16 * n, cudaMemcpyDeviceToHost, st));
+    }
+    k_unpack_vel_aos<<<g, 256, 0, st>>>((int)n, c->vel, reinterpret_cast<double2*>(t + 3 * cap), orig);
+    CU_TRY(c, cudaMemcpyAsync(vel, t + 3 * cap, 16 * n, cudaMemcpyDeviceToHost, st));
+    c->launches += 3;
+    if (fetch_fault(c)) return 1;
+    CU_TRY(c, cudaStreamSynchronize(st));
+    CU_TRY(c, cudaGetLastError());
+    return check_fault(c);
 }
 
 int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {

@@ -7,7 +7,15 @@
  */
 #include "systems/barnes_hut.hpp"
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstring>
+#include <functional>
 #include <iostream>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 #include "core/constants.hpp"
 #include "core/profile.hpp"
@@ -15,9 +23,110 @@
 
 namespace Systems {
 
-BarnesHutSystem::BarnesHutSystem() = default;
+static_assert(sizeof(Components::Position) == 2 * sizeof(double), "Position is an {x, y} record");
+static_assert(sizeof(Components::Velocity) == 2 * sizeof(double), "Velocity is an {x, y} record");
+static_assert(sizeof(Components::Mass) == sizeof(double), "Mass is one double");
+
+namespace {
+
+/** A handful of persistent worker threads: run(f) calls f(k, K) for k = 0..K-1 (k = 0 on the caller) and returns when
+ *  all are done. The registry is only ever touched from inside run(), i.e. while update() owns it. */
+class Workers {
+public:
+    explicit Workers(int extra) {
+        for (int i = 0; i < extra; ++i) threads_.emplace_back([this, i] { loop(i + 1); });
+    }
+    ~Workers() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    int size() const { return (int)threads_.size() + 1; }
+    void run(const std::function<void(int, int)>& f) {
+        const int K = size();
+        if (K == 1) { f(0, 1); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &f;
+            pending_ = K - 1;
+            ++epoch_;
+        }
+        cv_.notify_all();
+        f(0, K);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+
+private:
+    void loop(int k) {
+        unsigned long long seen = 0;
+        for (;;) {
+            const std::function<void(int, int)>* job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+                if (stop_) return;
+                job = job_;
+            }
+            (*job)(k, size());
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int, int)>* job_ = nullptr;
+    int pending_ = 0;
+    unsigned long long epoch_ = 0;
+    bool stop_ = false;
+};
+
+template <class T>
+struct PinnedArray {   // page-locked host memory (full PCIe rate, asynchronous copies); grows geometrically
+    T* p = nullptr;
+    std::size_t cap = 0;
+    bool reserve(std::size_t n) {
+        if (n <= cap) return true;
+        const std::size_t want = std::max(n, cap + cap / 2);
+        T* q = static_cast<T*>(lpe_bh_alloc_pinned(want * sizeof(T)));
+        if (!q) return false;
+        if (p) lpe_bh_free_pinned(p);
+        p = q;
+        cap = want;
+        return true;
+    }
+    ~PinnedArray() { if (p) lpe_bh_free_pinned(p); }
+};
+
+constexpr std::size_t kPage = ENTT_PACKED_PAGE;   // elements per pool page (entt.hpp:60)
+
+}  // namespace
+
+struct BarnesHutSystem::Staging {
+    PinnedArray<double> pos, vel, m;     // {x, y} records, {vx, vy} records, masses — in staging order
+    PinnedArray<std::uint8_t> comp;
+    PinnedArray<std::uint32_t> rank;
+    std::vector<entt::entity> entities;  // entity-by-entity path only
+    std::unique_ptr<Workers> workers;
+    int workerCount = -1;
+    bool reserve(std::size_t n) {
+        return pos.reserve(2 * n) && vel.reserve(2 * n) && m.reserve(n) && comp.reserve(n) && rank.reserve(n);
+    }
+};
+
+BarnesHutSystem::BarnesHutSystem() : st_(new Staging()) {}
 
 BarnesHutSystem::~BarnesHutSystem() {
+    st_.reset();   // page-locked buffers go before the context
     if (ctx_) lpe_bh_destroy(ctx_);
 }
 
@@ -32,6 +141,90 @@ bool BarnesHutSystem::ensureContext() {
         return false;
     }
     return true;
+}
+
+// Pool pages as they are. Valid when Position, Mass and Velocity hold exactly the same entities in the same packed
+// order and nothing is a Boundary: then buildTree's view (barnes_hut.cpp:117) and the force loop's view (:89) both
+// visit packed index n-1, n-2, ..., 0 (EnTT iterates the leading pool back to front), i.e. the body at packed index
+// i has insertion rank n-1-i — the C ABI's default when no rank array is given — and every body has every component.
+bool BarnesHutSystem::stagePagewise(entt::registry& registry, std::size_t& n) {
+    auto& ps = registry.storage<Components::Position>();
+    auto& ms = registry.storage<Components::Mass>();
+    auto& vs = registry.storage<Components::Velocity>();
+    n = ms.size();
+    if (n == 0 || ps.size() != n || vs.size() != n) return false;
+    if (!registry.storage<Components::Boundary>().empty()) return false;
+    if (options_.fuseMovement) {   // the fused drift needs per-entity phases (movement.cpp:25-29): any liquid -> slow path
+        for (const auto& ph : registry.storage<Components::ParticlePhase>())
+            if (ph.phase == Components::Phase::Liquid) return false;
+    }
+    if (!st_->reserve(n)) return false;
+    const auto* pe = ps.data();
+    const auto* me = ms.data();
+    const auto* ve = vs.data();
+    auto** ppages = ps.raw();
+    const std::size_t pages = (n + kPage - 1) / kPage;
+    std::atomic<bool> aligned{true};
+    double* pos = st_->pos.p;
+    // same entities in the same packed order in all three pools? (checked every tick: entities come and go) — and the
+    // positions, the first thing the device needs
+    st_->workers->run([&](int k, int K) {
+        const std::size_t p0 = pages * k / K, p1 = pages * (k + 1) / K;
+        for (std::size_t pg = p0; pg < p1 && aligned.load(std::memory_order_relaxed); ++pg) {
+            const std::size_t a = pg * kPage, cnt = std::min(kPage, n - a);
+            if (std::memcmp(pe + a, me + a, cnt * sizeof(entt::entity)) != 0 ||
+                std::memcmp(pe + a, ve + a, cnt * sizeof(entt::entity)) != 0) {
+                aligned.store(false, std::memory_order_relaxed);
+                break;
+            }
+            std::memcpy(pos + 2 * a, ppages[pg], cnt * sizeof(Components::Position));
+        }
+    });
+    return aligned.load();
+}
+
+// The reference's own views, entity by entity, in the iteration order of buildTree's view (barnes_hut.cpp:117): that
+// order IS the insertion order, which decides each cell's first occupant. Every target of the force
+// loop (view<Position,Velocity,Mass>, :89) is also in this view, so one pass stages sources and targets.
+std::size_t BarnesHutSystem::stagePerEntity(entt::registry& registry) {
+    auto insertView = registry.view<Components::Position, Components::Mass>(entt::exclude<Components::Boundary>);
+    auto& ents = st_->entities;
+    ents.clear();
+    for (auto entity : insertView) ents.push_back(entity);
+    const std::size_t nMass = ents.size();
+    if (options_.fuseMovement) {
+        // MovementSystem also moves entities without Mass (movement.cpp:20): they ride along as pure movers
+        auto moveView = registry.view<Components::Position, Components::Velocity>(entt::exclude<Components::Boundary>);
+        for (auto entity : moveView)
+            if (!registry.all_of<Components::Mass>(entity)) ents.push_back(entity);
+    }
+    const std::size_t n = ents.size();
+    if (n == 0 || !st_->reserve(n)) return 0;
+    for (std::size_t i = 0; i < n; ++i) {
+        const auto entity = ents[i];
+        const auto& pos = registry.get<Components::Position>(entity);
+        std::uint8_t comp = 0;
+        double mass = 0.0, vx = 0.0, vy = 0.0;
+        if (i < nMass) {
+            comp |= LPE_HAS_MASS;
+            mass = registry.get<Components::Mass>(entity).value;
+        }
+        if (const auto* vel = registry.try_get<Components::Velocity>(entity)) {
+            comp |= LPE_HAS_VELOCITY;
+            vx = vel->x;
+            vy = vel->y;
+        }
+        if (options_.fuseMovement) {
+            if (const auto* ph = registry.try_get<Components::ParticlePhase>(entity))
+                if (ph->phase == Components::Phase::Liquid) comp |= LPE_LIQUID;   // movement.cpp:25-29
+        }
+        st_->pos.p[2 * i] = pos.x; st_->pos.p[2 * i + 1] = pos.y;
+        st_->vel.p[2 * i] = vx;    st_->vel.p[2 * i + 1] = vy;
+        st_->m.p[i] = mass;
+        st_->comp.p[i] = comp;
+        st_->rank.p[i] = static_cast<std::uint32_t>(i);   // position in the view's iteration (massless movers: unused)
+    }
+    return n;
 }
 
 void BarnesHutSystem::update(entt::registry& registry) {
@@ -59,35 +252,17 @@ void BarnesHutSystem::update(entt::registry& registry) {
     const auto& simState = stateView.get<Components::SimulatorState>(stateView.front());
 
     if (!ensureContext()) return;
-
-    // Stage the bodies in the iteration order of buildTree's own view (barnes_hut.cpp:117): that order IS the
-    // insertion order, which decides each cell's first occupant. Every target of the force
-    // loop (view<Position,Velocity,Mass>, :89) is also in this view, so one pass stages sources and targets.
-    auto insertView = registry.view<Components::Position, Components::Mass>(entt::exclude<Components::Boundary>);
-    entities_.clear();
-    x_.clear(); y_.clear(); vx_.clear(); vy_.clear(); m_.clear(); comp_.clear(); rank_.clear();
-    for (auto entity : insertView) {
-        const auto& pos = insertView.get<Components::Position>(entity);
-        const auto& mass = insertView.get<Components::Mass>(entity);
-        std::uint8_t comp = LPE_HAS_MASS;
-        double vx = 0.0, vy = 0.0;
-        if (const auto* vel = registry.try_get<Components::Velocity>(entity)) {
-            comp |= LPE_HAS_VELOCITY;
-            vx = vel->x;
-            vy = vel->y;
-        }
-        if (options_.fuseMovement) {
-            if (const auto* ph = registry.try_get<Components::ParticlePhase>(entity))
-                if (ph->phase == Components::Phase::Liquid) comp |= LPE_LIQUID;   // movement.cpp:25-29
-        }
-        rank_.push_back(static_cast<std::uint32_t>(entities_.size()));
-        entities_.push_back(entity);
-        x_.push_back(pos.x); y_.push_back(pos.y);
-        vx_.push_back(vx); vy_.push_back(vy);
-        m_.push_back(mass.value);
-        comp_.push_back(comp);
+    const int wantWorkers = std::max(0, options_.stagingThreads);
+    if (!st_->workers || st_->workerCount != wantWorkers) {
+        st_->workers.reset(new Workers(wantWorkers > 0 ? wantWorkers - 1 : 0));
+        st_->workerCount = wantWorkers;
     }
-    if (entities_.empty()) return;
+
+    std::size_t n = 0;
+    const bool pagewise = options_.pagewiseStaging && stagePagewise(registry, n);
+    if (!pagewise) n = stagePerEntity(registry);
+    lastPath_ = pagewise ? 1 : 0;
+    if (n == 0) return;
 
     lpe_bh_params p{};
     p.universe_size = sysConfig.UniverseSizeMeters;
@@ -102,22 +277,57 @@ void BarnesHutSystem::update(entt::registry& registry) {
     p.do_drift = options_.fuseMovement ? 1 : 0;
     p.max_depth = 0;
 
-    if (lpe_bh_update_host(ctx_, &p, entities_.size(), x_.data(), y_.data(), vx_.data(), vy_.data(), m_.data(),
-                           rank_.data(), comp_.data()) != 0) {
+    // Three calls: each queues the device work its array unlocks, so the next pool is copied while the GPU runs
+    // (positions -> keys + sort | masses -> tree build | velocities -> traversal + kick).
+    auto failed = [&]() {
         std::cerr << "[BarnesHut] Warning: device step failed: " << lpe_bh_last_error(ctx_) << ". Skipping update.\n";
-        return;
+    };
+    if (lpe_bh_tick_begin(ctx_, &p, n, st_->pos.p, pagewise ? nullptr : st_->comp.p) != 0) { failed(); return; }
+    const std::size_t pages = (n + kPage - 1) / kPage;
+    if (pagewise) {
+        auto** mpages = registry.storage<Components::Mass>().raw();
+        st_->workers->run([&](int k, int K) {
+            for (std::size_t pg = pages * k / K; pg < pages * (k + 1) / K; ++pg) {
+                const std::size_t a = pg * kPage, cnt = std::min(kPage, n - a);
+                std::memcpy(st_->m.p + a, mpages[pg], cnt * sizeof(Components::Mass));
+            }
+        });
     }
+    if (lpe_bh_tick_mass(ctx_, st_->m.p, pagewise ? nullptr : st_->rank.p) != 0) { failed(); return; }
+    if (pagewise) {
+        auto** vpages = registry.storage<Components::Velocity>().raw();
+        st_->workers->run([&](int k, int K) {
+            for (std::size_t pg = pages * k / K; pg < pages * (k + 1) / K; ++pg) {
+                const std::size_t a = pg * kPage, cnt = std::min(kPage, n - a);
+                std::memcpy(st_->vel.p + 2 * a, vpages[pg], cnt * sizeof(Components::Velocity));
+            }
+        });
+    }
+    if (lpe_bh_tick_finish(ctx_, st_->pos.p, st_->vel.p) != 0) { failed(); return; }
 
     // The reference mutates Velocity in place through the view reference (barnes_hut.cpp:285-286): no signals.
-    for (std::size_t i = 0; i < entities_.size(); ++i) {
-        if (!(comp_[i] & LPE_HAS_VELOCITY)) continue;
-        auto& vel = registry.get<Components::Velocity>(entities_[i]);
-        vel.x = vx_[i];
-        vel.y = vy_[i];
-        if (options_.fuseMovement && !(comp_[i] & LPE_LIQUID)) {
-            auto& pos = registry.get<Components::Position>(entities_[i]);
-            pos.x = x_[i];
-            pos.y = y_[i];
+    if (pagewise) {
+        auto** vpages = registry.storage<Components::Velocity>().raw();
+        auto** ppages = registry.storage<Components::Position>().raw();
+        const bool drift = options_.fuseMovement;
+        st_->workers->run([&](int k, int K) {
+            for (std::size_t pg = pages * k / K; pg < pages * (k + 1) / K; ++pg) {
+                const std::size_t a = pg * kPage, cnt = std::min(kPage, n - a);
+                std::memcpy(vpages[pg], st_->vel.p + 2 * a, cnt * sizeof(Components::Velocity));
+                if (drift) std::memcpy(ppages[pg], st_->pos.p + 2 * a, cnt * sizeof(Components::Position));
+            }
+        });
+        return;
+    }
+    for (std::size_t i = 0; i < n; ++i) {
+        if (!(st_->comp.p[i] & LPE_HAS_VELOCITY)) continue;
+        auto& vel = registry.get<Components::Velocity>(st_->entities[i]);
+        vel.x = st_->vel.p[2 * i];
+        vel.y = st_->vel.p[2 * i + 1];
+        if (options_.fuseMovement) {
+            auto& pos = registry.get<Components::Position>(st_->entities[i]);
+            pos.x = st_->pos.p[2 * i];
+            pos.y = st_->pos.p[2 * i + 1];
         }
     }
 }

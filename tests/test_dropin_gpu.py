@@ -36,3 +36,26 @@ def test_registry_boundary_drop_in_is_bit_exact(n, seed):
         assert rep.get("mismatches") == 0, (rep, r.stderr[-500:])
     else:
         assert r.returncode == 0 and rep.get("ok") and rep["mismatches"] == 0 and rep["clamped_x"] > 0, (rep, r.stderr[-500:])
+
+
+BENCH = os.path.join(ROOT, "little-physics-engine_b200", "host", "_build", "dropin_bench")
+
+
+def test_pool_page_staging_equals_entity_by_entity_staging():
+    """Systems::BarnesHutSystem stages aligned EnTT pools page by page into page-locked buffers; the result must be
+    the one the entity-by-entity walk of the reference's views gives (same bodies, same insertion ranks)."""
+    if not os.path.exists(BENCH):
+        pytest.skip("host/_build/dropin_bench not built (needs the reference headers at build time)")
+    out = {}
+    for mode in ("pagewise", "per_entity"):
+        r = subprocess.run([BENCH, "150000", "2", mode], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-800:]
+        out[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["pagewise"]["staging_path_taken"] == 1 and out["per_entity"]["staging_path_taken"] == 0
+    # (the two paths hand the bodies over in opposite orders; bodies that share a finest cell may then sit in another
+    # warp, which changes the order of fp32 partial sums, never a decision)
+    a, b = out["pagewise"]["velocity_checksum"], out["per_entity"]["velocity_checksum"]
+    assert abs(a - b) <= 1e-8 * abs(b)
+    # the fused-movement variant runs and moves the bodies
+    r = subprocess.run([BENCH, "150000", "2", "pagewise", "fused"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and json.loads(r.stdout.strip().splitlines()[-1])["fused_movement"] is True
