@@ -476,20 +476,24 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
 
     def rebalance():
         st = bh.dd_stats()
-        local = st["ms_keygen"] + st["ms_sort"] + st["ms_build"] + st["ms_export"]
+        local = st["ms_keygen"] + st["ms_sort"] + st["ms_build"] + st["ms_export"] + st["ms_top"]
         allc = gather_costs()
         mean_cost = float(np.mean(np.concatenate([c for _, c in allc]))) if sum(len(c) for _, c in allc) else 1.0
-        t = torch.tensor([local, st["ms_traverse"]], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t)
-        beta = mean_cost * float(t[0].item()) / max(float(t[1].item()), 1e-9)     # sort + build share of a chunk, in list entries
-        new = lpe_bh.balanced_splitters(allc, world, beta)
+        mine = torch.tensor([local, st["ms_traverse"]], device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allt, mine)
+        tl = np.array([float(t[0].item()) for t in allt]); tt = np.array([float(t[1].item()) for t in allt])
+        beta = mean_cost * float(tl.sum()) / max(float(tt.sum()), 1e-9)     # sort + build share of a chunk, in list entries
+        busy = tl + tt                                                      # what each rank actually spent (no waiting)
+        scale = busy / max(float(busy.mean()), 1e-9)
+        new = lpe_bh.balanced_splitters(allc, world, beta, scale)
         bh.dd_set_splitters(new)
         return beta
 
     # settle: a few steps, re-balance on the measured per-chunk cost, a few more (the bodies move to their new owners)
     bh.set_instrumentation(timing=True)
     balance_log = []
-    for it in range(3):
+    for it in range(4):
         bh.dd_step(params, 2)
         bh.synchronize()
         balance_log.append({"traverse_ms": bh.dd_stats()["ms_traverse"], "n_live": bh.dd_stats()["n_live"]})

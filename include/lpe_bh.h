@@ -74,6 +74,11 @@ typedef struct {
     int32_t  hilbert;        /* 1 if the last step sorted by Hilbert index, 0 for Morton code */
     int32_t  pad_;
     float ms_keygen, ms_sort, ms_build, ms_traverse, ms_total; /* last step, CUDA events; only when timing is enabled */
+    float pad2_;
+    /* DebugStats::updateForce (reference include/core/debug.hpp:37-41, called per accepted node at barnes_hut.cpp:278):
+     * max and sum of force = G*M*m/distSq over the accepted interactions of the last step (count = interactions); only
+     * when stats are enabled */
+    double force_max, force_sum;
 } lpe_bh_stats;
 
 /* tree dump for parity tests; every pointer may be NULL. Arrays are sized by the caller from lpe_bh_get_stats. */
@@ -162,6 +167,11 @@ int  lpe_bh_get_stats(lpe_bh_ctx* ctx, lpe_bh_stats* out);          /* synchroni
 int  lpe_bh_dump_tree(lpe_bh_ctx* ctx, lpe_bh_tree_dump* out);      /* tree of the last step; synchronises */
 /* per-body accepted / visited counts of the last step in creation order (instrumentation bit1 must be on) */
 int  lpe_bh_get_counts(lpe_bh_ctx* ctx, uint32_t* accepted, uint32_t* visited);
+
+/* Largest mass among the resident bodies that have Mass and are not Boundary: the answer to the reference's two
+ * per-tick host scans over Mass (barnes_hut.cpp:55-71 early exit when it is below smallMassThreshold; gravity.cpp:41-49
+ * uniform field off when it reaches 1e10), reduced on the device at upload. Synchronises. */
+int  lpe_bh_max_source_mass(lpe_bh_ctx* ctx, double* max_mass);
 
 /* Direct O(N^2) sum with the same force law, for the accuracy cross-check: accelerations of bodies
  * [first, first+count) in creation order, fp64, from device-resident state. Synchronises. */

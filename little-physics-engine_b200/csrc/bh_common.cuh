@@ -43,6 +43,10 @@ struct Scal {
     unsigned long long work_cost;   // list entries evaluated by this rank's traversal (load-balance weight)
     unsigned int dd_rounds;     // generations of the exporter's breadth-first walk (longest destination)
     unsigned int pad_dd2;
+    // DebugStats::updateForce (reference include/core/debug.hpp:37-41, called per accepted node at barnes_hut.cpp:278):
+    // max and sum of force = G*M*m/distSq over the accepted interactions (stats runs only; the count is `interactions`)
+    unsigned long long force_max_bits;
+    double force_sum;
 };
 
 // Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         // at a greater depth until the walk is back at depth <= d (the node's next sibling or an ancestor's).
         int accDepth = target ? ACTIVE : -1;
         unsigned int nacc = 0, nvis = 0, nwarp = 0;
+        double fsum = 0.0, fmaxd = 0.0;   // STATS: DebugStats::updateForce (barnes_hut.cpp:278), real units
         double2 v = make_double2(0.0, 0.0);
         if (valid) v = a.vel[b];
 
@@ -211,7 +212,11 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 if (STATS) {
                     nwarp++;
                     nvis += active ? 1u : 0u;
-                    nacc += (active && !open && slot != self && Bq.y != -2.0f) ? 1u : 0u;
+                    const bool counted = active && !open && slot != self && Bq.y != -2.0f;
+                    nacc += counted ? 1u : 0u;
+                    const double q = counted ? (double)(Bq.x * rinv * rinv) : 0.0;   // gm / d2, scaled units
+                    fsum += q;
+                    fmaxd = fmax(fmaxd, q);
                 }
                 if (anyopen) {
                     kstack = (kstack & ~(3ull << (2 * d))) | ((unsigned long long)k << (2 * d));
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 v.x += (AX * accScale) * c.dtK;   // barnes_hut.cpp:284-286
                 v.y += (AY * accScale) * c.dtK;
             }
+            if (STATS) { fsum *= accScale * bodyMass; fmaxd *= accScale * bodyMass; }
         } else {
             // STRICT: the reference's arithmetic, operation for operation (barnes_hut.cpp:257-286), in real units.
             // The walk visits the children of a cell in key order; with Morton keys that is the reference's
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     const double invDistMass = __ddiv_rn(force, __dmul_rn(m, dist));
                     v.x = __dadd_rn(v.x, __dmul_rn(__dmul_rn(dx, invDistMass), c.dtK));
                     v.y = __dadd_rn(v.y, __dmul_rn(__dmul_rn(dy, invDistMass), c.dtK));
-                    if (STATS) nacc++;
+                    if (STATS) { nacc++; fsum += force; fmaxd = fmax(fmaxd, force); }
                 }
                 if (STATS) {
                     nwarp++;
@@ -337,8 +343,12 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
             for (int o = 16; o > 0; o >>= 1) {
                 nacc += __shfl_xor_sync(0xFFFFFFFFu, nacc, o);
                 nvis += __shfl_xor_sync(0xFFFFFFFFu, nvis, o);
+                fsum += __shfl_xor_sync(0xFFFFFFFFu, fsum, o);
+                fmaxd = fmax(fmaxd, __shfl_xor_sync(0xFFFFFFFFu, fmaxd, o));
             }
             if (lane == 0) {
+                atomicAdd(&a.s->force_sum, fsum);
+                atomicMax(&a.s->force_max_bits, (unsigned long long)__double_as_longlong(fmaxd));
                 atomicAdd(&a.s->interactions, (unsigned long long)nacc);
                 atomicAdd(&a.s->visits, (unsigned long long)nvis);
                 atomicAdd(&a.s->warp_visits, (unsigned long long)nwarp);

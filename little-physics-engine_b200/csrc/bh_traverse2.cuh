@@ -99,7 +99,8 @@ struct LanePos2 {   // the lane's negated two-float position, each component dup
 // two consecutive accept-list entries (m even) for one lane; the sums go to two partial accumulators per axis
 template <bool STATS, bool SELF>
 __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, unsigned int lanebit, unsigned int self,
-                                               const LanePos2& P, f32x2_t& AX2, f32x2_t& AY2, unsigned int& nacc) {
+                                               const LanePos2& P, f32x2_t& AX2, f32x2_t& AY2, unsigned int& nacc,
+                                               double& fsum, float& fmaxq) {
     const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(&W.ap[m >> 1]);
     const ulonglong2 vh = ap[0], vl = ap[1];
     const uint4 vg = *reinterpret_cast<const uint4*>(ap + 2);
@@ -114,15 +115,21 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
         const uint2 as = *reinterpret_cast<const uint2*>(&W.aslot[m]);
         self0 = (as.x & 0x7FFFFFFFu) == self;
         self1 = (as.y & 0x7FFFFFFFu) == self;
-        if (STATS) {
-            nacc += (r0 && (as.x & 0x7FFFFFFFu) != self && !(as.x >> 31)) ? 1u : 0u;
-            nacc += (r1 && (as.y & 0x7FFFFFFFu) != self && !(as.y >> 31)) ? 1u : 0u;
-        }
     }
     const f32x2_t dx = add2(add2(xh, P.nphx), add2(xl, P.nplx));
     const f32x2_t dy = add2(add2(yh, P.nphy), add2(yl, P.nply));
     const f32x2_t d2 = fma2(dx, dx, fma2(dy, dy, P.eps2));
     const f32x2_t rinv = pack2(rsqrt_approx(lo2(d2)), rsqrt_approx(hi2(d2)));
+    if (STATS) {   // SELF is on in every stats build
+        const uint2 as = *reinterpret_cast<const uint2*>(&W.aslot[m]);
+        const bool c0 = r0 && (as.x & 0x7FFFFFFFu) != self && !(as.x >> 31);
+        const bool c1 = r1 && (as.y & 0x7FFFFFFFu) != self && !(as.y >> 31);
+        nacc += (c0 ? 1u : 0u) + (c1 ? 1u : 0u);
+        // the reference's force = G*M*m/distSq of the interaction, here in scaled units without the target's mass
+        const float q0 = c0 ? g.x * lo2(rinv) * lo2(rinv) : 0.f, q1 = c1 ? g.y * hi2(rinv) * hi2(rinv) : 0.f;
+        fsum += (double)q0 + (double)q1;
+        fmaxq = fmaxf(fmaxq, fmaxf(q0, q1));
+    }
     f32x2_t f = mul2(mul2(pack2(g0, g1), rinv), mul2(rinv, rinv));
     // without softening a body's own leaf has d2 = 0 (0 * inf): drop it explicitly (barnes_hut.cpp:272)
     if (SELF) f = pack2(self0 ? 0.f : lo2(f), self1 ? 0.f : hi2(f));
@@ -161,11 +168,13 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
 
         unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
+        double bodyMass = 0.0;
         if (valid) {
             const Body sb = a.body[i];
             b = (unsigned int)i;
             cm = sb.comp;
             p = make_double2(sb.x, sb.y);
+            if (STATS) bodyMass = sb.m;
             if (SELF) self = a.selfslot[i];
         }
         const bool target = valid && (cm & 1u) && (cm & 2u) && !(cm & 4u);   // barnes_hut.cpp:89
@@ -178,6 +187,8 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
         LP.nplx = pack2(nplx, nplx); LP.nply = pack2(nply, nply);
         LP.eps2 = pack2(eps2f, eps2f);
         unsigned int nacc = 0, nwarp = 0, cost = 0;   // cost: nodes the warp classified (load-balance weight)
+        double fsum = 0.0;                            // STATS: DebugStats::updateForce, sum and max of G*M*m/distSq
+        float fmaxq = 0.f;
         unsigned int kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // STATS: A-clean, A-dirty, O-dirty, M->all accept, M->all open, M->split, rounds, frontier nodes
         double AX = 0.0, AY = 0.0;
         bool overflow = c.test_overflow != 0;
@@ -321,8 +332,12 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                         const bool self0 = (ms.x & 0x7FFFFFFFu) == self, self1 = (ms.y & 0x7FFFFFFFu) == self;
                         f = pack2(self0 ? 0.f : lo2(f), self1 ? 0.f : hi2(f));
                         if (STATS) {
-                            nacc += (reached0 && !open0 && !self0 && !(ms.x >> 31)) ? 1u : 0u;
-                            nacc += (reached1 && !open1 && !self1 && !(ms.y >> 31)) ? 1u : 0u;
+                            const bool c0 = reached0 && !open0 && !self0 && !(ms.x >> 31);
+                            const bool c1 = reached1 && !open1 && !self1 && !(ms.y >> 31);
+                            nacc += (c0 ? 1u : 0u) + (c1 ? 1u : 0u);
+                            const float q0 = c0 ? g.x * lo2(rinv) * lo2(rinv) : 0.f, q1 = c1 ? g.y * hi2(rinv) * hi2(rinv) : 0.f;
+                            fsum += (double)q0 + (double)q1;
+                            fmaxq = fmaxf(fmaxq, fmaxf(q0, q1));
                         }
                     }
                     AX2 = fma2(dx, f, AX2);
@@ -368,7 +383,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                     __syncwarp();
 #pragma unroll 4
                     for (unsigned int m = 0; m < nA; m += 2)
-                        t2_accept_pair<STATS, SELF>(W, m, lanebit, self, LP, AX2, AY2, nacc);
+                        t2_accept_pair<STATS, SELF>(W, m, lanebit, self, LP, AX2, AY2, nacc, fsum, fmaxq);
                     if (STATS) nwarp += nA;
                     nA = 0;
                 }
@@ -425,9 +440,18 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
         }
         if (STATS) {
             unsigned int tot = target ? nacc : 0u;
+            // force = (G * Ms / S^2) * m_target * (gm / d2) in real units
+            const double fscale = c.G * massScale * c.invS * c.invS * bodyMass;
+            double fs = target ? fsum * fscale : 0.0, fm = target ? (double)fmaxq * fscale : 0.0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+                fs += __shfl_xor_sync(0xFFFFFFFFu, fs, o);
+                fm = fmax(fm, __shfl_xor_sync(0xFFFFFFFFu, fm, o));
+            }
             if (lane == 0) {
+                atomicAdd(&a.s->force_sum, fs);
+                atomicMax(&a.s->force_max_bits, (unsigned long long)__double_as_longlong(fm));
                 atomicAdd(&a.s->interactions, (unsigned long long)tot);
                 atomicAdd(&a.s->warp_visits, (unsigned long long)nwarp);
                 for (int z = 0; z < 8; ++z) atomicAdd(&a.s->t2[z], (unsigned long long)kd[z]);

@@ -1180,6 +1180,8 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
         s.visits = h.visits;
         s.warp_visits = h.warp_visits;
         s.overflow_chunks = h.ovf_count;
+        s.force_sum = h.force_sum;
+        { double fm; std::memcpy(&fm, &h.force_max_bits, sizeof(fm)); s.force_max = fm; }
         for (int z = 0; z < 8; ++z) s.t2_kinds[z] = h.t2[z];
         if (c->instr & 1) {
             cudaEventElapsedTime(&s.ms_keygen, c->ev[0], c->ev[1]);
@@ -1279,6 +1281,23 @@ int lpe_bh_direct_accel(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t first, u
     CU_TRY(c, cudaMemcpyAsync(ax, dax, 8 * count, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(ay, day, 8 * count, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// the two per-tick host scans over Mass — BarnesHutSystem's early exit "no mass reaches
+// smallMassThreshold" (barnes_hut.cpp:55-71) and BasicGravitySystem's "some mass >= 1e10 disables the uniform field"
+// (gravity.cpp:41-49) — both only ask for the LARGEST mass among the non-Boundary bodies that have one. The upload
+// kernels reduce exactly that on the device (Scal::max_mass_bits, it also fixes the traversal's mass unit), so for
+// resident bodies the answer is one 8-byte read. Synchronises.
+int lpe_bh_max_source_mass(lpe_bh_ctx* c, double* max_mass) {
+    if (!c || !max_mass) return 1;
+    *max_mass = 0.0;
+    if (!c->scal || c->n == 0) return 0;
+    DevGuard _dg(c->device);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned long long bits = 0;
+    CU_TRY(c, cudaMemcpy(&bits, &c->scal->max_mass_bits, sizeof(bits), cudaMemcpyDeviceToHost));
+    std::memcpy(max_mass, &bits, sizeof(bits));
     return 0;
 }
 

@@ -282,6 +282,7 @@ void BarnesHutSystem::update(entt::registry& registry) {
     auto failed = [&]() {
         std::cerr << "[BarnesHut] Warning: device step failed: " << lpe_bh_last_error(ctx_) << ". Skipping update.\n";
     };
+    lpe_bh_set_instrumentation(ctx_, options_.collectForceStats ? 2 : 0);
     if (lpe_bh_tick_begin(ctx_, &p, n, st_->pos.p, pagewise ? nullptr : st_->comp.p) != 0) { failed(); return; }
     const std::size_t pages = (n + kPage - 1) / kPage;
     if (pagewise) {
@@ -304,6 +305,14 @@ void BarnesHutSystem::update(entt::registry& registry) {
         });
     }
     if (lpe_bh_tick_finish(ctx_, st_->pos.p, st_->vel.p) != 0) { failed(); return; }
+    if (options_.collectForceStats) {
+        lpe_bh_stats s{};
+        if (lpe_bh_get_stats(ctx_, &s) == 0) {
+            forceStats_.maxForce = s.force_max;
+            forceStats_.totalForce = s.force_sum;
+            forceStats_.count = s.interactions;
+        }
+    }
 
     // The reference mutates Velocity in place through the view reference (barnes_hut.cpp:285-286): no signals.
     if (pagewise) {

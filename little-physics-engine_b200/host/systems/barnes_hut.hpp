@@ -48,6 +48,11 @@ struct BarnesHutDeviceOptions {
      *  (movement.cpp:20-33), massless ones included; MovementSystem must then be skipped by the caller. The drift uses
      *  the velocity right after the kick, i.e. before any system that the tick would run between the two. */
     bool fuseMovement = false;
+    /** Collect what the reference feeds DebugStats::updateForce with at barnes_hut.cpp:278 (max / sum / count of
+     *  G*M*m/distSq over the accepted nodes) with a device reduction; read it with lastForceStats(). Uses the counting
+     *  kernels, which are slower. The reference's own counters are private statics with prints compiled out
+     *  (core/debug.hpp:6,76), so they are not written. */
+    bool collectForceStats = false;
     bool pagewiseStaging = true;  ///< take the pool-page fast path when the pools allow it
     int stagingThreads = 4;       ///< worker threads of the page-wise copies (0 = copy on the calling thread)
 };
@@ -66,6 +71,9 @@ public:
     const BarnesHutDeviceOptions& getDeviceOptions() const { return options_; }
     /** How the last update staged the registry: 1 = pool pages, 0 = entity by entity, -1 = no update yet. */
     int lastStagingPath() const { return lastPath_; }
+    struct ForceStats { double maxForce = 0.0, totalForce = 0.0; unsigned long long count = 0; };
+    /** DebugStats::updateForce's three numbers for the last update (collectForceStats). */
+    const ForceStats& lastForceStats() const { return forceStats_; }
 
 private:
     struct Staging;   // page-locked buffers + worker threads (barnes_hut.cpp)
@@ -77,6 +85,7 @@ private:
     lpe_bh_ctx* ctx_ = nullptr;
     bool contextFailed_ = false;
     int lastPath_ = -1;
+    ForceStats forceStats_;
     std::unique_ptr<Staging> st_;
 };
 

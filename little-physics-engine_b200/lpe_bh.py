@@ -43,6 +43,7 @@ class Stats(C.Structure):
         ("depth", C.c_int32), ("sort_passes", C.c_int32), ("hilbert", C.c_int32), ("pad_", C.c_int32),
         ("ms_keygen", C.c_float),
         ("ms_sort", C.c_float), ("ms_build", C.c_float), ("ms_traverse", C.c_float), ("ms_total", C.c_float),
+        ("pad2_", C.c_float), ("force_max", C.c_double), ("force_sum", C.c_double),
     ]
 
     def as_dict(self):
@@ -344,6 +345,11 @@ class BarnesHut:
                                                _dp(ay)), "direct_accel")
         return ax, ay
 
+    def max_source_mass(self):
+        v = C.c_double(0.0)
+        self._chk(self.lib.lpe_bh_max_source_mass(self.h, C.byref(v)), "max_source_mass")
+        return v.value
+
     def launch_count(self):
         return int(self.lib.lpe_bh_launch_count(self.h))
 
@@ -524,12 +530,15 @@ class DDGroup:
         return new
 
 
-def balanced_splitters(per_rank, nranks, beta=240.0):
+def balanced_splitters(per_rank, nranks, beta=240.0, scale=None):
     """Splitters (depth-30 keys) that give every rank the same share of sum(cost + beta) over the 32-body chunks.
     per_rank = [(first_key30, cost)] in rank order: the ranks' key ranges are disjoint and ascending, so the
-    concatenation is globally key-ordered. Pure host arithmetic, the same on every rank."""
+    concatenation is globally key-ordered. scale = optional per-rank correction factors (measured time of the rank /
+    mean over ranks): what the cost model missed on a rank (deeper tree, more cells per body) is charged to its chunks.
+    Pure host arithmetic, the same on every rank."""
     keys = np.concatenate([k for k, _ in per_rank])
-    w = np.concatenate([c for _, c in per_rank]).astype(np.float64) + float(beta)
+    scale = [1.0] * len(per_rank) if scale is None else scale
+    w = np.concatenate([(c.astype(np.float64) + float(beta)) * float(f) for (_, c), f in zip(per_rank, scale)])
     top = 1 << 60
     split = [0]
     if len(keys):

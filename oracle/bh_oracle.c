@@ -189,7 +189,7 @@ static int build(tree_t* t, const orc_params* p, uint64_t n, const double* x, co
     return t->failed;
 }
 
-typedef struct { uint64_t accepted, visited; } counts_t;
+typedef struct { uint64_t accepted, visited; double fmax, fsum; } counts_t;
 
 /* ---- tiny pthread parallel-for (dynamic chunks); threads <= 1 runs inline ---- */
 typedef void (*chunk_fn)(void* ctx, int64_t lo, int64_t hi, int tid);
@@ -237,6 +237,8 @@ static void force(const tree_t* t, int64_t k, int64_t e, double px, double py, d
         *vx += accX * dt;                                                 /* :285-286 */
         *vy += accY * dt;
         c->accepted++;
+        if (f > c->fmax) c->fmax = f;                                     /* :278 DebugStats::updateForce(force) */
+        c->fsum += f;
     } else {
         for (int q = 0; q < 4; ++q)                                       /* :289-292 nw, ne, sw, se */
             force(t, t->child[4 * k + q], e, px, py, vx, vy, mass, dt, c);
@@ -269,18 +271,23 @@ typedef struct {
 static void force_chunk(void* ctx, int64_t lo, int64_t hi, int tid) {
     force_job* j = (force_job*)ctx;
     uint64_t acc_loc = 0, vis_loc = 0;
+    double fmax_loc = 0.0, fsum_loc = 0.0;
     for (int64_t i = lo; i < hi; ++i) {
         uint8_t c = j->comp ? j->comp[i] : (ORC_HAS_MASS | ORC_HAS_VELOCITY);
         if (!is_target(c)) continue;
-        counts_t cn = {0, 0};
+        counts_t cn = {0, 0, 0.0, 0.0};
         double vxx = j->ovx[i], vyy = j->ovy[i];
         force(j->t, 0, i, j->ox[i], j->oy[i], &vxx, &vyy, j->m[i], j->dt, &cn);
         j->ovx[i] = vxx; j->ovy[i] = vyy;
         acc_loc += cn.accepted; vis_loc += cn.visited;
+        if (cn.fmax > fmax_loc) fmax_loc = cn.fmax;
+        fsum_loc += cn.fsum;
         if (j->acc_per_body) j->acc_per_body[i] = (uint32_t)cn.accepted;
         if (j->vis_per_body) j->vis_per_body[i] = (uint32_t)cn.visited;
     }
     j->tot[tid].accepted += acc_loc; j->tot[tid].visited += vis_loc;
+    if (fmax_loc > j->tot[tid].fmax) j->tot[tid].fmax = fmax_loc;
+    j->tot[tid].fsum += fsum_loc;
 }
 
 /* BarnesHutSystem::update (barnes_hut.cpp:50-99) then, if run_movement, MovementSystem::update
@@ -297,6 +304,7 @@ int orc_bh_run(const orc_params* p, uint64_t n, const double* x, const double* y
     tree_t t; memset(&t, 0, sizeof(t));
     double tb = 0.0, tf = 0.0, t00 = now_s();
     uint64_t acc_tot = 0, vis_tot = 0;
+    double fmax_tot = 0.0, fsum_tot = 0.0;
     int rc = 0;
     for (int s = 0; s < nsteps && !rc; ++s) {
         /* early exit, barnes_hut.cpp:55-71 */
@@ -315,9 +323,13 @@ int orc_bh_run(const orc_params* p, uint64_t n, const double* x, const double* y
             tb += t1 - t0;
             if (rc) break;
             double dt = p->seconds_per_tick * p->base_time_acceleration * p->time_scale; /* :284 */
-            force_job job = {&t, comp, ox, oy, ovx, ovy, m, dt, acc_per_body, vis_per_body, {{0, 0}}};
+            force_job job = {&t, comp, ox, oy, ovx, ovy, m, dt, acc_per_body, vis_per_body, {{0, 0, 0.0, 0.0}}};
             parallel_for((int64_t)n, 256, threads, force_chunk, &job);
-            for (int k = 0; k < 256; ++k) { acc_tot += job.tot[k].accepted; vis_tot += job.tot[k].visited; }
+            for (int k = 0; k < 256; ++k) {
+                acc_tot += job.tot[k].accepted; vis_tot += job.tot[k].visited;
+                if (job.tot[k].fmax > fmax_tot) fmax_tot = job.tot[k].fmax;
+                fsum_tot += job.tot[k].fsum;
+            }
             tf += now_s() - t1;
         }
     movement:
@@ -334,6 +346,7 @@ int orc_bh_run(const orc_params* p, uint64_t n, const double* x, const double* y
     if (st) {
         fill_stats(&t, st);
         st->accepted = acc_tot; st->visited = vis_tot;
+        st->force_max = fmax_tot; st->force_sum = fsum_tot; st->force_count = acc_tot;
         st->build_seconds = tb; st->force_seconds = tf; st->total_seconds = now_s() - t00;
     }
     tree_free(&t);

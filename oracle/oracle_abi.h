@@ -71,6 +71,10 @@ typedef struct {
     double   build_seconds;   /* port only (the reference does not split build from force) */
     double   force_seconds;
     double   total_seconds;
+    /* DebugStats::updateForce (include/core/debug.hpp:37-41), called once per accepted node at barnes_hut.cpp:278:
+     * max / sum / count of force = G*M*m/distSq over the run. ref: the reference's own process globals. */
+    double   force_max, force_sum;
+    uint64_t force_count;
 } orc_stats;
 
 /* BoundarySystem::update on flat arrays, in place: bodies with ORC_HAS_VELOCITY and without ORC_ASLEEP are clamped

@@ -54,7 +54,7 @@ class Stats(C.Structure):
         ("pool_nodes", C.c_uint64), ("nonempty_nodes", C.c_uint64), ("internal_nodes", C.c_uint64),
         ("accepted", C.c_uint64), ("visited", C.c_uint64), ("max_depth", C.c_int32),
         ("pool_overflow", C.c_int32), ("build_seconds", C.c_double), ("force_seconds", C.c_double),
-        ("total_seconds", C.c_double),
+        ("total_seconds", C.c_double), ("force_max", C.c_double), ("force_sum", C.c_double), ("force_count", C.c_uint64),
     ]
 
     def as_dict(self):

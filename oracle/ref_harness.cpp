@@ -22,6 +22,7 @@
 #include <vector>
 
 #define private public
+#include "core/debug.hpp"          // DebugStats' counters are private statics
 #include "systems/barnes_hut.hpp"
 #undef private
 #include "systems/movement.hpp"
@@ -29,6 +30,7 @@
 #include "entities/entity_components.hpp"
 #include "entities/sim_components.hpp"
 
+#include "core/debug.hpp"
 #include "oracle_abi.h"
 
 namespace {
@@ -121,6 +123,9 @@ int ref_bh_run(const orc_params* p, uint64_t n, const double* x, const double* y
     const uint64_t pool = autoPool(n, pool_nodes);
     bh.nodePool_.resize(pool);
 
+    DebugStats::max_force = 0.0;   // the reference's own process globals (core/debug.hpp:24-41)
+    DebugStats::total_force = 0.0;
+    DebugStats::force_count = 0;
     auto t0 = Clock::now();
     for (int s = 0; s < nsteps; ++s) {
         bh.update(w.reg);
@@ -130,6 +135,9 @@ int ref_bh_run(const orc_params* p, uint64_t n, const double* x, const double* y
 
     treeStats(bh, p->universe_size, st);
     if (st) {
+        st->force_max = DebugStats::max_force;
+        st->force_sum = DebugStats::total_force;
+        st->force_count = (uint64_t)DebugStats::force_count;
         st->total_seconds = std::chrono::duration<double>(t1 - t0).count();
         st->pool_overflow = bh.nodePool_.size() != pool ? 1 : 0;
     }

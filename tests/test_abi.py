@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert C.sizeof(lpe_bh.Params) == 7 * 8 + 6 * 4
-    assert C.sizeof(lpe_bh.Stats) == 16 * 8 + 4 * 4 + 5 * 4 + 4  # padded to 8
+    assert C.sizeof(lpe_bh.Stats) == 16 * 8 + 4 * 4 + 6 * 4 + 2 * 8
     assert C.sizeof(lpe_bh.TreeDump) == 10 * 8
     assert C.sizeof(lpe_bh.DeviceView) == 8 * 8
     assert C.sizeof(lpe_bh.BoundaryParams) == 4 * 8

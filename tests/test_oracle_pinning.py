@@ -9,6 +9,7 @@ import pytest
 
 import oracle_py as O
 from conftest import golden_names, load_golden
+from parity import gen_uniform
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -103,3 +104,15 @@ def test_direct_sum_vs_textbook_tree(port):
         e = np.hypot(r["vx"] - ax, r["vy"] - ay) / np.hypot(ax, ay)
         errs[quirk] = float(np.median(e))
     assert errs[0] < 2e-2 and errs[1] > 2 * errs[0], errs
+
+
+def test_debugstats_force_statistics_port_equals_compiled_reference(port, reflib):
+    """A10: DebugStats::updateForce (core/debug.hpp:37-41) is fed force = G*M*m/distSq once per accepted node
+    (barnes_hut.cpp:278). The port's max / sum / count against the reference's own process globals."""
+    x, y, vx, vy, m = gen_uniform(1500, 1024.0, 61)
+    p = O.make_params(1024.0, 0.25)
+    a = port.run(p, x, y, vx, vy, m, threads=1)["stats"]
+    b = reflib.run(p, x, y, vx, vy, m)["stats"]
+    assert a["force_count"] == b["force_count"] > 0
+    assert a["force_max"] == b["force_max"]
+    assert abs(a["force_sum"] - b["force_sum"]) <= 1e-12 * b["force_sum"]

@@ -378,3 +378,24 @@ def test_error_paths_report_and_leave_the_context_usable():
         c.step(good, 1)
     c.close()
 
+
+
+def test_debugstats_force_statistics_and_largest_mass(bh, port):
+    """SURVEY.md A10 / N4: what the reference feeds DebugStats::updateForce with (max / sum / count of G*M*m/distSq over
+    the accepted nodes, barnes_hut.cpp:277-278) reduced on the device, and the largest source mass the two per-tick
+    Mass scans ask for (barnes_hut.cpp:55-71, gravity.cpp:41-49)."""
+    x, y, vx, vy, m = gen_uniform(20000, 1024.0, 71)
+    comp = np.full(len(x), O.HAS_MASS | O.HAS_VELOCITY, np.uint8)
+    comp[np.argmax(m)] |= O.BOUNDARY                       # the heaviest body is a Boundary: it must not count
+    ref = port.run(O.make_params(1024.0, 0.25), x, y, vx, vy, m, comp=comp, threads=8)["stats"]
+    for precision, tol in ((lpe_bh.PREC_FAST, 1e-5), (lpe_bh.PREC_STRICT, 1e-10)):
+        bh.set_instrumentation(counts=True)
+        bh.upload(x, y, vx, vy, m, comp=comp)
+        bh.step(lpe_bh.make_params(1024.0, 0.25, precision=precision), 1)
+        st = bh.stats()
+        assert st["interactions"] == ref["force_count"]
+        assert abs(st["force_sum"] - ref["force_sum"]) <= tol * ref["force_sum"], (precision, st["force_sum"], ref["force_sum"])
+        assert abs(st["force_max"] - ref["force_max"]) <= tol * ref["force_max"]
+        want = np.max(m[(comp & O.BOUNDARY) == 0])
+        assert bh.max_source_mass() == want
+    bh.set_instrumentation()
