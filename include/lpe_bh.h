@@ -132,6 +132,11 @@ int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
  * in 180 GB of HBM at ~450 B/body). */
 int  lpe_bh_upload(lpe_bh_ctx* ctx, uint64_t n, const double* x, const double* y, const double* vx,
                    const double* vy, const double* m, const uint32_t* rank, const uint8_t* comp);
+/* make the bodies ON THE DEVICE instead of uploading them — kind 4 = the Keplerian-disk scenario's
+ * entity law (reference src/scenarios/keplerian_disk.cpp:45-146) with one independent random stream per body, so the
+ * same (kind, n, seed) always gives the same bodies and lpe_bh_workload(4, ...) restates them on the host to libm
+ * rounding. Bodies are in creation order with EnTT's default insertion ranks, all with Mass and Velocity. Asynchronous. */
+int  lpe_bh_generate(lpe_bh_ctx* ctx, int kind, uint64_t n, uint64_t seed, double universe_size);
 /* Positions only (e.g. after other ECS systems moved bodies); n must match the last upload. */
 int  lpe_bh_upload_positions(lpe_bh_ctx* ctx, const double* x, const double* y);
 int  lpe_bh_upload_velocities(lpe_bh_ctx* ctx, const double* vx, const double* vy);
@@ -297,7 +302,8 @@ void  lpe_bh_free_pinned(void* p);
 
 /* ---- deterministic synthetic workloads (host, std::mt19937_64, u=(g()>>11)*2^-53) ----
  * kind: 0 = uniform disk (C2), 1 = Plummer sphere projected (C3), 2 = two-galaxy collision (C4),
- *       3 = Keplerian disk with the law of reference src/scenarios/keplerian_disk.cpp:78-147 (C1 stand-in) */
+ *       3 = Keplerian disk with the law of reference src/scenarios/keplerian_disk.cpp:78-147 (C1 stand-in)
+ *       4 = the same law, counter-based: one random stream per body (what lpe_bh_generate makes on the device) */
 int  lpe_bh_workload(int kind, uint64_t n, uint64_t seed, double universe_size, double* x, double* y,
                      double* vx, double* vy, double* m);
 

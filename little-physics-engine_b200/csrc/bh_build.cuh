@@ -143,11 +143,14 @@ __global__ void __launch_bounds__(256)
 k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body* __restrict__ bodyIn,
          const double2* __restrict__ velIn, const unsigned int* __restrict__ origIn, Body* __restrict__ bodyOut,
          double2* __restrict__ velOut, unsigned int* __restrict__ origOut, unsigned int* __restrict__ selfslot,
-         const unsigned int* __restrict__ n_dev) {
+         const unsigned int* __restrict__ n_dev, unsigned int cap, Scal* __restrict__ chk) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev) n = (int)*n_dev;
     if (i >= n) return;
     const unsigned int b = sidx[i];
+#ifdef LPE_CHECKED
+    if (b >= cap) { atomicOr(&chk->check_fault, 1u << 1); return; }
+#endif
     bodyOut[i] = bodyIn[b];
     if (velIn) velOut[i] = velIn[b];
     origOut[i] = origIn ? origIn[b] : b;
@@ -232,6 +235,7 @@ k_witness(int D, const unsigned long long* __restrict__ tkey, signed char* __res
             delta[t] = (signed char)L;
             const int shift = 2 * (D - L);
             const int a = cell_first(tkey, t, shift);
+            LPE_CHECK_NR(a >= 0 && a <= t && L >= 0 && L < D, 2, const_cast<Scal*>(s));
             wstart[t] = (unsigned int)a;
             atomicOr(&mask[a], 1u << L);
             // the witness that sits in the cell's first non-empty child counts the cell (once per cell)
@@ -355,6 +359,7 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         // the terminal itself: a single-body leaf, or the sum of the bodies that share its depth-D cell
         const unsigned int idx = (unsigned int)t + Pt + ncell;
         const unsigned int first = o.tfirst[t], last = o.tfirst[t + 1];
+        LPE_CHECK(idx < c.nodeCap && first < last && last <= c.bodyCap && Pt + ncell <= c.bodyCap, 3, s);
         const bool single = (last - first) == 1u;
         o.tnode[t] = idx;
         NodeMeta mt;
@@ -416,6 +421,7 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
             const int L = (int)delta[t];
             const unsigned int a0 = o.wstart[t];
             const unsigned int q = P[a0] + (unsigned int)__popc(mask[a0] & ((1u << L) - 1u));
+            LPE_CHECK(a0 <= (unsigned int)t && q < c.bodyCap, 4, s);
             const unsigned int mk1 = mask[t + 1];
             unsigned int code = (unsigned int)(t + 1) + P[t + 1];   // shallowest cell starting at t+1, or that terminal's node
             if (mk1 == 0u) {
@@ -461,11 +467,11 @@ struct NodeOut {
 __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const NodeOut& o, unsigned int p,
                                                     unsigned int qd, int cellLevel,
                                                     const unsigned int* __restrict__ child, double msi, int q,
-                                                    unsigned int quadShift, bool live) {
+                                                    unsigned int quadShift, bool live, const Scal* chk) {
     // every lane of the warp runs this (the ballot / shuffles use the full mask); quads past the end of the list
     // carry live = false and neither read children nor store anything. The level list carries the cell's ordinal
     // next to its pre-order index, so the child codes are fetched without a detour through the cell's own meta.
-    const unsigned int ci = live ? child[(size_t)qd * 4 + q] : LPE_NONE;
+    const unsigned int ci = live ? child[(size_t)lpe_idx(qd, c.bodyCap, 5, chk) * 4 + q] : LPE_NONE;
     const bool valid = ci != LPE_NONE;
     Agg a;
     a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
@@ -475,11 +481,11 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
     if (valid) {
         if (ci & LPE_LEAF_FLAG) {
             // a single-body leaf: read the body itself (one sector), no aggregate was ever stored for it
-            leafpos = ci & ~LPE_LEAF_FLAG;
+            leafpos = lpe_idx(ci & ~LPE_LEAF_FLAG, c.bodyCap, 6, chk);
             a = body_agg(o.body[leafpos], leafpos, c.thr);
         } else {
-            a = o.agg[ci];
-            const NodeMeta mc = o.meta[ci];
+            a = o.agg[lpe_idx(ci, c.nodeCap, 7, chk)];
+            const NodeMeta mc = o.meta[lpe_idx(ci, c.nodeCap, 7, chk)];
             level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + c.blockBase;   // a deeper cell's skip is already final
         }
     }
@@ -506,7 +512,8 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         }
         skip = start;   // every lane of the quad now holds the end of the whole cell
     }
-    const unsigned int slot = 4u * (qd + c.blockBase) + r;
+    const unsigned int slot = lpe_idx(4u * (qd + c.blockBase) + r, c.recSlots, 8, chk);
+    p = lpe_idx(p, c.nodeCap, 9, chk);
     if (valid) {
         o.rec[slot] = make_record(c, a, level, myskip, cbi, msi);
         o.recnode[slot] = (leafpos != LPE_NONE) ? (LPE_LEAF_FLAG | leafpos) : ci;
@@ -560,7 +567,7 @@ k_agg_level(StepConst c, int L, const uint2* __restrict__ levelList, const unsig
     for (unsigned int k = 0; k < rounds; ++k, i += quads) {
         const bool live = i < count;
         const uint2 e = levelList[base + (live ? i : 0u)];
-        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live);
+        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live, s);
     }
 }
 
@@ -580,7 +587,7 @@ k_agg_top(StepConst c, int Ltop, const uint2* __restrict__ levelList, const unsi
         for (unsigned int k = 0; k < rounds; ++k, i += quads) {
             const bool live = i < count;
             const uint2 e = levelList[base + (live ? i : 0u)];
-            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live);
+            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live, s);
         }
         __syncthreads();
     }

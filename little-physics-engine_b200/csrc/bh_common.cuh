@@ -14,6 +14,22 @@
 #define LPE_NONE 0xFFFFFFFFu
 #define LPE_MAX_DEPTH 30
 
+// ---- checked build (liblpe_bh_checked.so, -DLPE_CHECKED) --------------------------------------------------------------
+// compute-sanitizer is not available on this pool, so the index arithmetic of the kernels carries its own bounds checks:
+// in the checked library every computed index into the big arrays is compared with the array's extent first; a
+// violation raises a bit in Scal::check_fault (reported as an error by the next synchronising call) and the access is
+// skipped. The GPU test-suite runs once against the checked library (tests/test_checked_build_gpu.py). In the
+// production library the macro is empty.
+#ifdef LPE_CHECKED
+#define LPE_CHECK(cond, code, scal) \
+    do { if (!(cond)) { atomicOr(&(scal)->check_fault, 1u << (code)); return; } } while (0)
+#define LPE_CHECK_NR(cond, code, scal) \
+    do { if (!(cond)) atomicOr(&(scal)->check_fault, 1u << (code)); } while (0)
+#else
+#define LPE_CHECK(cond, code, scal) ((void)0)
+#define LPE_CHECK_NR(cond, code, scal) ((void)0)
+#endif
+
 namespace lpe {
 
 constexpr int LPE_MAX_P2P = 8;   // ranks of one NVSwitch domain that can exchange by direct peer stores
@@ -47,6 +63,8 @@ struct Scal {
     // max and sum of force = G*M*m/distSq over the accepted interactions (stats runs only; the count is `interactions`)
     unsigned long long force_max_bits;
     double force_sum;
+    unsigned int check_fault;   // checked build: bit k = bounds check k failed in this step (see LPE_CHECK)
+    unsigned int pad_chk;
 };
 
 // Traversal node record, 32 bytes = two broadcast 16-byte shared-memory loads per visited node.
@@ -114,10 +132,26 @@ struct StepConst {
     int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
     int test_overflow;        // tests only: pretend every two-phase frontier overflows
     int hilbert;              // sort key: 0 = Morton code, 1 = Hilbert index of the same depth-D cell
+    unsigned int recSlots;    // extent of the record array (slots), nodeCap of the per-node arrays, bodyCap of the per-body ones
+    unsigned int nodeCap, bodyCap;
     int dd;                   // domain-decomposed rank: the local build leaves the root block and the top of the tree alone
     unsigned int blockBase;   // child block of the cell with ordinal q is blockBase + q (1 on a single GPU: block 0 = root)
     float eps2f;              // (float)eps2s, converted once on the host (the kernels would re-convert it in their loops)
 };
+
+// checked build: an index is compared with the array's extent before it is used; out of range raises bit `code` of
+// Scal::check_fault and the access goes to element 0 instead. Production build: the index, untouched.
+__device__ __forceinline__ unsigned int lpe_idx(unsigned int i, unsigned int extent, int code, const Scal* s) {
+#ifdef LPE_CHECKED
+    if (i >= extent) {
+        atomicOr(&const_cast<Scal*>(s)->check_fault, 1u << code);
+        return 0u;
+    }
+#else
+    (void)extent; (void)code; (void)s;
+#endif
+    return i;
+}
 
 // Mass and centre of mass of a node as the traversal sees it, in real units.
 //   leaf: exactly the body (barnes_hut.cpp:144-153); internal cell or aggregated terminal: with quirk, the first

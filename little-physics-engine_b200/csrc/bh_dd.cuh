@@ -195,7 +195,7 @@ k_dd_keygen(StepConst c, DDSplit sp, const Body* __restrict__ body, const double
         } else {
             DDHeader* oh = peers.hdr[owner];
             const unsigned int slot = oh->n_live + atomicAdd(&oh->inbox_count, 1u);
-            if (slot < (unsigned int)c.n) {
+            if (slot < (unsigned int)c.n) {   // (the bounds check of the migration: a full owner raises fault bit 0)
                 peers.body[owner][slot] = b;
                 peers.vel[owner][slot] = vel[i];
                 peers.orig[owner][slot] = orig[i];
@@ -472,7 +472,7 @@ k_dd_export(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDExportA
         bool any = false;
         for (unsigned int e = head + ((myQuad + quads - head % quads) % quads); e < tail; e += quads) {
             const unsigned int q = __ldcg(queue + e);
-            const uint4* src = reinterpret_cast<const uint4*>(a.rec + 4u * (c.blockBase + q) + r4);
+            const uint4* src = reinterpret_cast<const uint4*>(a.rec + lpe_idx(4u * (c.blockBase + q) + r4, c.recSlots, 15, s));
             uint4 v0 = src[0], v1 = src[1];
             TravRec R;
             R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
@@ -483,7 +483,7 @@ k_dd_export(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDExportA
                 any = any || open;
                 v1.w = (blk << 2) | (R.cblock & 3u);
             }
-            uint4* o = reinterpret_cast<uint4*>(peers.rec[d] + 4u * ((size_t)regionBase + e) + r4);
+            uint4* o = reinterpret_cast<uint4*>(peers.rec[d] + lpe_idx(4u * (regionBase + e) + r4, c.recSlots, 14, s));
             __stcs(o, v0);
             __stcs(o + 1, v1);
         }
@@ -596,6 +596,7 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
     }
     auto rootAt = [&](int i) -> const DDRoot& { return inShared ? sroots[i] : globalRoot(i); };
     auto writeChild = [&](unsigned int slot, const Agg& a, int level, unsigned int cblockIndex, const DDRoot* root) {
+        slot = lpe_idx(slot, 4u * DD_TOPCAP, 16, s);
         rec[slot] = make_record(c, a, level, 1u, cblockIndex, msi);
         xrec[slot] = dd_xrec(a, level, c.quirk);   // (node_centre is inlined in both: the divisions are shared)
         if (root && root->owner == (unsigned int)me && root->leafpos != LPE_NONE && c.need_self) selfslot[root->leafpos] = slot;

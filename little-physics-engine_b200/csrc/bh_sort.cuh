@@ -258,6 +258,9 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
         const unsigned long long kx = skey[j];
         const unsigned int d = (unsigned int)(kx >> shift) & dmask;
         const unsigned int dst = gbase[d] + ((unsigned int)j - dbase[d]);
+#ifdef LPE_CHECKED
+        if (dst >= (unsigned int)n) { atomicOr(fault, 2u); continue; }   // (bit 1 of the sort's fault word)
+#endif
         keysOut[dst] = kx;
         valsOut[dst] = sval[j];
     }

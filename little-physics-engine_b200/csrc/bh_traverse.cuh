@@ -85,8 +85,10 @@ __device__ __noinline__ bool exact_open_slot(const Agg* __restrict__ agg, const 
 }
 
 // 8 lanes copy one 128-byte child block into a frame of the warp's stack
-__device__ __forceinline__ void load_block(const TravRec* __restrict__ rec, unsigned int block, TravRec* frame, int lane) {
+__device__ __forceinline__ void load_block(const TravRec* __restrict__ rec, unsigned int block, TravRec* frame, int lane,
+                                           const StepConst& c, const Scal* s) {
     __syncwarp();
+    block = lpe_idx(block, c.recSlots >> 2, 12, s);
     if (lane < 8) {
         const uint4 v = reinterpret_cast<const uint4*>(rec + 4 * (size_t)block)[lane];
         reinterpret_cast<uint4*>(frame)[lane] = v;
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
         unsigned long long cstack = 0;   // 2 bits per depth: (number of children in that frame) - 1
         const bool alive = n_nodes != 0;
         if (alive) {
-            load_block(a.rec, 0u, frames, lane);
+            load_block(a.rec, 0u, frames, lane, c, a.s);
             if (lane == 0) fblock[0] = 0u;
             __syncwarp();
         }
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     ++d;
                     cstack = (cstack & ~(3ull << (2 * d))) | ((unsigned long long)(cb & 3u) << (2 * d));
                     k = 0;
-                    load_block(a.rec, cb >> 2, frames + d * 4, lane);
+                    load_block(a.rec, cb >> 2, frames + lpe_idx((unsigned int)d, (unsigned int)TRAV_FRAMES, 13, a.s) * 4, lane, c, a.s);
                     if (lane == 0) fblock[d] = cb >> 2;
                     __syncwarp();
                 } else {
@@ -301,7 +303,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                     ++d;
                     cstack = (cstack & ~(3ull << (2 * d))) | ((unsigned long long)(cblock & 3u) << (2 * d));
                     k = 0;
-                    load_block(a.rec, cblock >> 2, frames + d * 4, lane);
+                    load_block(a.rec, cblock >> 2, frames + lpe_idx((unsigned int)d, (unsigned int)TRAV_FRAMES, 13, a.s) * 4, lane, c, a.s);
                     if (lane == 0) fblock[d] = cblock >> 2;
                     __syncwarp();
                 } else {

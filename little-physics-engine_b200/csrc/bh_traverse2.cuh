@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                     const uint2 e = W.q[(head + lane) & QM];
                     slot = e.x;
                     mask = e.y;
-                    const uint4* src = reinterpret_cast<const uint4*>(a.rec + slot);
+                    const uint4* src = reinterpret_cast<const uint4*>(a.rec + lpe_idx(slot, c.recSlots, 10, a.s));
                     const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
                     R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
                     R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                 const unsigned int posM = __popc(maskM & lt);
                 const unsigned int cntM = __popc(maskM);
                 if (toA) {
-                    const unsigned int pos = nA + __popc(maskA & lt);
+                    const unsigned int pos = lpe_idx(nA + __popc(maskA & lt), (unsigned int)T2_ABUF - 1u, 11, a.s);
                     APair& E = W.ap[pos >> 1];
                     const unsigned int h = pos & 1u;
                     E.xh[h] = R.c.x; E.yh[h] = R.c.y; E.xl[h] = R.c.z; E.yl[h] = R.c.w;

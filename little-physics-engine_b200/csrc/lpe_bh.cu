@@ -23,6 +23,7 @@
 #include "bh_traverse.cuh"
 #include "bh_traverse2.cuh"
 #include "bh_dd.cuh"
+#include "kepler_gen.h"
 
 using namespace lpe;
 
@@ -326,6 +327,22 @@ __global__ void k_pack_mass(int n, const double* __restrict__ m, const unsigned 
     }
     block_max_mass(mi, cm, s);
 }
+// the scenario's bodies made on the device, one thread per body (kepler_gen.h)
+__global__ void __launch_bounds__(256)
+k_generate_keplerian(int n, unsigned long long seed, double U, Body* __restrict__ body, double2* __restrict__ vel, Scal* __restrict__ s) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    Body b;
+    b.m = 0.0; b.comp = 0u;
+    if (i < n) {
+        double vx, vy;
+        lpe_keplerian_body((uint64_t)i, seed, U, &b.x, &b.y, &vx, &vy, &b.m);
+        b.rank = (unsigned int)(n - 1 - i);    // EnTT's view order: newest entity first
+        b.comp = (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+        body[i] = b;
+        vel[i] = make_double2(vx, vy);
+    }
+    block_max_mass(b.m, b.comp, s);
+}
 // MovementSystem::update as its own pass (STRICT precision: the traversal reads leaf bodies from the state, so the
 // positions must not move under it). Same expression as the fused drift of the traversal kernels.
 __global__ void __launch_bounds__(256) k_drift(int n, double dtD, Body* __restrict__ body, const double2* __restrict__ vel,
@@ -501,9 +518,21 @@ int fetch_fault(lpe_bh_ctx* c) {
 }
 int check_fault(lpe_bh_ctx* c) {
     if (c->fault_host && *c->fault_host) {
+        const unsigned int f = *c->fault_host;
         *c->fault_host = 0;
+        if (f & 2u) return fail(c, "checked build: radix sort scatter index out of range");
         return fail(c, "radix sort look-back timed out (internal error): results of the last step are invalid");
     }
+#ifdef LPE_CHECKED
+    if (c->scal && c->have_step) {
+        unsigned int f = 0;
+        if (cudaMemcpy(&f, &c->scal->check_fault, sizeof(f), cudaMemcpyDeviceToHost) == cudaSuccess && f) {
+            char buf[96];
+            std::snprintf(buf, sizeof(buf), "checked build: index out of range, check bits 0x%x", f);
+            return fail(c, buf);
+        }
+    }
+#endif
     return 0;
 }
 
@@ -555,6 +584,9 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     k.hilbert = (p.key_order == LPE_KEYS_HILBERT || (p.key_order == LPE_KEYS_AUTO && p.precision == LPE_PREC_FAST)) ? 1 : 0;
     k.dd = 0;
     k.blockBase = 1u;
+    k.bodyCap = (unsigned int)c->cap;
+    k.nodeCap = (unsigned int)c->node_cap;
+    k.recSlots = 4u * ((unsigned int)c->cap + 8u);
     return 0;
 }
 
@@ -640,7 +672,8 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
     }
     // (host tick: the velocities are still on their way and are packed straight into key order before the kick)
     k_gather<<<g256, 256, 0, sg>>>(n, k.need_self, sidx, c->body, c->pend_vel ? nullptr : c->vel,
-                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfslot, n_dev);
+                                   c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfslot, n_dev,
+                                   (unsigned int)c->cap, c->scal);
     CU_TRY(c, cudaEventRecord(c->evs[1], sg));
     // from here on the state IS in key order
     std::swap(c->body, c->body2);
@@ -790,7 +823,11 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
 
 extern "C" {
 
+#ifdef LPE_CHECKED
+const char* lpe_bh_version(void) { return "lpe_bh 0.2 (sm_100a, ABI 2, CHECKED build: bounds checks on)"; }
+#else
 const char* lpe_bh_version(void) { return "lpe_bh 0.2 (sm_100a, ABI 2)"; }
+#endif
 
 int lpe_bh_device_count(void) {
     int n = 0;
@@ -894,6 +931,24 @@ int lpe_bh_upload(lpe_bh_ctx* c, uint64_t n, const double* x, const double* y, c
     if (vy) CU_TRY(c, cudaMemcpyAsync(t1, vy, bytes, cudaMemcpyHostToDevice, st));
     k_pack2<<<g, 256, 0, st>>>((int)n, vx ? t0 : nullptr, vy ? t1 : nullptr, c->vel, nullptr);
     CU_TRY(c, cudaGetLastError());
+    return 0;
+}
+
+int lpe_bh_generate(lpe_bh_ctx* c, int kind, uint64_t n, uint64_t seed, double universe_size) {
+    if (!c) return 1;
+    if (kind != 4) return fail(c, "lpe_bh_generate: only kind 4 (counter-based Keplerian disk) is made on the device");
+    if (n > LPE_MAX_BODIES) return fail(c, "too many bodies for one context (limit 2^28)");
+    if (!(universe_size > 0.0)) return fail(c, "universe_size must be positive");
+    DevGuard _dg(c->device);
+    if (ensure_capacity(c, n)) return 1;
+    c->n = n;
+    c->have_step = false;
+    c->orig_valid = false;
+    if (n == 0) return 0;
+    CU_TRY(c, cudaMemsetAsync(c->scal, 0, sizeof(Scal), c->stream));
+    k_generate_keplerian<<<cdiv((long long)n, 256), 256, 0, c->stream>>>((int)n, seed, universe_size, c->body, c->vel, c->scal);
+    CU_TRY(c, cudaGetLastError());
+    c->launches += 1;
     return 0;
 }
 

@@ -232,6 +232,7 @@ int dd_make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     if (p.universe_size != c->dd_U) return fail(c, "domain decomposition: universe_size differs from the one the bodies were distributed with");
     k.dd = 1;
     k.blockBase = DD_TOPCAP;
+    k.recSlots = 4u * dd_layout(c->cap, c->dd_R, c->dd_icap).nblocks;
     k.shard_rank = 0;
     k.shard_n = 1;
     k.n = (int)c->cap;

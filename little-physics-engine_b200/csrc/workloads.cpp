@@ -10,6 +10,8 @@
 //                                       pdf ~ (r_in/r)^(15/8) between r_in = U/60 and r_out = U/6 (the law of
 //                                       reference keplerian_disk.cpp:72-75,99-106), a central body of half the disk
 //                                       mass created first, circular Kepler speed plus a bulk approach velocity
+//   kind 4      Keplerian disk, counter-based (kepler_gen.h): body i from its own stream, identical law; the device
+//                                       makes the same bodies without any host array (lpe_bh_generate)
 //   kind 3  C1  Keplerian disk          restates reference src/scenarios/keplerian_disk.cpp:45-146 (central mass 1e36,
 //                                       density/height/mass power laws, velocity dispersion) with this RNG; the
 //                                       reference itself seeds from time() and is not reproducible
@@ -18,6 +20,7 @@
 #include <random>
 
 #include "../../include/lpe_bh.h"
+#include "kepler_gen.h"
 
 namespace {
 
@@ -143,6 +146,9 @@ extern "C" int lpe_bh_workload(int kind, uint64_t n, uint64_t seed, double U, do
         case 1: plummer(n, seed, U, x, y, vx, vy, m); return 0;
         case 2: two_galaxies(n, seed, U, x, y, vx, vy, m); return 0;
         case 3: keplerian(n, seed, U, x, y, vx, vy, m); return 0;
+        case 4:   // the same law, one independent stream per body: what lpe_bh_generate makes on the device
+            for (uint64_t i = 0; i < n; ++i) lpe_keplerian_body(i, seed, U, x + i, y + i, vx + i, vy + i, m + i);
+            return 0;
         default: return 1;
     }
 }

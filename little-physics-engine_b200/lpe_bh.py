@@ -16,7 +16,8 @@ import subprocess
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblpe_bh.so")
+# LPE_BH_LIB selects another build of the same library (tests: liblpe_bh_checked.so, the kernels' bounds checks on)
+LIB_PATH = os.environ.get("LPE_BH_LIB") or os.path.join(HERE, "liblpe_bh.so")
 
 HAS_MASS, HAS_VELOCITY, BOUNDARY, LIQUID, ASLEEP = 1, 2, 4, 8, 16
 PREC_FAST, PREC_STRICT = 0, 1
@@ -24,7 +25,7 @@ KEYS_AUTO, KEYS_MORTON, KEYS_HILBERT = 0, 1, 2
 SHARD_BLOCK = 2048
 G_REAL = 6.674e-11  # SimulatorConstants::RealG, reference src/core/constants.cpp:8
 
-WORKLOADS = {"disk": 0, "plummer": 1, "two_galaxies": 2, "keplerian": 3}
+WORKLOADS = {"disk": 0, "plummer": 1, "two_galaxies": 2, "keplerian": 3, "keplerian_counter": 4}
 
 
 class Params(C.Structure):
@@ -238,6 +239,12 @@ class BarnesHut:
         self._keep = (x, y, vx, vy, m, rank, comp)
         self._chk(self.lib.lpe_bh_upload(self.h, C.c_uint64(self.n), _dp(x), _dp(y), _dp(vx), _dp(vy), _dp(m),
                                          _dp(rank), _dp(comp)), "upload")
+
+    def generate(self, kind, n, seed, U):
+        """Make the bodies on the device (lpe_bh_generate): kind "keplerian_counter"."""
+        self.n = n
+        self._chk(self.lib.lpe_bh_generate(self.h, C.c_int(WORKLOADS[kind] if isinstance(kind, str) else kind), C.c_uint64(n),
+                                           C.c_uint64(seed), C.c_double(U)), "generate")
 
     def upload_positions(self, x, y):
         """Replace the positions of the resident bodies (creation order), e.g. after a host-side MovementSystem."""

@@ -10,7 +10,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libworkloads.so")
-KINDS = {"disk": 0, "plummer": 1, "two_galaxies": 2, "keplerian": 3}
+KINDS = {"disk": 0, "plummer": 1, "two_galaxies": 2, "keplerian": 3, "keplerian_counter": 4}
 _lib = None
 
 

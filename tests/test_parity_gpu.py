@@ -399,3 +399,25 @@ def test_debugstats_force_statistics_and_largest_mass(bh, port):
         want = np.max(m[(comp & O.BOUNDARY) == 0])
         assert bh.max_source_mass() == want
     bh.set_instrumentation()
+
+
+def test_scenario_bodies_made_on_the_device(bh, port):
+    """the Keplerian-disk scenario's entity law (keplerian_disk.cpp:45-146) evaluated one thread per body
+    on the device equals its host restatement (same counter-based streams) to libm rounding, is reproducible, and steps
+    like uploaded bodies do."""
+    n, Uk = 50000, 6e9
+    hx, hy, hvx, hvy, hm = lpe_bh.workload("keplerian_counter", n, 17, Uk)
+    bh.generate("keplerian_counter", n, 17, Uk)
+    d = bh.download()
+    for got, want, scale in ((d["x"], hx, Uk), (d["y"], hy, Uk), (d["vx"], hvx, np.abs(hvx).max()), (d["vy"], hvy, np.abs(hvy).max())):
+        assert np.max(np.abs(got - want)) <= 1e-11 * scale
+    assert bh.max_source_mass() == 1e36 and hm[0] == 1e36
+    assert 0.09 * Uk < hx.min() and hx.max() < 0.91 * Uk           # outer radius = ScreenLength / 2.5 = 240 of 300 px
+    kw = dict(theta=0.5, thr=1e3, dt_kick=1 / 120, dt_drift=6.756e-3)
+    bh.step(lpe_bh.make_params(Uk, 2e7, **kw), 1)
+    got = bh.download()
+    ref = port.run(O.make_params(Uk, 2e7, **kw), d["x"], d["y"], d["vx"], d["vy"], hm, threads=8)
+    assert rel_err((got["vx"] - d["vx"], got["vy"] - d["vy"]), (ref["vx"] - d["vx"], ref["vy"] - d["vy"]))["max"] <= FAST_TOL
+    bh.generate("keplerian_counter", n, 17, Uk)
+    again = bh.download()
+    assert np.array_equal(again["x"], d["x"]) and np.array_equal(again["vy"], d["vy"])
