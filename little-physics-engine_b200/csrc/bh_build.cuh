@@ -20,7 +20,6 @@
 //     first child of (a, L)  = the next deeper cell starting at a (preorder + 1), else terminal a
 //     other children         = for every witness t of the cell: the shallowest cell starting at t+1
 //                              ((t+1) + P[t+1]), else terminal t+1
-// Skip pointers are filled by the aggregation (a cell ends where its last child ends).
 // Aggregation is level-synchronous, deepest level first (one launch per level, cells of a level listed by a
 // block-aggregated counting pass in k_topology): a QUAD of lanes sums a cell's <= 4 children in the fixed order
 // (c0 + c1) + (c2 + c3) and writes their traversal records side by side into the cell's CHILD BLOCK (one 128-byte
@@ -269,11 +268,9 @@ __global__ void k_level_scan(const unsigned int* __restrict__ levelCount, unsign
 
 // ---- 5. topology: pre-order indices, skip pointers, child slots, per-level cell lists ------------------------
 struct Topo {
-    unsigned int* tnode;      // [terminal] pre-order index of the terminal's node
     const unsigned int* wstart; // [terminal] first terminal of the cell that t witnesses
     unsigned int* child;      // [4 * ordinal + digit] a cell's child: pre-order index, or LPE_LEAF_FLAG | sorted body
                               // position for a single-body leaf, or LPE_NONE
-    NodeMeta* meta;           // [preorder]
     Agg* agg;                 // [preorder] written here only for aggregated terminals (>= 2 bodies in a depth-D cell)
     uint2* levelList;         // cells grouped by level: levelList[levelBase[L] + i] = {pre-order index, cell ordinal}
     const unsigned int* levelBase;
@@ -282,7 +279,6 @@ struct Topo {
     const Body* body;         // state in key order
     unsigned int* selfslot;   // [sorted body] record slot of its own leaf (only written here for a one-terminal tree)
     TravRec* rec;
-    unsigned int* recnode;
 };
 
 // Power-of-two mass unit just above the largest source mass: node masses then fit fp32 comfortably
@@ -298,12 +294,12 @@ __device__ __forceinline__ Agg body_agg(const Body& sb, unsigned int pos, double
     Agg a;
     a.m = sb.m; a.sx = sb.m * sb.x; a.sy = sb.m * sb.y;
     a.mf = sb.m; a.xf = sb.x; a.yf = sb.y;
-    a.frank = sb.rank; a.fidx = pos; a.count = 1u; a.small = (sb.m >= thr) ? 0u : 1u;
+    a.frank = sb.rank; a.fidx = pos; a.ordinal = 0u; a.small = (sb.m >= thr) ? 0u : 1u;
     return a;
 }
 
 // Traversal record of a node from its aggregate.
-__device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a, int level, unsigned int skip,
+__device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a, int level, unsigned int node,
                                                unsigned int cblockIndex, double massScaleInv) {
     double M, cx, cy;
     node_centre(a, level, c.quirk, M, cx, cy);
@@ -320,7 +316,7 @@ __device__ __forceinline__ TravRec make_record(const StepConst& c, const Agg& a,
         const double s = ldexp(c.U, -level) * c.invS;
         r.open_t = (float)((s * s) / c.theta2);
     }
-    r.skip = skip;
+    r.node = node;
     r.cblock = (level >= 0) ? ((cblockIndex << 2) | ((a.small >> 1) & 3u)) : 0u;
     return r;
 }
@@ -330,7 +326,7 @@ __device__ __forceinline__ TravRec invalid_record() {
     r.c = make_float4(0.f, 0.f, 0.f, 0.f);
     r.gm = 0.f;
     r.open_t = -1.f;
-    r.skip = 0u;
+    r.node = LPE_NONE;
     r.cblock = 0u;
     return r;
 }
@@ -361,16 +357,12 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         const unsigned int first = o.tfirst[t], last = o.tfirst[t + 1];
         LPE_CHECK(idx < c.nodeCap && first < last && last <= c.bodyCap && Pt + ncell <= c.bodyCap, 3, s);
         const bool single = (last - first) == 1u;
-        o.tnode[t] = idx;
-        NodeMeta mt;
-        mt.skip = idx + 1; mt.start = (unsigned int)t; mt.level = single ? -1 : -2; mt.pad = first;
-        o.meta[idx] = mt;
         Agg a;
         if (single) {
             if (n_term == 1) a = body_agg(o.body[first], first, c.thr);
         } else {
             a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
-            a.frank = 0xFFFFFFFFu; a.fidx = first; a.count = last - first; a.small = 1u;
+            a.frank = 0xFFFFFFFFu; a.fidx = first; a.ordinal = 0u; a.small = 1u;   // (level bits 0 = aggregated terminal)
             // Bodies that share a depth-D cell are summed in insertion-rank order, not in sorted-position order (which
             // for equal keys is an accident of the previous permutation): the sums are then the same however the
             // bodies reached this GPU (single GPU, or migrated between the ranks of a domain-decomposed run).
@@ -396,9 +388,8 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         const unsigned int tcode = single ? (LPE_LEAF_FLAG | first) : idx;
         if (n_term == 1 && !c.dd) {   // a tree of one terminal: it is the root
             const double msi = mass_scale_inv(s->max_mass_bits);
-            o.rec[0] = make_record(c, a, single ? -1 : -2, idx + 1, 0u, msi);
+            o.rec[0] = make_record(c, a, single ? -1 : -2, single ? (LPE_LEAF_FLAG | first) : idx, 0u, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
-            o.recnode[0] = single ? (LPE_LEAF_FLAG | first) : idx;
             if (single && c.need_self) o.selfslot[first] = 0u;
         }
         // branching cells whose first terminal is t, shallow to deep: ordinal Pt + i, pre-order t + Pt + i
@@ -407,9 +398,6 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
             const int L = __ffs(rest) - 1;
             rest &= rest - 1;
             const unsigned int cidx = (unsigned int)t + Pt + i;
-            NodeMeta mc;
-            mc.skip = 0; mc.start = (unsigned int)t; mc.level = L; mc.pad = 0;
-            o.meta[cidx] = mc;
             // first child: the next deeper cell starting here, else the terminal
             const unsigned int digit = (unsigned int)(kt >> (2 * (D - L - 1))) & 3u;
             o.child[(size_t)(Pt + i) * 4 + digit] = rest ? cidx + 1u : tcode;
@@ -452,10 +440,8 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
 
 // ---- 6. aggregation and traversal records ---------------------------------------------------------------------
 struct NodeOut {
-    NodeMeta* meta;         // [preorder]
     Agg* agg;               // [preorder] (cells and aggregated terminals; single-body leaves have none)
     TravRec* rec;           // [4 * block + slot]; block 0 = {root}, block q+1 = children of the cell with ordinal q
-    unsigned int* recnode;  // [4 * block + slot] pre-order index of the cell stored in that slot (LPE_NONE for leaves)
     unsigned int* selfslot; // [sorted body] record slot of the body's own single-body leaf, LPE_NONE otherwise
     const Body* body;       // state in key order
 };
@@ -475,48 +461,29 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
     const bool valid = ci != LPE_NONE;
     Agg a;
     a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
-    a.frank = 0xFFFFFFFFu; a.fidx = 0; a.count = 0; a.small = 1u;
+    a.frank = 0xFFFFFFFFu; a.fidx = 0; a.ordinal = 0; a.small = 1u;
     int level = -1;
-    unsigned int skip = 0, cbi = 0, leafpos = LPE_NONE;
+    unsigned int cbi = 0, leafpos = LPE_NONE;
     if (valid) {
         if (ci & LPE_LEAF_FLAG) {
             // a single-body leaf: read the body itself (one sector), no aggregate was ever stored for it
             leafpos = lpe_idx(ci & ~LPE_LEAF_FLAG, c.bodyCap, 6, chk);
             a = body_agg(o.body[leafpos], leafpos, c.thr);
         } else {
+            // a deeper cell or an aggregated terminal: its aggregate says what it is (level) and where its children are
             a = o.agg[lpe_idx(ci, c.nodeCap, 7, chk)];
-            const NodeMeta mc = o.meta[lpe_idx(ci, c.nodeCap, 7, chk)];
-            level = mc.level; skip = mc.skip; cbi = (ci - mc.start) + c.blockBase;   // a deeper cell's skip is already final
+            level = agg_level(a);
+            cbi = (level >= 0) ? a.ordinal + c.blockBase : 0u;
         }
     }
     const unsigned int vmask = (__ballot_sync(0xFFFFFFFFu, valid) >> quadShift) & 0xFu;
     const unsigned int below = (1u << q) - 1u;
     const unsigned int nvalid = __popc(vmask);
     const unsigned int r = valid ? __popc(vmask & below) : nvalid + __popc(~vmask & below & 0xFu);
-    // Skip pointers, bottom up: children are consecutive in pre-order, so child k starts where child k-1's subtree
-    // ends, the first child starts at p + 1, and the cell ends where its last child ends. A childless node
-    // (leaf / aggregated terminal) ends at its own index + 1.
-    unsigned int myskip = 0;
-    {
-        const int lane = (int)(threadIdx.x & 31u);
-        const int qbase = lane & ~3;
-        unsigned int start = p + 1u;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // lane k of the quad: subtree end of its child, given where it starts
-            const unsigned int endk = (cbi != 0u) ? skip : start + 1u;
-            const unsigned int e = __shfl_sync(0xFFFFFFFFu, endk, qbase + k);
-            const bool vk = (vmask >> k) & 1u;
-            if (k == q) myskip = endk;
-            if (vk) start = e;
-        }
-        skip = start;   // every lane of the quad now holds the end of the whole cell
-    }
     const unsigned int slot = lpe_idx(4u * (qd + c.blockBase) + r, c.recSlots, 8, chk);
     p = lpe_idx(p, c.nodeCap, 9, chk);
     if (valid) {
-        o.rec[slot] = make_record(c, a, level, myskip, cbi, msi);
-        o.recnode[slot] = (leafpos != LPE_NONE) ? (LPE_LEAF_FLAG | leafpos) : ci;
+        o.rec[slot] = make_record(c, a, level, (leafpos != LPE_NONE) ? (LPE_LEAF_FLAG | leafpos) : ci, cbi, msi);
         if (leafpos != LPE_NONE && c.need_self) o.selfslot[leafpos] = slot;
     } else if (live) {
         o.rec[slot] = invalid_record();
@@ -529,24 +496,23 @@ __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const No
         const double osy = __shfl_xor_sync(0xFFFFFFFFu, a.sy, sft), omf = __shfl_xor_sync(0xFFFFFFFFu, a.mf, sft);
         const double oxf = __shfl_xor_sync(0xFFFFFFFFu, a.xf, sft), oyf = __shfl_xor_sync(0xFFFFFFFFu, a.yf, sft);
         const unsigned int ofr = __shfl_xor_sync(0xFFFFFFFFu, a.frank, sft), ofi = __shfl_xor_sync(0xFFFFFFFFu, a.fidx, sft);
-        const unsigned int ocn = __shfl_xor_sync(0xFFFFFFFFu, a.count, sft), osm = __shfl_xor_sync(0xFFFFFFFFu, a.small, sft);
+        const unsigned int osm = __shfl_xor_sync(0xFFFFFFFFu, a.small, sft);
         // the lower lane of each pair adds (own + other) so that the order is the same on both sides
         const bool lower = (q & sft) == 0;
         a.m = lower ? a.m + om : om + a.m;
         a.sx = lower ? a.sx + osx : osx + a.sx;
         a.sy = lower ? a.sy + osy : osy + a.sy;
         if (ofr < a.frank) { a.frank = ofr; a.fidx = ofi; a.mf = omf; a.xf = oxf; a.yf = oyf; }
-        a.count += ocn;
         a.small &= osm;
     }
     if (q == 0 && live) {
-        a.small |= (nvalid - 1u) << 1;   // children - 1, read back when this cell's own record is made
+        // children - 1 and the cell's own level and ordinal: read back when its parent makes this cell's record
+        a.small = (a.small & 1u) | ((nvalid - 1u) << 1) | ((unsigned int)(cellLevel + 2) << 8);
+        a.ordinal = qd;
         o.agg[p] = a;
-        o.meta[p].skip = skip;
         if (p == 0 && !c.dd) {   // the root has no parent to write its record
-            o.rec[0] = make_record(c, a, cellLevel, skip, c.blockBase, msi);
+            o.rec[0] = make_record(c, a, cellLevel, 0u, c.blockBase, msi);
             o.rec[1] = o.rec[2] = o.rec[3] = invalid_record();
-            o.recnode[0] = 0u;
         }
     }
 }

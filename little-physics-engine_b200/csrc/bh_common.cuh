@@ -4,8 +4,8 @@
 //   state:                   body Body[n] (32 B: x, y, m, rank, comp), vel double2[n], orig u32[n] (creation index of a
 //                            slot) — creation order right after an upload, KEY ORDER after every step's gather
 //   sort:                    keys u64[n], sidx u32[n]
-//   terminals (t < n_term):  tkey u64, tfirst u32, delta i8, mask u32, tnode u32
-//   nodes (pre-order index): meta NodeMeta (16 B), agg Agg (64 B)
+//   terminals (t < n_term):  tkey u64, tfirst u32, delta i8, mask u32, wstart u32
+//   nodes (pre-order index): agg Agg (64 B) for cells and aggregated terminals (it carries the cell's level and ordinal)
 //   cells (ordinal):         child uint4;  records: rec TravRec[4 * (cells + 1)] in child blocks of 128 B
 #pragma once
 #include <cstdint>
@@ -73,14 +73,16 @@ struct Scal {
 //           wherever in the universe the pair sits) with no FP64 instruction and no conversion in the inner loop.
 //   open_t: s^2/theta^2 in scaled units. d2 <= open_t*(1-band) opens, d2 >= open_t*(1+band) accepts, in between
 //           the reference's own fp64 expression decides. -1 for leaves / terminals, -2 for the small-mass skip.
-//   skip:   pre-order index of the first node after this subtree (0 marks an unused slot of a child block).
+//   node:   where the exact (fp64) data of the node lives on the rank that built it: pre-order index of its aggregate,
+//           or LPE_LEAF_FLAG | sorted position of the body for a single-body leaf. Read only by the rare fp64 re-test of a
+//           borderline theta decision and by STRICT precision.
 //   cblock: (index of the 128-byte block holding this cell's children) << 2 | (number of children - 1);
 //           0 for leaves / terminals.
 struct __align__(16) TravRec {
     float4 c;            // chx, chy, clx, cly
     float gm;            // node mass / mass scale (0 when the node is skipped by the small-mass rule)
     float open_t;
-    unsigned int skip;
+    unsigned int node;
     unsigned int cblock;
 };
 static_assert(sizeof(TravRec) == 32, "four records per 128-byte line");
@@ -103,18 +105,12 @@ struct __align__(16) Agg {
     double xf, yf;        // position of the first occupant
     unsigned int frank;   // its insertion rank
     unsigned int fidx;    // its sorted position
-    unsigned int count;   // bodies under the node
-    unsigned int small;   // bit 0: every mass under the node is < small_mass_threshold; bits 1-2: children - 1 (cells)
+    unsigned int ordinal; // cells: ordinal of the cell (its child block is blockBase + ordinal)
+    unsigned int small;   // bit 0: every mass under the node is < small_mass_threshold; bits 1-2: children - 1 (cells);
+                          // bits 8-13: level + 2 (a branching cell's level, 0 = aggregated terminal at the depth bound)
 };
+__host__ __device__ __forceinline__ int agg_level(const Agg& a) { return (int)((a.small >> 8) & 63u) - 2; }
 static_assert(sizeof(Agg) == 64, "Agg is two 32-byte sectors");
-
-// Per-node topology, one 16-byte word by pre-order index.
-struct __align__(16) NodeMeta {
-    unsigned int skip;    // pre-order index of the first node after this subtree
-    unsigned int start;   // first terminal under the node (ordinal of a branching cell = preorder - start)
-    int level;            // level of a branching cell; -1 single-body leaf; -2 aggregated terminal
-    unsigned int pad;
-};
 
 struct StepConst {
     double U, invS, S;        // universe size; power-of-two length scale and its inverse

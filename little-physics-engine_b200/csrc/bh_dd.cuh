@@ -289,7 +289,6 @@ __device__ __forceinline__ unsigned int dd_lower_bound(const unsigned long long*
 struct DDRootsIn {
     const unsigned long long* tkey;
     const unsigned int* tfirst;
-    const unsigned int* tnode;
     const unsigned int* mask;
     const unsigned int* P;
     const Agg* agg;
@@ -324,7 +323,7 @@ k_dd_roots(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDRootsIn 
             if (last - first == 1u) {
                 r.level = -1; r.agg = body_agg(a.body[first], first, c.thr); r.leafpos = first;
             } else {
-                r.level = -2; r.agg = a.agg[a.tnode[t0]];
+                r.level = -2; r.agg = a.agg[t0 + a.P[t0] + (unsigned int)__popc(a.mask[t0])];   // the terminal's own node
             }
         } else {               // the lowest cell that holds every body of the quadrant
             const int L = lca_level(a.tkey[t0], a.tkey[t1 - 1], c.D);
@@ -357,7 +356,6 @@ struct DDExportArgs {
     const DDRoot* myroots;
     const unsigned int* child;      // [4 * ordinal + digit]
     const TravRec* rec;             // own records (local blocks)
-    const NodeMeta* meta;
     const Agg* agg;
     const Body* body;
     unsigned int* queue;            // [dest][icap] ordinals of the exported cells
@@ -445,7 +443,7 @@ k_dd_export(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDExportA
             if (ordinal != LPE_NONE) {
                 if (!remote) r.cblock = c.blockBase + ordinal;
                 else {   // (a root has no record on this rank: make the one the top builders will make)
-                    const TravRec R = make_record(c, r.agg, r.level, 1u, 0u, mass_scale_inv(s->max_mass_bits));
+                    const TravRec R = make_record(c, r.agg, r.level, LPE_NONE, 0u, mass_scale_inv(s->max_mass_bits));
                     r.cblock = (R.open_t >= 0.f && mayOpen32(R)) ? pushCell(ordinal) : DD_POISON_BLOCK;
                 }
             }
@@ -476,7 +474,7 @@ k_dd_export(StepConst c, DDSplit sp, const DDDomain* __restrict__ dom, DDExportA
             uint4 v0 = src[0], v1 = src[1];
             TravRec R;
             R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
-            R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
+            R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.node = v1.z; R.cblock = v1.w;
             if (R.cblock != 0u) {   // a cell: its own child block as numbered on d, if d can open it at all
                 const bool open = R.open_t >= 0.f && mayOpen32(R);   // (open_t = -2: skipped by the small-mass rule, never opened)
                 const unsigned int blk = open ? pushCell((R.cblock >> 2) - c.blockBase) : DD_POISON_BLOCK;
@@ -524,7 +522,8 @@ k_dd_export_x(StepConst c, int me, DDExportArgs a, DDPeers peers, const Scal* __
                 const Body b = a.body[code & ~LPE_LEAF_FLAG];
                 X = make_double4(b.x, b.y, b.m, -1.0);
             } else {
-                X = dd_xrec(a.agg[code], a.meta[code].level, c.quirk);
+                const Agg ag = a.agg[code];
+                X = dd_xrec(ag, agg_level(ag), c.quirk);
             }
         }
         double2* ox = reinterpret_cast<double2*>(peers.xrec[d] + 4u * ((size_t)regionBase + e) + r4);
@@ -597,7 +596,7 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
     auto rootAt = [&](int i) -> const DDRoot& { return inShared ? sroots[i] : globalRoot(i); };
     auto writeChild = [&](unsigned int slot, const Agg& a, int level, unsigned int cblockIndex, const DDRoot* root) {
         slot = lpe_idx(slot, 4u * DD_TOPCAP, 16, s);
-        rec[slot] = make_record(c, a, level, 1u, cblockIndex, msi);
+        rec[slot] = make_record(c, a, level, LPE_NONE, cblockIndex, msi);
         xrec[slot] = dd_xrec(a, level, c.quirk);   // (node_centre is inlined in both: the divisions are shared)
         if (root && root->owner == (unsigned int)me && root->leafpos != LPE_NONE && c.need_self) selfslot[root->leafpos] = slot;
     };
@@ -668,7 +667,7 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
     auto childAgg = [&](unsigned int code, int& level, unsigned int& cb, const DDRoot*& root) -> Agg {
         Agg a;
         a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
-        a.frank = 0xFFFFFFFFu; a.fidx = 0; a.count = 0; a.small = 1u;
+        a.frank = 0xFFFFFFFFu; a.fidx = 0; a.ordinal = 0; a.small = 1u;
         level = -3; cb = 0u; root = nullptr;
         if (code != LPE_NONE) {
             if (code & DD_CELL_FLAG) {
@@ -705,8 +704,8 @@ k_dd_top(StepConst c, int me, int R, const DDHeader* __restrict__ hdr, const DDR
             for (int dg = 1; dg < 4; ++dg)
                 if (ch[dg].frank < ch[best].frank) best = dg;
             r.mf = ch[best].mf; r.xf = ch[best].xf; r.yf = ch[best].yf; r.frank = ch[best].frank; r.fidx = ch[best].fidx;
-            r.count = ch[0].count + ch[1].count + ch[2].count + ch[3].count;
-            r.small = (ch[0].small & ch[1].small & ch[2].small & ch[3].small & 1u) | ((nvalid - 1u) << 1);
+            r.ordinal = (unsigned int)ord;
+            r.small = (ch[0].small & ch[1].small & ch[2].small & ch[3].small & 1u) | ((nvalid - 1u) << 1) | ((unsigned int)(L + 2) << 8);
             cagg[ord] = r;
         }
         __syncthreads();
@@ -739,7 +738,6 @@ __global__ void k_dd_poison(TravRec* __restrict__ rec) {
     if (threadIdx.x < 4) {
         TravRec r = invalid_record();
         r.gm = __int_as_float(0x7fc00000);
-        r.skip = 1u;
         rec[4u * DD_POISON_BLOCK + threadIdx.x] = r;
     }
 }

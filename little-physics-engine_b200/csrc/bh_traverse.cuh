@@ -33,10 +33,8 @@ constexpr int TRAV_FRAMES = LPE_MAX_DEPTH + 2;   // a chain of branching cells i
 
 struct TravArgs {
     const TravRec* rec;        // child blocks
-    const Agg* agg;            // [preorder] exact sums: fp64 centre / mass for the rare exact test and STRICT mode
-    const NodeMeta* meta;      // [preorder]
+    const Agg* agg;            // [preorder] exact sums (+ level): fp64 centre / mass for the rare exact test and STRICT mode
     const unsigned int* selfslot;   // [sorted body] record slot of its own single-body leaf
-    const unsigned int* recnode;    // [record slot] pre-order index of the node, or LPE_LEAF_FLAG | sorted position of a leaf's body
     const unsigned int* chunk_list; // depth-first kernel only: when set, process these chunks (two-phase overflow)
     Body* body;                     // state in key order (positions are updated in place by the drift)
     double2* vel;
@@ -56,12 +54,13 @@ struct TravArgs {
 
 // The reference's test, barnes_hut.cpp:261-269, on exactly scaled operands (power-of-two scaling commutes
 // with IEEE rounding): returns true when the node must be opened.
-__device__ __noinline__ bool exact_open(const Agg* __restrict__ agg, const NodeMeta* __restrict__ meta, unsigned int j,
+__device__ __noinline__ bool exact_open(const Agg* __restrict__ agg, unsigned int j,
                                         int quirk, double invS, double pxs, double pys, double eps2s, double Us,
                                         double theta2) {
-    const int level = meta[j].level;
+    const Agg a = agg[j];
+    const int level = agg_level(a);
     double M, cx, cy;
-    node_centre(agg[j], level, quirk, M, cx, cy);
+    node_centre(a, level, quirk, M, cx, cy);
     const double dxs = cx * invS - pxs, dys = cy * invS - pys;
     const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dxs, dxs), __dmul_rn(dys, dys)), eps2s);
     const double size = ldexp(Us, -level);
@@ -69,19 +68,19 @@ __device__ __noinline__ bool exact_open(const Agg* __restrict__ agg, const NodeM
     return !(__ddiv_rn(sizeSq, distSq) < theta2);
 }
 
-// The same test for a record slot of the two-phase kernel, wherever the node came from.
-__device__ __noinline__ bool exact_open_slot(const Agg* __restrict__ agg, const NodeMeta* __restrict__ meta,
-                                             const unsigned int* __restrict__ recnode, const double4* __restrict__ xrec,
-                                             unsigned int localLo, unsigned int localHi, unsigned int slot, int quirk,
-                                             double invS, double pxs, double pys, double eps2s, double Us, double theta2) {
-    if (slot >= localLo && slot < localHi)
-        return exact_open(agg, meta, recnode[slot], quirk, invS, pxs, pys, eps2s, Us, theta2);
-    const double4 x = xrec[slot];
-    const double dxs = x.x * invS - pxs, dys = x.y * invS - pys;
-    const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dxs, dxs), __dmul_rn(dys, dys)), eps2s);
+// The same test for a record slot, wherever the node came from. Cold path (about one visit in 1e5): the kernel's
+// parameter blocks are passed by address (they are __grid_constant__), so the call costs the hot loop no registers.
+__device__ __noinline__ bool exact_open_slot(const TravArgs* __restrict__ a, const StepConst* __restrict__ c, unsigned int slot,
+                                             double pxs, double pys) {
+    const double Us = c->U * c->invS;
+    if (slot >= a->localLo && slot < a->localHi)
+        return exact_open(a->agg, a->rec[slot].node, c->quirk, c->invS, pxs, pys, c->eps2s, Us, c->theta2);
+    const double4 x = a->xrec[slot];
+    const double dxs = x.x * c->invS - pxs, dys = x.y * c->invS - pys;
+    const double distSq = __dadd_rn(__dadd_rn(__dmul_rn(dxs, dxs), __dmul_rn(dys, dys)), c->eps2s);
     const double size = ldexp(Us, -(int)x.w);
     const double sizeSq = __dmul_rn(size, size);
-    return !(__ddiv_rn(sizeSq, distSq) < theta2);
+    return !(__ddiv_rn(sizeSq, distSq) < c->theta2);
 }
 
 // 8 lanes copy one 128-byte child block into a frame of the warp's stack
@@ -97,7 +96,7 @@ __device__ __forceinline__ void load_block(const TravRec* __restrict__ rec, unsi
 }
 
 template <int PREC, bool STATS>
-__global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravArgs a) {
+__global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(const __grid_constant__ StepConst c, const __grid_constant__ TravArgs a) {
     __shared__ TravRec sFrames[TRAV_WARPS][TRAV_FRAMES][4];
     __shared__ unsigned int sBlock[TRAV_WARPS][TRAV_FRAMES];   // child block held by each frame (record slot = 4 * block + k)
     const int lane = threadIdx.x & 31;
@@ -188,7 +187,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 }
                 const TravRec* R = frames + (d * 4 + k);
                 const float4 C = R->c;
-                const float4 Bq = *reinterpret_cast<const float4*>(&R->gm);   // gm, open_t, skip, cblock
+                const float4 Bq = *reinterpret_cast<const float4*>(&R->gm);   // gm, open_t, node, cblock
                 const unsigned int cb = __float_as_uint(Bq.w);
                 const unsigned int slot = 4u * fblock[d] + (unsigned int)k;
                 const bool active = d <= accDepth;
@@ -200,8 +199,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 d2 = active ? d2 : INF;
                 float lo = Bq.y * bandLo;
                 if (d2 > lo && d2 < Bq.y * bandHi)   // rare: inside the guard band -> the reference's fp64 test decides
-                    lo = exact_open_slot(a.agg, a.meta, a.recnode, a.xrec, a.localLo, a.localHi, slot, c.quirk, c.invS, pxs,
-                                         pys, c.eps2s, Us, c.theta2) ? INF : -1.f;
+                    lo = exact_open_slot(&a, &c, slot, pxs, pys) ? INF : -1.f;
                 const bool open = d2 <= lo;
                 const bool anyopen = __any_sync(0xFFFFFFFFu, open);
                 if (active && !open) accDepth = d;   // accepted: the subtree below is ignored
@@ -261,13 +259,14 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(StepConst c, TravA
                 int level;
                 double M, cx, cy;
                 if (slot >= a.localLo && slot < a.localHi) {
-                    const unsigned int rn = a.recnode[slot];
+                    const unsigned int rn = R->node;
                     if (rn & LPE_LEAF_FLAG) {   // single-body leaf: no aggregate is stored, the node is the body
                         const Body lb = a.body[rn & ~LPE_LEAF_FLAG];
                         M = lb.m; cx = lb.x; cy = lb.y; level = -1;
                     } else {
-                        level = a.meta[rn].level;
-                        node_centre(a.agg[rn], level, c.quirk, M, cx, cy);
+                        const Agg ag = a.agg[rn];
+                        level = agg_level(ag);
+                        node_centre(ag, level, c.quirk, M, cx, cy);
                     }
                 } else {
                     const double4 x = a.xrec[slot];

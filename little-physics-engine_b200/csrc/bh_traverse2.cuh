@@ -138,7 +138,8 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
 }
 
 template <bool STATS, bool SELF>
-__global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravArgs a, unsigned int* __restrict__ ovf_list) {
+__global__ void __launch_bounds__(T2_THREADS, 7)
+k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArgs a, unsigned int* __restrict__ ovf_list) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -147,7 +148,6 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
     const unsigned int n_nodes = c.dd ? a.s->dd_nroots : a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = c.eps2f;
-    const double Us = c.U * c.invS;
     const float INF = __int_as_float(0x7f800000);
     const float FMAXV = 3.0e38f;
     constexpr unsigned int CHUNKS_PER_BLOCK = 2048u / 32u;  // LPE_SHARD_BLOCK / 32
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                 const bool has = (unsigned int)lane < cnt;
                 unsigned int slot = 0, mask = tmask;
                 TravRec R;
-                R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.skip = 0; R.cblock = 0;
+                R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.node = 0; R.cblock = 0;
                 if (has) {
                     const uint2 e = W.q[(head + lane) & QM];
                     slot = e.x;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                     const uint4* src = reinterpret_cast<const uint4*>(a.rec + lpe_idx(slot, c.recSlots, 10, a.s));
                     const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
                     R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
-                    R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.skip = v1.z; R.cblock = v1.w;
+                    R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.node = v1.z; R.cblock = v1.w;
                 }
                 head += cnt;
                 // distance bounds from the node centre to the targets' box
@@ -307,13 +307,9 @@ __global__ void __launch_bounds__(T2_THREADS, 7) k_traverse2(StepConst c, TravAr
                     const bool band0 = d20 > lo0 && d20 < th.x, band1 = d21 > lo1 && d21 < th.y;
                     if (EXACT) {
                         if (band0)   // guard band: the reference's fp64 test decides
-                            lo0 = exact_open_slot(a.agg, a.meta, a.recnode, a.xrec, a.localLo, a.localHi,
-                                                  W.mslot[m] & 0x7FFFFFFFu, c.quirk, c.invS, pxs, pys, c.eps2s, Us,
-                                                  c.theta2) ? FMAXV : -1.f;
+                            lo0 = exact_open_slot(&a, &c, W.mslot[m] & 0x7FFFFFFFu, pxs, pys) ? FMAXV : -1.f;
                         if (band1)
-                            lo1 = exact_open_slot(a.agg, a.meta, a.recnode, a.xrec, a.localLo, a.localHi,
-                                                  W.mslot[m + 1] & 0x7FFFFFFFu, c.quirk, c.invS, pxs, pys, c.eps2s, Us,
-                                                  c.theta2) ? FMAXV : -1.f;
+                            lo1 = exact_open_slot(&a, &c, W.mslot[m + 1] & 0x7FFFFFFFu, pxs, pys) ? FMAXV : -1.f;
                     } else {
                         bandAny = bandAny || band0 || band1;
                     }

@@ -87,18 +87,17 @@ struct lpe_bh_ctx {
     unsigned int epoch = 0;
     unsigned int* fault_host = nullptr;        // pinned copy of the sort's fault flag
     int sorted_sel = 0;
-    unsigned int *selfslot = nullptr, *recnode = nullptr, *ovf_list = nullptr;
+    unsigned int *selfslot = nullptr, *ovf_list = nullptr;
     // scans
     unsigned int* P = nullptr;
     // terminals
     unsigned long long* tkey = nullptr;
-    unsigned int *tfirst = nullptr, *mask = nullptr, *tnode = nullptr, *wstart = nullptr;
+    unsigned int *tfirst = nullptr, *mask = nullptr, *wstart = nullptr;
     signed char* delta = nullptr;
     // nodes (pre-order index), cells (ordinal), child blocks
     uint64_t node_cap = 0;
     unsigned int *child = nullptr, *levelMeta = nullptr;
     uint2* levelList = nullptr;
-    NodeMeta* meta = nullptr;
     Agg* agg = nullptr;
     TravRec* rec = nullptr;
     // stats
@@ -220,12 +219,12 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n, bool dd = false) {
               dalloc(c, c->orig, cap) | dalloc(c, c->orig2, cap) | dalloc(c, c->rec, recSlots);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
           dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512) + 2 * ((size_t)scanTiles + 2)) | dalloc(c, c->totals, 512 * 8 + 16);
-    rc |= dalloc(c, c->selfslot, cap) | dalloc(c, c->recnode, recSlots) |
+    rc |= dalloc(c, c->selfslot, cap) |
           dalloc(c, c->ovf_list, (size_t)cdiv((long long)cap, LPE_SHARD_BLOCK) * (LPE_SHARD_BLOCK / 32) + 8);
     rc |= dalloc(c, c->P, cap + 2);
     rc |= dalloc(c, c->tkey, cap + 2) | dalloc(c, c->tfirst, cap + 2) | dalloc(c, c->mask, cap + 2) |
-          dalloc(c, c->tnode, cap + 2) | dalloc(c, c->wstart, cap + 2) | dalloc(c, c->delta, cap + 2);
-    rc |= dalloc(c, c->child, 4 * (cap + 8)) | dalloc(c, c->meta, ncap) | dalloc(c, c->levelList, cap + 8) |
+          dalloc(c, c->wstart, cap + 2) | dalloc(c, c->delta, cap + 2);
+    rc |= dalloc(c, c->child, 4 * (cap + 8)) | dalloc(c, c->levelList, cap + 8) |
           dalloc(c, c->levelMeta, 3 * 32) | dalloc(c, c->agg, ncap);
     rc |= dalloc(c, c->cntAcc, cap) | dalloc(c, c->cntVis, cap) | dalloc(c, c->scal, 1);
     if (rc) {
@@ -693,11 +692,10 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
                                                        scanStatus + (size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 1, c->epoch,
                                                        scanTicket + 1, sortFault);
     k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
-    Topo topo{c->tnode, c->wstart, c->child, c->meta, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->body,
-              c->selfslot, c->rec, c->recnode};
+    Topo topo{c->wstart, c->child, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->body, c->selfslot, c->rec};
     CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
-    NodeOut no{c->meta, c->agg, c->rec, c->recnode, c->selfslot, c->body};
+    NodeOut no{c->agg, c->rec, c->selfslot, c->body};
     // branching cells, deepest level first; the handful of cells of levels <= 4 share one single-block launch
     const int sms = c->sms;
     const int Ltop = k.D - 1 < 4 ? k.D - 1 : 4;
@@ -723,7 +721,7 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
     const int g256 = cdiv(n, 256);
     const int sms = c->sms;
     TravArgs ta{};
-    ta.rec = c->rec; ta.agg = c->agg; ta.meta = c->meta;
+    ta.rec = c->rec; ta.agg = c->agg;
     ta.body = c->body; ta.vel = c->vel;
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     ta.npeer = 0;
@@ -743,7 +741,7 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
     const unsigned int nblocks = (unsigned int)cdiv(n, LPE_SHARD_BLOCK);
     const unsigned int own = (nblocks + (unsigned int)k.shard_n - 1u - (unsigned int)k.shard_rank) / (unsigned int)k.shard_n;
     ta.n_chunks_local = own * (LPE_SHARD_BLOCK / 32u);
-    ta.selfslot = c->selfslot; ta.recnode = c->recnode; ta.chunk_list = nullptr;
+    ta.selfslot = c->selfslot; ta.chunk_list = nullptr;
     const int maxGridCtas = sms * 8;
     int travLaunches = 1;
     if (p.precision == LPE_PREC_FAST && !c->force_dfs) {
@@ -1253,25 +1251,30 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
 int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     if (!c || !o) return 1;
     if (!c->have_step) return fail(c, "no step has been run since the last upload");
+    if (c->dd) return fail(c, "lpe_bh_dump_tree: not available for a domain-decomposed rank");
     DevGuard _dg(c->device);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     const size_t n = c->n;
     Scal h;
     CU_TRY(c, cudaMemcpy(&h, c->scal, sizeof(h), cudaMemcpyDeviceToHost));
-    const size_t nn = (size_t)h.n_term + h.n_internal;
+    const size_t nt = h.n_term, nn = (size_t)h.n_term + h.n_internal;
     if (o->sorted_keys) CU_TRY(c, cudaMemcpy(o->sorted_keys, c->keys[c->sorted_sel], 8 * n, cudaMemcpyDeviceToHost));
     std::vector<unsigned int> sidx(n);
     // creation index of the body at each sorted position (after a step the state is in sorted order itself)
     CU_TRY(c, cudaMemcpy(sidx.data(), c->orig, 4 * n, cudaMemcpyDeviceToHost));
     if (o->sorted_index) std::memcpy(o->sorted_index, sidx.data(), 4 * n);
     if (nn == 0) return 0;
-    std::vector<NodeMeta> mt(nn);
+    // The device keeps no per-node topology array: a node's level, first terminal and extent follow from the
+    // terminals' level masks and their prefix sums (bh_build.cuh), which is what this test-only call rebuilds.
     std::vector<Agg> ag(nn);
-    std::vector<unsigned long long> tk(h.n_term);
+    std::vector<unsigned long long> tk(nt);
+    std::vector<unsigned int> tf(nt + 1), mk(nt), P(nt + 1);
     std::vector<Body> sb(n);
-    CU_TRY(c, cudaMemcpy(mt.data(), c->meta, sizeof(NodeMeta) * nn, cudaMemcpyDeviceToHost));
     CU_TRY(c, cudaMemcpy(ag.data(), c->agg, sizeof(Agg) * nn, cudaMemcpyDeviceToHost));
-    CU_TRY(c, cudaMemcpy(tk.data(), c->tkey, 8 * (size_t)h.n_term, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(tk.data(), c->tkey, 8 * nt, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(tf.data(), c->tfirst, 4 * (nt + 1), cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(mk.data(), c->mask, 4 * nt, cudaMemcpyDeviceToHost));
+    CU_TRY(c, cudaMemcpy(P.data(), c->P, 4 * (nt + 1), cudaMemcpyDeviceToHost));
     // the bodies as the tree saw them: the step's drift has moved the key-ordered state since, but the buffer the gather
     // read from (now body2) still holds the pre-step bodies, and the sort's payload maps sorted position -> old slot
     {
@@ -1281,24 +1284,52 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
         CU_TRY(c, cudaMemcpy(perm.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < n; ++i) sb[i] = old[perm[i]];
     }
-    for (size_t i = 0; i < nn; ++i) {
-        Agg a = ag[i];
-        if (mt[i].level == -1) {   // single-body leaves keep no aggregate on the device: rebuild it from the body
-            const unsigned int pos = mt[i].pad;
-            const Body& s0 = sb[pos];
-            a.m = s0.m; a.sx = s0.m * s0.x; a.sy = s0.m * s0.y; a.mf = s0.m; a.xf = s0.x; a.yf = s0.y;
-            a.frank = s0.rank; a.fidx = pos; a.count = 1; a.small = 0;
+    const int D = c->last_c.D;
+    // first node that starts at terminal t (its shallowest cell, or the terminal itself); nn past the last terminal
+    auto nodeAt = [&](size_t t) -> size_t { return t >= nt ? nn : t + P[t]; };
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t base = t + P[t];
+        unsigned int rest = mk[t];
+        size_t j = 0;
+        auto emit = [&](size_t i, int level, size_t tEnd, const Agg& a) {
+            double M, cx, cy;
+            node_centre(a, level, c->last_c.quirk, M, cx, cy);
+            if (o->node_level) o->node_level[i] = level;
+            if (o->node_key) o->node_key[i] = tk[t];
+            if (o->node_skip) o->node_skip[i] = (uint32_t)nodeAt(tEnd);
+            if (o->node_first) o->node_first[i] = sidx[a.fidx];
+            if (o->node_count) o->node_count[i] = tf[tEnd] - tf[t];
+            if (o->node_mass) o->node_mass[i] = M;
+            if (o->node_comx) o->node_comx[i] = cx;
+            if (o->node_comy) o->node_comy[i] = cy;
+        };
+        while (rest) {   // the branching cells that start at t, shallow to deep
+            const int L = __builtin_ctz(rest);
+            rest &= rest - 1;
+            const int shift = 2 * (D - L);
+            size_t tEnd = t + 1;   // one past the last terminal that shares the cell's level-L prefix
+            {
+                size_t lo = t, hi = nt;   // tk[lo] shares it, tk[hi] (or the end) does not
+                while (hi - lo > 1) {
+                    const size_t mid = lo + (hi - lo) / 2;
+                    if ((tk[mid] >> shift) == (tk[t] >> shift)) lo = mid; else hi = mid;
+                }
+                tEnd = lo + 1;
+            }
+            emit(base + j, L, tEnd, ag[base + j]);
+            ++j;
         }
-        double M, cx, cy;
-        node_centre(a, mt[i].level, c->last_c.quirk, M, cx, cy);
-        if (o->node_level) o->node_level[i] = mt[i].level;
-        if (o->node_key) o->node_key[i] = tk[mt[i].start];
-        if (o->node_skip) o->node_skip[i] = mt[i].skip;
-        if (o->node_first) o->node_first[i] = sidx[a.fidx];
-        if (o->node_count) o->node_count[i] = a.count;
-        if (o->node_mass) o->node_mass[i] = M;
-        if (o->node_comx) o->node_comx[i] = cx;
-        if (o->node_comy) o->node_comy[i] = cy;
+        const size_t i = base + j;   // the terminal's own node
+        const unsigned int first = tf[t], last = tf[t + 1];
+        if (last - first == 1u) {    // single-body leaves keep no aggregate on the device: rebuild it from the body
+            const Body& s0 = sb[first];
+            Agg a{};
+            a.m = s0.m; a.sx = s0.m * s0.x; a.sy = s0.m * s0.y; a.mf = s0.m; a.xf = s0.x; a.yf = s0.y;
+            a.frank = s0.rank; a.fidx = first; a.ordinal = 0; a.small = 0;
+            emit(i, -1, t + 1, a);
+        } else {
+            emit(i, -2, t + 1, ag[i]);
+        }
     }
     return 0;
 }

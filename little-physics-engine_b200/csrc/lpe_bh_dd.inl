@@ -272,9 +272,9 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
         if (timing) cudaEventRecord(c->dd_ev[4], st);
         const DDLayout L = dd_layout(c->cap, c->dd_R, c->dd_icap);
         const DDPeers peers = dd_peers(c, c->dd_cur);
-        DDRootsIn ri{c->tkey, c->tfirst, c->tnode, c->mask, c->P, c->agg, c->body};
+        DDRootsIn ri{c->tkey, c->tfirst, c->mask, c->P, c->agg, c->body};
         k_dd_roots<<<1, 256, 0, st>>>(k, sp, c->dd_dom, ri, c->dd_myroots, c->scal, hdr);
-        DDExportArgs ea{c->dd_myroots, c->child, c->rec, c->meta, c->agg, c->body, c->dd_queue, c->dd_pushed, c->dd_icap, L.importBase};
+        DDExportArgs ea{c->dd_myroots, c->child, c->rec, c->agg, c->body, c->dd_queue, c->dd_pushed, c->dd_icap, L.importBase};
         {   // one cluster of DD_EXPORT_CLUSTER blocks per destination
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(DD_EXPORT_CLUSTER, c->dd_R);

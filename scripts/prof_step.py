@@ -6,11 +6,11 @@ import lpe_bh
 import bench
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-x, y, vx, vy, m = lpe_bh.workload(wl["kind"], wl["n"], wl["seed"], bench.U)
+x, y, vx, vy, m = lpe_bh.workload(wl["kind"], wl["n"], wl["seed"], bench.wl_params(wl)["U"])
 bh = lpe_bh.BarnesHut(0)
 bh.set_instrumentation(timing=True)
 bh.upload(x, y, vx, vy, m)
-p = lpe_bh.make_params(bench.U, bench.EPS, theta=bench.THETA, dt_kick=bench.DT, dt_drift=bench.DT)
+p = bench.make_gpu_params(lpe_bh, wl)
 for s in range(steps):
     bh.step(p, 1)
     st = bh.stats()
