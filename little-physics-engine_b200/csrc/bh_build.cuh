@@ -104,7 +104,7 @@ __device__ __forceinline__ unsigned long long hilbert_index_lut(const unsigned c
 }
 
 __global__ void __launch_bounds__(256)
-k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restrict__ keys,
+k_keygen(StepConst c, const Body* __restrict__ body, void* __restrict__ keys,
          unsigned int* __restrict__ vals, Scal* __restrict__ s) {
     __shared__ unsigned char lut[64];
     if (threadIdx.x < 64) lut[threadIdx.x] = hilbert_lut_entry(threadIdx.x);
@@ -126,8 +126,7 @@ k_keygen(StepConst c, const Body* __restrict__ body, unsigned long long* __restr
             key = c.hilbert ? hilbert_index_lut(lut, ix, iy, c.D) : (spread_bits32(ix) | (spread_bits32(iy) << 1));
             in = 1;
         }
-        keys[i] = key;
-        vals[i] = (unsigned int)i;
+        store_key(keys, vals, c.k32, c.D, i, key);
     }
     const unsigned int cnt = __syncthreads_count(in);
     if (threadIdx.x == 0 && cnt) atomicAdd(&s->n_in, cnt);
@@ -146,7 +145,7 @@ k_gather(int n, int need_self, const unsigned int* __restrict__ sidx, const Body
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (n_dev) n = (int)*n_dev;
     if (i >= n) return;
-    const unsigned int b = sidx[i];
+    const unsigned int b = sidx[i] & ~LPE_VAL_OUT;
 #ifdef LPE_CHECKED
     if (b >= cap) { atomicOr(&chk->check_fault, 1u << 1); return; }
 #endif
@@ -178,18 +177,20 @@ __device__ __forceinline__ void block_max_mass(double m, unsigned int comp, Scal
 
 // scan loader: 1 where sorted position i starts a new depth-D cell
 struct HeadFlag {
-    const unsigned long long* keys;
+    const void* keys;
     const Scal* s;
+    int k32;
     __device__ __forceinline__ unsigned int operator()(int i) const {
         if ((unsigned int)i >= s->n_in) return 0u;
-        return (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+        return (i == 0 || load_key(keys, k32, i) != load_key(keys, k32, i - 1)) ? 1u : 0u;
     }
 };
 
 // sinks of the single-pass scans
 // ---- 3. terminals: the head-flag scan writes the terminal arrays itself ----------------------------------------
 struct TerminalSink {
-    const unsigned long long* keys;
+    const void* keys;
+    int k32;
     unsigned long long* tkey;
     unsigned int* tfirst;
     Scal* s;
@@ -198,7 +199,7 @@ struct TerminalSink {
         const unsigned int n_in = s->n_in;
         if ((unsigned int)i < n_in) {
             if (head) {
-                tkey[excl] = keys[i];
+                tkey[excl] = load_key(keys, k32, i);
                 tfirst[excl] = (unsigned int)i;
             }
             if ((unsigned int)i == n_in - 1u) tfirst[excl + head] = n_in;

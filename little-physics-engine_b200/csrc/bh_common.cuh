@@ -12,6 +12,7 @@
 #include <cuda_runtime.h>
 
 #define LPE_NONE 0xFFFFFFFFu
+#define LPE_VAL_OUT 0x80000000u   // sort payload, 32-bit key mode: the body is not in the tree (sorts behind every cell)
 #define LPE_MAX_DEPTH 30
 
 // ---- checked build (liblpe_bh_checked.so, -DLPE_CHECKED) --------------------------------------------------------------
@@ -128,6 +129,7 @@ struct StepConst {
     int need_self;            // maintain selfnode / selfslot (eps == 0 or interaction counting)
     int test_overflow;        // tests only: pretend every two-phase frontier overflows
     int hilbert;              // sort key: 0 = Morton code, 1 = Hilbert index of the same depth-D cell
+    int k32;                  // depth <= 16: keys travel as 32-bit words, "not in the tree" in the payload's top bit
     unsigned int recSlots;    // extent of the record array (slots), nodeCap of the per-node arrays, bodyCap of the per-body ones
     unsigned int nodeCap, bodyCap;
     int dd;                   // domain-decomposed rank: the local build leaves the root block and the top of the tree alone
@@ -176,6 +178,24 @@ __device__ __forceinline__ unsigned long long spread_bits32(unsigned int v) {
     x = (x | (x << 2)) & 0x3333333333333333ull;
     x = (x | (x << 1)) & 0x5555555555555555ull;
     return x;
+}
+
+// Sorted / unsorted key i, whichever container the step uses (StepConst::k32)
+__device__ __forceinline__ unsigned long long load_key(const void* keys, int k32, long long i) {
+    return k32 ? (unsigned long long)reinterpret_cast<const unsigned int*>(keys)[i]
+               : reinterpret_cast<const unsigned long long*>(keys)[i];
+}
+// key + payload of body i as the sort wants them. key = cell index (in the tree), 1 << 2D (outside), (1 << 2D) | 1 (a
+// dead slot of a domain-decomposed rank)
+__device__ __forceinline__ void store_key(void* keys, unsigned int* vals, int k32, int D, long long i, unsigned long long key) {
+    if (k32) {
+        const bool out = (key >> (2 * D)) != 0ull;
+        reinterpret_cast<unsigned int*>(keys)[i] = out ? (unsigned int)(key & 1ull) : (unsigned int)key;
+        vals[i] = (unsigned int)i | (out ? LPE_VAL_OUT : 0u);
+    } else {
+        reinterpret_cast<unsigned long long*>(keys)[i] = key;
+        vals[i] = (unsigned int)i;
+    }
 }
 
 // Level of the lowest common ancestor cell of two distinct depth-D keys (= number of shared leading digits).

@@ -171,7 +171,7 @@ __device__ __forceinline__ unsigned long long dd_dead_key(int D) { return (1ull 
 // not touched here; their keys are made by k_dd_keygen_inbox after the barrier.
 __global__ void __launch_bounds__(256)
 k_dd_keygen(StepConst c, DDSplit sp, const Body* __restrict__ body, const double2* __restrict__ vel,
-            const unsigned int* __restrict__ orig, unsigned long long* __restrict__ keys, unsigned int* __restrict__ vals,
+            const unsigned int* __restrict__ orig, void* __restrict__ keys, unsigned int* __restrict__ vals,
             Scal* __restrict__ s, DDHeader* __restrict__ hdr, DDPeers peers, unsigned long long* __restrict__ oob) {
     __shared__ unsigned char lut[64];
     if (threadIdx.x < 64) lut[threadIdx.x] = hilbert_lut_entry(threadIdx.x);
@@ -204,8 +204,7 @@ k_dd_keygen(StepConst c, DDSplit sp, const Body* __restrict__ body, const double
             }
             key = dd_dead_key(c.D);   // sorts behind everything: the slot is free again after the gather
         }
-        keys[i] = key;
-        vals[i] = i;
+        store_key(keys, vals, c.k32, c.D, i, key);
     }
     const unsigned int cin = __syncthreads_count(in);
     const unsigned int clive = __syncthreads_count(live);
@@ -217,7 +216,7 @@ k_dd_keygen(StepConst c, DDSplit sp, const Body* __restrict__ body, const double
 
 // ---- phase B, first kernel: keys of the bodies that arrived behind the live ones; how many slots the sort covers -----
 __global__ void __launch_bounds__(256)
-k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, unsigned long long* __restrict__ keys,
+k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, void* __restrict__ keys,
                   unsigned int* __restrict__ vals, Scal* __restrict__ s, DDHeader* __restrict__ hdr) {
     __shared__ unsigned char lut[64];
     if (threadIdx.x < 64) lut[threadIdx.x] = hilbert_lut_entry(threadIdx.x);
@@ -243,8 +242,7 @@ k_dd_keygen_inbox(StepConst c, DDSplit sp, const Body* __restrict__ body, unsign
             ++live;
             in += inside ? 1u : 0u;
         }
-        keys[slot] = key;
-        vals[slot] = slot;
+        store_key(keys, vals, c.k32, c.D, slot, key);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -104,10 +104,25 @@ __device__ __forceinline__ unsigned int block_exclusive_scan_256(unsigned int v,
     return ex;
 }
 
+// Digit of a key in one pass. 64-bit keys carry everything (bit 2D = "not in the tree" lands in the top digit). 32-bit
+// keys (depth <= 16: the cell index fills all 32 bits) keep that flag in the top bit of the payload instead; it joins
+// the TOP pass as digit bit 8, so the top pass always has 512 bins and the containers are 4 + 4 bytes per element.
+template <class KeyT>
+__device__ __forceinline__ unsigned int sort_digit(KeyT key, unsigned int val, int shift, unsigned int dmask, bool top) {
+    if constexpr (sizeof(KeyT) == 8) {
+        (void)val; (void)top;
+        return (unsigned int)(key >> shift) & dmask;
+    } else {
+        const unsigned int d = (key >> shift) & 255u;
+        return top ? (d | ((val >> 31) << 8)) : d;
+    }
+}
+
 // hist[p * 512 + d] += number of keys whose digit in pass p is d, for every pass at once (keys read once).
+template <class KeyT>
 __global__ void __launch_bounds__(256)
-k_sort_hist(const unsigned long long* __restrict__ keys, int n, int passes, int lastBins, unsigned int* __restrict__ hist,
-            const unsigned int* __restrict__ n_dev) {
+k_sort_hist(const KeyT* __restrict__ keys, const unsigned int* __restrict__ vals, int n, int passes, int lastBins,
+            unsigned int* __restrict__ hist, const unsigned int* __restrict__ n_dev) {
     extern __shared__ unsigned int sh_hist[];   // passes * 512
     if (n_dev) n = (int)*n_dev;   // element count known only on the device (domain-decomposed ranks)
     const int words = passes * SORT_HIST_STRIDE;
@@ -115,10 +130,11 @@ k_sort_hist(const unsigned long long* __restrict__ keys, int n, int passes, int 
     __syncthreads();
     const unsigned int lastMask = (unsigned int)lastBins - 1u;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned long long key = keys[i];
+        const KeyT key = keys[i];
+        const unsigned int val = (sizeof(KeyT) == 4) ? vals[i] : 0u;
         for (int p = 0; p < passes - 1; ++p)
-            atomicAdd(&sh_hist[p * SORT_HIST_STRIDE + ((unsigned int)(key >> (8 * p)) & 255u)], 1u);
-        atomicAdd(&sh_hist[(passes - 1) * SORT_HIST_STRIDE + ((unsigned int)(key >> (8 * (passes - 1))) & lastMask)], 1u);
+            atomicAdd(&sh_hist[p * SORT_HIST_STRIDE + sort_digit<KeyT>(key, val, 8 * p, 255u, false)], 1u);
+        atomicAdd(&sh_hist[(passes - 1) * SORT_HIST_STRIDE + sort_digit<KeyT>(key, val, 8 * (passes - 1), lastMask, true)], 1u);
     }
     __syncthreads();
     for (int k = threadIdx.x; k < words; k += blockDim.x) {
@@ -144,10 +160,10 @@ __global__ void __launch_bounds__(512) k_sort_bases(unsigned int* __restrict__ h
     row[tid] = sh[tid] - v;
 }
 
-template <int BINS>
+template <int BINS, class KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
-k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
-                unsigned long long* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
+k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
+                KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift, int top,
                 const unsigned int* __restrict__ digitBase, unsigned long long* __restrict__ status,
                 unsigned int epoch, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault,
                 const unsigned int* __restrict__ n_dev) {
@@ -158,7 +174,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
     __shared__ unsigned int cnt[SORT_WARPS][BINS];     // per-warp digit counts -> tile-local offsets
     __shared__ unsigned int dbase[BINS];               // tile-local start of each digit's run
     __shared__ unsigned int gbase[BINS];               // global start of this tile's run of each digit
-    __shared__ unsigned long long skey[SORT_TILE];
+    __shared__ KeyT skey[SORT_TILE];
     __shared__ unsigned int sval[SORT_TILE];
     constexpr int bins = BINS;
     const int tid = threadIdx.x;
@@ -174,7 +190,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
 
     const long long tbase = (long long)tile * SORT_TILE;
     const long long wbase = tbase + (long long)w * (SORT_ITEMS * 32);
-    unsigned long long key[SORT_ITEMS];
+    KeyT key[SORT_ITEMS];
     unsigned int val[SORT_ITEMS];
     unsigned short rk[SORT_ITEMS];
     const unsigned int lt = (1u << lane) - 1u;
@@ -182,14 +198,14 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         const bool ok = i < n;
-        key[r] = ok ? keysIn[i] : ~0ull;
+        key[r] = ok ? keysIn[i] : (KeyT)~(KeyT)0;
         val[r] = ok ? valsIn[i] : 0u;
     }
 #pragma unroll
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         const bool ok = i < n;
-        const unsigned int d = ok ? ((unsigned int)(key[r] >> shift) & dmask) : 0xFFFFu;
+        const unsigned int d = ok ? sort_digit<KeyT>(key[r], val[r], shift, dmask, top != 0) : 0xFFFFu;
         const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
         const unsigned int before = __popc(peers & lt);
         const int leader = __ffs(peers) - 1;
@@ -235,7 +251,7 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
     for (int r = 0; r < SORT_ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         if (i < n) {
-            const unsigned int d = (unsigned int)(key[r] >> shift) & dmask;
+            const unsigned int d = sort_digit<KeyT>(key[r], val[r], shift, dmask, top != 0);
             const unsigned int lp = dbase[d] + cnt[w][d] + rk[r];
             skey[lp] = key[r];
             sval[lp] = val[r];
@@ -255,14 +271,15 @@ k_sort_onesweep(const unsigned long long* __restrict__ keysIn, const unsigned in
     __syncthreads();
     const int tileCount = (int)min((long long)SORT_TILE, (long long)n - tbase);
     for (int j = tid; j < tileCount; j += SORT_THREADS) {
-        const unsigned long long kx = skey[j];
-        const unsigned int d = (unsigned int)(kx >> shift) & dmask;
+        const KeyT kx = skey[j];
+        const unsigned int vx = sval[j];
+        const unsigned int d = sort_digit<KeyT>(kx, vx, shift, dmask, top != 0);
         const unsigned int dst = gbase[d] + ((unsigned int)j - dbase[d]);
 #ifdef LPE_CHECKED
         if (dst >= (unsigned int)n) { atomicOr(fault, 2u); continue; }   // (bit 1 of the sort's fault word)
 #endif
         keysOut[dst] = kx;
-        valsOut[dst] = sval[j];
+        valsOut[dst] = vx;
     }
 }
 

@@ -137,7 +137,9 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
     AY2 = fma2(dy, f, AY2);
 }
 
-template <bool STATS, bool SELF>
+// DD: the kernel serves a domain-decomposed rank (body count and tree size known only on the device, per-chunk cost
+// recorded for the load balancer); a template flag so that the single-GPU kernel carries none of it (measured: 1.5 %).
+template <bool STATS, bool SELF, bool DD>
 __global__ void __launch_bounds__(T2_THREADS, 7)
 k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArgs a, unsigned int* __restrict__ ovf_list) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
@@ -145,7 +147,7 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
     const int lane = threadIdx.x & 31;
     const unsigned int lt = (1u << lane) - 1u;
     const unsigned int lanebit = 1u << lane;
-    const unsigned int n_nodes = c.dd ? a.s->dd_nroots : a.s->n_term + a.s->n_internal;
+    const unsigned int n_nodes = DD ? a.s->dd_nroots : a.s->n_term + a.s->n_internal;
     const double massScale = 1.0 / mass_scale_inv(a.s->max_mass_bits);
     const float eps2f = c.eps2f;
     const float INF = __int_as_float(0x7f800000);
@@ -162,9 +164,12 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
         const unsigned int gblock = lblock * (unsigned int)c.shard_n + (unsigned int)c.shard_rank;
         const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
         // (a domain-decomposed rank knows its body count only on the device; the tail slots hold no bodies)
-        const long long n_bodies = c.dd ? (long long)a.s->n_live : (long long)c.n;
-        const bool valid = i < n_bodies;
-        if (c.dd && (long long)q * 32 >= n_bodies) continue;
+        bool valid = i < c.n;
+        if (DD) {
+            const unsigned int n_live = a.s->n_live;
+            if (q * 32u >= n_live) continue;
+            valid = (unsigned int)i < n_live;
+        }
 
         unsigned int b = 0, self = LPE_NONE, cm = 0;
         double2 p = make_double2(0.0, 0.0);
@@ -388,7 +393,7 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
                 AY += (double)(lo2(AY2) + hi2(AY2));
                 __syncwarp();
             }
-            cost = tail;   // every node that entered the ring was classified once
+            if (DD) cost = tail;   // every node that entered the ring was classified once
         }
 
         if (overflow) {
@@ -397,7 +402,7 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
             continue;
         }
 
-        if (a.chunk_cost && lane == 0) a.chunk_cost[q] = cost;
+        if (DD && lane == 0) a.chunk_cost[q] = cost;
         double2 v = make_double2(0.0, 0.0);
         if (valid) v = a.vel[b];
         const double accScale = c.G * massScale * c.invS * c.invS;   // a = G*sum M d/r^3; scaled units M/Ms, d/S

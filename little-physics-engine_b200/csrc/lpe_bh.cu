@@ -581,6 +581,7 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
     k.test_overflow = c->force_overflow ? 1 : 0;
     if (p.key_order < 0 || p.key_order > 2) return fail(c, "unknown key_order");
     k.hilbert = (p.key_order == LPE_KEYS_HILBERT || (p.key_order == LPE_KEYS_AUTO && p.precision == LPE_PREC_FAST)) ? 1 : 0;
+    k.k32 = (k.D <= 16) ? 1 : 0;
     k.dd = 0;
     k.blockBase = 1u;
     k.bodyCap = (unsigned int)c->cap;
@@ -592,9 +593,16 @@ int make_const(lpe_bh_ctx* c, const lpe_bh_params& p, StepConst& k) {
 // ---- one step, in the pieces the single-GPU step and the domain-decomposed phases are assembled from ------------------
 struct SortPlan { int passes, topBits; };
 SortPlan sort_plan(const StepConst& k) {
-    // 8-bit digits; a key of 8p+1 bits (33 for D = 16) gets a 9-bit top digit instead of one more pass
-    const int keyBits = 2 * k.D + 1;
     SortPlan sp;
+    if (k.k32) {
+        // 32-bit containers: 8-bit digits over the 2D bits of the cell index; "not in the tree" rides in the payload and
+        // joins the top pass as digit bit 8 (always 512 bins there)
+        sp.passes = std::max(1, (2 * k.D + 7) / 8);
+        sp.topBits = 9;
+        return sp;
+    }
+    // 8-bit digits; a key of 8p+1 bits gets a 9-bit top digit instead of one more pass
+    const int keyBits = 2 * k.D + 1;
     sp.passes = (keyBits + 7) / 8;
     sp.topBits = keyBits - 8 * (sp.passes - 1);
     if (sp.passes > 1 && sp.topBits == 1) { --sp.passes; sp.topBits = 9; }
@@ -633,20 +641,26 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_de
     unsigned int* fault = tileCounter + SORT_MAX_PASSES;
     const int lastBins = 1 << topBits;
     const int histBlocks = std::min(sortTiles, 148 * 8);
-    k_sort_hist<<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(c->keys[0], n, passes, lastBins, hist, n_dev);
-    k_sort_bases<<<passes, 512, 0, st>>>(hist);
-    for (int ps = 0; ps < passes; ++ps) {
-        const int shift = 8 * ps;
-        unsigned long long* status = c->lbstatus + (size_t)ps * 256 * sortTiles;
-        const unsigned int* base = hist + 512 * ps;
-        if (ps == passes - 1 && lastBins == 512)
-            k_sort_onesweep<512><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault, n_dev);
-        else
-            k_sort_onesweep<256><<<sortTiles, SORT_THREADS, 0, st>>>(c->keys[sel], c->vals[sel], c->keys[sel ^ 1], c->vals[sel ^ 1],
-                                                                      n, shift, base, status, c->epoch, tileCounter + ps, fault, n_dev);
-        sel ^= 1;
-    }
+    auto run = [&](auto keyTag) {
+        using KeyT = decltype(keyTag);
+        KeyT* kb[2] = {reinterpret_cast<KeyT*>(c->keys[0]), reinterpret_cast<KeyT*>(c->keys[1])};
+        k_sort_hist<KeyT><<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(kb[0], c->vals[0], n, passes, lastBins, hist, n_dev);
+        k_sort_bases<<<passes, 512, 0, st>>>(hist);
+        for (int ps = 0; ps < passes; ++ps) {
+            const int shift = 8 * ps;
+            const int top = ps == passes - 1;
+            unsigned long long* status = c->lbstatus + (size_t)ps * 256 * sortTiles;
+            const unsigned int* base = hist + 512 * ps;
+            if (top && lastBins == 512)
+                k_sort_onesweep<512, KeyT><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
+                                                                                n, shift, top, base, status, c->epoch, tileCounter + ps, fault, n_dev);
+            else
+                k_sort_onesweep<256, KeyT><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
+                                                                                n, shift, top, base, status, c->epoch, tileCounter + ps, fault, n_dev);
+            sel ^= 1;
+        }
+    };
+    if (k.k32) run((unsigned int)0); else run((unsigned long long)0);
     c->sorted_sel = sel;
     c->launches += 2 + (uint64_t)passes;
     c->last.sort_passes = passes;
@@ -684,7 +698,7 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
     unsigned int* scanTicket = c->totals + 512 * SORT_MAX_PASSES + SORT_MAX_PASSES + 1;
     unsigned int* sortFault = c->totals + 512 * SORT_MAX_PASSES + SORT_MAX_PASSES;
     unsigned long long* scanStatus = c->lbstatus + (size_t)cdiv((long long)c->cap, SORT_TILE) * (256 * (SORT_MAX_PASSES - 1) + 512);
-    k_scan_chained<<<scanTiles, SCAN_THREADS, 0, st>>>(HeadFlag{skeys, c->scal}, TerminalSink{skeys, c->tkey, c->tfirst, c->scal, n},
+    k_scan_chained<<<scanTiles, SCAN_THREADS, 0, st>>>(HeadFlag{skeys, c->scal, k.k32}, TerminalSink{skeys, k.k32, c->tkey, c->tfirst, c->scal, n},
                                                        n, scanStatus, c->epoch, scanTicket, sortFault);
     unsigned int *levelCount = c->levelMeta, *levelBase = c->levelMeta + 32, *levelCursor = c->levelMeta + 64;
     k_witness<<<g256, 256, 0, st>>>(k.D, c->tkey, c->delta, c->mask, c->wstart, levelCount, c->scal);
@@ -752,9 +766,15 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
         if (grid > sms * 7) grid = sms * 7;
         if (grid < 1) grid = 1;
-        if (stats) k_traverse2<true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-        else if (selfT) k_traverse2<false, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-        else k_traverse2<false, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        if (k.dd) {
+            if (stats) k_traverse2<true, true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            else if (selfT) k_traverse2<false, true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            else k_traverse2<false, false, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        } else {
+            if (stats) k_traverse2<true, true, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            else if (selfT) k_traverse2<false, true, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            else k_traverse2<false, false, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        }
         ta.chunk_list = c->ovf_list;
         if (stats) k_traverse<0, true><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
         else k_traverse<0, false><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
@@ -1258,7 +1278,17 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
     Scal h;
     CU_TRY(c, cudaMemcpy(&h, c->scal, sizeof(h), cudaMemcpyDeviceToHost));
     const size_t nt = h.n_term, nn = (size_t)h.n_term + h.n_internal;
-    if (o->sorted_keys) CU_TRY(c, cudaMemcpy(o->sorted_keys, c->keys[c->sorted_sel], 8 * n, cudaMemcpyDeviceToHost));
+    if (o->sorted_keys) {
+        if (c->last_c.k32) {   // 32-bit containers + "outside" flag in the payload -> the documented 64-bit form
+            std::vector<unsigned int> k32(n), v32(n);
+            CU_TRY(c, cudaMemcpy(k32.data(), c->keys[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
+            CU_TRY(c, cudaMemcpy(v32.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; ++i)
+                o->sorted_keys[i] = (v32[i] & LPE_VAL_OUT) ? ((1ull << (2 * c->last_c.D)) | k32[i]) : (uint64_t)k32[i];
+        } else {
+            CU_TRY(c, cudaMemcpy(o->sorted_keys, c->keys[c->sorted_sel], 8 * n, cudaMemcpyDeviceToHost));
+        }
+    }
     std::vector<unsigned int> sidx(n);
     // creation index of the body at each sorted position (after a step the state is in sorted order itself)
     CU_TRY(c, cudaMemcpy(sidx.data(), c->orig, 4 * n, cudaMemcpyDeviceToHost));
@@ -1282,7 +1312,7 @@ int lpe_bh_dump_tree(lpe_bh_ctx* c, lpe_bh_tree_dump* o) {
         std::vector<unsigned int> perm(n);
         CU_TRY(c, cudaMemcpy(old.data(), c->body2, sizeof(Body) * n, cudaMemcpyDeviceToHost));
         CU_TRY(c, cudaMemcpy(perm.data(), c->vals[c->sorted_sel], 4 * n, cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < n; ++i) sb[i] = old[perm[i]];
+        for (size_t i = 0; i < n; ++i) sb[i] = old[perm[i] & ~LPE_VAL_OUT];
     }
     const int D = c->last_c.D;
     // first node that starts at terminal t (its shallowest cell, or the terminal itself); nn past the last terminal

@@ -656,13 +656,20 @@ int lpe_bh_dd_chunk_costs(lpe_bh_ctx* c, uint64_t* n_chunks, uint64_t* first_key
     if (!nc) return 0;
     if (cost) CU_TRY(c, cudaMemcpy(cost, c->dd_chunk_cost, 4 * nc, cudaMemcpyDeviceToHost));
     if (first_key30) {
-        // every 32nd sorted key (strided copy: 8 bytes out of every 256)
-        CU_TRY(c, cudaMemcpy2D(first_key30, 8, c->keys[c->sorted_sel], 256, 8, nc, cudaMemcpyDeviceToHost));
         const int sh = 2 * (LPE_MAX_DEPTH - c->last_c.D);
         const uint64_t top = 1ull << (2 * LPE_MAX_DEPTH);
-        for (uint64_t i = 0; i < nc; ++i) {
-            const uint64_t k = first_key30[i];
-            first_key30[i] = (k >> (2 * c->last_c.D)) ? top : (k << sh);   // a chunk of bodies outside the tree sorts last
+        if (c->last_c.k32) {   // every 32nd sorted key and payload (strided copies: 4 bytes out of every 128)
+            std::vector<uint32_t> k32(nc), v32(nc);
+            CU_TRY(c, cudaMemcpy2D(k32.data(), 4, c->keys[c->sorted_sel], 128, 4, nc, cudaMemcpyDeviceToHost));
+            CU_TRY(c, cudaMemcpy2D(v32.data(), 4, c->vals[c->sorted_sel], 128, 4, nc, cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < nc; ++i)
+                first_key30[i] = (v32[i] & LPE_VAL_OUT) ? top : ((uint64_t)k32[i] << sh);   // bodies outside the tree sort last
+        } else {
+            CU_TRY(c, cudaMemcpy2D(first_key30, 8, c->keys[c->sorted_sel], 256, 8, nc, cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < nc; ++i) {
+                const uint64_t k = first_key30[i];
+                first_key30[i] = (k >> (2 * c->last_c.D)) ? top : (k << sh);
+            }
         }
     }
     return 0;
