@@ -484,8 +484,12 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
         dist.all_gather(allt, mine)
         tl = np.array([float(t[0].item()) for t in allt]); tt = np.array([float(t[1].item()) for t in allt])
         beta = mean_cost * float(tl.sum()) / max(float(tt.sum()), 1e-9)     # sort + build share of a chunk, in list entries
-        busy = tl + tt                                                      # what each rank actually spent (no waiting)
-        scale = busy / max(float(busy.mean()), 1e-9)
+        # what the cost model misses on a rank (deeper tree, more cells per body) is charged to its chunks: measured busy
+        # time of the rank per unit of model weight it holds now
+        busy = tl + tt
+        held = np.array([float(np.sum(c.astype(np.float64) + beta)) for _, c in allc])
+        rho = busy / np.maximum(held, 1e-9)
+        scale = rho / max(float(rho.mean()), 1e-30)
         new = lpe_bh.balanced_splitters(allc, world, beta, scale)
         bh.dd_set_splitters(new)
         return beta
