@@ -295,6 +295,23 @@ def e2e_registry(n, ticks):
                     "4 worker threads -> lpe_bh_update_host_aos -> velocities copied back into the pool pages); host wall clock"}
 
 
+def nvlink_counters(index):
+    """Sum of the NVLink data counters of one GPU (nvidia-smi nvlink -gt d), bytes; None when unavailable."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+    except Exception:
+        return None
+    tx = rx = 0
+    seen = False
+    for line in out.splitlines():
+        parts = line.replace(":", " ").split()
+        if "Tx" in parts and "KiB" in parts:
+            tx += int(parts[parts.index("KiB") - 1]) * 1024; seen = True
+        if "Rx" in parts and "KiB" in parts:
+            rx += int(parts[parts.index("KiB") - 1]) * 1024; seen = True
+    return {"tx": tx, "rx": rx} if seen else None
+
+
 def rooflines(meas, fma_peak, peaks, peak_kind, workload_key, world=1):
     n, trav_ms = meas["n"], meas["phases"]["traverse"]
     flops = FLOPS_PER_INTERACTION * meas["interactions"] / max(world, 1)
@@ -511,6 +528,7 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
     launches0 = bh.launch_count()
     dist.barrier()
     torch.cuda.synchronize()
+    nv0 = nvlink_counters(local_rank) if rank == 0 else None
     step_ms, phases = [], []
     for _ in range(args.steps):
         flush.zero_()
@@ -524,6 +542,13 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
         phases.append([s[k] for k in ("ms_keygen", "ms_wait_a", "ms_sort", "ms_build", "ms_export", "ms_wait_b", "ms_top", "ms_traverse")])
     torch.cuda.synchronize()
     dist.barrier()
+    nv1 = nvlink_counters(local_rank) if rank == 0 else None
+    nvlink = None
+    if nv0 and nv1:   # rank 0's GPU: what the step's own kernels moved over NVLink (exports, roots, migrants, mail)
+        nvlink = {"gpu": local_rank, "tx_bytes_per_step": (nv1["tx"] - nv0["tx"]) / args.steps,
+                  "rx_bytes_per_step": (nv1["rx"] - nv0["rx"]) / args.steps,
+                  "source": "nvidia-smi nvlink -gt d before / after the timed steps (includes the L2-flush-free idle gaps; "
+                            "no collective runs in between)"}
     launches = bh.launch_count() - launches0
     t = torch.tensor([float(np.sum(step_ms))], device="cuda", dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -562,7 +587,7 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
         "phases_ms_max_over_ranks": dict(zip(names, (float(v) for v in imax))),
         "phases_ms_per_rank": {nm: [float(v) for v in arr[:, i]] for i, nm in enumerate(names)},
         "per_rank": allst, "balance": {"beta_list_entries_per_chunk": beta, "settling": balance_log},
-        "interactions_per_body": interactions / n, "parity_check": parity,
+        "interactions_per_body": interactions / n, "parity_check": parity, "nvlink": nvlink,
         **rooflines(meas, fma_peak, peaks, peak_kind, key, world),
         "e2e": {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "path": "multi-GPU runs keep the bodies resident on their owners; the host round trip is measured at N=1"},

@@ -89,3 +89,46 @@ def test_block_cyclic_exchange_world2(n):
         assert sum(counts) == n                      # every body owned exactly once
         assert max(counts) <= chunk
         assert max(counts) - min(counts) <= 2048     # balanced to within one block
+
+
+def _balance_worker(rank, world, port, q):
+    """Host logic of the domain-decomposed run's load balancer (lpe_bh.balanced_splitters): every rank contributes its
+    per-chunk (first key, cost) arrays, gathers everybody's, and must arrive at the SAME splitters — the kernels of all
+    ranks then agree on who owns which key (no GPU involved)."""
+    sys.path.insert(0, os.path.join(ROOT, "little-physics-engine_b200"))
+    import lpe_bh
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(100 + rank)
+        nchunks = 3000 + 500 * rank
+        lo, hi = rank * (1 << 59), (rank + 1) * (1 << 59)               # disjoint ascending key ranges (depth-30 keys)
+        keys = np.sort(rng.integers(lo, hi, nchunks, dtype=np.int64)).astype(np.uint64)
+        cost = (200 + 400 * rng.random(nchunks) * (1 + 3 * rank)).astype(np.uint32)   # rank 1's chunks are dearer
+        allc = [None] * world
+        dist.all_gather_object(allc, (keys, cost))
+        split = lpe_bh.balanced_splitters(allc, world, beta=100.0)
+        scaled = lpe_bh.balanced_splitters(allc, world, beta=100.0, scale=[1.0, 2.0][:world])
+        allk = np.concatenate([k for k, _ in allc]); allw = np.concatenate([c for _, c in allc]).astype(np.float64) + 100.0
+        share = [float(allw[(allk >= split[r]) & (allk < split[r + 1])].sum()) for r in range(world)]
+        q.put((rank, split, scaled, share))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_balanced_splitters_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_balance_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, s0, sc0, share0), (_, s1, sc1, share1) = res
+    assert s0 == s1 and sc0 == sc1                       # every rank computes the same splitters
+    assert s0[0] == 0 and s0[-1] == 1 << 60 and all(a <= b for a, b in zip(s0, s0[1:]))
+    assert abs(share0[0] - share0[1]) <= 0.01 * sum(share0)   # equal shares of cost + beta (to one chunk)
+    assert sc0[1] > s0[1]                                # charging rank 1's chunks double moves the border into its range
