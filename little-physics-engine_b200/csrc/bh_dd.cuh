@@ -121,7 +121,7 @@ __global__ void k_dd_wait(int point, unsigned long long epoch, int R, DDHeader* 
     unsigned long long spins = 0;
     while (ld_acquire_sys(f) < epoch) {
         __nanosleep(200);
-        if (++spins > (1ull << 24)) {   // a few seconds
+        if (++spins > (1ull << 27)) {   // about half a minute: a peer that is merely slow (host stall) must not trip it
             atomicOr(&hdr->fault, 8u);
             break;
         }

@@ -160,8 +160,12 @@ __global__ void __launch_bounds__(512) k_sort_bases(unsigned int* __restrict__ h
     row[tid] = sh[tid] - v;
 }
 
-template <int BINS, class KeyT>
-__global__ void __launch_bounds__(SORT_THREADS)
+// ITEMS keys per thread: 8 (tile of 2048) for 64-bit keys, 16 (tile of 4096) for 32-bit keys. The pass is bound by
+// the look-back (ncu, 16 M keys, tile 2048: 36 % of the issued instructions and most of the stall samples sit in
+// lb_exclusive — with ~740 tiles in flight the finished prefix lags ~50 tiles behind, so every one of a tile's 256
+// digit columns walks that far); twice the keys per tile halves the number of walks.
+template <int BINS, class KeyT, int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, ITEMS == 16 ? 4 : 1)
 k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
                 KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift, int top,
                 const unsigned int* __restrict__ digitBase, unsigned long long* __restrict__ status,
@@ -171,11 +175,12 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     // The tile is first sorted by digit INSIDE shared memory, then written out: consecutive threads then store
     // consecutive addresses within each digit's run, so every 32-byte sector written is fully used (a direct
     // scatter from registers wrote 8-byte keys and 4-byte payloads to 32 different sectors per instruction).
-    __shared__ unsigned int cnt[SORT_WARPS][BINS];     // per-warp digit counts -> tile-local offsets
+    __shared__ unsigned short cnt[SORT_WARPS][BINS];   // per-warp digit counts -> tile-local offsets (a tile has <= 4096 keys)
     __shared__ unsigned int dbase[BINS];               // tile-local start of each digit's run
     __shared__ unsigned int gbase[BINS];               // global start of this tile's run of each digit
-    __shared__ KeyT skey[SORT_TILE];
-    __shared__ unsigned int sval[SORT_TILE];
+    constexpr int TILE = SORT_THREADS * ITEMS;
+    __shared__ KeyT skey[TILE];
+    __shared__ unsigned int sval[TILE];
     constexpr int bins = BINS;
     const int tid = threadIdx.x;
     const int w = tid >> 5;
@@ -183,26 +188,26 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     const unsigned int dmask = (unsigned int)bins - 1u;
     __shared__ unsigned int s_tile;
     if (tid == 0) s_tile = atomicAdd(tileCounter, 1u);   // tiles in start order: look-back never waits on a later block
-    for (int k = tid; k < SORT_WARPS * BINS; k += SORT_THREADS) (&cnt[0][0])[k] = 0;
+    for (int k = tid; k < SORT_WARPS * BINS / 2; k += SORT_THREADS) reinterpret_cast<unsigned int*>(&cnt[0][0])[k] = 0;
     __syncthreads();
     const unsigned int tile = s_tile;
-    if ((long long)tile * SORT_TILE >= n) return;
+    if ((long long)tile * TILE >= n) return;
 
-    const long long tbase = (long long)tile * SORT_TILE;
-    const long long wbase = tbase + (long long)w * (SORT_ITEMS * 32);
-    KeyT key[SORT_ITEMS];
-    unsigned int val[SORT_ITEMS];
-    unsigned short rk[SORT_ITEMS];
+    const long long tbase = (long long)tile * TILE;
+    const long long wbase = tbase + (long long)w * (ITEMS * 32);
+    KeyT key[ITEMS];
+    unsigned int val[ITEMS];
+    unsigned short rk[ITEMS];
     const unsigned int lt = (1u << lane) - 1u;
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         const bool ok = i < n;
         key[r] = ok ? keysIn[i] : (KeyT)~(KeyT)0;
         val[r] = ok ? valsIn[i] : 0u;
     }
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         const bool ok = i < n;
         const unsigned int d = ok ? sort_digit<KeyT>(key[r], val[r], shift, dmask, top != 0) : 0xFFFFu;
@@ -212,7 +217,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         unsigned int old = 0;
         if (ok && lane == leader) {
             old = cnt[w][d];
-            cnt[w][d] = old + __popc(peers);
+            cnt[w][d] = (unsigned short)(old + __popc(peers));
         }
         old = __shfl_sync(0xFFFFFFFFu, old, leader);
         rk[r] = (unsigned short)(old + before);
@@ -230,7 +235,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
 #pragma unroll
         for (int ww = 0; ww < SORT_WARPS; ++ww) {
             const unsigned int c = cnt[ww][d];
-            cnt[ww][d] = run;
+            cnt[ww][d] = (unsigned short)run;
             run += c;
         }
         total[k] = run;
@@ -248,7 +253,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < SORT_ITEMS; ++r) {
+    for (int r = 0; r < ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         if (i < n) {
             const unsigned int d = sort_digit<KeyT>(key[r], val[r], shift, dmask, top != 0);
@@ -269,7 +274,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         gbase[d] = digitBase[d] + excl;
     }
     __syncthreads();
-    const int tileCount = (int)min((long long)SORT_TILE, (long long)n - tbase);
+    const int tileCount = (int)min((long long)TILE, (long long)n - tbase);
     for (int j = tid; j < tileCount; j += SORT_THREADS) {
         const KeyT kx = skey[j];
         const unsigned int vx = sval[j];

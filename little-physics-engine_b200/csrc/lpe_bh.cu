@@ -626,7 +626,9 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_de
     cudaStream_t st = c->stream;
     const SortPlan plan = sort_plan(k);
     const int passes = plan.passes, topBits = plan.topBits;
-    const int sortTiles = cdiv(n, SORT_TILE);
+    // (status words are laid out for the smaller tile, so they also hold the 4096-key tiles of the 32-bit path)
+    const int statusTiles = cdiv(n, SORT_TILE);
+    const int sortTiles = k.k32 ? cdiv(n, 2 * SORT_TILE) : statusTiles;
     int sel = 0;
     // look-back words carry the step's epoch, so the status array is cleared only when the epoch wraps
     if (c->epoch == 0u || c->epoch >= (1u << 30) - 1u) {
@@ -643,19 +645,20 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_de
     const int histBlocks = std::min(sortTiles, 148 * 8);
     auto run = [&](auto keyTag) {
         using KeyT = decltype(keyTag);
+        constexpr int ITEMS = sizeof(KeyT) == 4 ? 2 * SORT_ITEMS : SORT_ITEMS;
         KeyT* kb[2] = {reinterpret_cast<KeyT*>(c->keys[0]), reinterpret_cast<KeyT*>(c->keys[1])};
         k_sort_hist<KeyT><<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(kb[0], c->vals[0], n, passes, lastBins, hist, n_dev);
         k_sort_bases<<<passes, 512, 0, st>>>(hist);
         for (int ps = 0; ps < passes; ++ps) {
             const int shift = 8 * ps;
             const int top = ps == passes - 1;
-            unsigned long long* status = c->lbstatus + (size_t)ps * 256 * sortTiles;
+            unsigned long long* status = c->lbstatus + (size_t)ps * 256 * statusTiles;
             const unsigned int* base = hist + 512 * ps;
             if (top && lastBins == 512)
-                k_sort_onesweep<512, KeyT><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
+                k_sort_onesweep<512, KeyT, ITEMS><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
                                                                                 n, shift, top, base, status, c->epoch, tileCounter + ps, fault, n_dev);
             else
-                k_sort_onesweep<256, KeyT><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
+                k_sort_onesweep<256, KeyT, ITEMS><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
                                                                                 n, shift, top, base, status, c->epoch, tileCounter + ps, fault, n_dev);
             sel ^= 1;
         }
