@@ -33,6 +33,14 @@
 
 namespace lpe {
 
+// The state update of the tick, one rounding per operation like the reference's own code (g++ -O2 on x86-64 never fuses
+// a*b+c): kick `vel += acc * dt` (barnes_hut.cpp:284-286) and drift `pos += vel * dt` (movement.cpp:32-33). Every
+// kernel that kicks or drifts goes through these two, so the fused epilogue of the traversal kernels, the separate
+// passes (k_drift, k_finish_tick) and the decomposed ranks produce the same bits.
+__device__ __forceinline__ double kick_step(double v, double acc, double dt) { return __dadd_rn(v, __dmul_rn(acc, dt)); }
+__device__ __forceinline__ double drift_step(double p, double v, double dt) { return __dadd_rn(p, __dmul_rn(v, dt)); }
+
+
 constexpr int LPE_MAX_P2P = 8;   // ranks of one NVSwitch domain that can exchange by direct peer stores
 
 

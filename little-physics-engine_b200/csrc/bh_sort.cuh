@@ -160,14 +160,46 @@ __global__ void __launch_bounds__(512) k_sort_bases(unsigned int* __restrict__ h
     row[tid] = sh[tid] - v;
 }
 
-// ITEMS keys per thread: 8 (tile of 2048) for 64-bit keys, 16 (tile of 4096) for 32-bit keys. The pass is bound by
-// the look-back (ncu, 16 M keys, tile 2048: 36 % of the issued instructions and most of the stall samples sit in
-// lb_exclusive — with ~740 tiles in flight the finished prefix lags ~50 tiles behind, so every one of a tile's 256
-// digit columns walks that far); twice the keys per tile halves the number of walks.
-template <int BINS, class KeyT, int ITEMS>
-__global__ void __launch_bounds__(SORT_THREADS, ITEMS == 16 ? 4 : 1)
+// exclusive scan of one value per thread across a block of WARPS warps (<= 32)
+template <int WARPS>
+__device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, unsigned int* sh) {
+    // sh: WARPS words
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned int s = (lane < WARPS) ? sh[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < WARPS; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < WARPS) sh[lane] = s;  // inclusive warp sums
+    }
+    __syncthreads();
+    const unsigned int wprefix = (w > 0) ? sh[w - 1] : 0u;
+    return wprefix + inc - v;
+}
+
+// One pass = one kernel. THREADS x ITEMS keys per tile: 256 x 8 (2048) for 64-bit keys, 512 x 8 (4096) for 32-bit keys.
+// The pass is latency-bound, not bandwidth-bound (ncu, 16 M keys): the ranking rounds are a chain of MATCH -> shared-memory
+// read-modify-write -> SHFL per key of a thread, and the look-back walks one status column per digit. Hence: few keys per
+// thread (short chains) in many warps (48 per SM at 512 x 8), and large tiles (with ~600 tiles in flight the finished
+// prefix lags dozens of tiles behind, so every digit column of a tile walks that far: half the tiles, half the walks).
+template <int BINS, class KeyT, int THREADS, int ITEMS>
+constexpr size_t sort_smem_bytes() {
+    return (size_t)THREADS * ITEMS * (sizeof(KeyT) + 4) + (size_t)BINS * 8 + 128 + (size_t)(THREADS / 32) * BINS * 2;
+}
+template <int BINS, class KeyT, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 3 : 1)
 k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
-                KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift, int top,
+                KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
                 const unsigned int* __restrict__ digitBase, unsigned long long* __restrict__ status,
                 unsigned int epoch, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault,
                 const unsigned int* __restrict__ n_dev) {
@@ -175,20 +207,24 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     // The tile is first sorted by digit INSIDE shared memory, then written out: consecutive threads then store
     // consecutive addresses within each digit's run, so every 32-byte sector written is fully used (a direct
     // scatter from registers wrote 8-byte keys and 4-byte payloads to 32 different sectors per instruction).
-    __shared__ unsigned short cnt[SORT_WARPS][BINS];   // per-warp digit counts -> tile-local offsets (a tile has <= 4096 keys)
-    __shared__ unsigned int dbase[BINS];               // tile-local start of each digit's run
-    __shared__ unsigned int gbase[BINS];               // global start of this tile's run of each digit
-    constexpr int TILE = SORT_THREADS * ITEMS;
-    __shared__ KeyT skey[TILE];
-    __shared__ unsigned int sval[TILE];
-    constexpr int bins = BINS;
+    constexpr int WARPS = THREADS / 32;
+    constexpr int TILE = THREADS * ITEMS;
+    constexpr bool TOP = BINS == 512;                  // (32-bit keys: the 512-bin pass is the top pass, payload bit 31 joins the digit)
+    // (dynamic shared memory: the 512-bin pass of a 4096-key tile needs 52 KB)
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    KeyT* skey = reinterpret_cast<KeyT*>(sort_smem);
+    unsigned int* sval = reinterpret_cast<unsigned int*>(skey + TILE);
+    unsigned int* dbase = sval + TILE;                 // tile-local start of each digit's run
+    unsigned int* gbase = dbase + BINS;                // global start of this tile's run of each digit
+    unsigned int* sh_scan = gbase + BINS;
+    unsigned short (*cnt)[BINS] = reinterpret_cast<unsigned short (*)[BINS]>(sh_scan + 32);   // per-warp digit counts -> tile-local offsets (a tile has <= 4096 keys)
     const int tid = threadIdx.x;
     const int w = tid >> 5;
     const int lane = tid & 31;
-    const unsigned int dmask = (unsigned int)bins - 1u;
+    constexpr unsigned int dmask = (unsigned int)BINS - 1u;
     __shared__ unsigned int s_tile;
     if (tid == 0) s_tile = atomicAdd(tileCounter, 1u);   // tiles in start order: look-back never waits on a later block
-    for (int k = tid; k < SORT_WARPS * BINS / 2; k += SORT_THREADS) reinterpret_cast<unsigned int*>(&cnt[0][0])[k] = 0;
+    for (int k = tid; k < WARPS * BINS / 2; k += THREADS) reinterpret_cast<unsigned int*>(&cnt[0][0])[k] = 0;
     __syncthreads();
     const unsigned int tile = s_tile;
     if ((long long)tile * TILE >= n) return;
@@ -206,18 +242,24 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         key[r] = ok ? keysIn[i] : (KeyT)~(KeyT)0;
         val[r] = ok ? valsIn[i] : 0u;
     }
+    // the MATCHes of all rounds are independent of each other: issue them together, then run the counter chain
+    unsigned int peers[ITEMS];
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
-        const long long i = wbase + r * 32 + lane;
-        const bool ok = i < n;
-        const unsigned int d = ok ? sort_digit<KeyT>(key[r], val[r], shift, dmask, top != 0) : 0xFFFFu;
-        const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
-        const unsigned int before = __popc(peers & lt);
-        const int leader = __ffs(peers) - 1;
+        const bool ok = wbase + r * 32 + lane < n;
+        const unsigned int d = ok ? sort_digit<KeyT>(key[r], val[r], shift, dmask, TOP) : 0xFFFFu;
+        peers[r] = __match_any_sync(0xFFFFFFFFu, d);
+    }
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const bool ok = wbase + r * 32 + lane < n;
+        const unsigned int d = sort_digit<KeyT>(key[r], val[r], shift, dmask, TOP);
+        const unsigned int before = __popc(peers[r] & lt);
+        const int leader = __ffs(peers[r]) - 1;
         unsigned int old = 0;
         if (ok && lane == leader) {
             old = cnt[w][d];
-            cnt[w][d] = (unsigned short)(old + __popc(peers));
+            cnt[w][d] = (unsigned short)(old + __popc(peers[r]));
         }
         old = __shfl_sync(0xFFFFFFFFu, old, leader);
         rk[r] = (unsigned short)(old + before);
@@ -226,59 +268,66 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     __syncthreads();
     // per digit: total in this tile, and the exclusive offsets of the warps inside the digit's run. The tile's counts
     // are published at once (aggregate), the wait for the tiles before it comes after the local reordering.
-    constexpr int PER = BINS / SORT_THREADS;   // 1 or 2 digits per thread: tid * PER + k
+    constexpr int PER = BINS > THREADS ? BINS / THREADS : 1;   // digits per thread: tid * PER + k (threads past BINS idle)
+    const bool owner = tid * PER < BINS;
     unsigned int total[PER];
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
-        const int d = tid * PER + k;
-        unsigned int run = 0;
+        total[k] = 0;
+        if (owner) {
+            const int d = tid * PER + k;
+            unsigned int run = 0;
 #pragma unroll
-        for (int ww = 0; ww < SORT_WARPS; ++ww) {
-            const unsigned int c = cnt[ww][d];
-            cnt[ww][d] = (unsigned short)run;
-            run += c;
+            for (int ww = 0; ww < WARPS; ++ww) {
+                const unsigned int c = cnt[ww][d];
+                cnt[ww][d] = (unsigned short)run;
+                run += c;
+            }
+            total[k] = run;
+            lb_store(status + (size_t)tile * BINS + d, epoch, tile == 0u ? LB_INCLUSIVE : LB_AGGREGATE, run);
         }
-        total[k] = run;
-        lb_store(status + (size_t)tile * BINS + d, epoch, tile == 0u ? LB_INCLUSIVE : LB_AGGREGATE, run);
     }
     // exclusive scan of the digit totals -> start of each digit's run inside the tile
     {
-        __shared__ unsigned int sh_scan[9];
         unsigned int sum = 0;
 #pragma unroll
         for (int k = 0; k < PER; ++k) sum += total[k];
-        unsigned int run = block_exclusive_scan_256(sum, sh_scan, nullptr);
+        unsigned int run = block_exclusive_scan<WARPS>(sum, sh_scan);
+        if (owner) {
 #pragma unroll
-        for (int k = 0; k < PER; ++k) { dbase[tid * PER + k] = run; run += total[k]; }
+            for (int k = 0; k < PER; ++k) { dbase[tid * PER + k] = run; run += total[k]; }
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
         if (i < n) {
-            const unsigned int d = sort_digit<KeyT>(key[r], val[r], shift, dmask, top != 0);
+            const unsigned int d = sort_digit<KeyT>(key[r], val[r], shift, dmask, TOP);
             const unsigned int lp = dbase[d] + cnt[w][d] + rk[r];
             skey[lp] = key[r];
             sval[lp] = val[r];
         }
     }
     // now add up the tiles before this one and publish the inclusive value for the tiles after it
+    if (owner) {
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        const int d = tid * PER + k;
-        unsigned int excl = 0;
-        if (tile != 0u) {
-            excl = lb_exclusive(status + d, BINS, tile, epoch, fault);
-            lb_store(status + (size_t)tile * BINS + d, epoch, LB_INCLUSIVE, excl + total[k]);
+        for (int k = 0; k < PER; ++k) {
+            const int d = tid * PER + k;
+            unsigned int excl = 0;
+            if (tile != 0u) {
+                excl = lb_exclusive(status + d, BINS, tile, epoch, fault);
+                lb_store(status + (size_t)tile * BINS + d, epoch, LB_INCLUSIVE, excl + total[k]);
+            }
+            gbase[d] = digitBase[d] + excl;
         }
-        gbase[d] = digitBase[d] + excl;
     }
     __syncthreads();
     const int tileCount = (int)min((long long)TILE, (long long)n - tbase);
-    for (int j = tid; j < tileCount; j += SORT_THREADS) {
+    for (int j = tid; j < tileCount; j += THREADS) {
         const KeyT kx = skey[j];
         const unsigned int vx = sval[j];
-        const unsigned int d = sort_digit<KeyT>(kx, vx, shift, dmask, top != 0);
+        const unsigned int d = sort_digit<KeyT>(kx, vx, shift, dmask, TOP);
         const unsigned int dst = gbase[d] + ((unsigned int)j - dbase[d]);
 #ifdef LPE_CHECKED
         if (dst >= (unsigned int)n) { atomicOr(fault, 2u); continue; }   // (bit 1 of the sort's fault word)

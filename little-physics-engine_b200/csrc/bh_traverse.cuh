@@ -50,6 +50,12 @@ struct TravArgs {
     const double4* xrec;
     unsigned int localLo, localHi;
     unsigned int* chunk_cost;     // [chunk] list entries evaluated for the chunk (load-balance weight); may be null
+    // host tick (FAST precision): the velocities are still on their way over PCIe while the tree is walked, so the kernel
+    // kicks nothing: it stores {x, y, dvx, dvy} — the body's position and its velocity CHANGE — as one 32-byte record at
+    // the body's creation index (orig, null = identity), and k_finish_tick does kick + drift in creation order with
+    // streaming accesses once the velocities have arrived. Null = kick and drift in the kernel's own epilogue.
+    double4* stage_out;
+    const unsigned int* orig;
 };
 
 // The reference's test, barnes_hut.cpp:261-269, on exactly scaled operands (power-of-two scaling commutes
@@ -151,7 +157,7 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(const __grid_const
         unsigned int nacc = 0, nvis = 0, nwarp = 0;
         double fsum = 0.0, fmaxd = 0.0;   // STATS: DebugStats::updateForce (barnes_hut.cpp:278), real units
         double2 v = make_double2(0.0, 0.0);
-        if (valid) v = a.vel[b];
+        if (valid && !(PREC == 0 && a.stage_out)) v = a.vel[b];   // (deferred kick: v stays the velocity CHANGE, 0 + x is exact)
 
         // ---- depth-first walk over child blocks; d, k are warp-uniform ----
         int d = 0, k = 0;
@@ -233,8 +239,8 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(const __grid_const
             // a = G * sum M d / r^3 ; scaled units: M/Ms, d/S  =>  factor G*Ms/S^2
             const double accScale = c.G * massScale * c.invS * c.invS;
             if (target) {
-                v.x += (AX * accScale) * c.dtK;   // barnes_hut.cpp:284-286
-                v.y += (AY * accScale) * c.dtK;
+                v.x = kick_step(v.x, AX * accScale, c.dtK);   // barnes_hut.cpp:284-286
+                v.y = kick_step(v.y, AY * accScale, c.dtK);
             }
             if (STATS) { fsum *= accScale * bodyMass; fmaxd *= accScale * bodyMass; }
         } else {
@@ -311,13 +317,15 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(const __grid_const
             }
         }
 
-        if (valid) {
+        if (PREC == 0 && a.stage_out) {
+            if (valid) a.stage_out[a.orig ? a.orig[b] : b] = make_double4(p.x, p.y, v.x, v.y);
+        } else if (valid) {
             // STRICT reads single-body leaves straight from the state (a.body), so positions must not move while the
             // kernel runs: its drift is a separate elementwise pass (k_drift) after the traversal.
             const bool mover = (PREC == 0 || c.shard_n > 1) && (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
             if (c.do_drift && mover) {
-                p.x += v.x * c.dtD;                                       // movement.cpp:32-33
-                p.y += v.y * c.dtD;
+                p.x = drift_step(p.x, v.x, c.dtD);                                      // movement.cpp:32-33
+                p.y = drift_step(p.y, v.y, c.dtD);
             }
             if (c.shard_n > 1) {
                 const unsigned long long slot = (unsigned long long)lblock * 2048ull + within * 32ull + lane;
@@ -334,10 +342,10 @@ __global__ void __launch_bounds__(TRAV_THREADS, 4) k_traverse(const __grid_const
                 if (target) a.vel[b] = v;
                 if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;
             }
-            if (STATS) {
-                a.cntAcc[b] = nacc;
-                a.cntVis[b] = nvis;
-            }
+        }
+        if (STATS && valid) {
+            a.cntAcc[b] = nacc;
+            a.cntVis[b] = nvis;
         }
         if (STATS) {
 #pragma unroll

@@ -31,6 +31,9 @@
 
 namespace lpe {
 
+#ifndef T2_MIN_CTAS
+#define T2_MIN_CTAS 7
+#endif
 constexpr int T2_THREADS = 128;
 constexpr int T2_WARPS = T2_THREADS / 32;
 constexpr int T2_CAP = 256;                 // ring entries per warp (power of two)
@@ -140,7 +143,7 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
 // DD: the kernel serves a domain-decomposed rank (body count and tree size known only on the device, per-chunk cost
 // recorded for the load balancer); a template flag so that the single-GPU kernel carries none of it (measured: 1.5 %).
 template <bool STATS, bool SELF, bool DD>
-__global__ void __launch_bounds__(T2_THREADS, 7)
+__global__ void __launch_bounds__(T2_THREADS, T2_MIN_CTAS)
 k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArgs a, unsigned int* __restrict__ ovf_list) {
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
@@ -404,17 +407,19 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
 
         if (DD && lane == 0) a.chunk_cost[q] = cost;
         double2 v = make_double2(0.0, 0.0);
-        if (valid) v = a.vel[b];
+        if (valid && !a.stage_out) v = a.vel[b];   // (deferred kick: v is the velocity CHANGE, 0 + x is exact)
         const double accScale = c.G * massScale * c.invS * c.invS;   // a = G*sum M d/r^3; scaled units M/Ms, d/S
         if (target) {
-            v.x += (AX * accScale) * c.dtK;   // barnes_hut.cpp:284-286
-            v.y += (AY * accScale) * c.dtK;
+            v.x = kick_step(v.x, AX * accScale, c.dtK);   // barnes_hut.cpp:284-286
+            v.y = kick_step(v.y, AY * accScale, c.dtK);
         }
-        if (valid) {
+        if (a.stage_out) {   // host tick: k_finish_tick kicks and drifts once the velocities have arrived
+            if (valid) a.stage_out[a.orig ? a.orig[b] : b] = make_double4(p.x, p.y, v.x, v.y);
+        } else if (valid) {
             const bool mover = (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29
             if (c.do_drift && mover) {
-                p.x += v.x * c.dtD;                                       // movement.cpp:32-33
-                p.y += v.y * c.dtD;
+                p.x = drift_step(p.x, v.x, c.dtD);                                      // movement.cpp:32-33
+                p.y = drift_step(p.y, v.y, c.dtD);
             }
             if (c.shard_n > 1) {
                 const unsigned long long slotx = (unsigned long long)lblock * 2048ull + within * 32ull + lane;
@@ -434,10 +439,10 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
                 if (target) a.vel[b] = v;
                 if (c.do_drift && mover) *reinterpret_cast<double2*>(&a.body[b].x) = p;
             }
-            if (STATS) {
-                a.cntAcc[b] = target ? nacc : 0u;
-                a.cntVis[b] = 0u;
-            }
+        }
+        if (STATS && valid) {
+            a.cntAcc[b] = target ? nacc : 0u;
+            a.cntVis[b] = 0u;
         }
         if (STATS) {
             unsigned int tot = target ? nacc : 0u;

@@ -62,6 +62,7 @@ struct lpe_bh_ctx {
     // every step's gather re-orders the state into key order (second set of buffers); orig[slot] is then the creation
     // index of the body in that slot (orig_valid = false: the state is in creation order, right after an upload)
     Body* body2 = nullptr;
+    double4* stage4 = nullptr;    // {x, y, vx, vy} records in creation order on their way to the host (k_finish_tick, k_stage_state)
     double2* vel2 = nullptr;
     unsigned int *orig = nullptr, *orig2 = nullptr;
     bool orig_valid = false;
@@ -76,6 +77,10 @@ struct lpe_bh_ctx {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t evs[2] = {nullptr, nullptr};
     bool pend_mass = false, pend_vel = false, pend_rank = false, pend_vel_aos = false;
+    bool tick_has_comp = false;
+    bool tracing = false;
+    cudaEvent_t trace_ev[7] = {};
+    bool defer_kick = false;      // host tick, FAST precision: the traversal stores velocity changes, k_finish_tick applies them
     int tick_stage = 0;           // lpe_bh_tick_begin / _mass / _finish: which call comes next
     StepConst tick_k{};
     lpe_bh_params tick_p{};
@@ -215,7 +220,7 @@ int ensure_capacity(lpe_bh_ctx* c, uint64_t n, bool dd = false) {
     int rc = 0;
     rc |= dalloc(c, c->rank_in, cap) | dalloc(c, c->comp_in, cap) | dalloc(c, c->tmp, 5 * cap);
     if (!dd)
-        rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->body2, cap) | dalloc(c, c->vel2, cap) |
+        rc |= dalloc(c, c->body, cap) | dalloc(c, c->vel, cap) | dalloc(c, c->body2, cap) | dalloc(c, c->vel2, cap) | dalloc(c, c->stage4, cap) |
               dalloc(c, c->orig, cap) | dalloc(c, c->orig2, cap) | dalloc(c, c->rec, recSlots);
     rc |= dalloc(c, c->keys[0], cap) | dalloc(c, c->keys[1], cap) | dalloc(c, c->vals[0], cap) |
           dalloc(c, c->vals[1], cap) | dalloc(c, c->lbstatus, (size_t)sortTiles * (256 * (SORT_MAX_PASSES - 1) + 512) + 2 * ((size_t)scanTiles + 2)) | dalloc(c, c->totals, 512 * 8 + 16);
@@ -353,9 +358,84 @@ __global__ void __launch_bounds__(256) k_drift(int n, double dtD, Body* __restri
     if (!mover) return;
     double2 p = *reinterpret_cast<const double2*>(&body[i].x);
     const double2 v = vel[i];
-    p.x += v.x * dtD;                                             // movement.cpp:32-33
-    p.y += v.y * dtD;
+    p.x = drift_step(p.x, v.x, dtD);                                            // movement.cpp:32-33
+    p.y = drift_step(p.y, v.y, dtD);
     *reinterpret_cast<double2*>(&body[i].x) = p;
+}
+// Host tick, FAST precision: the tree walk does not need the velocities, so it runs while they are still coming over
+// PCIe; its epilogue leaves {x, y, dvx, dvy} per body as one 32-byte record at the body's CREATION index (a random place
+// as far as key order is concerned: one full-sector store per body, hidden inside the compute-bound walk). This pass is
+// then the kick and the drift in creation order, every access streaming: uploaded velocity + change -> new velocity,
+// drifted position, written over the staging arrays the host's copies are made from (slot o is read and written by the
+// same thread). At 16 M bodies 0.2 ms, where kicking in key order and scattering four 8-byte values per body into the
+// host-shaped arrays took 2.9 ms (partial sectors: read-modify-write in DRAM).
+template <bool AOS>
+__global__ void __launch_bounds__(256)
+k_finish_tick(int n, int do_drift, double dtD, const double4* __restrict__ stage, const unsigned char* __restrict__ comp,
+              double* va, double* vb, double* xa, double* xb) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n) return;
+    const double4 r = stage[o];
+    double2 v = AOS ? reinterpret_cast<const double2*>(va)[o] : make_double2(va[o], vb[o]);
+    const unsigned int cm = comp ? (unsigned int)comp[o] : (unsigned int)(LPE_HAS_MASS | LPE_HAS_VELOCITY);
+    if ((cm & 1u) && (cm & 2u) && !(cm & 4u)) {                          // a target, barnes_hut.cpp:89
+        v.x = __dadd_rn(v.x, r.z);                                       // r.z = 0 + acc * dt (kick_step), barnes_hut.cpp:284-286
+        v.y = __dadd_rn(v.y, r.w);
+    }
+    double2 p = make_double2(r.x, r.y);
+    if (do_drift && (cm & 2u) && !(cm & 4u) && !(cm & 8u)) {             // a mover, movement.cpp:20-29
+        p.x = drift_step(p.x, v.x, dtD);                                 // movement.cpp:32-33
+        p.y = drift_step(p.y, v.y, dtD);
+    }
+    if (AOS) {
+        reinterpret_cast<double2*>(va)[o] = v;
+        reinterpret_cast<double2*>(xa)[o] = p;
+    } else {
+        va[o] = v.x; vb[o] = v.y;
+        xa[o] = p.x; xb[o] = p.y;
+    }
+}
+// ... and the resident state (key order) catches up from the same arrays on the side stream, beside the downloads
+template <bool AOS>
+__global__ void __launch_bounds__(256)
+k_refresh_state(int n, int do_drift, const unsigned int* __restrict__ orig, Body* __restrict__ body, double2* __restrict__ vel,
+                const double* __restrict__ va, const double* __restrict__ vb, const double* __restrict__ xa,
+                const double* __restrict__ xb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned int o = orig ? orig[i] : (unsigned int)i;
+    vel[i] = AOS ? reinterpret_cast<const double2*>(va)[o] : make_double2(va[o], vb[o]);
+    if (do_drift)
+        *reinterpret_cast<double2*>(&body[i].x) = AOS ? reinterpret_cast<const double2*>(xa)[o] : make_double2(xa[o], xb[o]);
+}
+// the resident state as {x, y, vx, vy} records in creation order (lpe_bh_download: same reason as above)
+__global__ void __launch_bounds__(256)
+k_stage_state(int n, const Body* __restrict__ body, const double2* __restrict__ vel, const unsigned int* __restrict__ orig,
+              double4* __restrict__ stage) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double2 p = *reinterpret_cast<const double2*>(&body[i].x);
+    const double2 v = vel[i];
+    stage[orig ? orig[i] : (unsigned int)i] = make_double4(p.x, p.y, v.x, v.y);
+}
+// records -> the arrays the host wants: four arrays of doubles (x, y, vx, vy; any may be null), or with AOS two arrays of
+// {x, y} records (pos = xa, vel = va)
+template <bool AOS>
+__global__ void __launch_bounds__(256)
+k_unstage(int n, const double4* __restrict__ stage, double* __restrict__ xa, double* __restrict__ xb,
+          double* __restrict__ va, double* __restrict__ vb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double4 r = stage[i];
+    if (AOS) {
+        if (xa) reinterpret_cast<double2*>(xa)[i] = make_double2(r.x, r.y);
+        if (va) reinterpret_cast<double2*>(va)[i] = make_double2(r.z, r.w);
+    } else {
+        if (xa) xa[i] = r.x;
+        if (xb) xb[i] = r.y;
+        if (va) va[i] = r.z;
+        if (vb) vb[i] = r.w;
+    }
 }
 // array-of-structs forms for the ECS drop-in: EnTT keeps Position / Velocity as {double x, y} records, so its pool pages
 // can be copied as they are (lpe_bh_update_host_aos)
@@ -645,7 +725,7 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_de
     const int histBlocks = std::min(sortTiles, 148 * 8);
     auto run = [&](auto keyTag) {
         using KeyT = decltype(keyTag);
-        constexpr int ITEMS = sizeof(KeyT) == 4 ? 2 * SORT_ITEMS : SORT_ITEMS;
+        constexpr int THREADS = sizeof(KeyT) == 4 ? 2 * SORT_THREADS : SORT_THREADS;   // tile = THREADS x SORT_ITEMS keys
         KeyT* kb[2] = {reinterpret_cast<KeyT*>(c->keys[0]), reinterpret_cast<KeyT*>(c->keys[1])};
         k_sort_hist<KeyT><<<histBlocks, 256, sizeof(unsigned int) * SORT_HIST_STRIDE * passes, st>>>(kb[0], c->vals[0], n, passes, lastBins, hist, n_dev);
         k_sort_bases<<<passes, 512, 0, st>>>(hist);
@@ -654,12 +734,17 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_de
             const int top = ps == passes - 1;
             unsigned long long* status = c->lbstatus + (size_t)ps * 256 * statusTiles;
             const unsigned int* base = hist + 512 * ps;
-            if (top && lastBins == 512)
-                k_sort_onesweep<512, KeyT, ITEMS><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
-                                                                                n, shift, top, base, status, c->epoch, tileCounter + ps, fault, n_dev);
-            else
-                k_sort_onesweep<256, KeyT, ITEMS><<<sortTiles, SORT_THREADS, 0, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1],
-                                                                                n, shift, top, base, status, c->epoch, tileCounter + ps, fault, n_dev);
+            auto pass = [&](auto binsTag) {
+                constexpr int BINS = decltype(binsTag)::value;
+                constexpr size_t smem = sort_smem_bytes<BINS, KeyT, THREADS, SORT_ITEMS>();
+                auto kern = k_sort_onesweep<BINS, KeyT, THREADS, SORT_ITEMS>;
+                // (more than 48 KB of shared memory has to be asked for, per kernel and per device: a host-side call, no stream work)
+                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                kern<<<sortTiles, THREADS, smem, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1], n, shift, base, status,
+                                                      c->epoch, tileCounter + ps, fault, n_dev);
+            };
+            if (top && lastBins == 512) pass(std::integral_constant<int, 512>{});
+            else pass(std::integral_constant<int, 256>{});
             sel ^= 1;
         }
     };
@@ -743,6 +828,8 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
     ta.xchg_send = c->xchg_send; ta.cntAcc = c->cntAcc; ta.cntVis = c->cntVis; ta.s = c->scal;
     ta.npeer = 0;
     ta.xrec = c->dd_xrec; ta.localLo = 0u; ta.localHi = 0xFFFFFFFFu; ta.chunk_cost = nullptr;
+    ta.stage_out = (c->defer_kick && !k.dd) ? c->stage4 : nullptr;
+    ta.orig = c->orig_valid ? c->orig : nullptr;
     if (k.dd) {
         ta.localLo = 4u * k.blockBase;
         ta.localHi = 4u * (k.blockBase + (unsigned int)c->cap + 8u);
@@ -767,7 +854,7 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
         const bool selfT = k.need_self != 0;
         static_assert(sizeof(T2Warp) * T2_WARPS <= 48 * 1024, "per-CTA work areas fit the default dynamic shared memory limit");
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
-        if (grid > sms * 7) grid = sms * 7;
+        if (grid > sms * T2_MIN_CTAS) grid = sms * T2_MIN_CTAS;
         if (grid < 1) grid = 1;
         if (k.dd) {
             if (stats) k_traverse2<true, true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
@@ -820,16 +907,20 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     if (timing) cudaEventRecord(c->ev[2], st);
     if (step_build(c, k, n)) return 1;
     if (timing) cudaEventRecord(c->ev[3], st);
-    if (c->pend_vel) {   // host path: velocities were uploaded behind the build; the kick is their first reader
+    // host path: the velocities were uploaded behind the build. FAST precision does not need them for the walk: the kick
+    // is deferred to k_finish_tick (the caller launches it once they have arrived). STRICT sums in the reference's
+    // order starting from the velocity itself, so it waits for them here.
+    c->defer_kick = c->pend_vel && p.precision == LPE_PREC_FAST && c->shard_n == 1;
+    if (c->pend_vel && !c->defer_kick) {
         CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
         if (c->pend_vel_aos)
             k_pack_vel_aos<<<cdiv(n, 256), 256, 0, st>>>(n, reinterpret_cast<const double2*>(c->tmp + 3 * c->cap), c->vel,
                                                          c->orig_valid ? c->orig : nullptr);
         else
             k_pack2<<<cdiv(n, 256), 256, 0, st>>>(n, c->tmp + 3 * c->cap, c->tmp + 4 * c->cap, c->vel, c->orig_valid ? c->orig : nullptr);
-        c->pend_vel = false;
-        c->pend_vel_aos = false;
     }
+    c->pend_vel = false;
+    c->pend_vel_aos = false;
     if (step_traverse(c, k, p, n, sharded_begin)) return 1;
     if (timing) cudaEventRecord(c->ev[4], st);
     CU_TRY(c, cudaGetLastError());
@@ -838,6 +929,55 @@ int run_step(lpe_bh_ctx* c, const lpe_bh_params& p, bool sharded_begin) {
     c->last.depth = k.D;
     c->last.hilbert = k.hilbert;
     return 0;
+}
+
+
+// Tail of a host tick whose kick was deferred (FAST precision): kick + drift in creation order over the staging arrays
+// (main stream), the downloads behind it, and the resident key-ordered state catching up on the side stream beside the
+// downloads. SoA: hx / hy / hvx / hvy are four host arrays; AoS: hx = {x, y} records, hvx = {vx, vy} records.
+int finish_deferred_tick(lpe_bh_ctx* c, bool aos, bool has_comp, bool want_pos, double* hx, double* hy, double* hvx, double* hvy) {
+    cudaStream_t st = c->stream, sg = c->side_stream;
+    const uint64_t n = c->n;
+    const size_t cap = c->cap, bytes = sizeof(double) * n;
+    const int g = cdiv((long long)n, 256);
+    double* t = c->tmp;
+    const int do_drift = c->last_c.do_drift;
+    const unsigned char* comp = has_comp ? c->comp_in : nullptr;
+    const unsigned int* orig = c->orig_valid ? c->orig : nullptr;
+    c->defer_kick = false;
+    if (aos) k_finish_tick<true><<<g, 256, 0, st>>>((int)n, do_drift, c->last_c.dtD, c->stage4, comp, t + 3 * cap, nullptr, t, nullptr);
+    else k_finish_tick<false><<<g, 256, 0, st>>>((int)n, do_drift, c->last_c.dtD, c->stage4, comp, t + 3 * cap, t + 4 * cap, t, t + cap);
+    CU_TRY(c, cudaEventRecord(c->evs[0], st));
+    if (c->tracing) cudaEventRecord(c->trace_ev[5], st);
+    CU_TRY(c, cudaStreamWaitEvent(sg, c->evs[0], 0));
+    if (aos) k_refresh_state<true><<<g, 256, 0, sg>>>((int)n, do_drift, orig, c->body, c->vel, t + 3 * cap, nullptr, t, nullptr);
+    else k_refresh_state<false><<<g, 256, 0, sg>>>((int)n, do_drift, orig, c->body, c->vel, t + 3 * cap, t + 4 * cap, t, t + cap);
+    CU_TRY(c, cudaEventRecord(c->evs[1], sg));
+    c->launches += 2;
+    if (aos) {
+        CU_TRY(c, cudaMemcpyAsync(hvx, t + 3 * cap, 2 * bytes, cudaMemcpyDeviceToHost, st));
+        if (want_pos) CU_TRY(c, cudaMemcpyAsync(hx, t, 2 * bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        CU_TRY(c, cudaMemcpyAsync(hvx, t + 3 * cap, bytes, cudaMemcpyDeviceToHost, st));
+        CU_TRY(c, cudaMemcpyAsync(hvy, t + 4 * cap, bytes, cudaMemcpyDeviceToHost, st));
+        if (want_pos) {
+            CU_TRY(c, cudaMemcpyAsync(hx, t, bytes, cudaMemcpyDeviceToHost, st));
+            CU_TRY(c, cudaMemcpyAsync(hy, t + cap, bytes, cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (c->tracing) cudaEventRecord(c->trace_ev[6], st);
+    CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: the context's stream is done when the state has caught up, too
+    if (fetch_fault(c)) return 1;
+    CU_TRY(c, cudaStreamSynchronize(st));
+    if (c->tracing) {
+        c->tracing = false;
+        float e[7] = {};
+        for (int z = 1; z < 7; ++z) cudaEventElapsedTime(&e[z], c->trace_ev[0], c->trace_ev[z]);
+        fprintf(stderr, "tick trace, ms after the first upload was queued: x,y up %.2f | m up %.2f | vx,vy up %.2f | traversal done %.2f | "
+                        "kick + drift done %.2f | downloads done %.2f\n", e[1], e[2], e[3], e[4], e[5], e[6]);
+    }
+    CU_TRY(c, cudaGetLastError());
+    return check_fault(c);
 }
 
 }  // namespace
@@ -903,6 +1043,7 @@ void lpe_bh_destroy(lpe_bh_ctx* c) {
     for (auto& ev : c->evc) if (ev) cudaEventDestroy(ev);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto& ev : c->evs) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->trace_ev) if (ev) cudaEventDestroy(ev);
     if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->fault_host) cudaFreeHost(c->fault_host);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -1010,6 +1151,7 @@ int lpe_bh_step(lpe_bh_ctx* c, const lpe_bh_params* p, int nsteps) {
 
 int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy) {
     if (!c) return 1;
+    if (c->dd) return fail(c, "context is in domain-decomposed mode: use lpe_bh_dd_download");
     DevGuard _dg(c->device);
     const uint64_t n = c->n;
     if (n) {
@@ -1017,16 +1159,14 @@ int lpe_bh_download(lpe_bh_ctx* c, double* x, double* y, double* vx, double* vy)
         const size_t bytes = sizeof(double) * n;
         const int g = cdiv((long long)n, 256);
         double *t0 = c->tmp, *t1 = c->tmp + c->cap, *t2 = c->tmp + 2 * c->cap, *t3 = c->tmp + 3 * c->cap;
-        if (x || y) {
-            k_get_pos<<<g, 256, 0, st>>>((int)n, c->body, t0, t1, c->orig_valid ? c->orig : nullptr);
-            if (x) CU_TRY(c, cudaMemcpyAsync(x, t0, bytes, cudaMemcpyDeviceToHost, st));
-            if (y) CU_TRY(c, cudaMemcpyAsync(y, t1, bytes, cudaMemcpyDeviceToHost, st));
-        }
-        if (vx || vy) {
-            k_unpack2<<<g, 256, 0, st>>>((int)n, c->vel, t2, t3, c->orig_valid ? c->orig : nullptr);
-            if (vx) CU_TRY(c, cudaMemcpyAsync(vx, t2, bytes, cudaMemcpyDeviceToHost, st));
-            if (vy) CU_TRY(c, cudaMemcpyAsync(vy, t3, bytes, cudaMemcpyDeviceToHost, st));
-        }
+        // one 32-byte record per body into creation order, then split into the four arrays (see k_finish_tick)
+        double4* stage = c->stage4;
+        k_stage_state<<<g, 256, 0, st>>>((int)n, c->body, c->vel, c->orig_valid ? c->orig : nullptr, stage);
+        k_unstage<false><<<g, 256, 0, st>>>((int)n, stage, x ? t0 : nullptr, y ? t1 : nullptr, vx ? t2 : nullptr, vy ? t3 : nullptr);
+        if (x) CU_TRY(c, cudaMemcpyAsync(x, t0, bytes, cudaMemcpyDeviceToHost, st));
+        if (y) CU_TRY(c, cudaMemcpyAsync(y, t1, bytes, cudaMemcpyDeviceToHost, st));
+        if (vx) CU_TRY(c, cudaMemcpyAsync(vx, t2, bytes, cudaMemcpyDeviceToHost, st));
+        if (vy) CU_TRY(c, cudaMemcpyAsync(vy, t3, bytes, cudaMemcpyDeviceToHost, st));
     }
     if (fetch_fault(c)) return 1;
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1070,16 +1210,25 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
         const size_t cap = c->cap;
         CU_TRY(c, cudaEventRecord(c->evc[0], st));           // the staging buffers are free once earlier work is done
         CU_TRY(c, cudaStreamWaitEvent(cs, c->evc[0], 0));
+        // LPE_TICK_TRACE=1: timeline of every tick on stderr (where the PCIe legs and the kernels overlap)
+        const bool trace = getenv("LPE_TICK_TRACE") != nullptr;
+        cudaEvent_t* tr = c->trace_ev;
+        if (trace && !tr[0]) for (int z = 0; z < 7; ++z) cudaEventCreate(&tr[z]);
+        c->tracing = trace;
+        if (trace) cudaEventRecord(tr[0], cs);
         CU_TRY(c, cudaMemcpyAsync(t, x, bytes, cudaMemcpyHostToDevice, cs));
         CU_TRY(c, cudaMemcpyAsync(t + cap, y, bytes, cudaMemcpyHostToDevice, cs));
         if (comp) CU_TRY(c, cudaMemcpyAsync(c->comp_in, comp, n, cudaMemcpyHostToDevice, cs));
         CU_TRY(c, cudaEventRecord(c->evc[1], cs));
+        if (trace) cudaEventRecord(tr[1], cs);
         CU_TRY(c, cudaMemcpyAsync(t + 2 * cap, m, bytes, cudaMemcpyHostToDevice, cs));
         if (rank) CU_TRY(c, cudaMemcpyAsync(c->rank_in, rank, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, cs));
         CU_TRY(c, cudaEventRecord(c->evc[2], cs));
+        if (trace) cudaEventRecord(tr[2], cs);
         CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vx, bytes, cudaMemcpyHostToDevice, cs));
         CU_TRY(c, cudaMemcpyAsync(t + 4 * cap, vy, bytes, cudaMemcpyHostToDevice, cs));
         CU_TRY(c, cudaEventRecord(c->evc[3], cs));
+        if (trace) cudaEventRecord(tr[3], cs);
         CU_TRY(c, cudaStreamWaitEvent(st, c->evc[1], 0));
         CU_TRY(c, cudaMemsetAsync(c->scal, 0, 8, st));   // the mass scale is rebuilt by k_pack_mass (side stream, after the sort)
         k_pack_pos<<<cdiv((long long)n, 256), 256, 0, st>>>((int)n, t, t + cap, comp ? c->comp_in : nullptr, c->body);
@@ -1087,13 +1236,18 @@ int lpe_bh_update_host(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, double
         c->pend_rank = rank != nullptr;
         c->pend_vel = true;
         const int rc = run_step(c, *p, false);
-        if (rc || c->pend_mass || c->pend_vel) {   // a failed step must not leave waits dangling for the next one
-            c->pend_mass = c->pend_vel = false;
+        if (rc || c->pend_mass) {   // a failed step must not leave waits dangling for the next one
+            c->pend_mass = c->pend_vel = c->defer_kick = false;
             cudaStreamSynchronize(cs);
             if (rc) return 1;
         }
+        if (c->defer_kick) {
+            if (trace) cudaEventRecord(tr[4], st);
+            CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
+            return finish_deferred_tick(c, false, comp != nullptr, p->do_drift != 0, x, y, vx, vy);
+        }
     }
-    // BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
+    // (STRICT precision) BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
     return lpe_bh_download(c, p->do_drift ? x : nullptr, p->do_drift ? y : nullptr, vx, vy);
 }
 
@@ -1133,10 +1287,14 @@ int lpe_bh_update_host_aos(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, do
     c->pend_vel = true;
     c->pend_vel_aos = true;
     const int rc = run_step(c, *p, false);
-    if (rc || c->pend_mass || c->pend_vel) {   // a failed step must not leave waits dangling for the next one
-        c->pend_mass = c->pend_vel = c->pend_vel_aos = false;
+    if (rc || c->pend_mass) {   // a failed step must not leave waits dangling for the next one
+        c->pend_mass = c->pend_vel = c->pend_vel_aos = c->defer_kick = false;
         cudaStreamSynchronize(cs);
         if (rc) return 1;
+    }
+    if (c->defer_kick) {
+        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
+        return finish_deferred_tick(c, true, comp != nullptr, p->do_drift != 0, pos, nullptr, vel, nullptr);
     }
     // BarnesHutSystem only changes Velocity (barnes_hut.cpp:285-286); positions move only when the drift is fused
     const unsigned int* orig = c->orig_valid ? c->orig : nullptr;
@@ -1166,6 +1324,8 @@ int lpe_bh_tick_begin(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, const d
     c->have_step = false;
     c->orig_valid = false;
     c->tick_stage = 0;
+    c->defer_kick = false;
+    c->tick_has_comp = comp != nullptr;
     if (make_const(c, *p, c->tick_k)) return 1;
     c->tick_p = *p;
     cudaStream_t st = c->stream;
@@ -1201,6 +1361,13 @@ int lpe_bh_tick_mass(lpe_bh_ctx* c, const double* m, const uint32_t* rank) {
     c->pend_vel = false;
     if (rc) return 1;
     if (c->instr & 1) cudaEventRecord(c->ev[3], st);
+    // FAST precision walks the tree without the velocities (the kick is deferred, see k_finish_tick): the traversal is
+    // queued here and runs while the caller is still staging its Velocity pool
+    c->defer_kick = c->tick_p.precision == LPE_PREC_FAST;
+    if (c->defer_kick) {
+        if (step_traverse(c, c->tick_k, c->tick_p, (int)n, false)) { c->defer_kick = false; return 1; }
+        if (c->instr & 1) cudaEventRecord(c->ev[4], st);
+    }
     CU_TRY(c, cudaGetLastError());
     c->launches += 1;
     c->tick_stage = 2;
@@ -1220,13 +1387,15 @@ int lpe_bh_tick_finish(lpe_bh_ctx* c, double* pos, double* vel) {
     const size_t cap = c->cap;
     const unsigned int* orig = c->orig_valid ? c->orig : nullptr;
     CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vel, 16 * n, cudaMemcpyHostToDevice, st));
-    k_pack_vel_aos<<<g, 256, 0, st>>>((int)n, reinterpret_cast<const double2*>(t + 3 * cap), c->vel, orig);
-    if (step_traverse(c, c->tick_k, c->tick_p, (int)n, false)) return 1;
-    if (c->instr & 1) cudaEventRecord(c->ev[4], st);
     c->last_c = c->tick_k;
     c->have_step = true;
     c->last.depth = c->tick_k.D;
     c->last.hilbert = c->tick_k.hilbert;
+    if (c->defer_kick)   // the traversal was queued by lpe_bh_tick_mass
+        return finish_deferred_tick(c, true, c->tick_has_comp, c->tick_p.do_drift && pos, pos, nullptr, vel, nullptr);
+    k_pack_vel_aos<<<g, 256, 0, st>>>((int)n, reinterpret_cast<const double2*>(t + 3 * cap), c->vel, orig);
+    if (step_traverse(c, c->tick_k, c->tick_p, (int)n, false)) return 1;
+    if (c->instr & 1) cudaEventRecord(c->ev[4], st);
     if (c->tick_p.do_drift && pos) {
         k_get_pos_aos<<<g, 256, 0, st>>>((int)n, c->body, reinterpret_cast<double2*>(t), orig);
         CU_TRY(c, cudaMemcpyAsync(pos, t, 16 * n, cudaMemcpyDeviceToHost, st));
