@@ -143,9 +143,12 @@ k_sort_hist(const KeyT* __restrict__ keys, const unsigned int* __restrict__ vals
     }
 }
 
-// One block per pass: hist row -> exclusive prefix (global start of each digit's run), in place.
-__global__ void __launch_bounds__(512) k_sort_bases(unsigned int* __restrict__ hist) {
+// One block per pass: hist row -> exclusive prefix (global start of each digit's run), in place. Also the place where
+// the step's look-back epoch advances: it lives in device memory (not in a kernel argument), so that a captured CUDA
+// graph of the step can be replayed unchanged; every kernel that uses the epoch runs after this one.
+__global__ void __launch_bounds__(512) k_sort_bases(unsigned int* __restrict__ hist, unsigned int* __restrict__ epoch) {
     __shared__ unsigned int sh[512];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *epoch += 1u;
     unsigned int* row = hist + blockIdx.x * SORT_HIST_STRIDE;
     const int tid = threadIdx.x;
     const unsigned int v = row[tid];
@@ -201,9 +204,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 3 : 1)
 k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
                 KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
                 const unsigned int* __restrict__ digitBase, unsigned long long* __restrict__ status,
-                unsigned int epoch, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault,
+                const unsigned int* __restrict__ epoch_ptr, unsigned int* __restrict__ tileCounter, unsigned int* __restrict__ fault,
                 const unsigned int* __restrict__ n_dev) {
     if (n_dev) n = (int)*n_dev;   // tiles past the device-side element count take a ticket and leave
+    const unsigned int epoch = *epoch_ptr;
     // The tile is first sorted by digit INSIDE shared memory, then written out: consecutive threads then store
     // consecutive addresses within each digit's run, so every 32-byte sector written is fully used (a direct
     // scatter from registers wrote 8-byte keys and 4-byte payloads to 32 different sectors per instruction).
@@ -382,8 +386,9 @@ __device__ __forceinline__ unsigned int lb_exclusive_warp(const unsigned long lo
 
 template <class Load, class Sink>
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_chained(Load load, Sink sink, int n, unsigned long long* __restrict__ status, unsigned int epoch,
+k_scan_chained(Load load, Sink sink, int n, unsigned long long* __restrict__ status, const unsigned int* __restrict__ epoch_ptr,
                unsigned int* __restrict__ ticket, unsigned int* __restrict__ fault) {
+    const unsigned int epoch = *epoch_ptr;
     __shared__ unsigned int sh[9];
     __shared__ unsigned int s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);   // tiles in start order
@@ -420,3 +425,8 @@ k_scan_chained(Load load, Sink sink, int n, unsigned long long* __restrict__ sta
 }
 
 }  // namespace lpe
+
+namespace lpe {
+__global__ void k_epoch_next(unsigned int* __restrict__ epoch) { *epoch += 1u; }   // (scans outside a step: the decomposed upload)
+__global__ void k_epoch_set(unsigned int* __restrict__ epoch, unsigned int v) { *epoch = v; }
+}

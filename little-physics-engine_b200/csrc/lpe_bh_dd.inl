@@ -509,6 +509,7 @@ int lpe_bh_dd_upload(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, const do
     CU_TRY(c, cudaMemsetAsync(c->lbstatus, 0, sizeof(unsigned long long) *
                                   ((size_t)cdiv((long long)c->cap, SORT_TILE) * (256 * (SORT_MAX_PASSES - 1) + 512) +
                                    2 * ((size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 2)), st));
+    CU_TRY(c, cudaMemsetAsync(c->epoch_dev, 0, sizeof(unsigned int), st));
     c->epoch = 0u;
     unsigned int kept = 0;
     unsigned int* total = c->totals + 512 * SORT_MAX_PASSES + 12;   // a free word of the per-step scratch
@@ -529,10 +530,11 @@ int lpe_bh_dd_upload(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, const do
         DDSelIn in{t, t + S, vx ? t + 3 * S : nullptr, vy ? t + 4 * S : nullptr, t + 2 * S, rank ? c->rank_in : nullptr,
                    comp ? c->comp_in : nullptr, (unsigned int)off, (unsigned int)n};
         ++c->epoch;
+        k_epoch_next<<<1, 1, 0, st>>>(c->epoch_dev);
         CU_TRY(c, cudaMemsetAsync(ticket, 0, sizeof(unsigned int), st));
         k_scan_chained<<<cdiv((long long)cnt + 1, SCAN_TILE), SCAN_THREADS, 0, st>>>(
             DDSelLoad{k, sp, in}, DDSelSink{in, c->body, c->vel, c->orig, kept, (unsigned int)S, total, (int)cnt}, (int)cnt,
-            scanStatus, c->epoch, ticket, sfault);
+            scanStatus, c->epoch_dev, ticket, sfault);
         unsigned int got = 0;
         CU_TRY(c, cudaMemcpyAsync(&got, total, sizeof(got), cudaMemcpyDeviceToHost, st));
         CU_TRY(c, cudaStreamSynchronize(st));

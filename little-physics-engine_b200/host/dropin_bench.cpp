@@ -53,6 +53,7 @@ int main(int argc, char** argv) {
     Systems::BarnesHutDeviceOptions opt;
     opt.pagewiseStaging = mode != "per_entity";
     opt.fuseMovement = fused;
+    if (const char* t = std::getenv("LPE_STAGING_THREADS")) opt.stagingThreads = std::atoi(t);   // (experiments)
     sys.setDeviceOptions(opt);
     for (int w = 0; w < 3; ++w) sys.update(reg);   // warm-up: context, buffers, page-locked staging
     const auto t0 = std::chrono::steady_clock::now();

@@ -9,6 +9,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -258,6 +261,15 @@ void BarnesHutSystem::update(entt::registry& registry) {
         st_->workerCount = wantWorkers;
     }
 
+    // LPE_DROPIN_TRACE=1: where the host time of one update goes (stderr, one line per update)
+    static const bool trace = std::getenv("LPE_DROPIN_TRACE") != nullptr;
+    double tms[8] = {};
+    int tk = 0;
+    const auto tstart = std::chrono::steady_clock::now();
+    auto mark = [&]() {
+        if (trace && tk < 8) tms[tk++] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tstart).count();
+    };
+
     std::size_t n = 0;
     const bool pagewise = options_.pagewiseStaging && stagePagewise(registry, n);
     if (!pagewise) n = stagePerEntity(registry);
@@ -283,7 +295,9 @@ void BarnesHutSystem::update(entt::registry& registry) {
         std::cerr << "[BarnesHut] Warning: device step failed: " << lpe_bh_last_error(ctx_) << ". Skipping update.\n";
     };
     lpe_bh_set_instrumentation(ctx_, options_.collectForceStats ? 2 : 0);
+    mark();
     if (lpe_bh_tick_begin(ctx_, &p, n, st_->pos.p, pagewise ? nullptr : st_->comp.p) != 0) { failed(); return; }
+    mark();
     const std::size_t pages = (n + kPage - 1) / kPage;
     if (pagewise) {
         auto** mpages = registry.storage<Components::Mass>().raw();
@@ -294,7 +308,9 @@ void BarnesHutSystem::update(entt::registry& registry) {
             }
         });
     }
+    mark();
     if (lpe_bh_tick_mass(ctx_, st_->m.p, pagewise ? nullptr : st_->rank.p) != 0) { failed(); return; }
+    mark();
     if (pagewise) {
         auto** vpages = registry.storage<Components::Velocity>().raw();
         st_->workers->run([&](int k, int K) {
@@ -304,7 +320,9 @@ void BarnesHutSystem::update(entt::registry& registry) {
             }
         });
     }
+    mark();
     if (lpe_bh_tick_finish(ctx_, st_->pos.p, st_->vel.p) != 0) { failed(); return; }
+    mark();
     if (options_.collectForceStats) {
         lpe_bh_stats s{};
         if (lpe_bh_get_stats(ctx_, &s) == 0) {
@@ -326,6 +344,11 @@ void BarnesHutSystem::update(entt::registry& registry) {
                 if (drift) std::memcpy(ppages[pg], st_->pos.p + 2 * a, cnt * sizeof(Components::Position));
             }
         });
+        mark();
+        if (trace)
+            std::fprintf(stderr, "[BarnesHut] update trace (ms): positions staged %.3f | tick_begin queued %.3f | masses staged %.3f | "
+                                 "tick_mass queued %.3f | velocities staged %.3f | tick_finish returned %.3f | velocities back in the pool %.3f\n",
+                         tms[0], tms[1], tms[2], tms[3], tms[4], tms[5], tms[6]);
         return;
     }
     for (std::size_t i = 0; i < n; ++i) {
