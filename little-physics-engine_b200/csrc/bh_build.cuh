@@ -453,12 +453,12 @@ struct NodeOut {
 // deterministic. `p` is uniform across the quad; lanes of a quad must call this together.
 __device__ __forceinline__ void aggregate_cell_quad(const StepConst& c, const NodeOut& o, unsigned int p,
                                                     unsigned int qd, int cellLevel,
-                                                    const unsigned int* __restrict__ child, double msi, int q,
+                                                    unsigned int ci, double msi, int q,
                                                     unsigned int quadShift, bool live, const Scal* chk) {
     // every lane of the warp runs this (the ballot / shuffles use the full mask); quads past the end of the list
     // carry live = false and neither read children nor store anything. The level list carries the cell's ordinal
     // next to its pre-order index, so the child codes are fetched without a detour through the cell's own meta.
-    const unsigned int ci = live ? child[(size_t)lpe_idx(qd, c.bodyCap, 5, chk) * 4 + q] : LPE_NONE;
+    // (ci = the lane's child code, child[4 * ordinal + q], fetched by the caller one round ahead; LPE_NONE when !live)
     const bool valid = ci != LPE_NONE;
     Agg a;
     a.m = 0.0; a.sx = 0.0; a.sy = 0.0; a.mf = 0.0; a.xf = 0.0; a.yf = 0.0;
@@ -528,13 +528,27 @@ k_agg_level(StepConst c, int L, const uint2* __restrict__ levelList, const unsig
     const int q = threadIdx.x & 3;
     const unsigned int quadShift = (threadIdx.x & 31) & ~3u;
     const unsigned int quads = (gridDim.x * blockDim.x) >> 2;
-    // whole warps stay in the loop together (the ballot inside needs all 32 lanes)
+    // whole warps stay in the loop together (the ballot inside needs all 32 lanes). A cell costs a chain of four dependent
+    // loads (list entry -> child code -> child aggregate -> ...): the first two links of the NEXT round's cell are fetched
+    // before this round's cell is worked on, so consecutive rounds overlap instead of queueing up their latencies.
     const unsigned int rounds = (count + quads - 1) / quads;
     unsigned int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    auto fetch = [&](unsigned int idx, uint2& e, unsigned int& ci) {
+        const bool lv = idx < count;
+        e = levelList[base + (lv ? idx : 0u)];
+        ci = lv ? child[(size_t)lpe_idx(e.y, c.bodyCap, 5, s) * 4 + q] : LPE_NONE;
+    };
+    uint2 e;
+    unsigned int ci;
+    fetch(i, e, ci);
     for (unsigned int k = 0; k < rounds; ++k, i += quads) {
         const bool live = i < count;
-        const uint2 e = levelList[base + (live ? i : 0u)];
-        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live, s);
+        uint2 en = e;
+        unsigned int cin = LPE_NONE;
+        if (k + 1 < rounds) fetch(i + quads, en, cin);
+        if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, ci, msi, q, quadShift, live, s);
+        e = en;
+        ci = cin;
     }
 }
 
@@ -554,7 +568,8 @@ k_agg_top(StepConst c, int Ltop, const uint2* __restrict__ levelList, const unsi
         for (unsigned int k = 0; k < rounds; ++k, i += quads) {
             const bool live = i < count;
             const uint2 e = levelList[base + (live ? i : 0u)];
-            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, child, msi, q, quadShift, live, s);
+            const unsigned int ci = live ? child[(size_t)lpe_idx(e.y, c.bodyCap, 5, s) * 4 + q] : LPE_NONE;
+            if (__any_sync(0xFFFFFFFFu, live)) aggregate_cell_quad(c, o, e.x, e.y, L, ci, msi, q, quadShift, live, s);
         }
         __syncthreads();
     }

@@ -140,11 +140,16 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
     AY2 = fma2(dy, f, AY2);
 }
 
-// DD: the kernel serves a domain-decomposed rank (body count and tree size known only on the device, per-chunk cost
-// recorded for the load balancer); a template flag so that the single-GPU kernel carries none of it (measured: 1.5 %).
-template <bool STATS, bool SELF, bool DD>
+// MODE: what the kernel serves besides the resident single-GPU step (T2_RESIDENT) — a domain-decomposed rank (T2_DD: body
+// count and tree size known only on the device, per-chunk cost recorded for the load balancer) or a host tick whose kick
+// is deferred (T2_STAGED: the epilogue stores {x, y, dvx, dvy} at the body's creation index instead of kicking). A
+// template parameter so that the resident kernel carries none of it: either costs it 1.5 % (registers, measured).
+constexpr int T2_RESIDENT = 0, T2_DD = 1, T2_STAGED = 2;
+template <bool STATS, bool SELF, int MODE>
 __global__ void __launch_bounds__(T2_THREADS, T2_MIN_CTAS)
 k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArgs a, unsigned int* __restrict__ ovf_list) {
+    constexpr bool DD = MODE == T2_DD;
+    constexpr bool STAGED = MODE == T2_STAGED;
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -407,13 +412,13 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
 
         if (DD && lane == 0) a.chunk_cost[q] = cost;
         double2 v = make_double2(0.0, 0.0);
-        if (valid && !a.stage_out) v = a.vel[b];   // (deferred kick: v is the velocity CHANGE, 0 + x is exact)
+        if (valid && !STAGED) v = a.vel[b];   // (deferred kick: v is the velocity CHANGE, 0 + x is exact)
         const double accScale = c.G * massScale * c.invS * c.invS;   // a = G*sum M d/r^3; scaled units M/Ms, d/S
         if (target) {
             v.x = kick_step(v.x, AX * accScale, c.dtK);   // barnes_hut.cpp:284-286
             v.y = kick_step(v.y, AY * accScale, c.dtK);
         }
-        if (a.stage_out) {   // host tick: k_finish_tick kicks and drifts once the velocities have arrived
+        if (STAGED) {   // host tick: k_finish_tick kicks and drifts once the velocities have arrived
             if (valid) a.stage_out[a.orig ? a.orig[b] : b] = make_double4(p.x, p.y, v.x, v.y);
         } else if (valid) {
             const bool mover = (cm & 2u) && !(cm & 4u) && !(cm & 8u);   // movement.cpp:20-29

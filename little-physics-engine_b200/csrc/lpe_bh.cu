@@ -895,15 +895,15 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
         if (grid > sms * T2_MIN_CTAS) grid = sms * T2_MIN_CTAS;
         if (grid < 1) grid = 1;
-        if (k.dd) {
-            if (stats) k_traverse2<true, true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-            else if (selfT) k_traverse2<false, true, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-            else k_traverse2<false, false, true><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-        } else {
-            if (stats) k_traverse2<true, true, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-            else if (selfT) k_traverse2<false, true, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-            else k_traverse2<false, false, false><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-        }
+        auto launch = [&](auto modeTag) {
+            constexpr int MODE = decltype(modeTag)::value;
+            if (stats) k_traverse2<true, true, MODE><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            else if (selfT) k_traverse2<false, true, MODE><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            else k_traverse2<false, false, MODE><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+        };
+        if (k.dd) launch(std::integral_constant<int, T2_DD>{});
+        else if (ta.stage_out) launch(std::integral_constant<int, T2_STAGED>{});
+        else launch(std::integral_constant<int, T2_RESIDENT>{});
         ta.chunk_list = c->ovf_list;
         if (stats) k_traverse<0, true><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
         else k_traverse<0, false><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
