@@ -252,7 +252,21 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     for (int r = 0; r < ITEMS; ++r) {
         const bool ok = wbase + r * 32 + lane < n;
         const unsigned int d = ok ? sort_digit<KeyT>(key[r], val[r], shift, dmask, TOP) : 0xFFFFu;
+#ifdef SORT_BALLOT_MATCH
+        // the lanes with the same digit, from one ballot per digit bit (+ one for "in range") instead of MATCH.ANY
+        constexpr int BITS = BINS == 512 ? 9 : 8;
+        unsigned int pm = 0xFFFFFFFFu;
+#pragma unroll
+        for (int b = 0; b < BITS; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned int bal = __ballot_sync(0xFFFFFFFFu, bit);
+            pm &= bit ? bal : ~bal;
+        }
+        const unsigned int balOk = __ballot_sync(0xFFFFFFFFu, ok);
+        peers[r] = pm & (ok ? balOk : ~balOk);
+#else
         peers[r] = __match_any_sync(0xFFFFFFFFu, d);
+#endif
     }
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
