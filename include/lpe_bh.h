@@ -122,7 +122,8 @@ const char* lpe_bh_last_error(const lpe_bh_ctx* ctx); /* ctx may be NULL: last c
 int  lpe_bh_set_stream(lpe_bh_ctx* ctx, void* cuda_stream);
 /* flags: bit0 = per-phase CUDA-event timing, bit1 = count interactions/visits (slower; parity tests only),
  *        bit2 = FAST precision uses the depth-first kernel instead of the two-phase kernel (A/B testing),
- *        bit3 = the two-phase kernel hands every chunk to its overflow path (tests of that path) */
+ *        bit3 = the two-phase kernel hands every chunk to its overflow path (tests of that path),
+ *        bit4 = plain launches: never replay a captured CUDA graph of the step (A/B testing; see lpe_bh_graph_replays) */
 int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
 
 /* Stage bodies into device SoA buffers. rank[i] = position of body i in the iteration of
@@ -290,8 +291,14 @@ int  lpe_bh_dd_set_splitters(lpe_bh_ctx* ctx, const uint64_t* split30);
 uint64_t lpe_bh_cell_key(uint32_t ix, uint32_t iy, int level, int hilbert);
 void lpe_bh_key_cell(uint64_t key, int level, int hilbert, uint32_t* ix, uint32_t* iy);
 
-/* cumulative number of this library's kernels launched by the context (bench.py's gpu_launches) */
+/* cumulative number of this library's kernels launched by the context (bench.py's gpu_launches; kernels inside a replayed
+ * CUDA graph count like plain launches) */
 uint64_t lpe_bh_launch_count(const lpe_bh_ctx* ctx);
+/* Whole steps are captured as CUDA graphs and replayed (lpe_bh_step, lpe_bh_update_host(_aos) and lpe_bh_tick_* with
+ * page-locked host buffers): one submission per step instead of ~30. A step is captured the second time the same
+ * (parameters, body count, buffers) come up; timing instrumentation, sharded and decomposed contexts, and the
+ * environment variable LPE_BH_GRAPHS=0 keep plain launches. Returns how many steps were replays so far. */
+uint64_t lpe_bh_graph_replays(const lpe_bh_ctx* ctx);
 /* FP32 FMA peak of the device by a register-resident FMA loop, TFLOP/s (2 flops per FMA): the roofline denominator
  * of the traversal, which is FP32-pipe bound, not HBM or tensor bound. Synchronises. */
 int  lpe_bh_fma_peak(lpe_bh_ctx* ctx, double* tflops);

@@ -1003,7 +1003,7 @@ bool graphs_on(lpe_bh_ctx* c) {
         c->use_graphs = (e && e[0] == '0') ? 0 : 1;
     }
     // (timing events between the phases and the sharded / decomposed modes keep the plain launches)
-    return c->use_graphs == 1 && !(c->instr & 1) && c->shard_n == 1 && !c->dd;
+    return c->use_graphs == 1 && !(c->instr & (1 | 16)) && c->shard_n == 1 && !c->dd;
 }
 // page-locked host memory? (asynchronous copies of pageable memory cannot be captured)
 bool is_pinned(const void* p) {
@@ -1951,6 +1951,7 @@ int lpe_bh_xchg_reset(lpe_bh_ctx* c) {
 }
 
 uint64_t lpe_bh_launch_count(const lpe_bh_ctx* c) { return c ? c->launches : 0; }
+uint64_t lpe_bh_graph_replays(const lpe_bh_ctx* c) { return c ? c->graph_replays : 0; }
 
 int lpe_bh_fma_peak(lpe_bh_ctx* c, double* tflops) {
     if (!c || !tflops) return 1;

@@ -114,6 +114,18 @@ def make_params(U, eps, theta=0.5, dt_kick=1.0 / 120, dt_drift=None, thr=0.0, qu
     return p
 
 
+def pinned_array(n, dtype=np.float64):
+    """A page-locked host array (lpe_bh_alloc_pinned): asynchronous copies at full PCIe rate, and host ticks on such arrays are
+    replayed as one CUDA graph. Keep the array referenced while in use; it is freed with the process."""
+    lib = load_library()
+    nbytes = int(n) * np.dtype(dtype).itemsize
+    p = lib.lpe_bh_alloc_pinned(C.c_uint64(max(nbytes, 8)))
+    if not p:
+        raise MemoryError("lpe_bh_alloc_pinned failed")
+    buf = (C.c_char * max(nbytes, 8)).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(n))
+
+
 def build_library(force=False):
     """Compile liblpe_bh.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
@@ -140,6 +152,8 @@ def load_library():
     lib.lpe_bh_last_error.argtypes = [C.c_void_p]
     lib.lpe_bh_launch_count.restype = C.c_uint64
     lib.lpe_bh_launch_count.argtypes = [C.c_void_p]
+    lib.lpe_bh_graph_replays.restype = C.c_uint64
+    lib.lpe_bh_graph_replays.argtypes = [C.c_void_p]
     lib.lpe_bh_alloc_pinned.restype = C.c_void_p
     lib.lpe_bh_alloc_pinned.argtypes = [C.c_uint64]
     lib.lpe_bh_free_pinned.argtypes = [C.c_void_p]
@@ -225,10 +239,10 @@ class BarnesHut:
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.lpe_bh_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
 
-    def set_instrumentation(self, timing=False, counts=False, force_dfs=False, force_overflow=False):
+    def set_instrumentation(self, timing=False, counts=False, force_dfs=False, force_overflow=False, plain_launches=False):
         self._chk(self.lib.lpe_bh_set_instrumentation(
             self.h, C.c_int((1 if timing else 0) | (2 if counts else 0) | (4 if force_dfs else 0) |
-                            (8 if force_overflow else 0))),
+                            (8 if force_overflow else 0) | (16 if plain_launches else 0))),
                   "set_instrumentation")
 
     def upload(self, x, y, vx, vy, m, rank=None, comp=None):
@@ -359,6 +373,10 @@ class BarnesHut:
 
     def launch_count(self):
         return int(self.lib.lpe_bh_launch_count(self.h))
+
+    def graph_replays(self):
+        """Steps / ticks so far that were replays of a captured CUDA graph."""
+        return int(self.lib.lpe_bh_graph_replays(self.h))
 
     def fma_peak_tflops(self):
         t = C.c_double(0.0)

@@ -421,3 +421,54 @@ def test_scenario_bodies_made_on_the_device(bh, port):
     bh.generate("keplerian_counter", n, 17, Uk)
     again = bh.download()
     assert np.array_equal(again["x"], d["x"]) and np.array_equal(again["vy"], d["vy"])
+
+
+def test_replayed_cuda_graph_of_the_step_equals_plain_launches():
+    """Resident steps are captured as a CUDA graph the second time their key comes up and replayed afterwards: the result
+    must be the plain launches' bit for bit, the replay counter must move, and the launch count must be the same."""
+    U = 1024.0
+    x, y, vx, vy, m = gen_uniform(20000, U, 77)
+    pg = lpe_bh.make_params(U, 0.25, dt_drift=0.004)
+    out = {}
+    for name, plain in (("plain", True), ("graph", False)):
+        c = lpe_bh.BarnesHut(0)
+        c.set_instrumentation(plain_launches=plain)
+        c.upload(x, y, vx, vy, m)
+        for _ in range(9):
+            c.step(pg, 1)
+        out[name] = (c.download(), c.graph_replays(), c.launch_count())
+        c.close()
+    assert out["plain"][1] == 0
+    assert out["graph"][1] >= 4, "steps 6..9 at the latest must be replays"
+    assert out["graph"][2] == out["plain"][2]
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(out["graph"][0][k], out["plain"][0][k]), k
+
+
+def test_host_tick_on_page_locked_arrays_replays_one_graph_and_equals_resident_steps():
+    """lpe_bh_update_host on page-locked arrays: copies, step, deferred kick and downloads are one CUDA graph from the third
+    tick on. Six ticks through the host arrays == six resident steps of a fresh context, bit for bit (FAST precision: the
+    kick is deferred to a creation-order pass, same roundings)."""
+    U = 1024.0
+    n = 12000
+    x, y, vx, vy, m = gen_uniform(n, U, 78)
+    pg = lpe_bh.make_params(U, 0.25, dt_drift=0.004)
+    ref = lpe_bh.BarnesHut(0)
+    ref.upload(x, y, vx, vy, m)
+    ref.step(pg, 6)
+    want = ref.download()
+    ref.close()
+    host = [lpe_bh.pinned_array(n) for _ in range(5)]
+    for h, a in zip(host, (x, y, vx, vy, m)):
+        h[:] = a
+    c = lpe_bh.BarnesHut(0)
+    for _ in range(6):
+        c.update_host_ptrs(pg, n, *[h.ctypes.data for h in host])
+    assert c.graph_replays() >= 2
+    for h, k in zip(host, ("x", "y", "vx", "vy")):
+        assert np.array_equal(h, want[k]), k
+    # the resident state followed the host arrays
+    got = c.download()
+    for k in ("x", "y", "vx", "vy"):
+        assert np.array_equal(got[k], want[k]), k
+    c.close()
