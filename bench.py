@@ -536,13 +536,28 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
     for _ in range(warmup):
         bh.dd_step(params, 1)
     bh.synchronize()
+    # phase table: a few steps with the library's own events between the phases (plain launches)
+    phases = []
+    for _ in range(min(args.steps, 5)):
+        flush.zero_()
+        bh.dd_step(params, 1)
+        s = bh.dd_stats()
+        phases.append([s[k] for k in ("ms_keygen", "ms_wait_a", "ms_sort", "ms_build", "ms_export", "ms_wait_b", "ms_top", "ms_traverse")])
+    # timed region: no instrumentation, so every rank replays its captured CUDA graph of the step (two buffer parities:
+    # captured on the 3rd / 4th step with the same splitters, 6 steps settle that)
+    bh.set_instrumentation()
+    for _ in range(6):
+        bh.dd_step(params, 1)
+    bh.synchronize()
     torch.cuda.synchronize()
     log(rank, "warm-up done")
     launches0 = bh.launch_count()
     dist.barrier()
     torch.cuda.synchronize()
     nv0 = nvlink_counters(local_rank) if rank == 0 else None
-    step_ms, phases = [], []
+    dist.barrier()   # (rank 0's nvidia-smi call takes tens of ms: nobody starts the timed steps before it is back)
+    torch.cuda.synchronize()
+    step_ms = []
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -551,8 +566,6 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
         e1.record(stream)
         e1.synchronize()
         step_ms.append(e0.elapsed_time(e1))
-        s = bh.dd_stats()
-        phases.append([s[k] for k in ("ms_keygen", "ms_wait_a", "ms_sort", "ms_build", "ms_export", "ms_wait_b", "ms_top", "ms_traverse")])
     torch.cuda.synchronize()
     dist.barrier()
     nv1 = nvlink_counters(local_rank) if rank == 0 else None
@@ -605,6 +618,9 @@ def dd_arm(args, torch, dist, lpe_bh, bh, stream, wl, key, bodies, params, rank,
         "e2e": {"value": None, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "path": "multi-GPU runs keep the bodies resident on their owners; the host round trip is measured at N=1"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "launch_mode": "timed steps replay each rank's captured CUDA graph of the whole decomposed step (three phases, two "
+                       "in-stream barriers; gpu_launches counts rank 0's kernels inside); the phase tables come from "
+                       "separate steps with events between the phases",
     }
 
 

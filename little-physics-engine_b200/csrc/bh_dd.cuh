@@ -103,9 +103,12 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
 // Signal: lane s stores this rank's payload and then the step's epoch into rank s's mailbox (own mailbox included).
 // Everything this rank stored into peer memory in earlier kernels of the stream is complete by then (kernel boundary
 // + fence), so a rank that sees the flag sees the data.
-__global__ void k_dd_signal(int point, unsigned long long epoch, int me, int R, DDPeers peers, const double* __restrict__ payload) {
+// (the step number lives in device memory, advanced by k_dd_next_step: a captured CUDA graph of the step replays unchanged)
+__global__ void k_dd_next_step(unsigned long long* __restrict__ step) { *step += 1ull; }
+__global__ void k_dd_signal(int point, const unsigned long long* __restrict__ step, int me, int R, DDPeers peers, const double* __restrict__ payload) {
     const int s = threadIdx.x;
     if (s >= R) return;
+    const unsigned long long epoch = *step;
     DDMail* m = &peers.hdr[s]->mail[point][me];
     if (payload)
         for (int k = 0; k < 6; ++k) m->payload[k] = payload[k];
@@ -114,9 +117,10 @@ __global__ void k_dd_signal(int point, unsigned long long epoch, int me, int R, 
 }
 // Wait: lane s spins until rank s's flag in the own mailbox carries this step's epoch. Bounded: a dead peer becomes an
 // error flag, not a hung device.
-__global__ void k_dd_wait(int point, unsigned long long epoch, int R, DDHeader* hdr) {
+__global__ void k_dd_wait(int point, const unsigned long long* __restrict__ step, int R, DDHeader* hdr) {
     const int s = threadIdx.x;
     if (s >= R) return;
+    const unsigned long long epoch = *step;
     const unsigned long long* f = &hdr->mail[point][s].flag;
     unsigned long long spins = 0;
     while (ld_acquire_sys(f) < epoch) {

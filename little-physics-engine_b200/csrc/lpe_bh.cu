@@ -126,7 +126,8 @@ struct lpe_bh_ctx {
     char* dd_peer_win[LPE_MAX_P2P] = {};      // every rank's window (own pointer, raw peer pointer, or an IPC mapping)
     void* dd_peer_opened[LPE_MAX_P2P] = {};   // IPC mappings to close
     int dd_cur = 0;                           // which of the two state buffer sets of the window is current
-    unsigned long long dd_epoch = 0;          // step number: the value the barrier flags carry
+    unsigned long long dd_epoch = 0;          // step number: the value the barrier flags carry (host mirror of *dd_step_dev)
+    unsigned long long* dd_step_dev = nullptr;
     unsigned long long dd_split30[LPE_MAX_P2P + 1] = {};   // splitters as depth-30 keys
     int dd_hilbert = -1;                      // key order the splitters were made for
     int dd_dom_depth = -1;                    // depth the device copy of the domain table was built for
@@ -159,6 +160,8 @@ struct lpe_bh_ctx {
         int sorted_sel = 0;
         uint64_t launches = 0;
         unsigned int epochs = 0;
+        bool dd_flip = false;
+        unsigned long long dd_steps = 0;
         lpe_bh_stats last{};
         StepConst last_c{};
     };
@@ -984,26 +987,29 @@ struct HostState {
     Body *body, *body2; double2 *vel, *vel2; unsigned int *orig, *orig2;
     bool orig_valid, have_step, pend_mass, pend_vel, pend_rank, pend_vel_aos, defer_kick;
     int sorted_sel; uint64_t launches; unsigned int epoch; lpe_bh_stats last; StepConst last_c;
+    int dd_cur; unsigned long long dd_epoch;
 };
 HostState host_state(const lpe_bh_ctx* c) {
     return HostState{c->body, c->body2, c->vel, c->vel2, c->orig, c->orig2, c->orig_valid, c->have_step, c->pend_mass, c->pend_vel,
-                     c->pend_rank, c->pend_vel_aos, c->defer_kick, c->sorted_sel, c->launches, c->epoch, c->last, c->last_c};
+                     c->pend_rank, c->pend_vel_aos, c->defer_kick, c->sorted_sel, c->launches, c->epoch, c->last, c->last_c,
+                     c->dd_cur, c->dd_epoch};
 }
 void restore_host_state(lpe_bh_ctx* c, const HostState& h) {
     c->body = h.body; c->body2 = h.body2; c->vel = h.vel; c->vel2 = h.vel2; c->orig = h.orig; c->orig2 = h.orig2;
     c->orig_valid = h.orig_valid; c->have_step = h.have_step; c->pend_mass = h.pend_mass; c->pend_vel = h.pend_vel;
     c->pend_rank = h.pend_rank; c->pend_vel_aos = h.pend_vel_aos; c->defer_kick = h.defer_kick;
     c->sorted_sel = h.sorted_sel; c->launches = h.launches; c->epoch = h.epoch; c->last = h.last; c->last_c = h.last_c;
+    c->dd_cur = h.dd_cur; c->dd_epoch = h.dd_epoch;
 }
 template <class T>
 void key_add(std::string& k, const T& v) { k.append(reinterpret_cast<const char*>(&v), sizeof(T)); }
-bool graphs_on(lpe_bh_ctx* c) {
+bool graphs_on(lpe_bh_ctx* c, bool dd_step = false) {
     if (c->use_graphs < 0) {
         const char* e = getenv("LPE_BH_GRAPHS");
         c->use_graphs = (e && e[0] == '0') ? 0 : 1;
     }
     // (timing events between the phases and the sharded / decomposed modes keep the plain launches)
-    return c->use_graphs == 1 && !(c->instr & (1 | 16)) && c->shard_n == 1 && !c->dd;
+    return c->use_graphs == 1 && !(c->instr & (1 | 16)) && c->shard_n == 1 && (dd_step || !c->dd);
 }
 // page-locked host memory? (asynchronous copies of pageable memory cannot be captured)
 bool is_pinned(const void* p) {
@@ -1014,8 +1020,8 @@ bool is_pinned(const void* p) {
 }
 
 template <class F>
-int run_graphed(lpe_bh_ctx* c, const std::string& key, F&& body) {
-    if (!graphs_on(c)) return body();
+int run_graphed(lpe_bh_ctx* c, const std::string& key, F&& body, bool dd_step = false) {
+    if (!graphs_on(c, dd_step)) return body();
     if (epoch_prepare(c)) return 1;   // never part of a graph
     for (auto& g : c->graphs) {
         if (g.key != key) continue;
@@ -1025,6 +1031,8 @@ int run_graphed(lpe_bh_ctx* c, const std::string& key, F&& body) {
         c->sorted_sel = g.sorted_sel;
         c->launches += g.launches;
         c->epoch += g.epochs;
+        if (g.dd_flip) c->dd_cur ^= 1;
+        c->dd_epoch += g.dd_steps;
         c->last = g.last;
         c->last_c = g.last_c;
         c->have_step = true;
@@ -1078,6 +1086,8 @@ int run_graphed(lpe_bh_ctx* c, const std::string& key, F&& body) {
     g.sorted_sel = c->sorted_sel;
     g.launches = c->launches - before.launches;
     g.epochs = c->epoch - before.epoch;
+    g.dd_flip = c->dd_cur != before.dd_cur;
+    g.dd_steps = c->dd_epoch - before.dd_epoch;
     g.last = c->last;
     g.last_c = c->last_c;
     c->graphs.push_back(std::move(g));

@@ -250,6 +250,7 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
     if (phase == 0) {
         if (dd_build_domain(c, k)) return 1;
         ++c->dd_epoch;
+        k_dd_next_step<<<1, 1, 0, st>>>(c->dd_step_dev);
         if (timing) cudaEventRecord(c->dd_ev[0], st);
         if (step_prologue(c, S)) return 1;
         CU_TRY(c, cudaMemsetAsync(c->dd_oob, 0xFF, 16, st));
@@ -259,10 +260,10 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
                                                   peers, c->dd_oob);
         k_dd_payload<<<1, 32, 0, st>>>(0, c->dd_oob, c->scal, c->dd_payload);
         if (timing) cudaEventRecord(c->dd_ev[1], st);
-        k_dd_signal<<<1, 32, 0, st>>>(0, c->dd_epoch, c->dd_rank, c->dd_R, peers, c->dd_payload);
+        k_dd_signal<<<1, 32, 0, st>>>(0, c->dd_step_dev, c->dd_rank, c->dd_R, peers, c->dd_payload);
         c->launches += 3;
     } else if (phase == 1) {
-        k_dd_wait<<<1, 32, 0, st>>>(0, c->dd_epoch, c->dd_R, hdr);
+        k_dd_wait<<<1, 32, 0, st>>>(0, c->dd_step_dev, c->dd_R, hdr);
         if (timing) cudaEventRecord(c->dd_ev[2], st);
         k_dd_keygen_inbox<<<64, 256, 0, st>>>(k, sp, c->body, c->keys[0], c->vals[0], c->scal, hdr);
         if (step_sort(c, k, S, &c->scal->n_sort)) return 1;
@@ -292,10 +293,10 @@ int dd_phase(lpe_bh_ctx* c, const lpe_bh_params& p, int phase) {
         if (c->dd_R > 1) k_dd_export_x<<<dim3(16, c->dd_R), 256, 0, st>>>(k, c->dd_rank, ea, peers, c->scal);
         k_dd_payload<<<1, 32, 0, st>>>(1, c->dd_oob, c->scal, c->dd_payload);
         if (timing) cudaEventRecord(c->dd_ev[5], st);
-        k_dd_signal<<<1, 32, 0, st>>>(1, c->dd_epoch, c->dd_rank, c->dd_R, peers, c->dd_payload + 6);
+        k_dd_signal<<<1, 32, 0, st>>>(1, c->dd_step_dev, c->dd_rank, c->dd_R, peers, c->dd_payload + 6);
         c->launches += 7;
     } else if (phase == 2) {
-        k_dd_wait<<<1, 32, 0, st>>>(1, c->dd_epoch, c->dd_R, hdr);
+        k_dd_wait<<<1, 32, 0, st>>>(1, c->dd_step_dev, c->dd_R, hdr);
         if (timing) cudaEventRecord(c->dd_ev[6], st);
         const DDLayout L = dd_layout(c->cap, c->dd_R, c->dd_icap);
         k_dd_top<<<1, 1024, DD_TOP_SMEM_BYTES, st>>>(k, c->dd_rank, c->dd_R, hdr, reinterpret_cast<const DDRoot*>(c->dd_win + L.roots), c->dd_top,
@@ -371,7 +372,9 @@ int lpe_bh_dd_init(lpe_bh_ctx* c, int rank, int nranks, uint64_t capacity, uint3
     c->dd_xrec = reinterpret_cast<double4*>(c->dd_win + L.xrec);
     int rc = 0;
     rc |= dalloc(c, c->dd_dom, 1) | dalloc(c, c->dd_myroots, DD_MAXROOTS) | dalloc(c, c->dd_queue, (size_t)nranks * c->dd_icap) |
-          dalloc(c, c->dd_oob, 4 + LPE_MAX_P2P * DD_EXPORT_ROUNDS / 2 + 2) | dalloc(c, c->dd_payload, 12) | dalloc(c, c->dd_chunk_cost, S / 32 + 64);
+          dalloc(c, c->dd_oob, 4 + LPE_MAX_P2P * DD_EXPORT_ROUNDS / 2 + 2) | dalloc(c, c->dd_payload, 12) | dalloc(c, c->dd_chunk_cost, S / 32 + 64) |
+          dalloc(c, c->dd_step_dev, 1);
+    if (!rc) cudaMemsetAsync(c->dd_step_dev, 0, sizeof(unsigned long long), c->stream);
     // (set on every init: the attribute is kept per device)
     if (cudaFuncSetAttribute(k_dd_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DD_TOP_SMEM_BYTES) != cudaSuccess) rc = 1;
     c->dd_pushed = reinterpret_cast<unsigned int*>(c->dd_oob + 4);
@@ -548,6 +551,8 @@ int lpe_bh_dd_upload(lpe_bh_ctx* c, const lpe_bh_params* p, uint64_t n, const do
     CU_TRY(c, cudaGetLastError());
     c->orig_valid = true;
     c->dd_epoch = 0;
+    CU_TRY(c, cudaMemset(c->dd_step_dev, 0, sizeof(unsigned long long)));
+    drop_graphs(c);   // (new splitters, new bodies)
     return 0;
 }
 
@@ -562,9 +567,24 @@ int lpe_bh_dd_phase(lpe_bh_ctx* c, const lpe_bh_params* p, int phase) {
 int lpe_bh_dd_step(lpe_bh_ctx* c, const lpe_bh_params* p, int nsteps) {
     if (!c || !p) return 1;
     DevGuard _dg(c->device);
-    for (int s = 0; s < nsteps; ++s)
-        for (int ph = 0; ph < 3; ++ph)
-            if (dd_phase(c, *p, ph)) return 1;
+    for (int s = 0; s < nsteps; ++s) {
+        // the whole step — three phases, two in-stream barriers — is one CUDA graph when nothing it depends on changed
+        // (parameters, splitters, buffer parity); the domain table is brought up to date outside the graph
+        StepConst k;
+        if (dd_make_const(c, *p, k)) return 1;
+        if (dd_build_domain(c, k)) return 1;
+        std::string key("dd");
+        key_add(key, *p); key_add(key, c->cap); key_add(key, c->instr); key_add(key, c->force_dfs); key_add(key, c->dd_cur);
+        key_add(key, c->dd_R); key_add(key, c->dd_rank); key_add(key, c->body); key_add(key, c->stream);
+        for (int r = 0; r <= c->dd_R; ++r) key_add(key, c->dd_split30[r]);
+        for (int r = 0; r < c->dd_R; ++r) key_add(key, c->dd_peer_win[r]);
+        auto body = [&]() -> int {
+            for (int ph = 0; ph < 3; ++ph)
+                if (dd_phase(c, *p, ph)) return 1;
+            return 0;
+        };
+        if (run_graphed(c, key, body, true)) return 1;
+    }
     return 0;
 }
 
