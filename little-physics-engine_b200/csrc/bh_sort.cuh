@@ -195,6 +195,12 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
 // read-modify-write -> SHFL per key of a thread, and the look-back walks one status column per digit. Hence: few keys per
 // thread (short chains) in many warps (48 per SM at 512 x 8), and large tiles (with ~600 tiles in flight the finished
 // prefix lags dozens of tiles behind, so every digit column of a tile walks that far: half the tiles, half the walks).
+#ifdef SORT_TRACE
+__device__ unsigned long long g_sort_trace[8];   // summed clock64 deltas of a tile's phases (thread 0), [7] = tiles
+#define SORT_MARK(k) do { if (threadIdx.x == 0) { const long long _t = clock64(); atomicAdd(&g_sort_trace[k], (unsigned long long)(_t - _tprev)); _tprev = _t; } } while (0)
+#else
+#define SORT_MARK(k) do { } while (0)
+#endif
 template <int BINS, class KeyT, int THREADS, int ITEMS>
 constexpr size_t sort_smem_bytes() {
     return (size_t)THREADS * ITEMS * (sizeof(KeyT) + 4) + (size_t)BINS * 8 + 128 + (size_t)(THREADS / 32) * BINS * 2;
@@ -232,6 +238,10 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     __syncthreads();
     const unsigned int tile = s_tile;
     if ((long long)tile * TILE >= n) return;
+#ifdef SORT_TRACE
+    long long _tprev = clock64();
+    if (threadIdx.x == 0) atomicAdd(&g_sort_trace[7], 1ull);
+#endif
 
     const long long tbase = (long long)tile * TILE;
     const long long wbase = tbase + (long long)w * (ITEMS * 32);
@@ -246,6 +256,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         key[r] = ok ? keysIn[i] : (KeyT)~(KeyT)0;
         val[r] = ok ? valsIn[i] : 0u;
     }
+    SORT_MARK(0);   // (loads issued)
     // the MATCHes of all rounds are independent of each other: issue them together, then run the counter chain
     unsigned int peers[ITEMS];
 #pragma unroll
@@ -284,6 +295,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         __syncwarp();
     }
     __syncthreads();
+    SORT_MARK(1);   // (keys arrived, ranked)
     // per digit: total in this tile, and the exclusive offsets of the warps inside the digit's run. The tile's counts
     // are published at once (aggregate), the wait for the tiles before it comes after the local reordering.
     constexpr int PER = BINS > THREADS ? BINS / THREADS : 1;   // digits per thread: tid * PER + k (threads past BINS idle)
@@ -317,6 +329,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         }
     }
     __syncthreads();
+    SORT_MARK(2);   // (counts published, scanned)
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {
         const long long i = wbase + r * 32 + lane;
@@ -327,6 +340,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
             sval[lp] = val[r];
         }
     }
+    SORT_MARK(3);   // (scattered into shared memory)
     // now add up the tiles before this one and publish the inclusive value for the tiles after it
     if (owner) {
 #pragma unroll
@@ -341,6 +355,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         }
     }
     __syncthreads();
+    SORT_MARK(4);   // (look-back done)
     const int tileCount = (int)min((long long)TILE, (long long)n - tbase);
     for (int j = tid; j < tileCount; j += THREADS) {
         const KeyT kx = skey[j];
@@ -353,6 +368,7 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
         keysOut[dst] = kx;
         valsOut[dst] = vx;
     }
+    SORT_MARK(5);   // (stores issued)
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1962,6 +1962,13 @@ int lpe_bh_xchg_reset(lpe_bh_ctx* c) {
 
 uint64_t lpe_bh_launch_count(const lpe_bh_ctx* c) { return c ? c->launches : 0; }
 uint64_t lpe_bh_graph_replays(const lpe_bh_ctx* c) { return c ? c->graph_replays : 0; }
+#ifdef SORT_TRACE
+void lpe_bh_debug_sort_trace(unsigned long long* out8, int reset) {   // (variant builds only)
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, lpe::g_sort_trace, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {}; cudaMemcpyToSymbol(lpe::g_sort_trace, z, sizeof(z)); }
+}
+#endif
 
 int lpe_bh_fma_peak(lpe_bh_ctx* c, double* tflops) {
     if (!c || !tflops) return 1;
