@@ -123,7 +123,8 @@ int  lpe_bh_set_stream(lpe_bh_ctx* ctx, void* cuda_stream);
 /* flags: bit0 = per-phase CUDA-event timing, bit1 = count interactions/visits (slower; parity tests only),
  *        bit2 = FAST precision uses the depth-first kernel instead of the two-phase kernel (A/B testing),
  *        bit3 = the two-phase kernel hands every chunk to its overflow path (tests of that path),
- *        bit4 = plain launches: never replay a captured CUDA graph of the step (A/B testing; see lpe_bh_graph_replays) */
+ *        bit4 = plain launches: never replay a captured CUDA graph of the step (A/B testing; see lpe_bh_graph_replays),
+ *        bit5 = the two-phase kernel walks per warp only, without the far field shared by the warps of a CTA (A/B testing) */
 int  lpe_bh_set_instrumentation(lpe_bh_ctx* ctx, int flags);
 
 /* Stage bodies into device SoA buffers. rank[i] = position of body i in the iteration of

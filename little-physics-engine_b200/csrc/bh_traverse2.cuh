@@ -140,18 +140,74 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
     AY2 = fma2(dy, f, AY2);
 }
 
+// ---- far field shared by the four warps of a CTA (template flag CTA) ----------------------------------------------
+// The four warps of a CTA own 128 key-consecutive bodies and walk almost the same nodes: everything far from the whole
+// block is classified four times. With CTA set, the block's bodies are taken together first: one breadth-first walk by
+// all 128 threads (one node per thread) against the bounding box of the 128 bodies. A node every body of the block
+// accepts goes to a shared accept list that each warp evaluates for its own lanes — without a lane mask, every body
+// reaches it —, a node every body opens passes its children on, and only the rest (mixed for the block) seeds the four
+// per-warp walks above, each of which then re-classifies against its own, smaller box. Per-body decisions are the
+// same: both group tests are conservative.
+constexpr int T3_QCAP = 256;                // block-level queue of record slots (power of two)
+constexpr int T3_ABUF = 130;                // shared accept list (one round adds at most T3_ABUF - 2 - fill entries)
+constexpr int T3_SEEDS = 160;               // mixed nodes handed to the warps (more: the block goes to the depth-first kernel)
+struct __align__(16) T3Cta {
+    APair ap[T3_ABUF / 2];
+    unsigned int aslot[T3_ABUF];
+    unsigned int q[T3_QCAP];
+    unsigned int seeds[T3_SEEDS];
+    float box[T2_WARPS][4];
+    uint4 wc[T2_WARPS];                     // per warp and round: entries for the accept list, seeds, children
+    unsigned int head, tail, nA, nSeeds, ovf, block, nodes, pad;
+};
+
+// two consecutive entries of the block's shared accept list: every lane reaches them, no mask
+template <bool STATS, bool SELF>
+__device__ __forceinline__ void t3_accept_pair(const T3Cta& C, unsigned int m, unsigned int self, const LanePos2& P,
+                                               f32x2_t& AX2, f32x2_t& AY2, unsigned int& nacc, double& fsum, float& fmaxq) {
+    const ulonglong2* ap = reinterpret_cast<const ulonglong2*>(&C.ap[m >> 1]);
+    const ulonglong2 vh = ap[0], vl = ap[1];
+    const uint2 vg = *reinterpret_cast<const uint2*>(ap + 2);
+    const f32x2_t xh = vh.x, yh = vh.y, xl = vl.x, yl = vl.y;
+    const float2 g = make_float2(__uint_as_float(vg.x), __uint_as_float(vg.y));
+    bool self0 = false, self1 = false;
+    if (SELF) {
+        const uint2 as = *reinterpret_cast<const uint2*>(&C.aslot[m]);
+        self0 = (as.x & 0x7FFFFFFFu) == self;
+        self1 = (as.y & 0x7FFFFFFFu) == self;
+    }
+    const f32x2_t dx = add2(add2(xh, P.nphx), add2(xl, P.nplx));
+    const f32x2_t dy = add2(add2(yh, P.nphy), add2(yl, P.nply));
+    const f32x2_t d2 = fma2(dx, dx, fma2(dy, dy, P.eps2));
+    const f32x2_t rinv = pack2(rsqrt_approx(lo2(d2)), rsqrt_approx(hi2(d2)));
+    if (STATS) {
+        const uint2 as = *reinterpret_cast<const uint2*>(&C.aslot[m]);
+        const bool c0 = as.x != LPE_NONE && (as.x & 0x7FFFFFFFu) != self && !(as.x >> 31);
+        const bool c1 = as.y != LPE_NONE && (as.y & 0x7FFFFFFFu) != self && !(as.y >> 31);
+        nacc += (c0 ? 1u : 0u) + (c1 ? 1u : 0u);
+        const float q0 = c0 ? g.x * lo2(rinv) * lo2(rinv) : 0.f, q1 = c1 ? g.y * hi2(rinv) * hi2(rinv) : 0.f;
+        fsum += (double)q0 + (double)q1;
+        fmaxq = fmaxf(fmaxq, fmaxf(q0, q1));
+    }
+    f32x2_t f = mul2(mul2(pack2(g.x, g.y), rinv), mul2(rinv, rinv));
+    if (SELF) f = pack2(self0 ? 0.f : lo2(f), self1 ? 0.f : hi2(f));
+    AX2 = fma2(dx, f, AX2);
+    AY2 = fma2(dy, f, AY2);
+}
+
 // MODE: what the kernel serves besides the resident single-GPU step (T2_RESIDENT) — a domain-decomposed rank (T2_DD: body
 // count and tree size known only on the device, per-chunk cost recorded for the load balancer) or a host tick whose kick
 // is deferred (T2_STAGED: the epilogue stores {x, y, dvx, dvy} at the body's creation index instead of kicking). A
 // template parameter so that the resident kernel carries none of it: either costs it 1.5 % (registers, measured).
 constexpr int T2_RESIDENT = 0, T2_DD = 1, T2_STAGED = 2;
-template <bool STATS, bool SELF, int MODE>
+template <bool STATS, bool SELF, int MODE, bool CTA>
 __global__ void __launch_bounds__(T2_THREADS, T2_MIN_CTAS)
 k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArgs a, unsigned int* __restrict__ ovf_list) {
     constexpr bool DD = MODE == T2_DD;
     constexpr bool STAGED = MODE == T2_STAGED;
     extern __shared__ __align__(16) unsigned char t2_smem[];
     T2Warp& W = reinterpret_cast<T2Warp*>(t2_smem)[threadIdx.x >> 5];
+    T3Cta& C = *reinterpret_cast<T3Cta*>(t2_smem + sizeof(T2Warp) * T2_WARPS);   // (only there when CTA)
     const int lane = threadIdx.x & 31;
     const unsigned int lt = (1u << lane) - 1u;
     const unsigned int lanebit = 1u << lane;
@@ -165,18 +221,29 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
 
     while (true) {
         unsigned int q = 0;
-        if (lane == 0) q = atomicAdd(&a.s->work_counter, 1u);
-        q = __shfl_sync(0xFFFFFFFFu, q, 0);
-        if (q >= a.n_chunks_local) break;
+        if (CTA) {
+            // the work unit is a block of four consecutive chunks, one per warp; every warp of the CTA stays in the loop
+            // until the blocks are used up (the block-level phase needs all of them at its barriers)
+            __syncthreads();   // the previous block's shared state is no longer in use
+            if (threadIdx.x == 0) C.block = atomicAdd(&a.s->work_counter, 1u);
+            __syncthreads();
+            const unsigned int Q = C.block;
+            if (Q * (unsigned int)T2_WARPS >= a.n_chunks_local) break;
+            q = Q * (unsigned int)T2_WARPS + (threadIdx.x >> 5);
+        } else {
+            if (lane == 0) q = atomicAdd(&a.s->work_counter, 1u);
+            q = __shfl_sync(0xFFFFFFFFu, q, 0);
+            if (q >= a.n_chunks_local) break;
+        }
         const unsigned int lblock = q / CHUNKS_PER_BLOCK, within = q % CHUNKS_PER_BLOCK;
         const unsigned int gblock = lblock * (unsigned int)c.shard_n + (unsigned int)c.shard_rank;
         const long long i = ((long long)gblock * CHUNKS_PER_BLOCK + within) * 32 + lane;
         // (a domain-decomposed rank knows its body count only on the device; the tail slots hold no bodies)
-        bool valid = i < c.n;
+        bool valid = i < c.n && q < a.n_chunks_local;
         if (DD) {
             const unsigned int n_live = a.s->n_live;
-            if (q * 32u >= n_live) continue;
-            valid = (unsigned int)i < n_live;
+            if (!CTA && q * 32u >= n_live) continue;
+            valid = valid && (unsigned int)i < n_live;
         }
 
         unsigned int b = 0, self = LPE_NONE, cm = 0;
@@ -207,11 +274,11 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
         bool overflow = c.test_overflow != 0;
 
         const unsigned int tmask = __ballot_sync(0xFFFFFFFFu, target);
-        if (tmask != 0u && n_nodes != 0u && !overflow) {
-            // ---- bounding box of the warp's targets (scaled units): fp32 edges rounded OUTWARD, so the box contains
-            // every fp64 position and the group classification stays conservative ----
-            float bx0 = target ? __double2float_rd(pxs) : INF, bx1 = target ? __double2float_ru(pxs) : -INF;
-            float by0 = target ? __double2float_rd(pys) : INF, by1 = target ? __double2float_ru(pys) : -INF;
+        // ---- bounding box of the warp's targets (scaled units): fp32 edges rounded OUTWARD, so the box contains
+        // every fp64 position and the group classification stays conservative ----
+        float bx0 = target ? __double2float_rd(pxs) : INF, bx1 = target ? __double2float_ru(pxs) : -INF;
+        float by0 = target ? __double2float_rd(pys) : INF, by1 = target ? __double2float_ru(pys) : -INF;
+        if (CTA || tmask != 0u) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 bx0 = fminf(bx0, __shfl_xor_sync(0xFFFFFFFFu, bx0, o));
@@ -219,9 +286,144 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
                 by0 = fminf(by0, __shfl_xor_sync(0xFFFFFFFFu, by0, o));
                 by1 = fmaxf(by1, __shfl_xor_sync(0xFFFFFFFFu, by1, o));
             }
-
+        }
+        unsigned int nSeeds = 0;
+        if (CTA) {
+            // ---------------- block-level phase: the far field of all 128 bodies, once ----------------
+            const int warp = threadIdx.x >> 5;
+            if (lane == 0) { C.box[warp][0] = bx0; C.box[warp][1] = bx1; C.box[warp][2] = by0; C.box[warp][3] = by1; }
+            if (threadIdx.x == 0) {
+                C.q[0] = 0u;   // the root
+                C.head = 0u; C.tail = (n_nodes != 0u && !overflow) ? 1u : 0u;
+                C.nA = 0u; C.nSeeds = 0u; C.ovf = 0u; C.nodes = 0u;
+            }
+            __syncthreads();
+            float cx0 = C.box[0][0], cx1 = C.box[0][1], cy0 = C.box[0][2], cy1 = C.box[0][3];
+#pragma unroll
+            for (int ww = 1; ww < T2_WARPS; ++ww) {
+                cx0 = fminf(cx0, C.box[ww][0]); cx1 = fmaxf(cx1, C.box[ww][1]);
+                cy0 = fminf(cy0, C.box[ww][2]); cy1 = fmaxf(cy1, C.box[ww][3]);
+            }
+            const bool anyTarget = cx0 <= cx1;
+            constexpr unsigned int CQM = (unsigned int)T3_QCAP - 1u;
+            for (;;) {
+                const unsigned int head = C.head, tail = C.tail, nA0 = C.nA, nS0 = C.nSeeds;
+                if (head == tail || !anyTarget || C.ovf) break;
+                // (a round never adds more entries than the accept list has room for)
+                const unsigned int cnt = min(min((unsigned int)T2_THREADS, tail - head), (unsigned int)T3_ABUF - 2u - nA0);
+                const bool has = threadIdx.x < cnt;
+                unsigned int slot = 0;
+                TravRec R;
+                R.c = make_float4(0.f, 0.f, 0.f, 0.f); R.gm = 0.f; R.open_t = -1.f; R.node = 0; R.cblock = 0;
+                bool toA = false, toS = false;
+                unsigned int nch = 0, mA = 0, mS = 0, b0 = 0, b1 = 0, b2 = 0;
+                float t = -1.f;
+                const unsigned int le = lt | lanebit;
+                // (measured: letting the warps without nodes skip the classification in the first, sparse rounds gains nothing)
+                {
+                    if (has) {
+                        slot = C.q[(head + threadIdx.x) & CQM];
+                        const uint4* src = reinterpret_cast<const uint4*>(a.rec + lpe_idx(slot, c.recSlots, 10, a.s));
+                        const uint4 v0 = __ldg(src), v1 = __ldg(src + 1);
+                        R.c = make_float4(__uint_as_float(v0.x), __uint_as_float(v0.y), __uint_as_float(v0.z), __uint_as_float(v0.w));
+                        R.gm = __uint_as_float(v1.x); R.open_t = __uint_as_float(v1.y); R.node = v1.z; R.cblock = v1.w;
+                    }
+                    const float ax0 = (R.c.x - cx0) + R.c.z, ax1 = (R.c.x - cx1) + R.c.z;
+                    const float ay0 = (R.c.y - cy0) + R.c.w, ay1 = (R.c.y - cy1) + R.c.w;
+                    const float dxmin = fmaxf(fmaxf(-ax0, ax1), 0.f), dxmax = fmaxf(fabsf(ax0), fabsf(ax1));
+                    const float dymin = fmaxf(fmaxf(-ay0, ay1), 0.f), dymax = fmaxf(fabsf(ay0), fabsf(ay1));
+                    const float d2min = fmaf(dxmin, dxmin, fmaf(dymin, dymin, eps2f));
+                    const float d2max = fmaf(dxmax, dxmax, fmaf(dymax, dymax, eps2f));
+                    t = R.open_t;
+                    const float tlo = t * (1.0f - OPEN_BAND), thi = t * (1.0f + OPEN_BAND);
+                    const bool allAcc = (t < 0.f) || (d2min * (1.0f - T2_MARGIN) >= thi);
+                    const bool allOpen = (t >= 0.f) && (d2max * (1.0f + T2_MARGIN) <= tlo);
+                    toA = has && allAcc;
+                    toS = has && !allAcc && !allOpen;      // mixed for the block: the warps decide
+                    nch = (has && allOpen) ? (R.cblock & 3u) + 1u : 0u;
+                    mA = __ballot_sync(0xFFFFFFFFu, toA); mS = __ballot_sync(0xFFFFFFFFu, toS);
+                    b0 = __ballot_sync(0xFFFFFFFFu, (nch & 1u) != 0u);
+                    b1 = __ballot_sync(0xFFFFFFFFu, (nch & 2u) != 0u);
+                    b2 = __ballot_sync(0xFFFFFFFFu, (nch & 4u) != 0u);
+                }
+                if (lane == 0) C.wc[warp] = make_uint4(__popc(mA), __popc(mS), __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2), 0u);
+                __syncthreads();
+                unsigned int offA = nA0, offS = nS0, offC = 0, totA = 0, totS = 0, totC = 0;
+#pragma unroll
+                for (int ww = 0; ww < T2_WARPS; ++ww) {
+                    const uint4 wv = C.wc[ww];
+                    if (ww < warp) { offA += wv.x; offS += wv.y; offC += wv.z; }
+                    totA += wv.x; totS += wv.y; totC += wv.z;
+                }
+                const bool fits = (tail - head - cnt) + totC <= (unsigned int)T3_QCAP && nS0 + totS <= (unsigned int)T3_SEEDS;
+                if (fits) {
+                    if (toA) {
+                        const unsigned int pos = lpe_idx(offA + __popc(mA & lt), (unsigned int)T3_ABUF - 1u, 11, a.s);
+                        APair& E = C.ap[pos >> 1];
+                        const unsigned int h = pos & 1u;
+                        E.xh[h] = R.c.x; E.yh[h] = R.c.y; E.xl[h] = R.c.z; E.yl[h] = R.c.w;
+                        E.g[h] = R.gm;
+                        C.aslot[pos] = slot | ((t == -2.0f) ? 0x80000000u : 0u);
+                    }
+                    if (toS) C.seeds[offS + __popc(mS & lt)] = slot;
+                    if (nch) {
+                        const unsigned int inc = __popc(b0 & le) + 2u * __popc(b1 & le) + 4u * __popc(b2 & le);
+                        const unsigned int at = tail + offC + inc - nch;
+                        const unsigned int cslot = (R.cblock >> 2) * 4u;
+                        C.q[at & CQM] = cslot;
+                        if (nch > 1u) C.q[(at + 1u) & CQM] = cslot + 1u;
+                        if (nch > 2u) C.q[(at + 2u) & CQM] = cslot + 2u;
+                        if (nch > 3u) C.q[(at + 3u) & CQM] = cslot + 3u;
+                    }
+                }
+                const unsigned int nA1 = nA0 + totA;
+                const bool lastRound = head + cnt == tail + totC;
+                const bool flush = fits && (nA1 >= 64u || lastRound) && nA1 != 0u;
+                if (threadIdx.x == 0) {
+                    if (!fits) C.ovf = 1u;   // block-level frontier or seed list too long: the depth-first kernel redoes the block
+                    else {
+                        C.head = head + cnt; C.tail = tail + totC; C.nSeeds = nS0 + totS; C.nodes += cnt;
+                        C.nA = flush ? 0u : nA1;
+                        if (flush && (nA1 & 1u)) {   // pad to an even count with an entry of zero mass
+                            APair& E = C.ap[nA1 >> 1];
+                            E.xh[1] = 4.f; E.yh[1] = 4.f; E.xl[1] = 0.f; E.yl[1] = 0.f; E.g[1] = 0.f;
+                            C.aslot[nA1] = LPE_NONE;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (flush) {
+                    if (tmask != 0u) {
+                        // fp32 partial sums go to fp64 every 64 entries, as in the per-warp walk (measured: two
+                        // straight-line loops instead of this nest are 3.5 % slower — register allocation)
+                        for (unsigned int m0 = 0; m0 < nA1; m0 += 64u) {
+                            f32x2_t AX2 = pack2(0.f, 0.f), AY2 = AX2;
+                            const unsigned int m1 = min(nA1, m0 + 64u);
+#pragma unroll 4
+                            for (unsigned int m = m0; m < m1; m += 2)
+                                t3_accept_pair<STATS, SELF>(C, m, self, LP, AX2, AY2, nacc, fsum, fmaxq);
+                            AX += (double)(lo2(AX2) + hi2(AX2));
+                            AY += (double)(lo2(AY2) + hi2(AY2));
+                        }
+                        if (STATS) { nwarp += nA1; if (warp == 0) kd[0] += nA1; }
+                    }
+                    __syncthreads();   // the list is consumed before the next round writes it
+                }
+            }
+            nSeeds = C.nSeeds;
+            if (STATS && warp == 0) { kd[6] += 1; kd[7] += C.nodes; }
+            if (DD) cost = C.nodes / (unsigned int)T2_WARPS;
+            if (C.ovf) overflow = true;
+        }
+        if (tmask != 0u && n_nodes != 0u && !overflow) {
             unsigned int head = 0, tail = 1, nA = 0;
-            if (lane == 0) W.q[0] = make_uint2(0u, tmask);   // the root, reached by every target
+            if (CTA) {
+                // the per-warp walk starts from the nodes the block could not decide, each reached by every target
+                tail = nSeeds;
+                for (unsigned int k = lane; k < nSeeds; k += 32u) W.q[k] = make_uint2(C.seeds[k], tmask);
+            } else {
+                if (lane == 0) W.q[0] = make_uint2(0u, tmask);   // the root, reached by every target
+            }
             __syncwarp();
             while (head != tail) {
                 // ---------------- phase 1: one node per lane ----------------
@@ -401,16 +603,16 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
                 AY += (double)(lo2(AY2) + hi2(AY2));
                 __syncwarp();
             }
-            if (DD) cost = tail;   // every node that entered the ring was classified once
+            if (DD) cost += tail;   // every node that entered the ring was classified once
         }
 
         if (overflow) {
             // frontier too wide for the shared-memory queue: the depth-first kernel redoes this chunk
-            if (lane == 0) ovf_list[atomicAdd(&a.s->ovf_count, 1u)] = q;
+            if (lane == 0 && q < a.n_chunks_local) ovf_list[atomicAdd(&a.s->ovf_count, 1u)] = q;
             continue;
         }
 
-        if (DD && lane == 0) a.chunk_cost[q] = cost;
+        if (DD && lane == 0 && q < a.n_chunks_local) a.chunk_cost[q] = cost;
         double2 v = make_double2(0.0, 0.0);
         if (valid && !STAGED) v = a.vel[b];   // (deferred kick: v is the velocity CHANGE, 0 + x is exact)
         const double accScale = c.G * massScale * c.invS * c.invS;   // a = G*sum M d/r^3; scaled units M/Ms, d/S

@@ -894,19 +894,27 @@ int step_traverse(lpe_bh_ctx* c, const StepConst& k, const lpe_bh_params& p, int
         // two-phase kernel, then the depth-first kernel for the (normally zero) chunks whose frontier overflowed
         const size_t smem = sizeof(T2Warp) * T2_WARPS;
         const bool selfT = k.need_self != 0;
-        static_assert(sizeof(T2Warp) * T2_WARPS <= 48 * 1024, "per-CTA work areas fit the default dynamic shared memory limit");
+        static_assert(sizeof(T2Warp) * T2_WARPS + sizeof(T3Cta) <= 48 * 1024, "per-CTA work areas fit the default dynamic shared memory limit");
         int grid = cdiv(ta.n_chunks_local, T2_WARPS);
         if (grid > sms * T2_MIN_CTAS) grid = sms * T2_MIN_CTAS;
         if (grid < 1) grid = 1;
-        auto launch = [&](auto modeTag) {
+        // the far field shared by the four warps of a CTA (bh_traverse2.cuh) unless instrumentation bit 5 asks for the
+        // warp-only walk (A/B testing)
+        const bool cta = !(c->instr & 32);
+        auto launch = [&](auto modeTag, auto ctaTag) {
             constexpr int MODE = decltype(modeTag)::value;
-            if (stats) k_traverse2<true, true, MODE><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-            else if (selfT) k_traverse2<false, true, MODE><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
-            else k_traverse2<false, false, MODE><<<grid, T2_THREADS, smem, st>>>(k, ta, c->ovf_list);
+            constexpr bool CTA = decltype(ctaTag)::value;
+            const size_t sm = smem + (CTA ? sizeof(T3Cta) : 0);
+            if (stats) k_traverse2<true, true, MODE, CTA><<<grid, T2_THREADS, sm, st>>>(k, ta, c->ovf_list);
+            else if (selfT) k_traverse2<false, true, MODE, CTA><<<grid, T2_THREADS, sm, st>>>(k, ta, c->ovf_list);
+            else k_traverse2<false, false, MODE, CTA><<<grid, T2_THREADS, sm, st>>>(k, ta, c->ovf_list);
         };
-        if (k.dd) launch(std::integral_constant<int, T2_DD>{});
-        else if (ta.stage_out) launch(std::integral_constant<int, T2_STAGED>{});
-        else launch(std::integral_constant<int, T2_RESIDENT>{});
+        auto launchMode = [&](auto ctaTag) {
+            if (k.dd) launch(std::integral_constant<int, T2_DD>{}, ctaTag);
+            else if (ta.stage_out) launch(std::integral_constant<int, T2_STAGED>{}, ctaTag);
+            else launch(std::integral_constant<int, T2_RESIDENT>{}, ctaTag);
+        };
+        if (cta) launchMode(std::true_type{}); else launchMode(std::false_type{});
         ta.chunk_list = c->ovf_list;
         if (stats) k_traverse<0, true><<<sms, TRAV_THREADS, 0, st>>>(k, ta);
         else k_traverse<0, false><<<sms, TRAV_THREADS, 0, st>>>(k, ta);

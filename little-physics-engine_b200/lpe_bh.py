@@ -239,10 +239,11 @@ class BarnesHut:
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.lpe_bh_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "set_stream")
 
-    def set_instrumentation(self, timing=False, counts=False, force_dfs=False, force_overflow=False, plain_launches=False):
+    def set_instrumentation(self, timing=False, counts=False, force_dfs=False, force_overflow=False, plain_launches=False,
+                            warp_only=False):
         self._chk(self.lib.lpe_bh_set_instrumentation(
             self.h, C.c_int((1 if timing else 0) | (2 if counts else 0) | (4 if force_dfs else 0) |
-                            (8 if force_overflow else 0) | (16 if plain_launches else 0))),
+                            (8 if force_overflow else 0) | (16 if plain_launches else 0) | (32 if warp_only else 0))),
                   "set_instrumentation")
 
     def upload(self, x, y, vx, vy, m, rank=None, comp=None):

@@ -191,13 +191,15 @@ def test_multi_step_trajectory(bh, port):
 
 @pytest.mark.parametrize("n,eps", [(30000, 0.25), (30000, 0.0), (3000, 0.25)])
 def test_traversal_kernels_agree(bh, port, n, eps):
-    """FAST precision has two kernels: the two-phase production kernel and the depth-first kernel (also its overflow
-    path). All three routes must take identical per-body decisions (= the oracle's) and agree to fp32 rounding."""
+    """FAST precision has two kernels: the two-phase production kernel — with the far field shared by the four warps of a
+    CTA (default) or walked per warp only — and the depth-first kernel (also its overflow path). All four routes must take
+    identical per-body decisions (= the oracle's) and agree to fp32 rounding."""
     x, y, vx, vy, m = gen_uniform(n, 1024.0, 41)
     pg = lpe_bh.make_params(1024.0, eps, dt_drift=0.004)
     ref = port.run(O.make_params(1024.0, eps, dt_drift=0.004), x, y, vx, vy, m, threads=8, per_body=True)
     outs = {}
-    for name, kw in (("two_phase", {}), ("depth_first", dict(force_dfs=True)), ("overflow", dict(force_overflow=True))):
+    for name, kw in (("two_phase", {}), ("two_phase_warp_only", dict(warp_only=True)), ("depth_first", dict(force_dfs=True)),
+                     ("overflow", dict(force_overflow=True))):
         bh.set_instrumentation(counts=True, **kw)
         bh.upload(x, y, vx, vy, m)
         bh.step(pg, 1)
@@ -207,7 +209,7 @@ def test_traversal_kernels_agree(bh, port, n, eps):
         assert np.array_equal(acc, ref["accepted"]), name
         if name == "overflow":
             assert st["overflow_chunks"] == ((n + 2047) // 2048) * 64   # every 32-body chunk of every 2048-body block
-        if name == "two_phase":
+        if name.startswith("two_phase"):
             assert st["overflow_chunks"] == 0
         dv = rel_err((outs[name]["vx"] - vx, outs[name]["vy"] - vy), (ref["vx"] - vx, ref["vy"] - vy))
         assert dv["max"] <= FAST_TOL, (name, dv)
