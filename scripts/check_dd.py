@@ -116,6 +116,8 @@ def multi_process(n, steps):
         bh.dd_step(p, steps - max(1, steps // 2))
         d = bh.dd_download(counts=fast)
         fails += not compare(f"rank {rank} of {world}, {'FAST' if fast else 'STRICT'}", d, ref, b, precision)
+        if rank == 0:
+            print(f"[rank 0] {bh.graph_replays()} of {steps} steps were replays of the rank's captured CUDA graph", flush=True)
         owned = torch.tensor([len(d["index"])], device="cuda")
         dist.all_reduce(owned)
         fails += int(owned.item()) != n

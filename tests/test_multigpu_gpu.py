@@ -34,13 +34,15 @@ def test_sharded_step_across_processes_matches_unsharded():
 @pytest.mark.gpu
 def test_domain_decomposed_step_across_processes():
     """scripts/check_dd.py under torchrun: CUDA IPC windows, in-stream flag barriers, migration, a re-balance in the
-    middle; FAST = identical decisions, STRICT = bit for bit against one GPU."""
+    middle; FAST = identical decisions, STRICT = bit for bit against one GPU. Ten steps: five with each set of splitters,
+    so that each rank's CUDA graph of the step is captured (steps 3, 4) and replayed (step 5) on both sides of the
+    re-balance."""
     if _gpu_count() < 2:
         pytest.skip("needs at least 2 GPUs")
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "scripts", "check_dd.py"),
-           "200000", "4"]
+           "200000", "10"]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("] OK") == 2 * world and "FAIL" not in r.stdout, r.stdout[-2000:]
