@@ -55,8 +55,8 @@ WORKLOADS = {
 }
 FLOPS_PER_INTERACTION = 20.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_traverse2 launch, from the committed ncu --set full captures
-NCU_TRAFFIC = {"c2": (155.6e6, "profiles/r02_ncu_traverse2_c2.txt (ncu --set full, one launch: dram read 127.9 MB + write 27.7 MB)"),
-               "c3": (2044.8e6, "profiles/r02_ncu_traverse2_c3.txt (ncu --set full, one launch: dram read 1298.3 MB + write 746.4 MB)")}
+NCU_TRAFFIC = {"c2": (154.6e6, "profiles/r02_ncu_traverse2_c2.txt (ncu --set full, one launch: dram read 127.9 MB + write 26.7 MB)"),
+               "c3": (2043.0e6, "profiles/r02_ncu_traverse2_c3.txt (ncu --set full, one launch: dram read 1298.8 MB + write 744.2 MB)")}
 # SURVEY.md §8(d) algorithmic bytes of the HBM phases: state 40 B read + 32 B written, key + index 12 B, 24 B per sort
 # pass, sorted gather 24 B, node arrays 85 B  ->  193 + 24 * passes (4 passes for the 33-bit keys of depth 16)
 def hbm_bytes_per_body(passes):
