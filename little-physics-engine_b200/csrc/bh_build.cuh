@@ -254,19 +254,6 @@ struct MaskPop {
     }
 };
 
-// levelBase = exclusive scan of levelCount (32 entries); levelCursor reset
-__global__ void k_level_scan(const unsigned int* __restrict__ levelCount, unsigned int* __restrict__ levelBase,
-                             unsigned int* __restrict__ levelCursor) {
-    if (threadIdx.x == 0) {
-        unsigned int run = 0;
-        for (int L = 0; L < 32; ++L) {
-            levelBase[L] = run;
-            run += levelCount[L];
-            levelCursor[L] = 0;
-        }
-    }
-}
-
 // ---- 5. topology: pre-order indices, skip pointers, child slots, per-level cell lists ------------------------
 struct Topo {
     const unsigned int* wstart; // [terminal] first terminal of the cell that t witnesses
@@ -274,8 +261,9 @@ struct Topo {
                               // position for a single-body leaf, or LPE_NONE
     Agg* agg;                 // [preorder] written here only for aggregated terminals (>= 2 bodies in a depth-D cell)
     uint2* levelList;         // cells grouped by level: levelList[levelBase[L] + i] = {pre-order index, cell ordinal}
-    const unsigned int* levelBase;
-    unsigned int* levelCursor;
+    const unsigned int* levelCount;   // cells per level (k_witness)
+    unsigned int* levelBase;          // exclusive scan of levelCount: every block makes its own copy, block 0 stores it for the aggregation
+    unsigned int* levelCursor;        // (zeroed with the step's scratch)
     const unsigned int* tfirst;
     const Body* body;         // state in key order
     unsigned int* selfslot;   // [sorted body] record slot of its own leaf (only written here for a one-terminal tree)
@@ -339,8 +327,20 @@ __device__ __forceinline__ TravRec invalid_record() {
 __global__ void __launch_bounds__(256)
 k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signed char* __restrict__ delta,
            const unsigned int* __restrict__ mask, const unsigned int* __restrict__ P, Topo o, Scal* __restrict__ s) {
-    __shared__ unsigned int cnt[32], base[32];
-    if (threadIdx.x < 32) cnt[threadIdx.x] = 0;
+    __shared__ unsigned int cnt[32], base[32], lbase[32];
+    if (threadIdx.x < 32) {
+        cnt[threadIdx.x] = 0;
+        // start of each level's list = exclusive scan of the 32 level counts (one warp; no launch of its own)
+        const unsigned int v = o.levelCount[threadIdx.x];
+        unsigned int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if ((int)threadIdx.x >= d) inc += u;
+        }
+        lbase[threadIdx.x] = inc - v;
+        if (blockIdx.x == 0) o.levelBase[threadIdx.x] = inc - v;
+    }
     __syncthreads();
     const int D = c.D;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -434,7 +434,7 @@ k_topology(StepConst c, const unsigned long long* __restrict__ tkey, const signe
         const int L = __ffs(rest) - 1;
         rest &= rest - 1;
         const unsigned int local = atomicAdd(&cnt[L], 1u);
-        o.levelList[o.levelBase[L] + base[L] + local] = make_uint2((unsigned int)t + Pt + i, Pt + i);
+        o.levelList[lbase[L] + base[L] + local] = make_uint2((unsigned int)t + Pt + i, Pt + i);
         ++i;
     }
 }

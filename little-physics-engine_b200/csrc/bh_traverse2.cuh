@@ -149,7 +149,14 @@ __device__ __forceinline__ void t2_accept_pair(const T2Warp& W, unsigned int m, 
 // per-warp walks above, each of which then re-classifies against its own, smaller box. Per-body decisions are the
 // same: both group tests are conservative.
 constexpr int T3_QCAP = 256;                // block-level queue of record slots (power of two)
-constexpr int T3_ABUF = 130;                // shared accept list (one round adds at most T3_ABUF - 2 - fill entries)
+#ifndef T3_ABUF_N
+#define T3_ABUF_N 130
+#endif
+#ifndef T3_FLUSH_N
+#define T3_FLUSH_N 64
+#endif
+constexpr int T3_ABUF = T3_ABUF_N;          // shared accept list (one round adds at most T3_ABUF - 2 - fill entries)
+constexpr unsigned int T3_FLUSH = T3_FLUSH_N; // ... evaluated by the four warps when it holds this many
 constexpr int T3_SEEDS = 160;               // mixed nodes handed to the warps (more: the block goes to the depth-first kernel)
 struct __align__(16) T3Cta {
     APair ap[T3_ABUF / 2];
@@ -378,7 +385,7 @@ k_traverse2(const __grid_constant__ StepConst c, const __grid_constant__ TravArg
                 }
                 const unsigned int nA1 = nA0 + totA;
                 const bool lastRound = head + cnt == tail + totC;
-                const bool flush = fits && (nA1 >= 64u || lastRound) && nA1 != 0u;
+                const bool flush = fits && (nA1 >= T3_FLUSH || lastRound) && nA1 != 0u;
                 if (threadIdx.x == 0) {
                     if (!fits) C.ovf = 1u;   // block-level frontier or seed list too long: the depth-first kernel redoes the block
                     else {

@@ -833,9 +833,8 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
     k_scan_chained<<<scanTiles, SCAN_THREADS, 0, st>>>(MaskPop{c->mask, c->scal}, StoreSink{c->P}, n,
                                                        scanStatus + (size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 1, c->epoch_dev,
                                                        scanTicket + 1, sortFault);
-    k_level_scan<<<1, 32, 0, st>>>(levelCount, levelBase, levelCursor);
     if (c->tracing) cudaEventRecord(c->dbg_ev[1], st);
-    Topo topo{c->wstart, c->child, c->agg, c->levelList, levelBase, levelCursor, c->tfirst, c->body, c->selfslot, c->rec};
+    Topo topo{c->wstart, c->child, c->agg, c->levelList, levelCount, levelBase, levelCursor, c->tfirst, c->body, c->selfslot, c->rec};
     CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
     if (c->tracing) cudaEventRecord(c->dbg_ev[2], st);
@@ -854,8 +853,8 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
         ++levelLaunches;
     }
     k_agg_top<<<1, 1024, 0, st>>>(k, Ltop, c->levelList, levelBase, levelCount, c->child, no, c->scal);
-    // gather, 2 scans, witness, level_scan, topology, one launch per level above Ltop, agg_top
-    c->launches += 1 + 2 + 1 + 1 + 1 + (uint64_t)levelLaunches + 1;
+    // gather, 2 scans, witness, topology, one launch per level above Ltop, agg_top
+    c->launches += 1 + 2 + 1 + 1 + (uint64_t)levelLaunches + 1;
     return 0;
 }
 
