@@ -304,7 +304,9 @@ def e2e_registry(n, ticks):
             "staging_path_taken": pw["staging_path_taken"],
             "ms_per_step_entity_by_entity_staging": out["per_entity"]["ms_per_update"],
             "path": "entt::registry -> Systems::BarnesHutSystem::update (pool pages copied into page-locked {x,y} buffers by "
-                    "4 worker threads -> lpe_bh_update_host_aos -> velocities copied back into the pool pages); host wall clock"}
+                    "4 worker threads -> lpe_bh_tick_begin / _mass / _finish, each pool staged while the device works on the one "
+                    "before, the pools' alignment checked beside the tree walk -> velocities copied back into the pool pages); "
+                    "host wall clock"}
 
 
 def nvlink_counters(index):

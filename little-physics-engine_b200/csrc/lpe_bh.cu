@@ -1576,6 +1576,13 @@ int lpe_bh_tick_mass(lpe_bh_ctx* c, const double* m, const uint32_t* rank) {
         c->pend_vel = false;
         if (rc) return 1;
         if (c->instr & 1) cudaEventRecord(c->ev[3], st);
+        // FAST precision walks the tree without the velocities (the kick is deferred, see k_finish_tick): the traversal is
+        // queued here, behind the build, and runs while the caller is still staging its Velocity pool
+        c->defer_kick = c->tick_p.precision == LPE_PREC_FAST;
+        if (c->defer_kick) {
+            if (step_traverse(c, c->tick_k, c->tick_p, (int)n, false)) { c->defer_kick = false; return 1; }
+            if (c->instr & 1) cudaEventRecord(c->ev[4], st);
+        }
         CU_TRY(c, cudaGetLastError());
         c->launches += 1;
         return 0;
@@ -1585,12 +1592,14 @@ int lpe_bh_tick_mass(lpe_bh_ctx* c, const double* m, const uint32_t* rank) {
         std::string key("tick2");
         key_add(key, c->tick_p); key_add(key, n); key_add(key, c->cap); key_add(key, c->instr); key_add(key, c->body); key_add(key, c->stream);
         key_add(key, m); key_add(key, rank);
+        key_add(key, c->force_dfs); key_add(key, c->force_overflow);
         rc = run_graphed(c, key, queue);
         c->have_step = false;
     } else {
         rc = queue();
     }
-    if (rc) { c->pend_mass = c->pend_vel = false; cudaStreamSynchronize(cs); return 1; }
+    if (rc) { c->pend_mass = c->pend_vel = c->defer_kick = false; cudaStreamSynchronize(cs); return 1; }
+    c->defer_kick = c->tick_p.precision == LPE_PREC_FAST;   // (a replay resets the flag with the other pending-work flags)
     c->tick_stage = 2;
     return 0;
 }
@@ -1607,37 +1616,22 @@ int lpe_bh_tick_finish(lpe_bh_ctx* c, double* pos, double* vel) {
     double* t = c->tmp;
     const size_t cap = c->cap;
     const bool want_pos = c->tick_p.do_drift && pos;
-    if (c->tick_p.precision == LPE_PREC_FAST) {
-        // FAST precision walks the tree without the velocities (the kick is deferred, see k_finish_tick): they go up on the
-        // copy stream beside the traversal
-        auto queue = [&]() -> int {
-            if (c->capturing) {
-                CU_TRY(c, cudaEventRecord(c->evc[0], st));
-                CU_TRY(c, cudaStreamWaitEvent(cs, c->evc[0], 0));
-            }
-            CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vel, 16 * n, cudaMemcpyHostToDevice, cs));
-            CU_TRY(c, cudaEventRecord(c->evc[3], cs));
-            c->defer_kick = true;
-            if (step_traverse(c, c->tick_k, c->tick_p, (int)n, false)) return 1;
-            if (c->instr & 1) cudaEventRecord(c->ev[4], st);
-            c->last_c = c->tick_k;
-            c->have_step = true;
-            c->last.depth = c->tick_k.D;
-            c->last.hilbert = c->tick_k.hilbert;
-            CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
-            return queue_deferred_finish(c, true, c->tick_has_comp, want_pos, pos, nullptr, vel, nullptr);
-        };
-        int rc;
-        if (graphs_on(c) && is_pinned(pos) && is_pinned(vel)) {
-            std::string key("tick3");
-            key_add(key, c->tick_p); key_add(key, n); key_add(key, c->cap); key_add(key, c->instr); key_add(key, c->force_dfs);
-            key_add(key, c->force_overflow); key_add(key, c->body); key_add(key, c->orig_valid); key_add(key, c->stream);
-            key_add(key, pos); key_add(key, vel); key_add(key, c->tick_has_comp);
-            rc = run_graphed(c, key, queue);
-        } else {
-            rc = queue();
+    if (c->defer_kick) {
+        // FAST precision: the traversal was queued by lpe_bh_tick_mass and stores velocity changes (k_finish_tick); the
+        // velocities go up on the copy stream beside it. Five plain operations: not worth a graph, and a graph on the
+        // context's stream could not start its copy before the traversal has finished.
+        CU_TRY(c, cudaMemcpyAsync(t + 3 * cap, vel, 16 * n, cudaMemcpyHostToDevice, cs));
+        CU_TRY(c, cudaEventRecord(c->evc[3], cs));
+        c->last_c = c->tick_k;
+        c->have_step = true;
+        c->last.depth = c->tick_k.D;
+        c->last.hilbert = c->tick_k.hilbert;
+        CU_TRY(c, cudaStreamWaitEvent(st, c->evc[3], 0));
+        if (queue_deferred_finish(c, true, c->tick_has_comp, want_pos, pos, nullptr, vel, nullptr)) {
+            c->defer_kick = false;
+            cudaStreamSynchronize(cs);
+            return 1;
         }
-        if (rc) { c->defer_kick = false; cudaStreamSynchronize(cs); return 1; }
         return wait_deferred_finish(c);
     }
     // STRICT precision sums in the reference's order starting from the velocity itself: upload, pack, walk, download

@@ -150,6 +150,10 @@ bool BarnesHutSystem::ensureContext() {
 // order and nothing is a Boundary: then buildTree's view (barnes_hut.cpp:117) and the force loop's view (:89) both
 // visit packed index n-1, n-2, ..., 0 (EnTT iterates the leading pool back to front), i.e. the body at packed index
 // i has insertion rank n-1-i — the C ABI's default when no rank array is given — and every body has every component.
+// This is the cheap part of the test and the copy of the positions, the first thing the device needs; whether the three
+// pools really hold the same entities in the same order is checked page by page while the velocities are copied
+// (update() below), i.e. while the device already builds and walks the tree: a tick that fails there is started over on
+// the entity-by-entity path, its queued device work is simply superseded.
 bool BarnesHutSystem::stagePagewise(entt::registry& registry, std::size_t& n) {
     auto& ps = registry.storage<Components::Position>();
     auto& ms = registry.storage<Components::Mass>();
@@ -162,28 +166,16 @@ bool BarnesHutSystem::stagePagewise(entt::registry& registry, std::size_t& n) {
             if (ph.phase == Components::Phase::Liquid) return false;
     }
     if (!st_->reserve(n)) return false;
-    const auto* pe = ps.data();
-    const auto* me = ms.data();
-    const auto* ve = vs.data();
     auto** ppages = ps.raw();
     const std::size_t pages = (n + kPage - 1) / kPage;
-    std::atomic<bool> aligned{true};
     double* pos = st_->pos.p;
-    // same entities in the same packed order in all three pools? (checked every tick: entities come and go) — and the
-    // positions, the first thing the device needs
     st_->workers->run([&](int k, int K) {
-        const std::size_t p0 = pages * k / K, p1 = pages * (k + 1) / K;
-        for (std::size_t pg = p0; pg < p1 && aligned.load(std::memory_order_relaxed); ++pg) {
+        for (std::size_t pg = pages * k / K; pg < pages * (k + 1) / K; ++pg) {
             const std::size_t a = pg * kPage, cnt = std::min(kPage, n - a);
-            if (std::memcmp(pe + a, me + a, cnt * sizeof(entt::entity)) != 0 ||
-                std::memcmp(pe + a, ve + a, cnt * sizeof(entt::entity)) != 0) {
-                aligned.store(false, std::memory_order_relaxed);
-                break;
-            }
             std::memcpy(pos + 2 * a, ppages[pg], cnt * sizeof(Components::Position));
         }
     });
-    return aligned.load();
+    return true;
 }
 
 // The reference's own views, entity by entity, in the iteration order of buildTree's view (barnes_hut.cpp:117): that
@@ -271,7 +263,7 @@ void BarnesHutSystem::update(entt::registry& registry) {
     };
 
     std::size_t n = 0;
-    const bool pagewise = options_.pagewiseStaging && stagePagewise(registry, n);
+    bool pagewise = options_.pagewiseStaging && stagePagewise(registry, n);
     if (!pagewise) n = stagePerEntity(registry);
     lastPath_ = pagewise ? 1 : 0;
     if (n == 0) return;
@@ -298,7 +290,7 @@ void BarnesHutSystem::update(entt::registry& registry) {
     mark();
     if (lpe_bh_tick_begin(ctx_, &p, n, st_->pos.p, pagewise ? nullptr : st_->comp.p) != 0) { failed(); return; }
     mark();
-    const std::size_t pages = (n + kPage - 1) / kPage;
+    std::size_t pages = (n + kPage - 1) / kPage;
     if (pagewise) {
         auto** mpages = registry.storage<Components::Mass>().raw();
         st_->workers->run([&](int k, int K) {
@@ -312,13 +304,35 @@ void BarnesHutSystem::update(entt::registry& registry) {
     if (lpe_bh_tick_mass(ctx_, st_->m.p, pagewise ? nullptr : st_->rank.p) != 0) { failed(); return; }
     mark();
     if (pagewise) {
-        auto** vpages = registry.storage<Components::Velocity>().raw();
+        // the velocities, and — while the device builds the tree and walks it — the check that the three pools hold the
+        // same entities in the same packed order (entities come and go: checked every tick)
+        auto& vsr = registry.storage<Components::Velocity>();
+        auto** vpages = vsr.raw();
+        const auto* pe = registry.storage<Components::Position>().data();
+        const auto* me = registry.storage<Components::Mass>().data();
+        const auto* ve = vsr.data();
+        std::atomic<bool> aligned{true};
         st_->workers->run([&](int k, int K) {
             for (std::size_t pg = pages * k / K; pg < pages * (k + 1) / K; ++pg) {
                 const std::size_t a = pg * kPage, cnt = std::min(kPage, n - a);
+                if (std::memcmp(pe + a, me + a, cnt * sizeof(entt::entity)) != 0 ||
+                    std::memcmp(pe + a, ve + a, cnt * sizeof(entt::entity)) != 0) {
+                    aligned.store(false, std::memory_order_relaxed);
+                    return;
+                }
                 std::memcpy(st_->vel.p + 2 * a, vpages[pg], cnt * sizeof(Components::Velocity));
             }
         });
+        if (!aligned.load()) {
+            // start the tick over, entity by entity: lpe_bh_tick_begin supersedes everything queued so far (the masses
+            // staged above went to the wrong bodies, nothing of that tick is kept)
+            pagewise = false;
+            lastPath_ = 0;
+            n = stagePerEntity(registry);
+            if (n == 0) return;
+            if (lpe_bh_tick_begin(ctx_, &p, n, st_->pos.p, st_->comp.p) != 0) { failed(); return; }
+            if (lpe_bh_tick_mass(ctx_, st_->m.p, st_->rank.p) != 0) { failed(); return; }
+        }
     }
     mark();
     if (lpe_bh_tick_finish(ctx_, st_->pos.p, st_->vel.p) != 0) { failed(); return; }
