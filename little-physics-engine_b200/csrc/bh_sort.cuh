@@ -17,6 +17,7 @@ constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_MAX_PASSES = 8;
+constexpr int SORT_BALLOT_MAX = 3500000;             // keys: up to here the passes rank by ballots (see k_sort_onesweep)
 constexpr int SORT_HIST_STRIDE = 512;                 // words per pass in the histogram / base arrays
 
 // ---- look-back status words: high half = epoch << 2 | state, low half = value -------------------------------
@@ -205,7 +206,9 @@ template <int BINS, class KeyT, int THREADS, int ITEMS>
 constexpr size_t sort_smem_bytes() {
     return (size_t)THREADS * ITEMS * (sizeof(KeyT) + 4) + (size_t)BINS * 8 + 128 + (size_t)(THREADS / 32) * BINS * 2;
 }
-template <int BINS, class KeyT, int THREADS, int ITEMS>
+// BALLOT: the lanes with the same digit come from one ballot per digit bit instead of MATCH.ANY — more instructions, less
+// latency: faster while a pass is a single wave of tiles (-8 % at 1 M keys), slower at 16 M (+3 %); the host picks by size.
+template <int BINS, class KeyT, int THREADS, int ITEMS, bool BALLOT>
 __global__ void __launch_bounds__(THREADS, THREADS == 512 ? 3 : 1)
 k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict__ valsIn,
                 KeyT* __restrict__ keysOut, unsigned int* __restrict__ valsOut, int n, int shift,
@@ -263,21 +266,21 @@ k_sort_onesweep(const KeyT* __restrict__ keysIn, const unsigned int* __restrict_
     for (int r = 0; r < ITEMS; ++r) {
         const bool ok = wbase + r * 32 + lane < n;
         const unsigned int d = ok ? sort_digit<KeyT>(key[r], val[r], shift, dmask, TOP) : 0xFFFFu;
-#ifdef SORT_BALLOT_MATCH
-        // the lanes with the same digit, from one ballot per digit bit (+ one for "in range") instead of MATCH.ANY
-        constexpr int BITS = BINS == 512 ? 9 : 8;
-        unsigned int pm = 0xFFFFFFFFu;
+        if constexpr (BALLOT) {
+            // the lanes with the same digit, from one ballot per digit bit (+ one for "in range")
+            constexpr int BITS = BINS == 512 ? 9 : 8;
+            unsigned int pm = 0xFFFFFFFFu;
 #pragma unroll
-        for (int b = 0; b < BITS; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const unsigned int bal = __ballot_sync(0xFFFFFFFFu, bit);
-            pm &= bit ? bal : ~bal;
+            for (int b = 0; b < BITS; ++b) {
+                const bool bit = (d >> b) & 1u;
+                const unsigned int bal = __ballot_sync(0xFFFFFFFFu, bit);
+                pm &= bit ? bal : ~bal;
+            }
+            const unsigned int balOk = __ballot_sync(0xFFFFFFFFu, ok);
+            peers[r] = pm & (ok ? balOk : ~balOk);
+        } else {
+            peers[r] = __match_any_sync(0xFFFFFFFFu, d);
         }
-        const unsigned int balOk = __ballot_sync(0xFFFFFFFFu, ok);
-        peers[r] = pm & (ok ? balOk : ~balOk);
-#else
-        peers[r] = __match_any_sync(0xFFFFFFFFu, d);
-#endif
     }
 #pragma unroll
     for (int r = 0; r < ITEMS; ++r) {

@@ -773,14 +773,19 @@ int step_sort(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_de
             const int top = ps == passes - 1;
             unsigned long long* status = c->lbstatus + (size_t)ps * 256 * statusTiles;
             const unsigned int* base = hist + 512 * ps;
+            // (ranking by ballots while a pass is about one wave of tiles, by MATCH.ANY beyond: bh_sort.cuh)
+            const bool ballot = sizeof(KeyT) == 4 && n <= SORT_BALLOT_MAX;
             auto pass = [&](auto binsTag) {
                 constexpr int BINS = decltype(binsTag)::value;
                 constexpr size_t smem = sort_smem_bytes<BINS, KeyT, THREADS, SORT_ITEMS>();
-                auto kern = k_sort_onesweep<BINS, KeyT, THREADS, SORT_ITEMS>;
-                // (more than 48 KB of shared memory has to be asked for, per kernel and per device: a host-side call, no stream work)
-                if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                kern<<<sortTiles, THREADS, smem, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1], n, shift, base, status,
-                                                      c->epoch_dev, tileCounter + ps, fault, n_dev);
+                auto go = [&](auto kern) {
+                    // (more than 48 KB of shared memory has to be asked for, per kernel and per device: a host-side call, no stream work)
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    kern<<<sortTiles, THREADS, smem, st>>>(kb[sel], c->vals[sel], kb[sel ^ 1], c->vals[sel ^ 1], n, shift, base, status,
+                                                          c->epoch_dev, tileCounter + ps, fault, n_dev);
+                };
+                if (ballot) go(k_sort_onesweep<BINS, KeyT, THREADS, SORT_ITEMS, true>);
+                else go(k_sort_onesweep<BINS, KeyT, THREADS, SORT_ITEMS, false>);
             };
             if (top && lastBins == 512) pass(std::integral_constant<int, 512>{});
             else pass(std::integral_constant<int, 256>{});
