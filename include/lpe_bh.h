@@ -162,10 +162,13 @@ int  lpe_bh_update_host_aos(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n,
 /* The same tick in three calls for a caller that first has to gather its components (the ECS drop-in): each call
  * queues the device work its array unlocks and returns, so the next array is gathered while the GPU runs.
  *   lpe_bh_tick_begin   positions ({x,y} records) [+ component masks]  -> keys, sort          (asynchronous)
- *   lpe_bh_tick_mass    masses [+ insertion ranks]                       -> gather, tree build  (asynchronous)
- *   lpe_bh_tick_finish  velocities ({vx,vy} records, updated in place)   -> traversal + kick [+ drift: pos updated in
- *                       place when do_drift]; synchronises
- * Host arrays should be page-locked (lpe_bh_alloc_pinned) and must stay untouched until lpe_bh_tick_finish returns. */
+ *   lpe_bh_tick_mass    masses [+ insertion ranks]                       -> gather, tree build and, in FAST precision,
+ *                       the tree walk, which does not need the velocities (asynchronous)
+ *   lpe_bh_tick_finish  velocities ({vx,vy} records, updated in place)   -> kick [+ drift: pos updated in place when
+ *                       do_drift] (STRICT precision: tree walk + kick); synchronises
+ * Calling lpe_bh_tick_begin again before lpe_bh_tick_finish abandons the tick that was under way.
+ * Host arrays should be page-locked (lpe_bh_alloc_pinned: the first two calls then replay captured CUDA graphs) and must
+ * stay untouched until lpe_bh_tick_finish returns. */
 int  lpe_bh_tick_begin(lpe_bh_ctx* ctx, const lpe_bh_params* p, uint64_t n, const double* pos, const uint8_t* comp);
 int  lpe_bh_tick_mass(lpe_bh_ctx* ctx, const double* m, const uint32_t* rank);
 int  lpe_bh_tick_finish(lpe_bh_ctx* ctx, double* pos, double* vel);

@@ -1,12 +1,14 @@
-// bh_sort.cuh — LSD radix sort (u64 key, u32 payload, 8-bit digits) and a device-wide exclusive scan.
+// bh_sort.cuh — LSD radix sort (u32 or u64 key, u32 payload, 8-bit digits) and a device-wide exclusive scan.
 //
-// HBM-bound integer work. One histogram kernel reads the keys once and counts the digits of EVERY pass; each pass
-// is then a single kernel that reads keys + payload once and writes them once (algorithmic 8 + passes * 24 B per
-// element): a tile's position inside each digit's run comes from a decoupled look-back over the tiles before it
-// (status word = flag | count, one word per tile and digit), not from a separate count + scan launch pair.
-// Tiles are 2048 elements (256 threads x 8); a warp owns a contiguous 256-element run of its tile, so loads
-// are coalesced and the stable rank of an element is (warps before) + (earlier rounds of this warp) +
-// (lower lanes with the same digit), found with __match_any_sync — no per-element atomics.
+// HBM-bound integer work by its bytes, latency-bound in practice. One histogram kernel reads the keys once and counts
+// the digits of EVERY pass; each pass is then a single kernel that reads keys + payload once and writes them once
+// (algorithmic 4 + passes * 16 B per element with 32-bit keys, 8 + passes * 24 B with 64-bit keys): a tile's position
+// inside each digit's run comes from a decoupled look-back over the tiles before it (status word = epoch | flag | count,
+// one word per tile and digit), not from a separate count + scan launch pair.
+// Tiles are 4096 elements (512 threads x 8) for 32-bit keys, 2048 (256 x 8) for 64-bit keys; a warp owns a contiguous
+// 256-element run of its tile, so loads are coalesced and the stable rank of an element is (warps before) + (earlier
+// rounds of this warp) + (lower lanes with the same digit), found with __match_any_sync or, for small inputs, with one
+// ballot per digit bit — no per-element atomics.
 #pragma once
 #include "bh_common.cuh"
 

@@ -24,6 +24,9 @@
 //     mask only selects a zero mass.
 //
 // A warp whose ring would overflow hands its chunk to the depth-first kernel (second launch).
+//
+// In front of the per-warp walk, the four warps of a CTA take the far field of their 128 bodies together (template flag
+// CTA, see T3Cta below): what every body of the block accepts or opens is classified once, not four times.
 #pragma once
 #include <type_traits>
 #include "bh_common.cuh"
