@@ -19,7 +19,10 @@ constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // 2048
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_MAX_PASSES = 8;
-constexpr int SORT_BALLOT_MAX = 3500000;             // keys: up to here the passes rank by ballots (see k_sort_onesweep)
+#ifndef SORT_BALLOT_MAX_N
+#define SORT_BALLOT_MAX_N 2500000
+#endif
+constexpr int SORT_BALLOT_MAX = SORT_BALLOT_MAX_N;    // keys: up to here the passes rank by ballots (see k_sort_onesweep)
 constexpr int SORT_HIST_STRIDE = 512;                 // words per pass in the histogram / base arrays
 
 // ---- look-back status words: high half = epoch << 2 | state, low half = value -------------------------------
