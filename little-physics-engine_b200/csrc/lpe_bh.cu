@@ -1681,6 +1681,7 @@ int lpe_bh_get_stats(lpe_bh_ctx* c, lpe_bh_stats* out) {
         s.force_sum = h.force_sum;
         { double fm; std::memcpy(&fm, &h.force_max_bits, sizeof(fm)); s.force_max = fm; }
         for (int z = 0; z < 8; ++z) s.t2_kinds[z] = h.t2[z];
+        s.ms_keygen = s.ms_sort = s.ms_build = s.ms_traverse = s.ms_total = 0.f;   // (only with timing instrumentation)
         if (c->instr & 1) {
             cudaEventElapsedTime(&s.ms_keygen, c->ev[0], c->ev[1]);
             cudaEventElapsedTime(&s.ms_sort, c->ev[1], c->ev[2]);
