@@ -853,7 +853,7 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
         long long maxCells = (L < 15) ? (1ll << (2 * L)) : (long long)n;
         if (maxCells > n) maxCells = n;
         int grid = cdiv(maxCells * 4, 256);   // four lanes per cell
-        if (grid > sms * 7) grid = sms * 7;
+        if (grid > sms * 4) grid = sms * 4;   // (64 registers: four blocks are resident per SM; 7 / 8 / 16 per SM measured 1-2 % slower)
         k_agg_level<<<grid, 256, 0, st>>>(k, L, c->levelList, levelBase, levelCount, c->child, no, c->scal);
         ++levelLaunches;
     }
