@@ -81,7 +81,6 @@ struct lpe_bh_ctx {
     bool capturing = false;       // the calls being made are recorded into a CUDA graph (run_graphed)
     bool tracing = false;
     cudaEvent_t trace_ev[7] = {};
-    cudaEvent_t dbg_ev[6] = {};
     bool defer_kick = false;      // host tick, FAST precision: the traversal stores velocity changes, k_finish_tick applies them
     int tick_stage = 0;           // lpe_bh_tick_begin / _mass / _finish: which call comes next
     StepConst tick_k{};
@@ -820,7 +819,6 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
                                    c->orig_valid ? c->orig : nullptr, c->body2, c->vel2, c->orig2, c->selfslot, n_dev,
                                    (unsigned int)c->cap, c->scal);
     CU_TRY(c, cudaEventRecord(c->evs[1], sg));
-    if (c->tracing) { if (!c->dbg_ev[0]) for (auto& e : c->dbg_ev) cudaEventCreate(&e); cudaEventRecord(c->dbg_ev[0], sg); }
     // from here on the state IS in key order
     std::swap(c->body, c->body2);
     std::swap(c->vel, c->vel2);
@@ -838,11 +836,9 @@ int step_build(lpe_bh_ctx* c, const StepConst& k, int n, const unsigned int* n_d
     k_scan_chained<<<scanTiles, SCAN_THREADS, 0, st>>>(MaskPop{c->mask, c->scal}, StoreSink{c->P}, n,
                                                        scanStatus + (size_t)cdiv((long long)c->cap + 1, SCAN_TILE) + 1, c->epoch_dev,
                                                        scanTicket + 1, sortFault);
-    if (c->tracing) cudaEventRecord(c->dbg_ev[1], st);
     Topo topo{c->wstart, c->child, c->agg, c->levelList, levelCount, levelBase, levelCursor, c->tfirst, c->body, c->selfslot, c->rec};
     CU_TRY(c, cudaStreamWaitEvent(st, c->evs[1], 0));   // join: bodies are in key order
     k_topology<<<g256, 256, 0, st>>>(k, c->tkey, c->delta, c->mask, c->P, topo, c->scal);
-    if (c->tracing) cudaEventRecord(c->dbg_ev[2], st);
     NodeOut no{c->agg, c->rec, c->selfslot, c->body};
     // branching cells, deepest level first; the handful of cells of levels <= 4 share one single-block launch
     const int sms = c->sms;
